@@ -1,0 +1,485 @@
+"""Fused layer ops with explicit forward AND backward (no autograd tape).
+
+Each op is the unit the static executor schedules: conv+BN+activation(+residual) is one op,
+conv+bias+activation is one op, and so on.  Library GEMM/conv kernels (cuDNN/cuBLAS through
+``torch.ops.aten``) are used where no hand-written kernel exists yet; everything elementwise
+or reduction-shaped runs in the hand-written kernels of ``ddlbench_b200.ops`` (on CPU: their
+fp32 references), and 1x1 convolutions / FC layers can run on the tcgen05 GEMM
+(``csrc/gemm_tcgen05.cu``) with the BatchNorm statistics fused into its epilogue.
+
+Parameter gradients are written straight into views of the flat gradient buffer
+(write-not-accumulate on the first micro-batch), so no ``zero_grad`` pass exists.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..ops import ACT_NONE, ACT_RELU, ACT_RELU6
+
+aten = torch.ops.aten
+Ctx = Dict[str, object]
+# set by the executor: route 1x1 convs / FC through the tcgen05 GEMM kernels
+TCGEN05 = {"conv1x1": False, "linear": False}
+
+
+def _write(dst: torch.Tensor, src: torch.Tensor, accumulate: bool) -> None:
+    if accumulate:
+        dst.add_(src.to(dst.dtype) if src.dtype != dst.dtype else src)
+    else:
+        dst.copy_(src)
+
+
+def _sum_grads(dys: Sequence[torch.Tensor]) -> torch.Tensor:
+    out = dys[0]
+    for d in dys[1:]:
+        out = out + d
+    return out
+
+
+def _pair(v) -> List[int]:
+    return [v, v] if isinstance(v, int) else list(v)
+
+
+class Op:
+    kind = "op"
+
+    def __init__(self, name: str, inputs: Sequence[str], output: str):
+        self.name = name
+        self.inputs = list(inputs)
+        self.output = output
+        self.params: List[str] = []       # names inside the ParamStore
+        self.order = 0                    # forward execution index
+
+    def param_specs(self):                # -> List[ParamSpec]
+        return []
+
+    def buffers(self) -> Dict[str, torch.Tensor]:
+        return {}
+
+    def forward(self, P, B, xs: List[torch.Tensor], ctx: Ctx, training: bool) -> torch.Tensor:
+        raise NotImplementedError
+
+    def backward(self, P, G, dys: List[torch.Tensor], ctx: Ctx, accumulate: bool,
+                 need: List[bool]) -> List[Optional[torch.Tensor]]:
+        raise NotImplementedError
+
+    def to_device(self, device) -> None:
+        pass
+
+    def __repr__(self):
+        return f"{self.kind}({self.name}: {self.inputs} -> {self.output})"
+
+
+# ------------------------------------------------------------------------------- conv helpers
+class _ConvMixin:
+    def _conv_cfg(self, conv: nn.Conv2d):
+        self.stride = _pair(conv.stride)
+        self.padding = _pair(conv.padding)
+        self.dilation = _pair(conv.dilation)
+        self.groups = conv.groups
+        self.wshape = tuple(conv.weight.shape)
+
+    def _is_gemm(self, x: torch.Tensor) -> bool:
+        co, ci, kh, kw = self.wshape
+        return (TCGEN05["conv1x1"] and kh == 1 and kw == 1 and self.stride == [1, 1] and
+                self.padding == [0, 0] and self.groups == 1 and x.is_cuda and
+                x.dtype == torch.bfloat16 and ci % 8 == 0 and co % 8 == 0 and
+                x.is_contiguous(memory_format=torch.channels_last))
+
+    def _conv_fwd(self, x, w, bias=None, col_sums=None, relu=False):
+        """Returns (y, stats_fused)."""
+        if self._is_gemm(x):
+            n, ci, h, wd = x.shape
+            co = self.wshape[0]
+            a = x.permute(0, 2, 3, 1).reshape(n * h * wd, ci)
+            d = ops.gemm_tn(a, w.reshape(co, ci), col_sums=col_sums, bias=bias, relu=relu)
+            return d.view(n, h, wd, co).permute(0, 3, 1, 2), col_sums is not None
+        y = aten.convolution(x, w, None, self.stride, self.padding, self.dilation, False, [0, 0],
+                             self.groups)
+        return y, False
+
+    def _conv_bwd(self, dy, x, w, need_dx: bool):
+        dx, dw, _ = aten.convolution_backward(dy, x, w, None, self.stride, self.padding,
+                                              self.dilation, False, [0, 0], self.groups,
+                                              [need_dx, True, False])
+        return dx, dw
+
+
+class ConvBnAct(Op, _ConvMixin):
+    """y = act(BN(conv(x)) [+ res]) — one op forward, one op backward."""
+    kind = "conv_bn_act"
+
+    def __init__(self, name, inputs, output, conv: nn.Conv2d, bn: nn.BatchNorm2d, act: int,
+                 has_res: bool, conv_name: str, bn_name: str):
+        super().__init__(name, inputs, output)
+        self._conv_cfg(conv)
+        self.act, self.has_res = act, has_res
+        self.eps, self.momentum = bn.eps, (bn.momentum if bn.momentum is not None else 0.1)
+        self.channels = bn.num_features
+        self.k_w, self.k_g, self.k_b = conv_name + ".weight", bn_name + ".weight", bn_name + ".bias"
+        self.k_rm, self.k_rv = bn_name + ".running_mean", bn_name + ".running_var"
+        self.params = [self.k_w, self.k_g, self.k_b]
+        self._init = {self.k_w: conv.weight.detach().float(), self.k_g: bn.weight.detach().float(),
+                      self.k_b: bn.bias.detach().float()}
+        self._bufs = {self.k_rm: bn.running_mean.detach().float().clone(),
+                      self.k_rv: bn.running_var.detach().float().clone()}
+        self.ws: Optional[ops.BnWorkspace] = None
+
+    def param_specs(self):
+        from .store import ParamSpec
+        return [ParamSpec(self.k_w, self.wshape, self._init[self.k_w], True, self.order),
+                ParamSpec(self.k_g, (self.channels,), self._init[self.k_g], False, self.order),
+                ParamSpec(self.k_b, (self.channels,), self._init[self.k_b], False, self.order)]
+
+    def buffers(self):
+        return self._bufs
+
+    def to_device(self, device):
+        if torch.device(device).type == "cuda":
+            self.ws = ops.BnWorkspace(self.channels, device)
+
+    def forward(self, P, B, xs, ctx, training):
+        x = xs[0]
+        res = xs[1] if self.has_res else None
+        fuse_stats = training and self.ws is not None and self._is_gemm(x)
+        c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums if fuse_stats else None)
+        y, stat = ops.bn_forward(c, res, P[self.k_g], P[self.k_b], B[self.k_rm], B[self.k_rv],
+                                 self.eps, self.momentum, self.act, self.ws, stats_ready=fused,
+                                 training=training)
+        if training:
+            ctx["x"], ctx["c"], ctx["stat"] = x, c, stat
+            ctx["y"] = y if self.act != ACT_NONE else None
+        return y
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        dy2 = dys[1] if len(dys) > 1 else None
+        if len(dys) > 2:
+            dys = [_sum_grads(dys[:-1]), dys[-1]]
+            dy2 = dys[1]
+        dc, dz = ops.bn_backward(dys[0], dy2, ctx["y"], ctx["c"], ctx["stat"], P[self.k_g],
+                                 self.act, self.has_res and need[1], G[self.k_g], G[self.k_b],
+                                 accumulate, self.ws)
+        dx, dw = self._conv_bwd(dc, ctx["x"], P[self.k_w], need[0])
+        _write(G[self.k_w], dw, accumulate)
+        return [dx, dz] if self.has_res else [dx]
+
+
+class ConvBiasAct(Op, _ConvMixin):
+    """y = act(conv(x) + bias) (VGG)."""
+    kind = "conv_bias_act"
+
+    def __init__(self, name, inputs, output, conv: nn.Conv2d, act: int, conv_name: str):
+        super().__init__(name, inputs, output)
+        self._conv_cfg(conv)
+        self.act = act
+        self.has_bias = conv.bias is not None
+        self.channels = conv.out_channels
+        self.k_w, self.k_b = conv_name + ".weight", conv_name + ".bias"
+        self.params = [self.k_w] + ([self.k_b] if self.has_bias else [])
+        self._init = {self.k_w: conv.weight.detach().float()}
+        if self.has_bias:
+            self._init[self.k_b] = conv.bias.detach().float()
+        self.ws: Optional[ops.BnWorkspace] = None
+
+    def param_specs(self):
+        from .store import ParamSpec
+        s = [ParamSpec(self.k_w, self.wshape, self._init[self.k_w], True, self.order)]
+        if self.has_bias:
+            s.append(ParamSpec(self.k_b, (self.channels,), self._init[self.k_b], False, self.order))
+        return s
+
+    def to_device(self, device):
+        if torch.device(device).type == "cuda":
+            self.ws = ops.BnWorkspace(self.channels, device)
+
+    def forward(self, P, B, xs, ctx, training):
+        x = xs[0]
+        bias = P[self.k_b] if self.has_bias else None
+        if self._is_gemm(x) and self.act in (ACT_NONE, ACT_RELU):
+            y, _ = self._conv_fwd(x, P[self.k_w], bias=bias, relu=self.act == ACT_RELU)
+        else:
+            c, _ = self._conv_fwd(x, P[self.k_w])
+            y = ops.bias_act(c, bias, self.act) if (bias is not None or self.act) else c
+        if training:
+            ctx["x"] = x
+            ctx["y"] = y if self.act != ACT_NONE else None
+        return y
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        if self.act != ACT_NONE or len(dys) > 1:
+            if len(dys) > 2:
+                dys = [_sum_grads(dys[:-1]), dys[-1]]
+            dz = ops.act_bwd(dys[0], dys[1] if len(dys) > 1 else None, ctx["y"], self.act)
+        else:
+            dz = dys[0]
+        if self.has_bias:
+            ops.bias_grad_(dz, G[self.k_b], accumulate, self.ws)
+        dx, dw = self._conv_bwd(dz, ctx["x"], P[self.k_w], need[0])
+        _write(G[self.k_w], dw, accumulate)
+        return [dx]
+
+
+class LinearAct(Op):
+    """y = act(x @ W^T + b)."""
+    kind = "linear_act"
+
+    def __init__(self, name, inputs, output, lin: nn.Linear, act: int, lin_name: str):
+        super().__init__(name, inputs, output)
+        self.act = act
+        self.in_f, self.out_f = lin.in_features, lin.out_features
+        self.has_bias = lin.bias is not None
+        self.k_w, self.k_b = lin_name + ".weight", lin_name + ".bias"
+        self.params = [self.k_w] + ([self.k_b] if self.has_bias else [])
+        self._init = {self.k_w: lin.weight.detach().float()}
+        if self.has_bias:
+            self._init[self.k_b] = lin.bias.detach().float()
+
+    def param_specs(self):
+        from .store import ParamSpec
+        s = [ParamSpec(self.k_w, (self.out_f, self.in_f), self._init[self.k_w], False, self.order)]
+        if self.has_bias:
+            s.append(ParamSpec(self.k_b, (self.out_f,), self._init[self.k_b], False, self.order))
+        return s
+
+    def forward(self, P, B, xs, ctx, training):
+        x = xs[0]
+        w = P[self.k_w]
+        b = P[self.k_b] if self.has_bias else None
+        if (TCGEN05["linear"] and self.act in (ACT_NONE, ACT_RELU) and x.dim() == 2 and
+                ops.gemm_tn_supported(x, w) and self.out_f % 8 == 0):
+            y = ops.gemm_tn(x, w, bias=b, relu=self.act == ACT_RELU)
+        else:
+            y = torch.addmm(b, x, w.t()) if b is not None else x @ w.t()
+            if self.act != ACT_NONE:
+                y = torch.relu(y) if self.act == ACT_RELU else torch.clamp(y, 0, 6)
+        if training:
+            ctx["x"] = x
+            ctx["y"] = y if self.act != ACT_NONE else None
+        return y
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        dy = _sum_grads(dys)
+        if self.act != ACT_NONE:
+            dy = ops.act_bwd(dy, None, ctx["y"], self.act)
+        x = ctx["x"]
+        _write(G[self.k_w], dy.t() @ x, accumulate)
+        if self.has_bias:
+            _write(G[self.k_b], dy.float().sum(0).to(dy.dtype), accumulate)
+        return [dy @ P[self.k_w] if need[0] else None]
+
+
+class MaxPool(Op):
+    kind = "maxpool"
+
+    def __init__(self, name, inputs, output, m: nn.MaxPool2d):
+        super().__init__(name, inputs, output)
+        self.k, self.s = _pair(m.kernel_size), _pair(m.stride if m.stride is not None else m.kernel_size)
+        self.p, self.d, self.ceil = _pair(m.padding), _pair(m.dilation), bool(m.ceil_mode)
+
+    def forward(self, P, B, xs, ctx, training):
+        y, idx = aten.max_pool2d_with_indices(xs[0], self.k, self.s, self.p, self.d, self.ceil)
+        if training:
+            ctx["x"], ctx["idx"] = xs[0], idx
+        return y
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        dy = _sum_grads(dys)
+        if not need[0]:
+            return [None]
+        return [aten.max_pool2d_with_indices_backward(dy, ctx["x"], self.k, self.s, self.p, self.d,
+                                                      self.ceil, ctx["idx"])]
+
+
+class AvgPool(Op):
+    """AvgPool2d / AdaptiveAvgPool2d (general case through aten)."""
+    kind = "avgpool"
+
+    def __init__(self, name, inputs, output, m: nn.Module):
+        super().__init__(name, inputs, output)
+        self.adaptive = isinstance(m, nn.AdaptiveAvgPool2d)
+        if self.adaptive:
+            self.out = _pair(m.output_size)
+        else:
+            self.k = _pair(m.kernel_size)
+            self.s = _pair(m.stride if m.stride is not None else m.kernel_size)
+            self.p = _pair(m.padding)
+            self.ceil, self.cip = bool(m.ceil_mode), bool(m.count_include_pad)
+
+    def _identity(self, x) -> bool:
+        if self.adaptive:
+            return list(x.shape[2:]) == self.out
+        return self.k == [1, 1] and self.s == [1, 1] and self.p == [0, 0]
+
+    def forward(self, P, B, xs, ctx, training):
+        x = xs[0]
+        if self._identity(x):
+            ctx["id"] = True
+            return x
+        ctx["id"] = False
+        if training:
+            ctx["x"] = x
+        if self.adaptive:
+            return aten._adaptive_avg_pool2d(x, self.out)
+        return aten.avg_pool2d(x, self.k, self.s, self.p, self.ceil, self.cip, None)
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        dy = _sum_grads(dys)
+        if not need[0]:
+            return [None]
+        if ctx["id"]:
+            return [dy]
+        if self.adaptive:
+            return [aten._adaptive_avg_pool2d_backward(dy, ctx["x"])]
+        return [aten.avg_pool2d_backward(dy, ctx["x"], self.k, self.s, self.p, self.ceil, self.cip,
+                                         None)]
+
+
+class GlobalAvgPoolFlatten(Op):
+    """avg-pool to 1x1 + flatten, fused ([N,C,H,W] -> [N,C])."""
+    kind = "gap_flatten"
+
+    def forward(self, P, B, xs, ctx, training):
+        ctx["shape"] = tuple(xs[0].shape)
+        return ops.global_avg_pool(xs[0])
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        if not need[0]:
+            return [None]
+        return [ops.global_avg_pool_bwd(_sum_grads(dys), ctx["shape"])]
+
+
+class FlattenOp(Op):
+    kind = "flatten"
+
+    def forward(self, P, B, xs, ctx, training):
+        x = xs[0]
+        ctx["shape"] = tuple(x.shape)
+        ctx["cl"] = x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and \
+            not x.is_contiguous()
+        return x.reshape(x.shape[0], -1)
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        if not need[0]:
+            return [None]
+        dx = _sum_grads(dys).reshape(ctx["shape"])
+        if ctx["cl"]:
+            dx = dx.contiguous(memory_format=torch.channels_last)
+        return [dx]
+
+
+class DropoutOp(Op):
+    kind = "dropout"
+
+    def __init__(self, name, inputs, output, m: nn.Dropout):
+        super().__init__(name, inputs, output)
+        self.p = float(m.p)
+
+    def forward(self, P, B, xs, ctx, training):
+        if not training or self.p == 0.0:
+            ctx["mask"] = None
+            return xs[0]
+        y, mask = aten.native_dropout(xs[0], self.p, True)
+        ctx["mask"] = mask
+        return y
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        dy = _sum_grads(dys)
+        if ctx.get("mask") is None:
+            return [dy]
+        return [aten.native_dropout_backward(dy, ctx["mask"], 1.0 / (1.0 - self.p))]
+
+
+class AddAct(Op):
+    """y = act(a + b) for joins that are not preceded by a BatchNorm."""
+    kind = "add_act"
+
+    def __init__(self, name, inputs, output, act: int):
+        super().__init__(name, inputs, output)
+        self.act = act
+
+    def forward(self, P, B, xs, ctx, training):
+        y = xs[0]
+        for x in xs[1:]:
+            y = y + x
+        if self.act == ACT_RELU:
+            y = torch.relu(y)
+        elif self.act == ACT_RELU6:
+            y = torch.clamp(y, 0, 6)
+        if training:
+            ctx["y"] = y if self.act != ACT_NONE else None
+        return y
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        if self.act != ACT_NONE or len(dys) > 1:
+            if len(dys) > 2:
+                dys = [_sum_grads(dys[:-1]), dys[-1]]
+            dz = ops.act_bwd(dys[0], dys[1] if len(dys) > 1 else None, ctx["y"], self.act)
+        else:
+            dz = dys[0]
+        return [dz if n else None for n in need]
+
+
+class ModuleOp(Op):
+    """Fallback: any ``nn.Module`` runs under a local autograd tape, with its parameters
+    aliased to views of the flat store.  Keeps the engine complete for arbitrary layers
+    (LSTM/attention stages of GNMT, exotic pooling...) at the cost of no fusion."""
+    kind = "module"
+
+    def __init__(self, name, inputs, output, module: nn.Module, prefix: str):
+        super().__init__(name, inputs, output)
+        self.module = module
+        self.prefix = prefix
+        self._pnames = [n for n, _ in module.named_parameters()]
+        self.params = [f"{prefix}.{n}" for n in self._pnames]
+        self._bnames = [n for n, _ in module.named_buffers()]
+
+    def param_specs(self):
+        from .store import ParamSpec
+        return [ParamSpec(f"{self.prefix}.{n}", tuple(p.shape), p.detach().float(), False, self.order)
+                for n, p in self.module.named_parameters()]
+
+    def buffers(self):
+        return {f"{self.prefix}.{n}": b.detach().clone() for n, b in self.module.named_buffers()}
+
+    def forward(self, P, B, xs, ctx, training):
+        self.module.train(training)
+        pb = {n: P[f"{self.prefix}.{n}"] for n in self._pnames}
+        pb.update({n: B[f"{self.prefix}.{n}"] for n in self._bnames})
+        if not training:
+            with torch.no_grad():
+                return torch.func.functional_call(self.module, pb, tuple(xs))
+        with torch.enable_grad():
+            ins = [x.detach().requires_grad_(x.is_floating_point()) for x in xs]
+            leafs = {n: P[f"{self.prefix}.{n}"].detach().requires_grad_(True) for n in self._pnames}
+            call = dict(leafs)
+            call.update({n: B[f"{self.prefix}.{n}"] for n in self._bnames})
+            y = torch.func.functional_call(self.module, call, tuple(ins))
+        ctx["ins"], ctx["leafs"], ctx["y"] = ins, leafs, y
+        return y.detach()
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        ins, leafs, y = ctx["ins"], ctx["leafs"], ctx["y"]
+        wrt = [i for i, n in zip(ins, need) if n and i.requires_grad] + list(leafs.values())
+        grads = torch.autograd.grad(y, wrt, _sum_grads(dys), allow_unused=True) if wrt else []
+        out: List[Optional[torch.Tensor]] = []
+        gi = 0
+        for i, n in zip(ins, need):
+            if n and i.requires_grad:
+                out.append(grads[gi])
+                gi += 1
+            else:
+                out.append(None)
+        for n in self._pnames:
+            g = grads[gi]
+            gi += 1
+            dst = G[f"{self.prefix}.{n}"]
+            if g is None:
+                if not accumulate:
+                    dst.zero_()
+            else:
+                _write(dst, g, accumulate)
+        return out

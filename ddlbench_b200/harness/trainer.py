@@ -1,0 +1,158 @@
+"""Training-step driver for the single-GPU (`pytorch`) and data-parallel (`horovod`) modes.
+
+The reference step is five eager lines — H2D copy, forward, loss, ``zero_grad``+backward,
+``optimizer.step`` — issued as ~600 separate library kernels every iteration
+(``benchmark/imagenet/imagenet_pytorch.py:149-157``).  At the benchmark's per-GPU batch of 32
+a B200 finishes each of those kernels faster than the host can launch the next one, so here
+the WHOLE step (forward, fused loss, backward, bucketed fused all-reduce+SGD on the
+communication stream) is captured once into a CUDA graph and replayed; input staging
+(pinned host -> device copy of the raw uint8 batch on a copy stream, double-buffered) and the
+loss read-back overlap the previous / next replay.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from ..engine import StageExecutor
+from ..models import build_model
+from ..models.graph import LayerGraphModel
+
+
+class Trainer:
+    def __init__(self, arch: str = "resnet50", dataset: str = "imagenet", batch_size: int = 32,
+                 device: Optional[str] = None, dtype: Optional[torch.dtype] = None,
+                 lr: float = 0.1, momentum: float = 0.9, weight_decay: float = 1e-4,
+                 cuda_graph: bool = True, distributed: bool = False, allreduce: str = "fused",
+                 tcgen05: bool = False, seed: int = 1, model: Optional[LayerGraphModel] = None,
+                 bucket_elems: int = 8 << 20, comm_blocks: int = 32, group=None):
+        torch.manual_seed(seed)
+        self.device = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+        on_gpu = self.device.type == "cuda"
+        if on_gpu:
+            torch.cuda.manual_seed(seed)
+            torch.backends.cudnn.benchmark = True
+        self.dtype = dtype or (torch.bfloat16 if on_gpu else torch.float32)
+        self.batch_size = batch_size
+        self.model = model if model is not None else build_model(arch, dataset)
+        self.arch, self.dataset = arch, dataset
+        self.distributed = distributed and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.allreduce = allreduce if self.distributed else "none"
+        self.cuda_graph = cuda_graph and on_gpu
+        self.fdp = None
+        self._sym: Dict[str, list] = {}
+        kw = dict(device=self.device, dtype=self.dtype, lr=lr, momentum=momentum,
+                  weight_decay=weight_decay, bucket_elems=bucket_elems, tcgen05=tcgen05)
+        if self.distributed and self.allreduce == "fused" and on_gpu:
+            from ..dist.symm import SymmContext
+            from ..parallel.dp import FusedDataParallel
+            self.symm = SymmContext(self.device, group)
+            alloc = FusedDataParallel.make_allocator(self.symm, self._sym)
+            self.ex = StageExecutor.from_model(self.model, world=self.world, rank=self.rank,
+                                               shard_optimizer=True, allocator=alloc, **kw)
+            bufs = self._sym["bufs"]
+            self.ex._sym_w, self.ex._sym_g = bufs[:-1], bufs[-1]
+            self.fdp = FusedDataParallel(self.ex, self.symm, blocks=comm_blocks)
+            self.fdp.broadcast_from(0)
+        else:
+            self.ex = StageExecutor.from_model(self.model, **kw)
+            if self.distributed:
+                self.ex.store.set_grad_scale(1.0 / self.world)
+                full = self.ex.store.master
+                dist.broadcast(full, src=0, group=group)
+                self.ex.store.load_full_master(full.clone())
+        self.group = group
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.static_x: Optional[torch.Tensor] = None
+        self.static_t: Optional[torch.Tensor] = None
+        self.static_stats: Optional[torch.Tensor] = None
+        self.launches_per_step = 0
+        self.steps_done = 0
+
+    # ------------------------------------------------------------------ one eager step
+    def _step_eager(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        ex = self.ex
+        outs, ctx = ex.forward([x], training=True)
+        stats, dlogits = ex.loss(outs[0], target)
+        ex.backward(ctx, [dlogits])
+        if self.fdp is not None:
+            self.fdp.finish_step()
+        else:
+            if self.distributed:   # baseline: NCCL all-reduce of the flat gradient buffer
+                dist.all_reduce(ex.store.g_flat, group=self.group)
+            ex.store.sgd_step()
+        return stats
+
+    # ------------------------------------------------------------------ public step
+    def step(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """One training step on device tensors.  Returns stats[3] (mean loss, #top1, #top5) —
+        a device tensor; reading it is the caller's (asynchronous) business."""
+        if not self.cuda_graph:
+            self.steps_done += 1
+            return self._step_eager(self.ex.prepare_input(x), target)
+        if self.graph is None:
+            self._capture(x, target)
+        if x.data_ptr() != self.static_x.data_ptr():
+            self.static_x.copy_(x, non_blocking=True)
+        if target.data_ptr() != self.static_t.data_ptr():
+            self.static_t.copy_(target, non_blocking=True)
+        self.graph.replay()
+        self.steps_done += 1
+        return self.static_stats
+
+    def step_u8(self, x_u8: torch.Tensor, target: torch.Tensor, mean, std) -> torch.Tensor:
+        """Step from a raw uint8 [B, H, W, C] device batch: the uint8 -> normalised
+        channels-last conversion is one fused kernel writing the graph's static input."""
+        if self.cuda_graph:
+            if self.graph is None:
+                self._capture(ops.normalize_u8(x_u8, mean, std, dtype=self.dtype), target)
+            ops.normalize_u8(x_u8, mean, std, dtype=self.dtype, out=self.static_x)
+            self.static_t.copy_(target, non_blocking=True)
+            self.graph.replay()
+            self.steps_done += 1
+            return self.static_stats
+        return self.step(ops.normalize_u8(x_u8, mean, std, dtype=self.dtype), target)
+
+    def _capture(self, x: torch.Tensor, target: torch.Tensor) -> None:
+        ex = self.ex
+        self.static_x = ex.prepare_input(x).clone()
+        self.static_t = target.to(self.device).clone()
+        # warm-up on a side stream: cuDNN autotune, workspace allocation, lazy inits
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._step_eager(self.static_x, self.static_t)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        if self.distributed:
+            dist.barrier(self.group)
+        before = ops.launches
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.static_stats = self._step_eager(self.static_x, self.static_t)
+        self.launches_per_step = ops.launches - before
+        self.graph = g
+        torch.cuda.synchronize(self.device)
+        if self.distributed:
+            dist.barrier(self.group)
+
+    # ------------------------------------------------------------------ evaluation
+    @torch.no_grad()
+    def eval_step(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        outs, _ = self.ex.forward([self.ex.prepare_input(x)], training=False)
+        stats, _ = self.ex.loss(outs[0], target.to(self.device), want_grad=False)
+        return stats
+
+    def set_lr(self, lr: float) -> None:
+        self.ex.store.set_lr(lr)
+
+    def check(self) -> None:
+        if self.fdp is not None:
+            self.symm.check()

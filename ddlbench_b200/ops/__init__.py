@@ -1,0 +1,342 @@
+"""Native-op front end.
+
+``ops.<name>(...)`` runs the hand-written sm_100a kernel when its tensors live on a GPU and
+the plain-PyTorch fp32 reference (``ops.reference``) on CPU, so every layer above this module
+is device-agnostic and testable without a GPU.  On a machine that HAS a GPU the extension
+must load: a missing ``.so`` raises instead of silently falling back (the driver records which
+shared objects a GPU run actually loaded).
+
+``ops.launches`` counts kernel launches issued through this module; ``bench.py`` reports it
+as ``gpu_launches``.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import reference as ref
+from .reference import ACT_NONE, ACT_RELU, ACT_RELU6
+
+_ext = None
+_ext_err: Optional[BaseException] = None
+_lock = threading.Lock()
+launches = 0  # number of native kernel launches issued through this module
+
+
+def _count(n: int = 1) -> None:
+    global launches
+    launches += n
+
+
+def load_ext(build_if_missing: bool = True):
+    """Import the in-tree extension (building it first if the .so is absent)."""
+    global _ext, _ext_err
+    if _ext is not None:
+        return _ext
+    with _lock:
+        if _ext is not None:
+            return _ext
+        from .build import build, so_path
+        try:
+            p = so_path()
+            if not p.exists():
+                if not build_if_missing:
+                    raise FileNotFoundError(str(p))
+                build()
+            spec = importlib.util.spec_from_file_location("_ddlb_ext", str(p))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _ext = mod
+        except BaseException as e:  # noqa: BLE001 - remembered and re-raised on GPU use
+            _ext_err = e
+            raise
+    return _ext
+
+
+def ext():
+    """The extension module; raises loudly on a GPU box where it cannot be loaded."""
+    if _ext is not None:
+        return _ext
+    try:
+        return load_ext()
+    except BaseException as e:  # noqa: BLE001
+        raise RuntimeError(
+            "ddlbench_b200 native extension (_ddlb_ext) is not available but a CUDA tensor "
+            "was passed to a native op; run `python -m ddlbench_b200.ops.build`") from e
+
+
+def available() -> bool:
+    try:
+        load_ext(build_if_missing=False)
+        return True
+    except BaseException:  # noqa: BLE001
+        return False
+
+
+def _on_gpu(t: torch.Tensor) -> bool:
+    return t.is_cuda
+
+
+# ------------------------------------------------------------------------------- optimizer
+def sgd_flat_(master: torch.Tensor, mom: torch.Tensor, grad: torch.Tensor, hyper: torch.Tensor,
+              w_out: torch.Tensor, w_out2: Optional[torch.Tensor] = None) -> None:
+    """One fused SGD(momentum, wd) step on flat buffers; see csrc/sgd.cu."""
+    if _on_gpu(master):
+        ext().sgd_flat(master, mom, grad, w_out, w_out2, hyper)
+        _count()
+    else:
+        ref.sgd_flat(master, mom, grad, hyper, [w_out, w_out2])
+
+
+def l2norm(x: torch.Tensor) -> torch.Tensor:
+    if _on_gpu(x):
+        _count()
+        return ext().sumsq(x.reshape(-1)).sqrt()
+    return x.float().norm().reshape(1)
+
+
+# ------------------------------------------------------------------------------- loss
+class XentWorkspace:
+    def __init__(self, rows: int, device):
+        self.row_stats = torch.zeros(rows * 3, dtype=torch.float32, device=device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def xent(logits: torch.Tensor, target: torch.Tensor, smoothing: float = 0.0,
+         grad_scale: float = 1.0, want_grad: bool = True,
+         ws: Optional[XentWorkspace] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Fused softmax cross-entropy.  Returns (stats[3]: mean loss, #top-1 hits, #top-5 hits;
+    dlogits = grad_scale * d(mean loss)/d(logits) or None)."""
+    if _on_gpu(logits):
+        if ws is None or ws.row_stats.numel() < logits.shape[0] * 3:
+            ws = XentWorkspace(logits.shape[0], logits.device)
+        logits = logits.contiguous()
+        d = torch.empty_like(logits) if want_grad else None
+        stats = ext().xent(logits, target, d, ws.row_stats, ws.ticket, float(smoothing),
+                           float(grad_scale) / logits.shape[0])
+        _count()
+        return stats, d
+    stats, d = ref.xent(logits, target, smoothing, grad_scale / logits.shape[0])
+    return stats, (d if want_grad else None)
+
+
+# ------------------------------------------------------------------------------- batch norm
+def _mc(x: torch.Tensor) -> Tuple[int, int]:
+    c = x.shape[1]
+    return x.numel() // c, c
+
+
+def _nhwc_ok(x: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0 and
+            (x.dim() == 2 or x.is_contiguous(memory_format=torch.channels_last)))
+
+
+class BnWorkspace:
+    """Per-layer fp32 scratch: partial sums (self-zeroing), (mean, invstd), bwd coefficients."""
+
+    def __init__(self, channels: int, device):
+        self.sums = torch.zeros(2 * channels, dtype=torch.float32, device=device)
+        self.coef = torch.empty(3 * channels, dtype=torch.float32, device=device)
+
+
+def bn_forward(x, res, gamma, beta, running_mean, running_var, eps: float, momentum: float,
+               act: int, ws: Optional[BnWorkspace] = None, stats_ready: bool = False,
+               training: bool = True):
+    """y = act(BN(x) [+ res]).  Returns (y, stat[2, C]).  ``stats_ready``: the producer
+    (tcgen05 GEMM epilogue) already accumulated sum / sum-of-squares into ``ws.sums``."""
+    M, C = _mc(x)
+    if not training:
+        stat = torch.stack([running_mean.float(), torch.rsqrt(running_var.float() + eps)])
+        if _nhwc_ok(x):
+            y = torch.empty_like(x)
+            ext().bn_apply(x, res, y, stat.contiguous(), gamma, beta, M, C, act)
+            _count()
+            return y, stat
+        return ref.bn_apply(x, res, stat, gamma, beta, act), stat
+    if _nhwc_ok(x):
+        e = ext()
+        if ws is None:
+            ws = BnWorkspace(C, x.device)
+        stat = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+        if not stats_ready:
+            e.bn_stats(x, ws.sums, M, C)
+            _count()
+        e.bn_finalize(ws.sums, stat, running_mean, running_var, M, C, eps, momentum)
+        y = torch.empty_like(x)
+        e.bn_apply(x, res, y, stat, gamma, beta, M, C, act)
+        _count(2)
+        return y, stat.view(2, C)
+    stat = ref.bn_stat(x, eps)
+    if running_mean is not None:
+        ref.bn_update_running(stat, M, eps, momentum, running_mean, running_var)
+    return ref.bn_apply(x, res, stat, gamma, beta, act), stat
+
+
+def bn_backward(dy, dy2, y, x, stat, gamma, act: int, want_dz: bool, dgamma_out, dbeta_out,
+                accumulate: bool = False, ws: Optional[BnWorkspace] = None):
+    """Backward of ``bn_forward``.  Writes dgamma/dbeta into the given (flat-buffer) views.
+    Returns (dx, dz) where dz (if requested) is the gradient flowing to the residual input."""
+    M, C = _mc(x)
+    if _nhwc_ok(x):
+        e = ext()
+        if ws is None:
+            ws = BnWorkspace(C, x.device)
+        stat_f = stat.reshape(-1)
+        dz = torch.empty_like(x) if want_dz else None
+        e.bn_bwd_reduce(dy, dy2, y if act != ACT_NONE else None, x, dz, stat_f, ws.sums, M, C, act)
+        e.bn_bwd_finalize(ws.sums, stat_f, gamma, ws.coef, dgamma_out, dbeta_out, accumulate, M, C)
+        dx = torch.empty_like(x)
+        if want_dz:
+            e.bn_bwd_apply(dz, None, None, None, x, dx, stat_f, ws.coef, M, C, ACT_NONE)
+        else:
+            e.bn_bwd_apply(None, dy, dy2, y if act != ACT_NONE else None, x, dx, stat_f, ws.coef,
+                           M, C, act)
+        _count(3)
+        return dx, dz
+    dx, dz, dgamma, dbeta = ref.bn_backward(dy, dy2, y, x, stat, gamma, act, want_dz)
+    if accumulate:
+        dgamma_out.add_(dgamma.to(dgamma_out.dtype))
+        dbeta_out.add_(dbeta.to(dbeta_out.dtype))
+    else:
+        dgamma_out.copy_(dgamma.to(dgamma_out.dtype))
+        dbeta_out.copy_(dbeta.to(dbeta_out.dtype))
+    return dx, dz
+
+
+def bias_act(x, bias, act: int):
+    if _nhwc_ok(x):
+        M, C = _mc(x)
+        y = torch.empty_like(x)
+        ext().bias_act(x, bias, y, M, C, act)
+        _count()
+        return y
+    return ref.bias_act(x, bias, act)
+
+
+def act_bwd(dy, dy2, y, act: int):
+    """dz = (dy [+ dy2]) * act'(y)."""
+    if dy.is_cuda and dy.dtype == torch.bfloat16 and dy.numel() % 8 == 0 and \
+            (dy2 is None or dy2.stride() == dy.stride()) and (y is None or y.stride() == dy.stride()):
+        dz = torch.empty_like(dy)
+        ext().act_bwd(dy, dy2, y if act != ACT_NONE else None, dz, act)
+        _count()
+        return dz
+    return ref.act_bwd(dy, dy2, y, act)
+
+
+def bias_grad_(dy, out, accumulate: bool = False, ws: Optional[BnWorkspace] = None):
+    """out[c] (+)= sum over all non-channel dims of dy."""
+    if _nhwc_ok(dy):
+        M, C = _mc(dy)
+        if ws is None:
+            ws = BnWorkspace(C, dy.device)
+        ext().colsum(dy, ws.sums, out, accumulate, M, C)
+        _count(2)
+        return
+    dims = [0] + list(range(2, dy.dim()))
+    g = dy.float().sum(dim=dims)
+    if accumulate:
+        out.add_(g.to(out.dtype))
+    else:
+        out.copy_(g.to(out.dtype))
+
+
+# ------------------------------------------------------------------------------- misc
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def normalize_u8(x_u8: torch.Tensor, mean: Sequence[float], std: Sequence[float],
+                 dtype=torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 [N, H, W, C] -> normalised logical [N, C, H, W] channels-last tensor."""
+    n, h, w, c = x_u8.shape
+    if x_u8.is_cuda and dtype == torch.bfloat16:
+        if out is None:
+            out = torch.empty((n, c, h, w), dtype=dtype, device=x_u8.device,
+                              memory_format=torch.channels_last)
+        ext().u8_to_bf16_norm(x_u8.contiguous(), out, c, list(mean), list(std))
+        _count()
+        return out
+    y = ref.u8_to_norm(x_u8, list(mean), list(std), dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def revert_varlen(x: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
+    if x.is_cuda:
+        _count()
+        return ext().revert_varlen(x.contiguous(), lengths.to(x.device, torch.int64))
+    return ref.revert_varlen(x, lengths)
+
+
+def set_mask(lengths: torch.Tensor, T: int) -> torch.Tensor:
+    if lengths.is_cuda:
+        _count()
+        return ext().set_mask(lengths.to(torch.int64), T)
+    return ref.set_mask(lengths, T)
+
+
+def global_avg_pool(x: torch.Tensor) -> torch.Tensor:
+    """[N, C, H, W] -> [N, C]."""
+    if _nhwc_ok(x) and x.dim() == 4:
+        n, c, h, w = x.shape
+        y = torch.empty((n, c), dtype=x.dtype, device=x.device)
+        ext().gap_fwd(x, y, n, h * w, c)
+        _count()
+        return y
+    return ref.global_avg_pool(x)
+
+
+def global_avg_pool_bwd(dy: torch.Tensor, shape) -> torch.Tensor:
+    n, c, h, w = shape
+    if dy.is_cuda and dy.dtype == torch.bfloat16 and c % 8 == 0:
+        dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device,
+                         memory_format=torch.channels_last)
+        ext().gap_bwd(dy.contiguous(), dx, n, h * w, c)
+        _count()
+        return dx
+    return (dy.float() / (h * w)).to(dy.dtype).view(n, c, 1, 1).expand(n, c, h, w).contiguous()
+
+
+# ------------------------------------------------------------------------------- GEMM
+def gemm_tn_supported(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and
+            a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1 and
+            a.shape[1] % 8 == 0 and b.shape[0] % 8 == 0 and a.stride(0) % 8 == 0 and
+            b.stride(0) % 8 == 0 and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0)
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, col_sums: Optional[torch.Tensor] = None,
+            bias: Optional[torch.Tensor] = None, relu: bool = False,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """D[M, N] = A[M, K] @ B[N, K]^T on the tcgen05 tensor cores (csrc/gemm_tcgen05.cu).
+    ``col_sums`` ([2, N] fp32, pre-zeroed) receives per-column sum / sum-of-squares of D."""
+    if gemm_tn_supported(a, b):
+        if out is None:
+            out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.bfloat16, device=a.device)
+        ext().gemm_bf16_tn(a, b, out, col_sums, bias, relu)
+        _count()
+        return out
+    d = a.float() @ b.float().t()
+    if bias is not None:
+        d = d + bias.float()
+    if relu:
+        d = torch.relu(d)
+    d = d.to(a.dtype)
+    if col_sums is not None:
+        df = d.float()
+        col_sums.view(2, -1)[0].add_(df.sum(0))
+        col_sums.view(2, -1)[1].add_((df * df).sum(0))
+    if out is not None:
+        out.copy_(d)
+        return out
+    return d
+
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,91 @@
+// C launch API of the ddlbench_b200 sm_100a kernels.  Pure CUDA (no torch headers) so
+// each .cu compiles in seconds; bindings.cpp adapts torch tensors to these calls.
+// Every function returns 0 on success, a cudaError_t value, or -1 for bad arguments.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// ---- sgd.cu
+int ddl_sgd_flat(void* master, void* mom, const void* grad, int grad_is_bf16, void* w_out,
+                 void* w_out2, int w_is_bf16, const float* hyper, int64_t n, int sms,
+                 cudaStream_t stream);
+int ddl_sumsq(const void* x, int is_bf16, float* out, int64_t n, int sms, cudaStream_t stream);
+
+// ---- xent.cu
+int ddl_xent(const void* logits, int is_bf16, const int64_t* target, void* dlogits,
+             float* row_stats, float* out, unsigned int* ticket, int rows, int C, float smoothing,
+             float grad_scale, cudaStream_t stream);
+
+// ---- bn.cu
+int ddl_bn_stats(const void* x, float* sums, int64_t M, int C, int sms, cudaStream_t st);
+int ddl_bn_finalize(float* sums, float* stat, float* running_mean, float* running_var, int64_t M,
+                    int C, float eps, float momentum, cudaStream_t st);
+int ddl_bn_apply(const void* x, const void* res, void* y, const float* stat, const void* gamma,
+                 const void* beta, int param_is_bf16, int64_t M, int C, int act, int sms,
+                 cudaStream_t st);
+int ddl_bn_bwd_reduce(const void* dy, const void* dy2, const void* y, const void* x, void* dz_out,
+                      const float* stat, float* sums, int64_t M, int C, int act, int sms,
+                      cudaStream_t st);
+int ddl_bn_bwd_finalize(float* sums, const float* stat, const void* gamma, int param_is_bf16,
+                        float* coef, void* dgamma, void* dbeta, int grad_is_bf16, int accumulate,
+                        int64_t M, int C, cudaStream_t st);
+int ddl_bn_bwd_apply(const void* dz_in, const void* dy, const void* dy2, const void* y, const void* x, void* dx,
+                     const float* stat, const float* coef, int64_t M, int C, int act, int sms,
+                     cudaStream_t st);
+int ddl_bias_act(const void* x, const void* bias, int bias_is_bf16, void* y, int64_t M, int C,
+                 int act, int sms, cudaStream_t st);
+int ddl_act_bwd(const void* dy, const void* dy2, const void* y, void* dz, int64_t n, int act,
+                int sms, cudaStream_t st);
+int ddl_colsum(const void* x, float* sums, void* out, int out_is_bf16, int accumulate, int64_t M,
+               int C, int sms, cudaStream_t st);
+
+// ---- allreduce.cu
+int ddl_ar_sgd_twoshot(void* const* grad_ptrs, void* const* weight_ptrs, void* const* flag_ptrs,
+                       void* grad_mc, void* weight_mc, float* master, float* mom,
+                       const float* hyper, uint32_t* epoch, int* status, int64_t bucket_off,
+                       int64_t slice_len, int rank, int world, int blocks, int max_blocks,
+                       int use_multimem, cudaStream_t st);
+int ddl_ar_twoshot(void* const* buf_ptrs, void* const* flag_ptrs, void* buf_mc, int is_bf16,
+                   uint32_t* epoch, int* status, int64_t off, int64_t slice_len, float scale,
+                   int rank, int world, int blocks, int max_blocks, int use_multimem,
+                   cudaStream_t st);
+int ddl_ar_oneshot(void* const* buf_ptrs, void* const* flag_ptrs, int is_bf16, void* out,
+                   uint32_t* epoch, int* status, int64_t off, int64_t n, float scale, int rank,
+                   int world, int blocks, int max_blocks, cudaStream_t st);
+int ddl_peer_barrier(void* const* flag_ptrs, uint32_t* epoch, int* status, int rank, int world,
+                     int max_blocks, cudaStream_t st);
+int ddl_p2p_put(const void* src, void* dst_peer, int64_t nbytes, uint32_t* peer_flag,
+                uint32_t* local_seq, unsigned int* ticket, int blocks, cudaStream_t st);
+int ddl_p2p_wait(const uint32_t* flag, uint32_t* local_seq, int* status, cudaStream_t st);
+
+// ---- misc.cu
+int ddl_u8_to_bf16_norm(const void* in, void* out, int64_t n, int C, const float* mean,
+                        const float* stdv, int sms, cudaStream_t st);
+int ddl_revert_varlen(const void* in, void* out, const int64_t* lengths, int T, int B,
+                      int64_t row_bytes, int sms, cudaStream_t st);
+int ddl_set_mask(const int64_t* lengths, void* mask, int T, int B, cudaStream_t st);
+int ddl_gap_fwd(const void* x, void* y, int N, int HW, int C, cudaStream_t st);
+int ddl_gap_bwd(const void* dy, void* dx, int N, int HW, int C, int sms, cudaStream_t st);
+
+// ---- gemm_tcgen05.cu  (TMA + tcgen05/TMEM GEMM; see the file header)
+// D[M,N] = A[M,K] * B[N,K]^T  (both K-major bf16), fp32 accumulate in TMEM, bf16 output.
+// Optional epilogue: per-column (output-channel) sum / sum-of-squares into col_sums[2][N]
+// (BatchNorm statistics), optional bias[N] add and ReLU.
+int ddl_gemm_bf16_tn(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb,
+                     int ldd, float* col_sums, const void* bias, int relu, int sms,
+                     cudaStream_t st);
+// D[M,N] (+)= A^T B with A stored [K,M] (M contiguous) and B stored [K,N] (N contiguous):
+// both operands MN-major (weight gradient: A = dY[pixels, Cout], B = X[pixels, Cin]).
+// Split-K over `splits` CTAs per tile with fp32 atomics into D32 when splits > 1.
+int ddl_gemm_bf16_nt_mn(const void* A, const void* B, void* D, int M, int N, int K, int lda,
+                        int ldb, int ldd, int out_is_bf16, int splits, float* workspace, int sms,
+                        cudaStream_t st);
+int ddl_gemm_selftest_info(char* buf, int len);
+
+#ifdef __cplusplus
+}
+#endif

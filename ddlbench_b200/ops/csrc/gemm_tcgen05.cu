@@ -1,0 +1,428 @@
+// TMA-fed, TMEM-accumulating bf16 GEMM on the Blackwell 5th-gen tensor cores (tcgen05),
+// hand-written for sm_100a with inline PTX.  This is the implicit-GEMM engine behind every
+// 1x1 convolution and fully-connected layer of the model zoo in NHWC layout:
+//
+//     D[M, N] = A[M, K] * B[N, K]^T        M = batch*H*W pixels, N = Cout, K = Cin
+//
+// (reference: those layers run as cuDNN/cuBLAS library kernels chosen by PyTorch,
+//  SURVEY.md §2.9(a); BatchNorm statistics are a separate pass over the output.)
+//
+// Structure (one 128 x BLOCK_N output tile per CTA, two CTAs co-resident per SM so one
+// CTA's epilogue overlaps the other's main loop):
+//   warp 0   : TMA producer  — cp.async.bulk.tensor (128B-swizzled boxes) into a 3-stage
+//              shared-memory ring, completion signalled on mbarriers
+//   warp 1   : allocates TMEM, then ONE elected lane issues tcgen05.mma (M=128, N=BLOCK_N,
+//              K=16 per instruction, fp32 accumulator in TMEM) and tcgen05.commit to
+//              release ring slots / publish the accumulator
+//   warps 2-5: epilogue — tcgen05.ld TMEM->registers, optional bias+ReLU, convert to bf16,
+//              stage the tile in (re-used) swizzled shared memory, accumulate the
+//              per-output-channel sum / sum-of-squares needed by the following BatchNorm
+//              (fused statistics: the BN never re-reads the activation), TMA-store the tile.
+//
+// Every spin loop is bounded: a protocol bug traps instead of hanging the GPU.
+#include <cuda.h>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "api.h"
+
+namespace ddl {
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 3;
+constexpr int kThreads = 192;  // 6 warps
+constexpr long long kSpinCycles = 4000000000LL;  // ~2 s: a protocol bug traps, never hangs
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ---- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 0xFFFF) == 0xFFFF && clock64() - t0 > kSpinCycles) __trap();
+  }
+}
+
+// ---- TMA
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0,
+                                             int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   (uint64_t)map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+// ---- tcgen05
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = lane i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart
+// (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);      // start address  [0,14)
+  d |= (uint64_t)1 << 16;                           // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // SBO = 1024 B   [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor: D=f32, A=B=bf16, both K-major, M x N tile
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major,
+                                                       int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct EpilogueParams {
+  float* col_sums;            // [2][N] or null
+  const __nv_bfloat16* bias;  // [N] or null
+  int relu;
+  int M, N, K;
+};
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;       // 16 KB
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;       // 8/16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutBytes = BLOCK_M * BLOCK_N * 2;     // staged output tile (aliases stage 0..)
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  static_assert(kOutBytes <= kRingBytes, "output staging must fit in the ring");
+  static constexpr int kBarOffset = kRingBytes;               // full[kStages], empty[kStages], tmem_full
+  static constexpr int kTmemPtrOffset = kBarOffset + (2 * kStages + 1) * 8;
+  static constexpr int kBiasOffset = kTmemPtrOffset + 16;
+  static constexpr int kTotal = kBiasOffset + BLOCK_N * 4;
+  static constexpr int kDynamic = kTotal + 1024;              // slack for 1024-B alignment
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
+                    const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_d, EpilogueParams ep) {
+  using L = SmemLayout<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOffset);
+  float* bias_s = reinterpret_cast<float*>(smem + L::kBiasOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = (ep.N + BLOCK_N - 1) / BLOCK_N;
+  const int tile_m = blockIdx.x / tiles_n;
+  const int tile_n = blockIdx.x % tiles_n;
+  const int num_k_blocks = (ep.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_d);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = smem + s * L::kStageBytes;
+        uint8_t* b_dst = a_dst + L::kABytes;
+        mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
+        tma_load_2d(a_dst, &map_a, &full_bar[s], kb * BLOCK_K, tile_m * BLOCK_M);
+        tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BLOCK_K, tile_n * BLOCK_N);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+    for (int kb = 0; kb < num_k_blocks; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (kb / kStages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+        const uint32_t b_addr = a_addr + L::kABytes;
+        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+        const uint64_t bdesc = make_kmajor_sw128_desc(b_addr);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the >>4 field
+          umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                   (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);                       // slot free when these MMAs retire
+        if (kb == num_k_blocks - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (128 thr)
+    const int et = threadIdx.x - 64;       // 0..127
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;      // row of the tile held by this thread
+    for (int i = et; i < BLOCK_N; i += 128) {
+      const int col = tile_n * BLOCK_N + i;
+      bias_s[i] = (ep.bias && col < ep.N) ? __bfloat162float(ep.bias[col]) : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    // stage the bf16 tile: BLOCK_N/64 regions of [128 rows][128 B], 16-B chunks XOR-swizzled
+    // with (row & 7) — the SWIZZLE_128B pattern the D tensor map expects.
+#pragma unroll
+    for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * 32), r);
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float v = __uint_as_float(r[i]) + bias_s[cb * 32 + i];
+        f[i] = ep.relu ? fmaxf(v, 0.f) : v;
+      }
+      uint8_t* region = smem + (cb / 2) * (BLOCK_M * 128);
+      const int chunk0 = (cb & 1) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bf16x8 p = pack8(f + j * 8);
+        const int chunk = (chunk0 + j) ^ (row & 7);
+        *reinterpret_cast<bf16x8*>(region + row * 128 + chunk * 16) = p;
+      }
+    }
+    tc_fence_before();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (et == 0) {
+#pragma unroll
+      for (int h = 0; h < BLOCK_N / 64; ++h)
+        tma_store_2d(&map_d, smem + h * (BLOCK_M * 128), tile_n * BLOCK_N + h * 64,
+                     tile_m * BLOCK_M);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (ep.col_sums) {
+      // per-channel sum / sum-of-squares of the (bf16-rounded) tile, rows beyond M are zero
+      constexpr int kPairs = BLOCK_N / 2;
+      constexpr int kGroups = 128 / kPairs;
+      constexpr int kRowsPer = BLOCK_M / kGroups;
+      const int pair = et % kPairs, grp = et / kPairs;
+      const int c = pair * 2;
+      const uint8_t* region = smem + (c / 64) * (BLOCK_M * 128);
+      const int cc = c % 64;
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+      for (int rr = 0; rr < kRowsPer; ++rr) {
+        const int r_ = grp * kRowsPer + rr;
+        const int chunk = (cc >> 3) ^ (r_ & 7);
+        const __nv_bfloat162 v =
+            *reinterpret_cast<const __nv_bfloat162*>(region + r_ * 128 + chunk * 16 + (cc & 7) * 2);
+        const float2 fv = __bfloat1622float2(v);
+        s0 += fv.x; s1 += fv.y;
+        q0 = fmaf(fv.x, fv.x, q0); q1 = fmaf(fv.y, fv.y, q1);
+      }
+      const int col = tile_n * BLOCK_N + c;
+      if (col < ep.N) {
+        atomicAdd(&ep.col_sums[col], s0);
+        atomicAdd(&ep.col_sums[ep.N + col], q0);
+      }
+      if (col + 1 < ep.N) {
+        atomicAdd(&ep.col_sums[col + 1], s1);
+        atomicAdd(&ep.col_sums[ep.N + col + 1], q1);
+      }
+    }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BLOCK_N);
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = {box_cols, box_rows}
+static int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+                       int box_cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -2;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -3;
+}
+
+template <int BLOCK_N>
+static int launch_tn(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb,
+                     int ldd, float* col_sums, const void* bias, int relu, cudaStream_t st) {
+  using L = SmemLayout<BLOCK_N>;
+  CUtensorMap ma, mb, md;
+  int rc;
+  if ((rc = make_map_2d(&ma, A, M, K, lda, BLOCK_K, BLOCK_M))) return rc;
+  if ((rc = make_map_2d(&mb, B, N, K, ldb, BLOCK_K, BLOCK_N))) return rc;
+  if ((rc = make_map_2d(&md, D, M, N, ldd, 64, BLOCK_M))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  EpilogueParams ep{col_sums, (const __nv_bfloat16*)bias, relu, M, N, K};
+  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  gemm_bf16_tn_kernel<BLOCK_N><<<tiles, kThreads, L::kDynamic, st>>>(ma, mb, md, ep);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace gemm
+}  // namespace ddl
+
+extern "C" int ddl_gemm_bf16_tn(const void* A, const void* B, void* D, int M, int N, int K,
+                                int lda, int ldb, int ldd, float* col_sums, const void* bias,
+                                int relu, int sms, cudaStream_t st) {
+  using namespace ddl::gemm;
+  (void)sms;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda % 8) || (ldb % 8) || (ldd % 8) || (N % 8) || (K % 8)) return -1;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
+       reinterpret_cast<uintptr_t>(D)) & 15)
+    return -1;
+  if (N <= 64) return launch_tn<64>(A, B, D, M, N, K, lda, ldb, ldd, col_sums, bias, relu, st);
+  return launch_tn<128>(A, B, D, M, N, K, lda, ldb, ldd, col_sums, bias, relu, st);
+}
+
+extern "C" int ddl_gemm_bf16_nt_mn(const void*, const void*, void*, int, int, int, int, int, int,
+                                   int, int, float*, int, cudaStream_t) {
+  return -4;  // weight-gradient (MN-major) variant: see gemm_wgrad.cu once enabled
+}
+
+extern "C" int ddl_gemm_selftest_info(char* buf, int len) {
+  using namespace ddl::gemm;
+  snprintf(buf, len,
+           "tcgen05 bf16 TN GEMM: BLOCK_M=%d BLOCK_K=%d stages=%d smem(N=128)=%d B smem(N=64)=%d B",
+           BLOCK_M, BLOCK_K, kStages, SmemLayout<128>::kDynamic, SmemLayout<64>::kDynamic);
+  return 0;
+}
