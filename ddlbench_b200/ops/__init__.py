@@ -50,6 +50,7 @@ def load_ext(build_if_missing: bool = True):
             spec = importlib.util.spec_from_file_location("_ddlb_ext", str(p))
             mod = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(mod)
+            assert mod.bn_replicas() == BN_REPLICAS, "BN_REPLICAS mismatch with the extension"
             _ext = mod
         except BaseException as e:  # noqa: BLE001 - remembered and re-raised on GPU use
             _ext_err = e
@@ -135,11 +136,16 @@ def _nhwc_ok(x: torch.Tensor) -> bool:
             (x.dim() == 2 or x.is_contiguous(memory_format=torch.channels_last)))
 
 
+BN_REPLICAS = 8  # must match DDL_BN_REPLICAS (csrc/common.cuh); checked at first use
+
+
 class BnWorkspace:
-    """Per-layer fp32 scratch: partial sums (self-zeroing), (mean, invstd), bwd coefficients."""
+    """Per-layer fp32 scratch: R replicated partial-sum buffers (self-zeroing), the
+    last-CTA ticket counters, and the backward coefficients."""
 
     def __init__(self, channels: int, device):
-        self.sums = torch.zeros(2 * channels, dtype=torch.float32, device=device)
+        self.sums = torch.zeros(BN_REPLICAS * 2 * channels, dtype=torch.float32, device=device)
+        self.counter = torch.zeros(64, dtype=torch.int32, device=device)
         self.coef = torch.empty(3 * channels, dtype=torch.float32, device=device)
 
 
@@ -162,10 +168,10 @@ def bn_forward(x, res, gamma, beta, running_mean, running_var, eps: float, momen
         if ws is None:
             ws = BnWorkspace(C, x.device)
         stat = torch.empty(2 * C, dtype=torch.float32, device=x.device)
-        if not stats_ready:
-            e.bn_stats(x, ws.sums, M, C)
-            _count()
-        e.bn_finalize(ws.sums, stat, running_mean, running_var, M, C, eps, momentum)
+        if stats_ready:
+            e.bn_finalize(ws.sums, stat, running_mean, running_var, M, C, eps, momentum)
+        else:
+            e.bn_stats(x, ws.sums, ws.counter, stat, running_mean, running_var, M, C, eps, momentum)
         y = torch.empty_like(x)
         e.bn_apply(x, res, y, stat, gamma, beta, M, C, act)
         _count(2)
@@ -187,15 +193,15 @@ def bn_backward(dy, dy2, y, x, stat, gamma, act: int, want_dz: bool, dgamma_out,
             ws = BnWorkspace(C, x.device)
         stat_f = stat.reshape(-1)
         dz = torch.empty_like(x) if want_dz else None
-        e.bn_bwd_reduce(dy, dy2, y if act != ACT_NONE else None, x, dz, stat_f, ws.sums, M, C, act)
-        e.bn_bwd_finalize(ws.sums, stat_f, gamma, ws.coef, dgamma_out, dbeta_out, accumulate, M, C)
+        yy = y if act != ACT_NONE else None
+        e.bn_bwd_reduce(dy, dy2, yy, x, dz, stat_f, ws.sums, ws.counter, gamma, ws.coef,
+                        dgamma_out, dbeta_out, accumulate, M, C, act)
         dx = torch.empty_like(x)
         if want_dz:
             e.bn_bwd_apply(dz, None, None, None, x, dx, stat_f, ws.coef, M, C, ACT_NONE)
         else:
-            e.bn_bwd_apply(None, dy, dy2, y if act != ACT_NONE else None, x, dx, stat_f, ws.coef,
-                           M, C, act)
-        _count(3)
+            e.bn_bwd_apply(None, dy, dy2, yy, x, dx, stat_f, ws.coef, M, C, act)
+        _count(2)
         return dx, dz
     dx, dz, dgamma, dbeta = ref.bn_backward(dy, dy2, y, x, stat, gamma, act, want_dz)
     if accumulate:
@@ -234,8 +240,8 @@ def bias_grad_(dy, out, accumulate: bool = False, ws: Optional[BnWorkspace] = No
         M, C = _mc(dy)
         if ws is None:
             ws = BnWorkspace(C, dy.device)
-        ext().colsum(dy, ws.sums, out, accumulate, M, C)
-        _count(2)
+        ext().colsum(dy, ws.sums, ws.counter, out, accumulate, M, C)
+        _count()
         return
     dims = [0] + list(range(2, dy.dim()))
     g = dy.float().sum(dim=dims)
@@ -316,7 +322,8 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, col_sums: Optional[torch.Tensor] =
             bias: Optional[torch.Tensor] = None, relu: bool = False,
             out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D[M, N] = A[M, K] @ B[N, K]^T on the tcgen05 tensor cores (csrc/gemm_tcgen05.cu).
-    ``col_sums`` ([2, N] fp32, pre-zeroed) receives per-column sum / sum-of-squares of D."""
+    ``col_sums`` (the [R, 2, N] fp32 replicated BN workspace, zero on entry) receives the
+    per-column sum / sum-of-squares of D spread over its R replicas."""
     if gemm_tn_supported(a, b):
         if out is None:
             out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.bfloat16, device=a.device)
@@ -331,8 +338,9 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, col_sums: Optional[torch.Tensor] =
     d = d.to(a.dtype)
     if col_sums is not None:
         df = d.float()
-        col_sums.view(2, -1)[0].add_(df.sum(0))
-        col_sums.view(2, -1)[1].add_((df * df).sum(0))
+        n = d.shape[1]
+        col_sums[:n].add_(df.sum(0))
+        col_sums[n:2 * n].add_((df * df).sum(0))
     if out is not None:
         out.copy_(d)
         return out

@@ -21,18 +21,19 @@ int ddl_xent(const void* logits, int is_bf16, const int64_t* target, void* dlogi
              float grad_scale, cudaStream_t stream);
 
 // ---- bn.cu
-int ddl_bn_stats(const void* x, float* sums, int64_t M, int C, int sms, cudaStream_t st);
+int ddl_bn_replicas();
+int ddl_bn_stats(const void* x, float* sums, unsigned int* counter, float* stat,
+                 float* running_mean, float* running_var, int64_t M, int C, float eps,
+                 float momentum, int sms, cudaStream_t st);
 int ddl_bn_finalize(float* sums, float* stat, float* running_mean, float* running_var, int64_t M,
                     int C, float eps, float momentum, cudaStream_t st);
 int ddl_bn_apply(const void* x, const void* res, void* y, const float* stat, const void* gamma,
                  const void* beta, int param_is_bf16, int64_t M, int C, int act, int sms,
                  cudaStream_t st);
 int ddl_bn_bwd_reduce(const void* dy, const void* dy2, const void* y, const void* x, void* dz_out,
-                      const float* stat, float* sums, int64_t M, int C, int act, int sms,
-                      cudaStream_t st);
-int ddl_bn_bwd_finalize(float* sums, const float* stat, const void* gamma, int param_is_bf16,
-                        float* coef, void* dgamma, void* dbeta, int grad_is_bf16, int accumulate,
-                        int64_t M, int C, cudaStream_t st);
+                      const float* stat, float* sums, unsigned int* counter, const void* gamma,
+                      int param_is_bf16, float* coef, void* dgamma, void* dbeta, int grad_is_bf16,
+                      int accumulate, int64_t M, int C, int act, int sms, cudaStream_t st);
 int ddl_bn_bwd_apply(const void* dz_in, const void* dy, const void* dy2, const void* y, const void* x, void* dx,
                      const float* stat, const float* coef, int64_t M, int C, int act, int sms,
                      cudaStream_t st);
@@ -40,8 +41,8 @@ int ddl_bias_act(const void* x, const void* bias, int bias_is_bf16, void* y, int
                  int act, int sms, cudaStream_t st);
 int ddl_act_bwd(const void* dy, const void* dy2, const void* y, void* dz, int64_t n, int act,
                 int sms, cudaStream_t st);
-int ddl_colsum(const void* x, float* sums, void* out, int out_is_bf16, int accumulate, int64_t M,
-               int C, int sms, cudaStream_t st);
+int ddl_colsum(const void* x, float* sums, unsigned int* counter, void* out, int out_is_bf16,
+               int accumulate, int64_t M, int C, int sms, cudaStream_t st);
 
 // ---- allreduce.cu
 int ddl_ar_sgd_twoshot(void* const* grad_ptrs, void* const* weight_ptrs, void* const* flag_ptrs,

@@ -81,9 +81,14 @@ at::Tensor xent(at::Tensor logits, at::Tensor target, c10::optional<at::Tensor> 
 }
 
 // ------------------------------------------------------------------------------ batch norm
-void bn_stats(at::Tensor x, at::Tensor sums, int64_t M, int64_t C) {
+void bn_stats(at::Tensor x, at::Tensor sums, at::Tensor counter, at::Tensor stat,
+              c10::optional<at::Tensor> rmean, c10::optional<at::Tensor> rvar, int64_t M, int64_t C,
+              double eps, double mom) {
   c10::cuda::CUDAGuard g(x.device());
-  check(ddl_bn_stats(x.data_ptr(), sums.data_ptr<float>(), M, (int)C, sm_count(), cur_stream()),
+  TORCH_CHECK(sums.numel() >= ddl_bn_replicas() * 2 * C, "bn workspace too small");
+  check(ddl_bn_stats(x.data_ptr(), sums.data_ptr<float>(), (unsigned int*)counter.data_ptr(),
+                     stat.data_ptr<float>(), (float*)optr(rmean), (float*)optr(rvar), M, (int)C,
+                     (float)eps, (float)mom, sm_count(), cur_stream()),
         "bn_stats");
 }
 void bn_finalize(at::Tensor sums, at::Tensor stat, c10::optional<at::Tensor> rmean,
@@ -102,23 +107,19 @@ void bn_apply(at::Tensor x, c10::optional<at::Tensor> res, at::Tensor y, at::Ten
         "bn_apply");
 }
 void bn_bwd_reduce(at::Tensor dy, c10::optional<at::Tensor> dy2, c10::optional<at::Tensor> y,
-                   at::Tensor x,
-                   c10::optional<at::Tensor> dz_out, at::Tensor stat, at::Tensor sums, int64_t M,
-                   int64_t C, int64_t act) {
+                   at::Tensor x, c10::optional<at::Tensor> dz_out, at::Tensor stat,
+                   at::Tensor sums, at::Tensor counter, at::Tensor gamma, at::Tensor coef,
+                   at::Tensor dgamma, at::Tensor dbeta, bool accumulate, int64_t M, int64_t C,
+                   int64_t act) {
   c10::cuda::CUDAGuard g(x.device());
+  TORCH_CHECK(sums.numel() >= ddl_bn_replicas() * 2 * C, "bn workspace too small");
   check(ddl_bn_bwd_reduce(dy.data_ptr(), optr(dy2), optr(y), x.data_ptr(), optr(dz_out),
-                          stat.data_ptr<float>(), sums.data_ptr<float>(), M, (int)C, (int)act,
-                          sm_count(), cur_stream()),
+                          stat.data_ptr<float>(), sums.data_ptr<float>(),
+                          (unsigned int*)counter.data_ptr(), gamma.data_ptr(), is_bf16(gamma),
+                          coef.data_ptr<float>(), dgamma.data_ptr(), dbeta.data_ptr(),
+                          is_bf16(dgamma), accumulate, M, (int)C, (int)act, sm_count(),
+                          cur_stream()),
         "bn_bwd_reduce");
-}
-void bn_bwd_finalize(at::Tensor sums, at::Tensor stat, at::Tensor gamma, at::Tensor coef,
-                     at::Tensor dgamma, at::Tensor dbeta, bool accumulate, int64_t M, int64_t C) {
-  c10::cuda::CUDAGuard g(sums.device());
-  check(ddl_bn_bwd_finalize(sums.data_ptr<float>(), stat.data_ptr<float>(), gamma.data_ptr(),
-                            is_bf16(gamma), coef.data_ptr<float>(), dgamma.data_ptr(),
-                            dbeta.data_ptr(), is_bf16(dgamma), accumulate, M, (int)C,
-                            cur_stream()),
-        "bn_bwd_finalize");
 }
 void bn_bwd_apply(c10::optional<at::Tensor> dz_in, c10::optional<at::Tensor> dy,
                   c10::optional<at::Tensor> dy2, c10::optional<at::Tensor> y, at::Tensor x, at::Tensor dx, at::Tensor stat,
@@ -144,12 +145,14 @@ void act_bwd(at::Tensor dy, c10::optional<at::Tensor> dy2, c10::optional<at::Ten
                     sm_count(), cur_stream()),
         "act_bwd");
 }
-void colsum(at::Tensor x, at::Tensor sums, at::Tensor out, bool accumulate, int64_t M, int64_t C) {
+void colsum(at::Tensor x, at::Tensor sums, at::Tensor counter, at::Tensor out, bool accumulate,
+            int64_t M, int64_t C) {
   c10::cuda::CUDAGuard g(x.device());
-  check(ddl_colsum(x.data_ptr(), sums.data_ptr<float>(), out.data_ptr(), is_bf16(out), accumulate,
-                   M, (int)C, sm_count(), cur_stream()),
+  check(ddl_colsum(x.data_ptr(), sums.data_ptr<float>(), (unsigned int*)counter.data_ptr(),
+                   out.data_ptr(), is_bf16(out), accumulate, M, (int)C, sm_count(), cur_stream()),
         "colsum");
 }
+int64_t bn_replicas() { return ddl_bn_replicas(); }
 
 // ------------------------------------------------------------------------------ misc
 void u8_to_bf16_norm(at::Tensor in, at::Tensor out, int64_t C, std::vector<double> mean,
@@ -501,11 +504,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_finalize", &bn_finalize);
   m.def("bn_apply", &bn_apply);
   m.def("bn_bwd_reduce", &bn_bwd_reduce);
-  m.def("bn_bwd_finalize", &bn_bwd_finalize);
   m.def("bn_bwd_apply", &bn_bwd_apply);
   m.def("bias_act", &bias_act);
   m.def("act_bwd", &act_bwd);
   m.def("colsum", &colsum);
+  m.def("bn_replicas", &bn_replicas);
   m.def("u8_to_bf16_norm", &u8_to_bf16_norm);
   m.def("revert_varlen", &revert_varlen);
   m.def("set_mask", &set_mask);

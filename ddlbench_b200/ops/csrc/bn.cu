@@ -6,14 +6,20 @@
 // resnet.py:33-39,61-67; benchmark/imagenet/gpipemodels/resnet/block.py:31-79), i.e.
 // 8 full passes over the activation forward.  Here:
 //
-//   forward : bn_stats (1 read)  -> bn_finalize (C elems) -> bn_apply (read x [+res], write y)
-//   backward: bn_bwd_reduce (read dy,y,x [write dz]) -> bn_bwd_finalize (C elems)
-//             -> bn_bwd_apply (read dz|dy+y, x; write dx)
+//   forward : bn_stats  (1 read; the LAST CTA to finish turns the partial sums into
+//                        mean/invstd, updates the running statistics and re-zeroes the
+//                        workspace — no separate finalize launch, no memset)
+//             bn_apply  (read x [+res], write y = act(BN(x) [+ res]))
+//   backward: bn_bwd_reduce (read dy[,dy2],y,x [write dz]; last CTA produces the per-channel
+//                        coefficients and writes dgamma/dbeta into the flat gradient buffer)
+//             bn_bwd_apply  (read dz|dy+y, x; write dx)
 //
-// The per-channel partial sums live in a small fp32 workspace that the finalize kernels
-// re-zero after consuming, so no memset is ever launched and the sequence can be replayed
-// from a captured CUDA graph.  When the convolution that produces x is one of our tcgen05
-// GEMM kernels, bn_stats is skipped: the GEMM epilogue accumulates the same sums.
+// Partial sums are accumulated with fp32 atomics into R REPLICATED copies of the [2][C]
+// workspace (CTA b uses replica b % R): same-address L2 atomics from hundreds of CTAs
+// serialise (measured: the single-copy version spent 58 us/launch, 32% of the training step,
+// in that serialisation), replication divides the contention by R.
+// When the convolution that produces x is one of our tcgen05 GEMM kernels, bn_stats is
+// skipped: the GEMM epilogue accumulates the same sums and bn_finalize closes them.
 //
 // Thread mapping: blockDim = (CVb, RL) with CVb = min(C/8, 256) 16-byte channel vectors
 // and RL row lanes, so a warp always touches one contiguous span of memory.
@@ -23,6 +29,7 @@
 namespace ddl {
 
 constexpr int kBnThreads = 256;
+constexpr int kRep = DDL_BN_REPLICAS;  // replicas of the partial-sum workspace
 
 struct BnDims {
   int cvb;   // channel vectors per block (blockDim.x)
@@ -32,7 +39,7 @@ struct BnDims {
   int rows_per_block;
 };
 
-static inline BnDims bn_dims(int64_t M, int C, int sms, int waves) {
+static inline BnDims bn_dims(int64_t M, int C, int sms, int waves, int min_rows_per_lane) {
   BnDims d;
   const int cv = C / 8;
   d.cvb = cv < kBnThreads ? cv : kBnThreads;
@@ -41,11 +48,12 @@ static inline BnDims bn_dims(int64_t M, int C, int sms, int waves) {
   d.gy = (cv + d.cvb - 1) / d.cvb;
   int64_t target = (int64_t)sms * waves / d.gy;
   if (target < 1) target = 1;
-  int64_t max_useful = (M + d.rl - 1) / d.rl;  // at least one row per lane
+  int64_t max_useful = (M + (int64_t)d.rl * min_rows_per_lane - 1) / ((int64_t)d.rl * min_rows_per_lane);
   if (target > max_useful) target = max_useful;
   if (target < 1) target = 1;
   d.gx = (int)target;
   d.rows_per_block = (int)((M + d.gx - 1) / d.gx);
+  d.gx = (int)((M + d.rows_per_block - 1) / d.rows_per_block);
   return d;
 }
 
@@ -61,73 +69,147 @@ __device__ __forceinline__ float act_mask(float y, int act) {
   return 1.f;
 }
 
-// --------------------------------------------------------------------------- forward
-// sums: [2][C] fp32 (sum, sumsq), must be zero on entry
-__global__ void __launch_bounds__(kBnThreads)
-bn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, int64_t M, int C,
-                int rows_per_block) {
-  __shared__ float red[16][kBnThreads];
-  const int cv_total = C >> 3;
-  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
+  int4 raw = ld_stream(p);
+  unpack8(*reinterpret_cast<bf16x8*>(&raw), f);
+}
+
+// block-level reduction of NV (8 or 16) per-thread values over the row lanes, then one
+// atomicAdd per (value, channel) into replica `rep` of the workspace.
+template <int NV>
+__device__ __forceinline__ void block_reduce_to_workspace(const float* vals, float (*red)[kBnThreads],
+                                                          float* sums, int C, int cv_total,
+                                                          int rep) {
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  float s[8], q[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
-  if (cv < cv_total) {
-    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    int64_t r1 = r0 + rows_per_block;
-    if (r1 > M) r1 = M;
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-      int4 raw = ld_stream(x + r * C + (int64_t)cv * 8);
-      float f[8];
-      unpack8(*reinterpret_cast<bf16x8*>(&raw), f);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        s[k] += f[k];
-        q[k] = fmaf(f[k], f[k], q[k]);
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    red[k][tid] = s[k];
-    red[8 + k][tid] = q[k];
-  }
+  for (int k = 0; k < NV; ++k) red[k][tid] = vals[k];
   __syncthreads();
   const int nthreads = blockDim.x * blockDim.y;
-  const int nout = blockDim.x * 16;
+  const int nout = blockDim.x * NV;
+  float* dst = sums + (size_t)rep * 2 * C;
   for (int o = tid; o < nout; o += nthreads) {
     const int tx = o % blockDim.x, k = o / blockDim.x;
     const int c_vec = blockIdx.y * blockDim.x + tx;
     if (c_vec >= cv_total) continue;
     float acc = 0.f;
     for (int ty = 0; ty < blockDim.y; ++ty) acc += red[k][ty * blockDim.x + tx];
-    const int ch = c_vec * 8 + (k & 7);
-    atomicAdd(&sums[(k >> 3) * C + ch], acc);
+    atomicAdd(&dst[(k >> 3) * C + c_vec * 8 + (k & 7)], acc);
   }
 }
 
-// mean/invstd from the sums; running-stat update; re-zero the sums.
-// stat_out: [2][C] (mean, invstd)
+// true in every thread of the LAST CTA (of this channel chunk) to get here
+__device__ __forceinline__ bool last_cta_of_chunk(unsigned int* counter) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const unsigned int t = atomicAdd(&counter[blockIdx.y], 1u);
+    is_last = (t == gridDim.x - 1);
+    if (is_last) counter[blockIdx.y] = 0u;  // self-reset for the next launch / graph replay
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// sum the R replicas of channel c (both rows) and zero them
+__device__ __forceinline__ void gather_and_clear(float* sums, int C, int c, float& s0, float& s1) {
+  s0 = 0.f;
+  s1 = 0.f;
+#pragma unroll
+  for (int r = 0; r < kRep; ++r) {
+    float* p = sums + (size_t)r * 2 * C;
+    s0 += __ldcg(p + c);
+    s1 += __ldcg(p + C + c);
+    p[c] = 0.f;
+    p[C + c] = 0.f;
+  }
+}
+
+__device__ __forceinline__ void finalize_stats(float s, float q, int c, int C, int64_t M, float eps,
+                                               float momentum, float* stat_out, float* rmean,
+                                               float* rvar) {
+  const float inv_m = 1.f / (float)M;
+  const float mean = s * inv_m;
+  float var = fmaf(-mean, mean, q * inv_m);
+  var = fmaxf(var, 0.f);
+  stat_out[c] = mean;
+  stat_out[C + c] = rsqrtf(var + eps);
+  if (rmean) {
+    const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+    rmean[c] = fmaf(momentum, mean - rmean[c], rmean[c]);
+    rvar[c] = fmaf(momentum, unbiased - rvar[c], rvar[c]);
+  }
+}
+
+// --------------------------------------------------------------------------- forward
+// sums: [R][2][C] fp32 (sum, sumsq), zero on entry, zero again on exit.
+__global__ void __launch_bounds__(kBnThreads)
+bn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums,
+                unsigned int* __restrict__ counter, float* __restrict__ stat_out,
+                float* __restrict__ running_mean, float* __restrict__ running_var, int64_t M,
+                int C, int rows_per_block, float eps, float momentum) {
+  __shared__ float red[16][kBnThreads];
+  const int cv_total = C >> 3;
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = 0.f;
+  if (cv < cv_total) {
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    const __nv_bfloat16* base = x + (int64_t)cv * 8;
+    const int step = blockDim.y;
+    int64_t r = r0 + threadIdx.y;
+    for (; r + 3 * step < r1; r += 4 * step) {  // 4 independent 16-byte loads in flight
+      float f0[8], f1[8], f2[8], f3[8];
+      load8(base + r * C, f0);
+      load8(base + (r + step) * C, f1);
+      load8(base + (r + 2 * step) * C, f2);
+      load8(base + (r + 3 * step) * C, f3);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[k] += (f0[k] + f1[k]) + (f2[k] + f3[k]);
+        v[8 + k] = fmaf(f0[k], f0[k], v[8 + k]);
+        v[8 + k] = fmaf(f1[k], f1[k], v[8 + k]);
+        v[8 + k] = fmaf(f2[k], f2[k], v[8 + k]);
+        v[8 + k] = fmaf(f3[k], f3[k], v[8 + k]);
+      }
+    }
+    for (; r < r1; r += step) {
+      float f[8];
+      load8(base + r * C, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[k] += f[k];
+        v[8 + k] = fmaf(f[k], f[k], v[8 + k]);
+      }
+    }
+  }
+  block_reduce_to_workspace<16>(v, red, sums, C, cv_total, blockIdx.x % kRep);
+  if (last_cta_of_chunk(counter)) {
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int c0 = blockIdx.y * blockDim.x * 8;
+    const int nch = min(blockDim.x * 8, C - c0);
+    for (int i = tid; i < nch; i += blockDim.x * blockDim.y) {
+      float s, q;
+      gather_and_clear(sums, C, c0 + i, s, q);
+      finalize_stats(s, q, c0 + i, C, M, eps, momentum, stat_out, running_mean, running_var);
+    }
+  }
+}
+
+// Stand-alone finalize for statistics produced by the GEMM epilogue.
 __global__ void bn_finalize_kernel(float* __restrict__ sums, float* __restrict__ stat_out,
                                    float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int64_t M, int C, float eps,
                                    float momentum) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float inv_m = 1.f / (float)M;
-  const float mean = sums[c] * inv_m;
-  float var = fmaf(-mean, mean, sums[C + c] * inv_m);
-  var = fmaxf(var, 0.f);
-  stat_out[c] = mean;
-  stat_out[C + c] = rsqrtf(var + eps);
-  if (running_mean) {
-    const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
-    running_mean[c] = fmaf(momentum, mean - running_mean[c], running_mean[c]);
-    running_var[c] = fmaf(momentum, unbiased - running_var[c], running_var[c]);
-  }
-  sums[c] = 0.f;
-  sums[C + c] = 0.f;
+  float s, q;
+  gather_and_clear(sums, C, c, s, q);
+  finalize_stats(s, q, c, C, M, eps, momentum, stat_out, running_mean, running_var);
 }
 
 // y = act((x - mean) * invstd * gamma + beta [+ res])
@@ -151,40 +233,67 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
   if (r1 > M) r1 = M;
-  for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    const int64_t off = r * C + (int64_t)cv * 8;
-    int4 raw = ld_stream(x + off);
-    float f[8];
-    unpack8(*reinterpret_cast<bf16x8*>(&raw), f);
+  const int step = blockDim.y;
+  int64_t r = r0 + threadIdx.y;
+  for (; r + step < r1; r += 2 * step) {  // two rows in flight
+    const int64_t o0 = r * C + (int64_t)cv * 8, o1 = (r + step) * C + (int64_t)cv * 8;
+    float f0[8], f1[8];
+    load8(x + o0, f0);
+    load8(x + o1, f1);
     if (res) {
-      int4 rr = ld_stream(res + off);
+      float g0[8], g1[8];
+      load8(res + o0, g0);
+      load8(res + o1, g1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        f0[k] = act_fwd(fmaf(f0[k], sc[k], sh[k]) + g0[k], act);
+        f1[k] = act_fwd(fmaf(f1[k], sc[k], sh[k]) + g1[k], act);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        f0[k] = act_fwd(fmaf(f0[k], sc[k], sh[k]), act);
+        f1[k] = act_fwd(fmaf(f1[k], sc[k], sh[k]), act);
+      }
+    }
+    *reinterpret_cast<bf16x8*>(y + o0) = pack8(f0);  // stays in L2: the next conv reads it
+    *reinterpret_cast<bf16x8*>(y + o1) = pack8(f1);
+  }
+  for (; r < r1; r += step) {
+    const int64_t off = r * C + (int64_t)cv * 8;
+    float f[8];
+    load8(x + off, f);
+    if (res) {
       float g[8];
-      unpack8(*reinterpret_cast<bf16x8*>(&rr), g);
+      load8(res + off, g);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = act_fwd(fmaf(f[k], sc[k], sh[k]) + g[k], act);
     } else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = act_fwd(fmaf(f[k], sc[k], sh[k]), act);
     }
-    bf16x8 o = pack8(f);
-    *reinterpret_cast<bf16x8*>(y + off) = o;  // keep in L2: the next conv reads it
+    *reinterpret_cast<bf16x8*>(y + off) = pack8(f);
   }
 }
 
 // -------------------------------------------------------------------------- backward
-// sums[0][c] += sum dz ; sums[1][c] += sum dz * xhat ; optionally materialise dz
+// sums[0][c] += sum dz ; sums[1][c] += sum dz * xhat ; optionally materialise dz.
+// Last CTA: coef[3][C] = {gamma*invstd, sum_dz/M, sum_dz_xhat/M}, dgamma/dbeta written.
+template <typename PT, typename GT>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
-                     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dz_out,
-                     const float* __restrict__ stat, float* __restrict__ sums, int64_t M, int C,
-                     int rows_per_block, int act) {
+                     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
+                     __nv_bfloat16* __restrict__ dz_out, const float* __restrict__ stat,
+                     float* __restrict__ sums, unsigned int* __restrict__ counter,
+                     const PT* __restrict__ gamma, float* __restrict__ coef,
+                     GT* __restrict__ dgamma, GT* __restrict__ dbeta, int accumulate, int64_t M,
+                     int C, int rows_per_block, int act) {
   __shared__ float red[16][kBnThreads];
   const int cv_total = C >> 3;
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  float s[8], q[8], mean[8], istd[8];
+  float v[16], mean[8], istd[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) s[k] = q[k] = mean[k] = istd[k] = 0.f;
+  for (int k = 0; k < 16; ++k) v[k] = 0.f;
   if (cv < cv_total) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -194,84 +303,89 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     int64_t r1 = r0 + rows_per_block;
     if (r1 > M) r1 = M;
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-      const int64_t off = r * C + (int64_t)cv * 8;
-      int4 a = ld_stream(dy + off);
-      int4 b = *reinterpret_cast<const int4*>(x + off);  // re-read by bwd_apply: keep cached
-      float d[8], xv[8];
-      unpack8(*reinterpret_cast<bf16x8*>(&a), d);
-      unpack8(*reinterpret_cast<bf16x8*>(&b), xv);
+    const int step = blockDim.y;
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 2 * step) {
+      const bool two = (r + step) < r1;
+      const int64_t o0 = r * C + (int64_t)cv * 8;
+      const int64_t o1 = two ? (r + step) * C + (int64_t)cv * 8 : o0;
+      float d0[8], d1[8], x0[8], x1[8];
+      load8(dy + o0, d0);
+      load8(dy + o1, d1);
+      {  // x is re-read by bn_bwd_apply: ordinary (cacheable) load
+        int4 b0 = *reinterpret_cast<const int4*>(x + o0);
+        int4 b1 = *reinterpret_cast<const int4*>(x + o1);
+        unpack8(*reinterpret_cast<bf16x8*>(&b0), x0);
+        unpack8(*reinterpret_cast<bf16x8*>(&b1), x1);
+      }
       if (dy2) {  // gradient fan-in (block output feeds the next conv AND the next skip)
-        int4 a2 = ld_stream(dy2 + off);
-        float d2[8];
-        unpack8(*reinterpret_cast<bf16x8*>(&a2), d2);
+        float e0[8], e1[8];
+        load8(dy2 + o0, e0);
+        load8(dy2 + o1, e1);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) d[k] += d2[k];
+        for (int k = 0; k < 8; ++k) {
+          d0[k] += e0[k];
+          d1[k] += e1[k];
+        }
       }
       if (act) {
-        int4 c4 = ld_stream(y + off);
-        float yv[8];
-        unpack8(*reinterpret_cast<bf16x8*>(&c4), yv);
+        float y0[8], y1[8];
+        load8(y + o0, y0);
+        load8(y + o1, y1);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) d[k] *= act_mask(yv[k], act);
+        for (int k = 0; k < 8; ++k) {
+          d0[k] *= act_mask(y0[k], act);
+          d1[k] *= act_mask(y1[k], act);
+        }
       }
-      if (dz_out) *reinterpret_cast<bf16x8*>(dz_out + off) = pack8(d);
+      if (dz_out) {
+        *reinterpret_cast<bf16x8*>(dz_out + o0) = pack8(d0);
+        if (two) *reinterpret_cast<bf16x8*>(dz_out + o1) = pack8(d1);
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        s[k] += d[k];
-        q[k] = fmaf(d[k], (xv[k] - mean[k]) * istd[k], q[k]);
+        v[k] += d0[k];
+        v[8 + k] = fmaf(d0[k], (x0[k] - mean[k]) * istd[k], v[8 + k]);
+      }
+      if (two) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[k] += d1[k];
+          v[8 + k] = fmaf(d1[k], (x1[k] - mean[k]) * istd[k], v[8 + k]);
+        }
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    red[k][tid] = s[k];
-    red[8 + k][tid] = q[k];
+  block_reduce_to_workspace<16>(v, red, sums, C, cv_total, blockIdx.x % kRep);
+  if (last_cta_of_chunk(counter)) {
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int c0 = blockIdx.y * blockDim.x * 8;
+    const int nch = min(blockDim.x * 8, C - c0);
+    const float inv_m = 1.f / (float)M;
+    for (int i = tid; i < nch; i += blockDim.x * blockDim.y) {
+      const int c = c0 + i;
+      float sdz, sdzx;
+      gather_and_clear(sums, C, c, sdz, sdzx);
+      coef[c] = to_f(gamma[c]) * stat[C + c];
+      coef[C + c] = sdz * inv_m;
+      coef[2 * C + c] = sdzx * inv_m;
+      if (accumulate) {
+        dgamma[c] = from_f<GT>(to_f(dgamma[c]) + sdzx);
+        dbeta[c] = from_f<GT>(to_f(dbeta[c]) + sdz);
+      } else {
+        dgamma[c] = from_f<GT>(sdzx);
+        dbeta[c] = from_f<GT>(sdz);
+      }
+    }
   }
-  __syncthreads();
-  const int nthreads = blockDim.x * blockDim.y;
-  const int nout = blockDim.x * 16;
-  for (int o = tid; o < nout; o += nthreads) {
-    const int tx = o % blockDim.x, k = o / blockDim.x;
-    const int c_vec = blockIdx.y * blockDim.x + tx;
-    if (c_vec >= cv_total) continue;
-    float acc = 0.f;
-    for (int ty = 0; ty < blockDim.y; ++ty) acc += red[k][ty * blockDim.x + tx];
-    atomicAdd(&sums[(k >> 3) * C + c_vec * 8 + (k & 7)], acc);
-  }
-}
-
-// coef: [3][C] = {gamma*invstd, sum_dz/M, sum_dz_xhat/M}; writes dgamma/dbeta; re-zeroes sums
-template <typename PT, typename GT>
-__global__ void bn_bwd_finalize_kernel(float* __restrict__ sums, const float* __restrict__ stat,
-                                       const PT* __restrict__ gamma, float* __restrict__ coef,
-                                       GT* __restrict__ dgamma, GT* __restrict__ dbeta,
-                                       int accumulate, int64_t M, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float sdz = sums[c], sdzx = sums[C + c];
-  const float inv_m = 1.f / (float)M;
-  coef[c] = to_f(gamma[c]) * stat[C + c];
-  coef[C + c] = sdz * inv_m;
-  coef[2 * C + c] = sdzx * inv_m;
-  if (accumulate) {
-    dgamma[c] = from_f<GT>(to_f(dgamma[c]) + sdzx);
-    dbeta[c] = from_f<GT>(to_f(dbeta[c]) + sdz);
-  } else {
-    dgamma[c] = from_f<GT>(sdzx);
-    dbeta[c] = from_f<GT>(sdz);
-  }
-  sums[c] = 0.f;
-  sums[C + c] = 0.f;
 }
 
 // dx = coef0 * (dz - coef1 - xhat * coef2); dz is read from dz_in, or rebuilt from dy & y
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz_in, const __nv_bfloat16* __restrict__ dy,
-                    const __nv_bfloat16* __restrict__ dy2, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
-                    __nv_bfloat16* __restrict__ dx, const float* __restrict__ stat,
-                    const float* __restrict__ coef, int64_t M, int C, int rows_per_block,
-                    int act) {
+                    const __nv_bfloat16* __restrict__ dy2, const __nv_bfloat16* __restrict__ y,
+                    const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dx,
+                    const float* __restrict__ stat, const float* __restrict__ coef, int64_t M, int C,
+                    int rows_per_block, int act) {
   const int cv_total = C >> 3;
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv >= cv_total) return;
@@ -288,38 +402,48 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz_in, const __nv_bfloat16
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
   if (r1 > M) r1 = M;
-  for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    const int64_t off = r * C + (int64_t)cv * 8;
-    float d[8], xv[8];
+  const int step = blockDim.y;
+  for (int64_t r = r0 + threadIdx.y; r < r1; r += 2 * step) {
+    const bool two = (r + step) < r1;
+    const int64_t o0 = r * C + (int64_t)cv * 8;
+    const int64_t o1 = two ? (r + step) * C + (int64_t)cv * 8 : o0;
+    float d0[8], d1[8], x0[8], x1[8];
     if (dz_in) {
-      int4 a = ld_stream(dz_in + off);
-      unpack8(*reinterpret_cast<bf16x8*>(&a), d);
+      load8(dz_in + o0, d0);
+      load8(dz_in + o1, d1);
     } else {
-      int4 a = ld_stream(dy + off);
-      unpack8(*reinterpret_cast<bf16x8*>(&a), d);
+      load8(dy + o0, d0);
+      load8(dy + o1, d1);
       if (dy2) {
-        int4 a2 = ld_stream(dy2 + off);
-        float d2[8];
-        unpack8(*reinterpret_cast<bf16x8*>(&a2), d2);
+        float e0[8], e1[8];
+        load8(dy2 + o0, e0);
+        load8(dy2 + o1, e1);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) d[k] += d2[k];
+        for (int k = 0; k < 8; ++k) {
+          d0[k] += e0[k];
+          d1[k] += e1[k];
+        }
       }
       if (act) {
-        int4 c4 = ld_stream(y + off);
-        float yv[8];
-        unpack8(*reinterpret_cast<bf16x8*>(&c4), yv);
+        float y0[8], y1[8];
+        load8(y + o0, y0);
+        load8(y + o1, y1);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) d[k] *= act_mask(yv[k], act);
+        for (int k = 0; k < 8; ++k) {
+          d0[k] *= act_mask(y0[k], act);
+          d1[k] *= act_mask(y1[k], act);
+        }
       }
     }
-    int4 b = ld_stream(x + off);
-    unpack8(*reinterpret_cast<bf16x8*>(&b), xv);
+    load8(x + o0, x0);
+    load8(x + o1, x1);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float xhat = (xv[k] - mean[k]) * istd[k];
-      d[k] = c0[k] * (d[k] - c1[k] - xhat * c2[k]);
+      d0[k] = c0[k] * (d0[k] - c1[k] - (x0[k] - mean[k]) * istd[k] * c2[k]);
+      d1[k] = c0[k] * (d1[k] - c1[k] - (x1[k] - mean[k]) * istd[k] * c2[k]);
     }
-    *reinterpret_cast<bf16x8*>(dx + off) = pack8(d);
+    *reinterpret_cast<bf16x8*>(dx + o0) = pack8(d0);
+    if (two) *reinterpret_cast<bf16x8*>(dx + o1) = pack8(d1);
   }
 }
 
@@ -332,36 +456,32 @@ bias_act_kernel(const __nv_bfloat16* __restrict__ x, const PT* __restrict__ bias
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
     const int cv = (int)(v % cv_total);
-    int4 raw = ld_stream(x + v * 8);
     float f[8];
-    unpack8(*reinterpret_cast<bf16x8*>(&raw), f);
+    load8(x + v * 8, f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = act_fwd(f[k] + (bias ? to_f(bias[cv * 8 + k]) : 0.f), act);
     *reinterpret_cast<bf16x8*>(y + v * 8) = pack8(f);
   }
 }
 
-// dz = dy * mask(y) [written in place of dy allowed], plus optional second addend (fan-out sum)
+// dz = (dy [+ dy2]) * mask(y)
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
                const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dz, int64_t nvec,
                int act) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    int4 a = ld_stream(dy + v * 8);
     float d[8];
-    unpack8(*reinterpret_cast<bf16x8*>(&a), d);
+    load8(dy + v * 8, d);
     if (dy2) {
-      int4 a2 = ld_stream(dy2 + v * 8);
       float d2[8];
-      unpack8(*reinterpret_cast<bf16x8*>(&a2), d2);
+      load8(dy2 + v * 8, d2);
 #pragma unroll
       for (int k = 0; k < 8; ++k) d[k] += d2[k];
     }
     if (act) {
-      int4 c4 = ld_stream(y + v * 8);
       float yv[8];
-      unpack8(*reinterpret_cast<bf16x8*>(&c4), yv);
+      load8(y + v * 8, yv);
 #pragma unroll
       for (int k = 0; k < 8; ++k) d[k] *= act_mask(yv[k], act);
     }
@@ -369,53 +489,40 @@ act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
   }
 }
 
-// per-channel sum over rows of an NHWC bf16 tensor (bias gradient), sums zeroed on entry.
+// per-channel sum over rows of an NHWC bf16 tensor (bias gradient); last CTA writes `out`.
+template <typename GT>
 __global__ void __launch_bounds__(kBnThreads)
-colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, int64_t M, int C,
-              int rows_per_block) {
-  __shared__ float red[8][kBnThreads];
+colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums,
+              unsigned int* __restrict__ counter, GT* __restrict__ out, int accumulate, int64_t M,
+              int C, int rows_per_block) {
+  __shared__ float red[16][kBnThreads];
   const int cv_total = C >> 3;
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  float s[8];
+  float v[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) s[k] = 0.f;
+  for (int k = 0; k < 8; ++k) v[k] = 0.f;
   if (cv < cv_total) {
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     int64_t r1 = r0 + rows_per_block;
     if (r1 > M) r1 = M;
     for (int64_t r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-      int4 raw = ld_stream(x + r * C + (int64_t)cv * 8);
       float f[8];
-      unpack8(*reinterpret_cast<bf16x8*>(&raw), f);
+      load8(x + r * C + (int64_t)cv * 8, f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s[k] += f[k];
+      for (int k = 0; k < 8; ++k) v[k] += f[k];
     }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) red[k][tid] = s[k];
-  __syncthreads();
-  const int nthreads = blockDim.x * blockDim.y;
-  const int nout = blockDim.x * 8;
-  for (int o = tid; o < nout; o += nthreads) {
-    const int tx = o % blockDim.x, k = o / blockDim.x;
-    const int c_vec = blockIdx.y * blockDim.x + tx;
-    if (c_vec >= cv_total) continue;
-    float acc = 0.f;
-    for (int ty = 0; ty < blockDim.y; ++ty) acc += red[k][ty * blockDim.x + tx];
-    atomicAdd(&sums[c_vec * 8 + k], acc);
+  block_reduce_to_workspace<8>(v, red, sums, C, cv_total, blockIdx.x % kRep);
+  if (last_cta_of_chunk(counter)) {
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int c0 = blockIdx.y * blockDim.x * 8;
+    const int nch = min(blockDim.x * 8, C - c0);
+    for (int i = tid; i < nch; i += blockDim.x * blockDim.y) {
+      float s, unused;
+      gather_and_clear(sums, C, c0 + i, s, unused);
+      out[c0 + i] = accumulate ? from_f<GT>(to_f(out[c0 + i]) + s) : from_f<GT>(s);
+    }
   }
-}
-
-// out[c] = (GT) sums[c] (or +=); re-zero sums
-template <typename GT>
-__global__ void colsum_finalize_kernel(float* __restrict__ sums, GT* __restrict__ out,
-                                       int accumulate, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float v = sums[c];
-  out[c] = accumulate ? from_f<GT>(to_f(out[c]) + v) : from_f<GT>(v);
-  sums[c] = 0.f;
 }
 
 }  // namespace ddl
@@ -423,12 +530,16 @@ __global__ void colsum_finalize_kernel(float* __restrict__ sums, GT* __restrict_
 using namespace ddl;
 typedef __nv_bfloat16 bf16;
 
-extern "C" int ddl_bn_stats(const void* x, float* sums, int64_t M, int C, int sms,
-                            cudaStream_t st) {
+extern "C" int ddl_bn_replicas() { return kRep; }
+
+extern "C" int ddl_bn_stats(const void* x, float* sums, unsigned int* counter, float* stat,
+                            float* running_mean, float* running_var, int64_t M, int C, float eps,
+                            float momentum, int sms, cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 4);
-  bn_stats_kernel<<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>((const bf16*)x, sums, M, C,
-                                                                 d.rows_per_block);
+  BnDims d = bn_dims(M, C, sms, 3, 8);
+  bn_stats_kernel<<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
+      (const bf16*)x, sums, counter, stat, running_mean, running_var, M, C, d.rows_per_block, eps,
+      momentum);
   return (int)cudaGetLastError();
 }
 
@@ -443,7 +554,7 @@ extern "C" int ddl_bn_apply(const void* x, const void* res, void* y, const float
                             const void* gamma, const void* beta, int param_is_bf16, int64_t M,
                             int C, int act, int sms, cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 8);
+  BnDims d = bn_dims(M, C, sms, 6, 4);
   if (param_is_bf16)
     bn_apply_kernel<bf16><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
         (const bf16*)x, (const bf16*)res, (bf16*)y, stat, (const bf16*)gamma, (const bf16*)beta, M,
@@ -456,25 +567,18 @@ extern "C" int ddl_bn_apply(const void* x, const void* res, void* y, const float
 }
 
 extern "C" int ddl_bn_bwd_reduce(const void* dy, const void* dy2, const void* y, const void* x,
-                                 void* dz_out,
-                                 const float* stat, float* sums, int64_t M, int C, int act,
-                                 int sms, cudaStream_t st) {
+                                 void* dz_out, const float* stat, float* sums,
+                                 unsigned int* counter, const void* gamma, int param_is_bf16,
+                                 float* coef, void* dgamma, void* dbeta, int grad_is_bf16,
+                                 int accumulate, int64_t M, int C, int act, int sms,
+                                 cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 4);
-  bn_bwd_reduce_kernel<<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
-      (const bf16*)dy, (const bf16*)dy2, (const bf16*)y, (const bf16*)x, (bf16*)dz_out, stat, sums,
-      M, C, d.rows_per_block, act);
-  return (int)cudaGetLastError();
-}
-
-extern "C" int ddl_bn_bwd_finalize(float* sums, const float* stat, const void* gamma,
-                                   int param_is_bf16, float* coef, void* dgamma, void* dbeta,
-                                   int grad_is_bf16, int accumulate, int64_t M, int C,
-                                   cudaStream_t st) {
-  const int g = (C + 127) / 128;
-#define L(PT, GT)                                                                           \
-  bn_bwd_finalize_kernel<PT, GT><<<g, 128, 0, st>>>(sums, stat, (const PT*)gamma, coef,       \
-                                                     (GT*)dgamma, (GT*)dbeta, accumulate, M, C)
+  BnDims d = bn_dims(M, C, sms, 3, 8);
+#define L(PT, GT)                                                                              \
+  bn_bwd_reduce_kernel<PT, GT><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(                 \
+      (const bf16*)dy, (const bf16*)dy2, (const bf16*)y, (const bf16*)x, (bf16*)dz_out, stat,   \
+      sums, counter, (const PT*)gamma, coef, (GT*)dgamma, (GT*)dbeta, accumulate, M, C,         \
+      d.rows_per_block, act)
   if (param_is_bf16 && grad_is_bf16) L(bf16, bf16);
   else if (param_is_bf16) L(bf16, float);
   else if (grad_is_bf16) L(float, bf16);
@@ -484,11 +588,10 @@ extern "C" int ddl_bn_bwd_finalize(float* sums, const float* stat, const void* g
 }
 
 extern "C" int ddl_bn_bwd_apply(const void* dz_in, const void* dy, const void* dy2, const void* y,
-                                const void* x,
-                                void* dx, const float* stat, const float* coef, int64_t M, int C,
-                                int act, int sms, cudaStream_t st) {
+                                const void* x, void* dx, const float* stat, const float* coef,
+                                int64_t M, int C, int act, int sms, cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 8);
+  BnDims d = bn_dims(M, C, sms, 6, 4);
   bn_bwd_apply_kernel<<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
       (const bf16*)dz_in, (const bf16*)dy, (const bf16*)dy2, (const bf16*)y, (const bf16*)x,
       (bf16*)dx, stat, coef, M, C, d.rows_per_block, act);
@@ -523,15 +626,16 @@ extern "C" int ddl_act_bwd(const void* dy, const void* dy2, const void* y, void*
   return (int)cudaGetLastError();
 }
 
-extern "C" int ddl_colsum(const void* x, float* sums, void* out, int out_is_bf16, int accumulate,
-                          int64_t M, int C, int sms, cudaStream_t st) {
+extern "C" int ddl_colsum(const void* x, float* sums, unsigned int* counter, void* out,
+                          int out_is_bf16, int accumulate, int64_t M, int C, int sms,
+                          cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 4);
-  colsum_kernel<<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>((const bf16*)x, sums, M, C,
-                                                               d.rows_per_block);
+  BnDims d = bn_dims(M, C, sms, 3, 8);
   if (out_is_bf16)
-    colsum_finalize_kernel<bf16><<<(C + 127) / 128, 128, 0, st>>>(sums, (bf16*)out, accumulate, C);
+    colsum_kernel<bf16><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
+        (const bf16*)x, sums, counter, (bf16*)out, accumulate, M, C, d.rows_per_block);
   else
-    colsum_finalize_kernel<float><<<(C + 127) / 128, 128, 0, st>>>(sums, (float*)out, accumulate, C);
+    colsum_kernel<float><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
+        (const bf16*)x, sums, counter, (float*)out, accumulate, M, C, d.rows_per_block);
   return (int)cudaGetLastError();
 }

@@ -10,6 +10,10 @@
     if (_e != cudaSuccess) return (int)_e;                                       \
   } while (0)
 
+// Replicas of the per-channel partial-sum workspace ([R][2][C] fp32): spreads same-address
+// L2 atomics from many CTAs over R copies (bn.cu, gemm_tcgen05.cu epilogue).
+#define DDL_BN_REPLICAS 8
+
 namespace ddl {
 
 constexpr int kWarp = 32;

@@ -160,7 +160,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 }
 
 struct EpilogueParams {
-  float* col_sums;            // [2][N] or null
+  float* col_sums;            // [R][2][N] replicated partial sums, or null
   const __nv_bfloat16* bias;  // [N] or null
   int relu;
   int M, N, K;
@@ -322,13 +322,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
         q0 = fmaf(fv.x, fv.x, q0); q1 = fmaf(fv.y, fv.y, q1);
       }
       const int col = tile_n * BLOCK_N + c;
+      // replicated workspace [R][2][N]: M-tile t adds into replica t % R (see bn.cu)
+      float* cs = ep.col_sums + (size_t)(tile_m % DDL_BN_REPLICAS) * 2 * ep.N;
       if (col < ep.N) {
-        atomicAdd(&ep.col_sums[col], s0);
-        atomicAdd(&ep.col_sums[ep.N + col], q0);
+        atomicAdd(&cs[col], s0);
+        atomicAdd(&cs[ep.N + col], q0);
       }
       if (col + 1 < ep.N) {
-        atomicAdd(&ep.col_sums[col + 1], s1);
-        atomicAdd(&ep.col_sums[ep.N + col + 1], q1);
+        atomicAdd(&cs[col + 1], s1);
+        atomicAdd(&cs[ep.N + col + 1], q1);
       }
     }
     if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

@@ -14,6 +14,11 @@ import torch.nn.functional as F
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 
 
+def _up(t: torch.Tensor) -> torch.Tensor:
+    """Compute dtype: at least fp32 (fp64 inputs stay fp64 so tests can separate bugs from rounding)."""
+    return t if t.dtype in (torch.float32, torch.float64) else t.to(torch.float32)
+
+
 def act_fwd(x: torch.Tensor, act: int) -> torch.Tensor:
     if act == ACT_RELU:
         return torch.relu(x)
@@ -34,7 +39,7 @@ def sgd_flat(master, mom, grad, hyper, w_outs):
     """hyper = [lr, momentum, weight_decay, grad_scale]; updates master/mom in place and
     writes the new weights (cast) into every tensor of ``w_outs``."""
     lr, mu, wd, gs = [float(v) for v in hyper.tolist()[:4]]
-    g = grad.float() * gs + wd * master
+    g = _up(grad) * gs + wd * master
     mom.mul_(mu).add_(g)
     master.add_(mom, alpha=-lr)
     for w in w_outs:
@@ -45,7 +50,7 @@ def sgd_flat(master, mom, grad, hyper, w_outs):
 def xent(logits: torch.Tensor, target: torch.Tensor, smoothing: float = 0.0,
          grad_scale: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
     """Returns (stats[3] = mean loss, #top1, #top5; dlogits = d(mean loss)/dlogits * grad_scale)."""
-    x = logits.float()
+    x = _up(logits)
     n, c = x.shape
     logp = F.log_softmax(x, dim=1)
     nll = -logp.gather(1, target.view(-1, 1)).squeeze(1)
@@ -68,7 +73,7 @@ def _cview(t: torch.Tensor) -> Tuple[int, ...]:
 
 def bn_stat(x: torch.Tensor, eps: float) -> torch.Tensor:
     """[2, C] = (mean, invstd) over all dims but channel (dim 1)."""
-    xf = x.float()
+    xf = _up(x)
     dims = [0] + list(range(2, x.dim()))
     mean = xf.mean(dim=dims)
     var = xf.var(dim=dims, unbiased=False)
@@ -77,9 +82,9 @@ def bn_stat(x: torch.Tensor, eps: float) -> torch.Tensor:
 
 def bn_apply(x, res, stat, gamma, beta, act: int):
     v = _cview(x)
-    y = (x.float() - stat[0].view(v)) * (stat[1] * gamma.float()).view(v) + beta.float().view(v)
+    y = (_up(x) - stat[0].view(v)) * (stat[1] * _up(gamma)).view(v) + _up(beta).view(v)
     if res is not None:
-        y = y + res.float()
+        y = y + _up(res)
     return act_fwd(y, act).to(x.dtype)
 
 
@@ -95,33 +100,33 @@ def bn_update_running(stat, x_numel_per_channel: int, eps: float, momentum: floa
 def bn_backward(dy, dy2, y, x, stat, gamma, act: int, want_dz: bool):
     """Returns (dx, dz or None, dgamma, dbeta) — all fp32 except dx/dz in x.dtype."""
     v = _cview(x)
-    d = dy.float()
+    d = _up(dy)
     if dy2 is not None:
-        d = d + dy2.float()
+        d = d + _up(dy2)
     if act != ACT_NONE:
-        d = d * act_mask(y.float(), act)
+        d = d * act_mask(_up(y), act)
     dims = [0] + list(range(2, x.dim()))
     m = x.numel() // x.shape[1]
-    xhat = (x.float() - stat[0].view(v)) * stat[1].view(v)
+    xhat = (_up(x) - stat[0].view(v)) * stat[1].view(v)
     dbeta = d.sum(dim=dims)
     dgamma = (d * xhat).sum(dim=dims)
-    dx = (gamma.float() * stat[1]).view(v) * (d - dbeta.view(v) / m - xhat * dgamma.view(v) / m)
+    dx = (_up(gamma) * stat[1]).view(v) * (d - dbeta.view(v) / m - xhat * dgamma.view(v) / m)
     return dx.to(x.dtype), (d.to(x.dtype) if want_dz else None), dgamma, dbeta
 
 
 def bias_act(x, bias, act: int):
-    y = x.float()
+    y = _up(x)
     if bias is not None:
-        y = y + bias.float().view(_cview(x))
+        y = y + _up(bias).view(_cview(x))
     return act_fwd(y, act).to(x.dtype)
 
 
 def act_bwd(dy, dy2, y, act: int):
-    d = dy.float()
+    d = _up(dy)
     if dy2 is not None:
-        d = d + dy2.float()
+        d = d + _up(dy2)
     if act != ACT_NONE:
-        d = d * act_mask(y.float(), act)
+        d = d * act_mask(_up(y), act)
     return d.to(dy.dtype)
 
 
@@ -130,7 +135,7 @@ def u8_to_norm(x_u8: torch.Tensor, mean, std, dtype) -> torch.Tensor:
     c = x_u8.shape[-1]
     m = torch.tensor(mean[:c], dtype=torch.float32, device=x_u8.device)
     s = torch.tensor(std[:c], dtype=torch.float32, device=x_u8.device)
-    y = (x_u8.float() / 255.0 - m) / s
+    y = (_up(x_u8) / 255.0 - m) / s
     return y.to(dtype).permute(0, 3, 1, 2)
 
 
@@ -152,4 +157,4 @@ def set_mask(lengths: torch.Tensor, T: int) -> torch.Tensor:
 
 
 def global_avg_pool(x: torch.Tensor) -> torch.Tensor:
-    return x.float().mean(dim=(2, 3)).to(x.dtype)
+    return _up(x).mean(dim=(2, 3)).to(x.dtype)

@@ -1,0 +1,125 @@
+"""Static engine (explicit forward/backward, flat buffers, fused SGD) against torch autograd."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ddlbench_b200.engine import StageExecutor, compile_plan
+from ddlbench_b200.models import build_model
+
+
+def _global_rel_err(ex, model):
+    num = den = 0.0
+    for name, p in model.named_parameters():
+        g = ex.store.g_views[name]
+        num += (g - p.grad).pow(2).sum().item()
+        den += p.grad.pow(2).sum().item()
+    return (num / max(den, 1e-30)) ** 0.5
+
+
+@pytest.mark.parametrize("arch,ds", [("resnet18", "cifar10"), ("resnet50", "mnist"),
+                                     ("vgg11", "cifar10"), ("mobilenetv2", "cifar10")])
+def test_engine_matches_autograd(arch, ds):
+    # fp64 so that a wiring bug cannot hide behind rounding noise of a deep BatchNorm net
+    torch.manual_seed(0)
+    m = build_model(arch, ds).double().train()
+    ex = StageExecutor.from_model(m, device="cpu", dtype=torch.float64, lr=0.1, momentum=0.9,
+                                  weight_decay=1e-4)
+    for name, p in m.named_parameters():
+        ex.store.weights()[name].copy_(p.detach())
+    x = torch.randn(8, *m.input_shape, dtype=torch.float64)
+    t = torch.randint(0, 10, (8,))
+    y = m(x)
+    loss = F.cross_entropy(y, t)
+    loss.backward()
+    outs, ctx = ex.forward([ex.prepare_input(x)])
+    stats, d = ex.loss(outs[0], t)
+    ex.backward(ctx, [d])
+    assert torch.allclose(outs[0], y, atol=1e-9)
+    assert abs(stats[0].item() - loss.item()) < 1e-5
+    assert _global_rel_err(ex, m) < 1e-6
+    # BatchNorm running statistics were updated like nn.BatchNorm2d does
+    for k, v in ex.buffers.items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            ref = dict(m.named_buffers())[k]
+            assert torch.allclose(v.double(), ref, atol=1e-5), k
+
+
+def test_fused_sgd_matches_torch_optim():
+    torch.manual_seed(0)
+    m = build_model("vgg11", "mnist").train()
+    ex = StageExecutor.from_model(m, device="cpu", dtype=torch.float32, lr=0.1, momentum=0.9,
+                                  weight_decay=1e-4)
+    opt = torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    x = torch.randn(4, 1, 28, 28)
+    t = torch.randint(0, 10, (4,))
+    for _ in range(3):
+        opt.zero_grad()
+        F.cross_entropy(m(x), t).backward()
+        opt.step()
+        o, c = ex.forward([x])
+        s, d = ex.loss(o[0], t)
+        ex.backward(c, [d])
+        ex.store.sgd_step()
+    for name, p in m.named_parameters():
+        assert torch.allclose(ex.store.weights()[name], p, atol=1e-4), name
+
+
+def test_fusion_patterns_resnet50():
+    plan = compile_plan(build_model("resnet50", "imagenet"))
+    kinds = [op.kind for op in plan.ops]
+    assert kinds.count("conv_bn_act") == 53
+    assert "gap_flatten" in kinds and "maxpool" in kinds and kinds[-1] == "linear_act"
+    # every residual join is fused into a conv+bn op
+    assert "add_act" not in kinds
+
+
+def test_gradient_accumulation_over_microbatches():
+    torch.manual_seed(1)
+    m = build_model("vgg11", "mnist").train()
+    ex = StageExecutor.from_model(m, device="cpu", dtype=torch.float32)
+    x = torch.randn(8, 1, 28, 28)
+    t = torch.randint(0, 10, (8,))
+    o, c = ex.forward([x])
+    s, d = ex.loss(o[0], t)
+    ex.backward(c, [d])
+    full = ex.store.g_flat.clone()
+    for k, (a, b) in enumerate([(0, 4), (4, 8)]):
+        o, c = ex.forward([x[a:b]])
+        s, d = ex.loss(o[0], t[a:b], grad_scale=0.5)
+        ex.backward(c, [d], accumulate=k > 0, final=k == 1)
+    assert torch.allclose(ex.store.g_flat, full, atol=1e-5, rtol=1e-4)
+
+
+def test_bucket_ready_hook_fires_in_order():
+    m = build_model("resnet18", "cifar10").train()
+    ex = StageExecutor.from_model(m, device="cpu", dtype=torch.float32, bucket_elems=1 << 20)
+    fired = []
+    ex.on_bucket_ready = fired.append
+    x = torch.randn(2, 3, 32, 32)
+    o, c = ex.forward([x])
+    s, d = ex.loss(o[0], torch.tensor([1, 2]))
+    ex.backward(c, [d])
+    assert fired == list(range(len(ex.store.layout.buckets))) and len(fired) > 3
+
+
+def test_stage_split_equals_whole():
+    torch.manual_seed(2)
+    m = build_model("resnet18", "cifar10").train()
+    whole = StageExecutor.from_model(m, device="cpu", dtype=torch.float32)
+    cut = next(i for i, n in enumerate(m.nodes) if n.name == "layer2.0.bn1") + 1  # inside a block
+    s0 = StageExecutor.from_model(m, 0, cut, device="cpu", dtype=torch.float32)
+    s1 = StageExecutor.from_model(m, cut, None, device="cpu", dtype=torch.float32)
+    assert len(s0.plan.out_names) == 2 and s1.plan.in_names == s0.plan.out_names
+    x = torch.randn(4, 3, 32, 32)
+    t = torch.randint(0, 10, (4,))
+    o, c = whole.forward([x]); s, d = whole.loss(o[0], t); whole.backward(c, [d])
+    a, ca = s0.forward([x])
+    b, cb = s1.forward(a)
+    s2, d2 = s1.loss(b[0], t)
+    gin = s1.backward(cb, [d2])
+    s0.backward(ca, gin)
+    assert abs(s[0].item() - s2[0].item()) < 1e-5
+    for name in s0.store.layout.entries:
+        assert torch.allclose(s0.store.g_views[name], whole.store.g_views[name], atol=1e-5), name
+    for name in s1.store.layout.entries:
+        assert torch.allclose(s1.store.g_views[name], whole.store.g_views[name], atol=1e-5), name

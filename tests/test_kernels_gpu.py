@@ -1,0 +1,181 @@
+"""Numerics of every hand-written CUDA kernel against a plain PyTorch fp32 reference of the
+same op (ops/reference.py).  All tests here need the B200."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from ddlbench_b200 import ops
+from ddlbench_b200.ops import reference as ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _nhwc(n, c, h, w, scale=1.0, shift=0.0):
+    x = (torch.randn(n, c, h, w, device=DEV) * scale + shift).to(torch.bfloat16)
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def test_extension_loaded():
+    e = ops.ext()
+    assert "tcgen05" in e.gemm_info()
+
+
+@pytest.mark.parametrize("n", [8, 1000, 4096 + 3, 1 << 20])
+@pytest.mark.parametrize("gdt,wdt", [(torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32),
+                                     (torch.bfloat16, torch.float32)])
+def test_sgd_flat(n, gdt, wdt):
+    torch.manual_seed(0)
+    master = torch.randn(n, device=DEV)
+    mom = torch.randn(n, device=DEV) * 0.1
+    grad = torch.randn(n, device=DEV).to(gdt)
+    hyper = torch.tensor([0.1, 0.9, 1e-4, 0.5], device=DEV)
+    w = torch.empty(n, device=DEV, dtype=wdt)
+    w2 = torch.empty(n, device=DEV, dtype=wdt)
+    m_ref, v_ref = master.clone(), mom.clone()
+    w_ref = torch.empty(n, device=DEV, dtype=wdt)
+    ref.sgd_flat(m_ref, v_ref, grad, hyper, [w_ref])
+    ops.sgd_flat_(master, mom, grad, hyper, w, w2)
+    torch.testing.assert_close(master, m_ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(mom, v_ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(w.float(), w_ref.float(), rtol=1e-2, atol=1e-3)
+    assert torch.equal(w, w2)
+
+
+@pytest.mark.parametrize("rows,C", [(32, 1000), (7, 10), (128, 32320), (256, 1000)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("smoothing", [0.0, 0.1])
+def test_xent(rows, C, dtype, smoothing):
+    torch.manual_seed(1)
+    logits = (torch.randn(rows, C, device=DEV) * 3).to(dtype)
+    target = torch.randint(0, C, (rows,), device=DEV)
+    for _ in range(2):  # twice: the ticket counter must self-reset
+        stats, d = ops.xent(logits, target, smoothing=smoothing, grad_scale=2.0)
+    rs, rd = ref.xent(logits, target, smoothing, 2.0 / rows)
+    torch.testing.assert_close(stats[0], rs[0], rtol=2e-3, atol=2e-3)
+    assert stats[1].item() == rs[1].item() and stats[2].item() == rs[2].item()
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-5
+    torch.testing.assert_close(d.float(), rd.float(), rtol=tol, atol=tol / rows)
+
+
+@pytest.mark.parametrize("n,c,h,w", [(32, 64, 56, 56), (4, 2048, 7, 7), (8, 24, 16, 16),
+                                     (2, 960, 7, 7), (3, 1280, 5, 5), (16, 8, 9, 11)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("has_res", [False, True])
+def test_bn_forward_backward(n, c, h, w, act, has_res):
+    torch.manual_seed(2)
+    x = _nhwc(n, c, h, w, scale=1.5, shift=0.3)
+    res = _nhwc(n, c, h, w) if has_res else None
+    gamma = (torch.rand(c, device=DEV) + 0.5).to(torch.bfloat16)
+    beta = (torch.randn(c, device=DEV) * 0.2).to(torch.bfloat16)
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    ws = ops.BnWorkspace(c, DEV)
+    for _ in range(2):  # workspace must self-zero
+        y, stat = ops.bn_forward(x, res, gamma, beta, rm, rv, 1e-5, 0.1, act, ws)
+    stat_ref = ref.bn_stat(x, 1e-5)
+    ref.bn_update_running(stat_ref, x.numel() // c, 1e-5, 0.1, rm_ref, rv_ref)
+    ref.bn_update_running(stat_ref, x.numel() // c, 1e-5, 0.1, rm_ref, rv_ref)
+    y_ref = ref.bn_apply(x, res, stat_ref, gamma, beta, act)
+    torch.testing.assert_close(stat.view(2, c)[0], stat_ref[0], rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(stat.view(2, c)[1], stat_ref[1], rtol=2e-3, atol=1e-3)
+    torch.testing.assert_close(rm, rm_ref, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(rv, rv_ref, rtol=2e-3, atol=1e-3)
+    torch.testing.assert_close(y.float(), y_ref.float(), rtol=2e-2, atol=2e-2)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    # backward
+    dy = _nhwc(n, c, h, w)
+    dy2 = _nhwc(n, c, h, w) if has_res else None
+    dg = torch.empty(c, device=DEV, dtype=torch.bfloat16)
+    db = torch.empty(c, device=DEV, dtype=torch.bfloat16)
+    for _ in range(2):
+        dx, dz = ops.bn_backward(dy, dy2, y, x, stat, gamma, act, has_res, dg, db, False, ws)
+    dx_r, dz_r, dg_r, db_r = ref.bn_backward(dy, dy2, y_ref, x, stat_ref, gamma, act, has_res)
+    scale = max(dg_r.abs().max().item(), 1.0)
+    torch.testing.assert_close(dg.float(), dg_r, rtol=3e-2, atol=3e-2 * scale)
+    torch.testing.assert_close(db.float(), db_r, rtol=3e-2, atol=3e-2 * max(db_r.abs().max().item(), 1.0))
+    # elements whose activation mask flips between bf16 y and fp32 y_ref are excluded
+    err = (dx.float() - dx_r.float()).abs()
+    assert (err > 0.05 * max(dx_r.float().abs().max().item(), 1e-3)).float().mean().item() < 2e-3
+    if has_res:
+        errz = (dz.float() - dz_r.float()).abs()
+        assert (errz > 0.05).float().mean().item() < 2e-3
+
+
+def test_bn_eval_mode():
+    x = _nhwc(4, 32, 8, 8)
+    g = torch.ones(32, device=DEV, dtype=torch.bfloat16)
+    b = torch.zeros(32, device=DEV, dtype=torch.bfloat16)
+    rm, rv = torch.randn(32, device=DEV) * 0.1, torch.rand(32, device=DEV) + 0.5
+    y, _ = ops.bn_forward(x, None, g, b, rm, rv, 1e-5, 0.1, 1, training=False)
+    y_ref = torch.relu((x.float() - rm.view(1, -1, 1, 1)) * torch.rsqrt(rv + 1e-5).view(1, -1, 1, 1))
+    torch.testing.assert_close(y.float(), y_ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("act", [0, 1])
+def test_bias_act_and_grads(act):
+    torch.manual_seed(3)
+    x = _nhwc(8, 64, 14, 14)
+    bias = torch.randn(64, device=DEV).to(torch.bfloat16)
+    y = ops.bias_act(x, bias, act)
+    torch.testing.assert_close(y.float(), ref.bias_act(x, bias, act).float(), rtol=2e-2, atol=2e-2)
+    dy, dy2 = _nhwc(8, 64, 14, 14), _nhwc(8, 64, 14, 14)
+    dz = ops.act_bwd(dy, dy2, y, act)
+    torch.testing.assert_close(dz.float(), ref.act_bwd(dy, dy2, y, act).float(), rtol=2e-2, atol=2e-2)
+    out = torch.empty(64, device=DEV, dtype=torch.bfloat16)
+    ws = ops.BnWorkspace(64, DEV)
+    ops.bias_grad_(dz, out, False, ws)
+    ops.bias_grad_(dz, out, False, ws)
+    torch.testing.assert_close(out.float(), dz.float().sum(dim=(0, 2, 3)), rtol=2e-2, atol=0.5)
+
+
+def test_normalize_u8():
+    x = torch.randint(0, 256, (4, 32, 32, 3), dtype=torch.uint8, device=DEV)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    y = ops.normalize_u8(x, mean, std)
+    y_ref = ref.u8_to_norm(x, list(mean), list(std), torch.float32)
+    assert y.shape == (4, 3, 32, 32) and y.is_contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(y.float(), y_ref, rtol=1e-2, atol=2e-2)
+    x1 = torch.randint(0, 256, (5, 28, 28, 1), dtype=torch.uint8, device=DEV)
+    y1 = ops.normalize_u8(x1, (0.1307,), (0.3081,))
+    torch.testing.assert_close(y1.float(), ref.u8_to_norm(x1, [0.1307], [0.3081], torch.float32),
+                               rtol=1e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("F", [1024, 7, 2])
+def test_revert_varlen_and_mask(dtype, F):
+    T, B = 13, 5
+    x = torch.randn(T, B, F, device=DEV).to(dtype)
+    lengths = torch.tensor([13, 1, 7, 4, 10], device=DEV)
+    y = ops.revert_varlen(x, lengths)
+    assert torch.equal(y, ref.revert_varlen(x, lengths))
+    assert torch.equal(ops.set_mask(lengths, T), ref.set_mask(lengths, T))
+
+
+def test_global_avg_pool():
+    x = _nhwc(32, 2048, 7, 7)
+    y = ops.global_avg_pool(x)
+    torch.testing.assert_close(y.float(), x.float().mean(dim=(2, 3)), rtol=2e-2, atol=1e-2)
+    dy = torch.randn(32, 2048, device=DEV).to(torch.bfloat16)
+    dx = ops.global_avg_pool_bwd(dy, x.shape)
+    torch.testing.assert_close(dx.float(), (dy.float() / 49).view(32, 2048, 1, 1).expand(32, 2048, 7, 7),
+                               rtol=2e-2, atol=1e-3)
+
+
+def test_l2norm():
+    x = torch.randn(100003, device=DEV).to(torch.bfloat16)
+    torch.testing.assert_close(ops.l2norm(x)[0], x.float().norm(), rtol=1e-3, atol=1e-3)
+
+
+# The tcgen05 GEMM runs in a child process with a timeout: a descriptor / barrier bug must
+# fail this test, not take the whole session (or the GPU) down.
+def test_tcgen05_gemm_subprocess():
+    script = os.path.join(os.path.dirname(__file__), "gemm_check.py")
+    p = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=600)
+    sys.stdout.write(p.stdout[-4000:])
+    sys.stderr.write(p.stderr[-4000:])
+    assert p.returncode == 0, "tcgen05 GEMM check failed"
