@@ -24,7 +24,7 @@ import torch
 import torch.distributed as dist
 
 MAX_BLOCKS = 64
-MAX_RANKS = 16
+MAX_RANKS = 8
 FLAG_WORDS = 2 * MAX_BLOCKS * MAX_RANKS
 
 

@@ -76,18 +76,28 @@ class Trainer:
         self.steps_done = 0
 
     # ------------------------------------------------------------------ one eager step
-    def _step_eager(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    def _step_eager(self, x: torch.Tensor, target: torch.Tensor, update: bool = True) -> torch.Tensor:
         ex = self.ex
         outs, ctx = ex.forward([x], training=True)
         stats, dlogits = ex.loss(outs[0], target)
         ex.backward(ctx, [dlogits])
         if self.fdp is not None:
             self.fdp.finish_step()
-        else:
-            if self.distributed:   # baseline: NCCL all-reduce of the flat gradient buffer
-                dist.all_reduce(ex.store.g_flat, group=self.group)
-            ex.store.sgd_step()
+        elif update:
+            self._update_baseline()
         return stats
+
+    def _update_baseline(self) -> None:
+        """Non-fused update: (NCCL all-reduce of the flat gradient buffer, then) fused SGD."""
+        if self.distributed:
+            dist.all_reduce(self.ex.store.g_flat, group=self.group)
+        self.ex.store.sgd_step()
+
+    @property
+    def _nccl_outside_graph(self) -> bool:
+        # the NCCL baseline keeps its collective OUT of the captured graph (forward+backward
+        # are replayed, the all-reduce and the optimizer kernel are launched eagerly after it)
+        return self.distributed and self.fdp is None
 
     # ------------------------------------------------------------------ public step
     def step(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
@@ -102,7 +112,7 @@ class Trainer:
             self.static_x.copy_(x, non_blocking=True)
         if target.data_ptr() != self.static_t.data_ptr():
             self.static_t.copy_(target, non_blocking=True)
-        self.graph.replay()
+        self._replay()
         self.steps_done += 1
         return self.static_stats
 
@@ -114,10 +124,15 @@ class Trainer:
                 self._capture(ops.normalize_u8(x_u8, mean, std, dtype=self.dtype), target)
             ops.normalize_u8(x_u8, mean, std, dtype=self.dtype, out=self.static_x)
             self.static_t.copy_(target, non_blocking=True)
-            self.graph.replay()
+            self._replay()
             self.steps_done += 1
             return self.static_stats
         return self.step(ops.normalize_u8(x_u8, mean, std, dtype=self.dtype), target)
+
+    def _replay(self) -> None:
+        self.graph.replay()
+        if self._nccl_outside_graph:
+            self._update_baseline()
 
     def _capture(self, x: torch.Tensor, target: torch.Tensor) -> None:
         ex = self.ex
@@ -136,7 +151,8 @@ class Trainer:
         before = ops.launches
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.static_stats = self._step_eager(self.static_x, self.static_t)
+            self.static_stats = self._step_eager(self.static_x, self.static_t,
+                                                 update=not self._nccl_outside_graph)
         self.launches_per_step = ops.launches - before
         self.graph = g
         torch.cuda.synchronize(self.device)

@@ -30,7 +30,7 @@
 
 namespace ddl {
 
-constexpr int kMaxRanks = 16;
+constexpr int kMaxRanks = 8;   // one NVSwitch domain of 8 GPUs
 constexpr int kArThreads = 512;
 
 struct PeerPtrs {
@@ -129,53 +129,77 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_sgd_twoshot_kernel(ArSgdArgs
   const int64_t nvec = a.slice_len >> 3;
   const int64_t base = a.bucket_off + (int64_t)a.rank * a.slice_len;  // my slice, in elements
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    const int64_t e = base + (v << 3);
-    float g[8];
+  // U independent 16-byte vectors per thread per trip: NVLink round trips are ~2-3 us, so the
+  // bytes in flight (CTAs x threads x U x 16 B [x world for peer loads]) set the bandwidth.
+  constexpr int U = (MODE == 1) ? 4 : 2;
+  for (int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * U) {
+    float g[U][8];
     if (MODE == 1) {
-      int4 red = mc_ld_reduce_bf16x8((const __nv_bfloat16*)a.grad_mc + e);
-      unpack8(*reinterpret_cast<bf16x8*>(&red), g);
+      int4 red[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = v0 + u * stride;
+        if (v < nvec) red[u] = mc_ld_reduce_bf16x8((const __nv_bfloat16*)a.grad_mc + base + (v << 3));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) unpack8(*reinterpret_cast<bf16x8*>(&red[u]), g[u]);
     } else {
-      int4 raw[kMaxRanks];
+      int4 raw[U][kMaxRanks];
 #pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r)
-        if (r < a.world) raw[r] = ld_peer16((const __nv_bfloat16*)a.grad.p[(a.rank + r) % a.world] + e);
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = v0 + u * stride;
+        if (v < nvec) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] = 0.f;
-#pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r)
-        if (r < a.world) {
-          float f[8];
-          unpack8(*reinterpret_cast<bf16x8*>(&raw[r]), f);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) g[k] += f[k];
+          for (int r = 0; r < kMaxRanks; ++r)
+            if (r < a.world)
+              raw[u][r] = ld_peer16((const __nv_bfloat16*)a.grad.p[(a.rank + r) % a.world] + base + (v << 3));
         }
-    }
-    // SGD on the local shard
-    float* mp = a.master + (v << 3);
-    float* vp = a.mom + (v << 3);
-    float4 p0 = *reinterpret_cast<float4*>(mp), p1 = *reinterpret_cast<float4*>(mp + 4);
-    float4 m0 = *reinterpret_cast<float4*>(vp), m1 = *reinterpret_cast<float4*>(vp + 4);
-    float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-    float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float gk = fmaf(wd, p[k], g[k] * gs);
-      m[k] = fmaf(mu, m[k], gk);
-      p[k] = fmaf(-lr, m[k], p[k]);
-    }
-    *reinterpret_cast<float4*>(mp) = make_float4(p[0], p[1], p[2], p[3]);
-    *reinterpret_cast<float4*>(mp + 4) = make_float4(p[4], p[5], p[6], p[7]);
-    *reinterpret_cast<float4*>(vp) = make_float4(m[0], m[1], m[2], m[3]);
-    *reinterpret_cast<float4*>(vp + 4) = make_float4(m[4], m[5], m[6], m[7]);
-    bf16x8 w = pack8(p);
-    const int4 wv = *reinterpret_cast<int4*>(&w);
-    if (MODE == 1) {
-      mc_st16((__nv_bfloat16*)a.weight_mc + e, wv);
-    } else {
+      for (int u = 0; u < U; ++u) {
 #pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r)
-        if (r < a.world) st_peer16((__nv_bfloat16*)a.weight.p[(a.rank + r) % a.world] + e, wv);
+        for (int k = 0; k < 8; ++k) g[u][k] = 0.f;
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+          if (r < a.world) {
+            float f[8];
+            unpack8(*reinterpret_cast<bf16x8*>(&raw[u][r]), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[u][k] += f[k];
+          }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v >= nvec) break;
+      const int64_t e = base + (v << 3);
+      // SGD on the local shard
+      float* mp = a.master + (v << 3);
+      float* vp = a.mom + (v << 3);
+      float4 p0 = *reinterpret_cast<float4*>(mp), p1 = *reinterpret_cast<float4*>(mp + 4);
+      float4 m0 = *reinterpret_cast<float4*>(vp), m1 = *reinterpret_cast<float4*>(vp + 4);
+      float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float gk = fmaf(wd, p[k], g[u][k] * gs);
+        m[k] = fmaf(mu, m[k], gk);
+        p[k] = fmaf(-lr, m[k], p[k]);
+      }
+      *reinterpret_cast<float4*>(mp) = make_float4(p[0], p[1], p[2], p[3]);
+      *reinterpret_cast<float4*>(mp + 4) = make_float4(p[4], p[5], p[6], p[7]);
+      *reinterpret_cast<float4*>(vp) = make_float4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<float4*>(vp + 4) = make_float4(m[4], m[5], m[6], m[7]);
+      bf16x8 w = pack8(p);
+      const int4 wv = *reinterpret_cast<int4*>(&w);
+      if (MODE == 1) {
+        mc_st16((__nv_bfloat16*)a.weight_mc + e, wv);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+          if (r < a.world) st_peer16((__nv_bfloat16*)a.weight.p[(a.rank + r) % a.world] + e, wv);
+      }
     }
   }
   peer_barrier(a.flags, a.rank, a.world, 1, a.max_blocks, epoch, a.status);

@@ -1,0 +1,327 @@
+"""PipeDream stage runtime: asynchronous 1F1B pipelining with weight stashing and intra-stage
+replication, one process per GPU.
+
+Reference: ``StageRuntime`` + ``CommunicationHandler`` + ``OptimizerWithWeightStashing``
+(``pipedream-fork/runtime/{runtime,communication,optimizer}.py``) driven by the loop in
+``runtime/image_classification/main_with_runtime.py:406-500``.  What is kept: the stage /
+rank configuration files, the warm-up formula, the 1F1B order, the replica routing, per-stage
+LR scaling, the iteration reconciliation, macrobatching, ``--no_input_pipelining``, per-stage
+checkpoints.  What is different by design:
+
+* each stage is a compiled plan on the static engine — no autograd tape, explicit backward;
+* weight stashing = V slots of the flat bf16 weight buffer + an index; "load_old_params" is
+  "run backward against slot v", "step" writes slot (latest+1) % V from the fp32 master in the
+  fused SGD kernel — zero copies (reference: 2 ``load_state_dict`` + 1 full copy per step);
+* stage-boundary tensors have static shapes (meta-device dry run), receives are pre-posted
+  into rings on a communication stream, no helper threads, no per-message allocation;
+* replica gradient reduction uses the fused all-reduce+SGD kernel over the stage's replica
+  group on GPUs (Gloo/NCCL ``all_reduce`` + fused SGD otherwise);
+* evaluation needs no ack tokens: back-pressure comes from the bounded receive rings.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Dict, Iterator, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ...dist.transport import DistP2P, PairGroups, TensorSpec
+from ...engine import FwdContext, StageExecutor
+from ...models.graph import INPUT, LayerGraphModel
+from .config import PipelineConfig, RankTopology
+from .schedule import B, F, Routing, one_f_one_b
+
+
+def infer_boundary_specs(model: LayerGraphModel, cuts: Sequence[int], batch: int,
+                         dtype: torch.dtype, channels_last: bool) -> List[List[TensorSpec]]:
+    """Shapes of the tensors crossing each cut (``cuts[k]`` = index of the first node of stage
+    k+1), from a meta-device dry run (reference: CPU dry run with ``torch.zeros``,
+    ``main_with_runtime.py:168-192``)."""
+    shapes: Dict[str, Tuple[int, ...]] = {}
+    with torch.no_grad():
+        x = torch.empty((batch,) + tuple(model.input_shape), device="meta")
+        live = {INPUT: x}
+        shapes[INPUT] = tuple(x.shape)
+        for i, n in enumerate(model.nodes):
+            mod = model.node_module(i)
+            ins = [live[k] for k in n.inputs]
+            # the real modules stay where they are; only meta ALIASES of their state are used
+            state = {k: torch.empty_like(v, device="meta")
+                     for k, v in list(mod.named_parameters()) + list(mod.named_buffers())}
+            was_training = mod.training
+            mod.eval()
+            out = torch.func.functional_call(mod, state, tuple(ins))
+            mod.train(was_training)
+            live[n.name] = out
+            shapes[n.name] = tuple(out.shape)
+    specs = []
+    for c in cuts:
+        names = model.live_after(c - 1)
+        specs.append([TensorSpec(nm, shapes[nm], dtype, channels_last and len(shapes[nm]) == 4)
+                      for nm in names])
+    return specs
+
+
+def reorder_by_stage(model: LayerGraphModel, stage_of_node: Sequence[int]) -> Tuple[LayerGraphModel, List[int]]:
+    """Stable-sort the nodes by stage id so every stage is a contiguous slice (the partitioner
+    assigns stages along a topological order of *its* graph, which need not be the definition
+    order for branchy blocks).  Returns the re-ordered model view and the cut indices."""
+    order = sorted(range(len(model.nodes)), key=lambda i: (stage_of_node[i], i))
+    nodes = [model.nodes[i] for i in order]
+    m = LayerGraphModel(nodes, name=model.arch, input_shape=model.input_shape,
+                        num_classes=model.num_classes)
+    stages = [stage_of_node[i] for i in order]
+    cuts = [k for k in range(1, len(stages)) if stages[k] != stages[k - 1]]
+    return m, cuts
+
+
+class StageRuntime:
+    def __init__(self, model: LayerGraphModel, cuts: Sequence[int], cfg: PipelineConfig,
+                 batch_size: int, device="cpu", dtype: torch.dtype = torch.float32,
+                 lr: float = 0.1, momentum: float = 0.9, weight_decay: float = 1e-4,
+                 rank: Optional[int] = None, num_versions: Optional[int] = None,
+                 no_input_pipelining: bool = False, macrobatch: bool = False,
+                 tcgen05: bool = False, fused_replica_allreduce: bool = True,
+                 groups: Optional[PairGroups] = None, verbose: bool = False):
+        self.cfg = cfg
+        self.rank = dist.get_rank() if rank is None else rank
+        self.topo = RankTopology.of(cfg, self.rank)
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.batch_size = batch_size
+        t = self.topo
+        assert cfg.num_stages == len(cuts) + 1, "number of cuts must be num_stages - 1"
+        bounds = [0] + list(cuts) + [len(model.nodes)]
+        start, stop = bounds[t.stage], bounds[t.stage + 1]
+        self.warmup = 0 if no_input_pipelining else t.warmup
+        versions = num_versions if num_versions is not None else self.warmup + 1
+        self.macrobatch = macrobatch
+        self.update_interval = 1
+        if macrobatch:
+            # PipeDream-2BW-like: <= 2 versions, one step per `versions` minibatches with the
+            # gradients averaged (reference optimizer.py:36-52,118-149)
+            self.update_interval = max(versions, 1)
+            versions = min(2, versions)
+        on_gpu = self.device.type == "cuda"
+        self.channels_last = on_gpu
+        # replica group of this stage (gradient averaging among the stage's replicas)
+        self.replica_group = None
+        self._replica_groups = {}
+        for s in sorted(cfg.stage_to_rank_map):
+            ranks = cfg.stage_to_rank_map[s]
+            if len(ranks) > 1:
+                g = dist.new_group(ranks)          # collective: same order on every rank
+                self._replica_groups[s] = g
+                if s == t.stage:
+                    self.replica_group = g
+        self.fdp = None
+        kw = dict(device=self.device, dtype=dtype, versions=versions,
+                  lr=lr * cfg.lr_scale(t.stage), momentum=momentum, weight_decay=weight_decay,
+                  tcgen05=tcgen05, first_stage=t.is_first)
+        if self.replica_group is not None and on_gpu and fused_replica_allreduce and versions == 1:
+            from ...dist.symm import SymmContext
+            from ..dp import FusedDataParallel
+            self.symm = SymmContext(self.device, self.replica_group)
+            keep: Dict[str, list] = {}
+            alloc = FusedDataParallel.make_allocator(self.symm, keep)
+            self.ex = StageExecutor.from_model(model, start, stop, world=t.num_ranks_in_stage,
+                                               rank=t.rank_in_stage, shard_optimizer=True,
+                                               allocator=alloc, **kw)
+            self.ex._sym_w, self.ex._sym_g = keep["bufs"][:-1], keep["bufs"][-1]
+            self.fdp = FusedDataParallel(self.ex, self.symm)
+            self.fdp.broadcast_from(0)
+        else:
+            self.ex = StageExecutor.from_model(model, start, stop, **kw)
+            if self.replica_group is not None:
+                full = self.ex.store.master.clone()
+                dist.broadcast(full, src=t.stage_ranks[0], group=self.replica_group)
+                self.ex.store.load_full_master(full)
+                self.ex.store.set_grad_scale(1.0 / t.num_ranks_in_stage)
+        if verbose and self.replica_group is not None:
+            print("Replicating stage: ranks=%d, module_size=%d" % (
+                t.num_ranks_in_stage, self.ex.num_params() * 4), flush=True)
+        # boundary tensor specs (+ the labels, forwarded hop by hop as int64 [B])
+        specs = infer_boundary_specs(model, cuts, batch_size, dtype, self.channels_last)
+        lab = TensorSpec("target", (batch_size,), torch.int64)
+        self.in_specs = (specs[t.stage - 1] + [lab]) if not t.is_first else []
+        self.out_specs = (specs[t.stage] + [lab]) if not t.is_last else []
+        self.grad_in_specs = specs[t.stage] if not t.is_last else []     # grads of my outputs
+        self.grad_out_specs = specs[t.stage - 1] if not t.is_first else []  # grads I send back
+        if groups is None and dist.is_initialized() and dist.get_world_size() > 1:
+            pairs = []
+            for s in range(cfg.num_stages - 1):
+                for a in cfg.stage_to_rank_map[s]:
+                    for b in cfg.stage_to_rank_map[s + 1]:
+                        pairs.append((a, b))
+            groups = PairGroups(pairs)
+        self.p2p = DistP2P(self.device, groups)
+        self.ring = self.warmup + 3
+        self.routing = Routing(self.topo)
+        self.fwd_id = self.bwd_id = 0
+        self._ctxs: List[Tuple[FwdContext, Optional[torch.Tensor], Optional[int]]] = []
+        self._next_fwd = None
+        self._next_bwd = None
+        self.loss_stats: Optional[torch.Tensor] = None
+        self.training = True
+        self.verbose = verbose
+        self._accum = 0
+
+    # ------------------------------------------------------------------ epoch control
+    def train(self, num_iterations: int) -> None:
+        self.training = True
+        self.n_iter = num_iterations
+        self.fwd_id = self.bwd_id = 0
+        self._ctxs = []
+        self.routing = Routing(self.topo)
+        self._next_fwd = self._next_bwd = None
+        self._posted_fwd = self._posted_bwd = 0
+        self._accum = 0
+        self._prepost_fwd()
+
+    def eval(self, num_iterations: int) -> None:
+        self.train(num_iterations)
+        self.training = False
+
+    def _prepost_fwd(self) -> None:
+        """Post the receive of the NEXT forward input so its transfer overlaps compute."""
+        if self.topo.is_first or self._next_fwd is not None or self._posted_fwd >= self.n_iter:
+            return
+        src = self.routing.next_fwd_recv_peer()
+        self._next_fwd = (src, self.p2p.post_recv(src, self.in_specs, "fwd", ring=self.ring))
+        self._posted_fwd += 1
+
+    def _prepost_bwd(self) -> None:
+        if self.topo.is_last or self._next_bwd is not None or self._posted_bwd >= self.n_iter:
+            return
+        src = self.routing.bwd_recv_peer(self._posted_bwd)
+        self._next_bwd = (src, self.p2p.post_recv(src, self.grad_in_specs, "bwd", ring=3))
+        self._posted_bwd += 1
+
+    # ------------------------------------------------------------------ forward
+    def run_forward(self, inputs: Optional[torch.Tensor] = None,
+                    target: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        """One forward pass.  First stage: ``inputs`` / ``target`` come from the loader; other
+        stages receive them.  Last stage returns stats[3] (loss, #top1, #top5)."""
+        t = self.topo
+        ex = self.ex
+        if t.is_first:
+            xs = [ex.prepare_input(inputs)]
+            target = target.to(self.device)
+        else:
+            if self._next_fwd is None:
+                self._prepost_fwd()
+            _, pending = self._next_fwd
+            self._next_fwd = None
+            bufs = pending.wait()
+            xs, target = list(bufs[:-1]), bufs[-1]
+            self._prepost_fwd()               # overlap the next transfer with this compute
+        version = ex.store.latest
+        outs, ctx = ex.forward(xs, training=self.training, version=version)
+        stats = None
+        dl = None
+        if t.is_last:
+            stats, dl = ex.loss(outs[0], target, want_grad=self.training,
+                                grad_scale=1.0 / self.update_interval)
+            self.loss_stats = stats
+        else:
+            self.p2p.send(self.routing.fwd_send_peer(self.fwd_id), list(outs) + [target], "fwd")
+        if self.training:
+            self._ctxs.append((ctx, dl, None))
+        self.fwd_id += 1
+        return stats
+
+    # ------------------------------------------------------------------ backward
+    def run_backward(self) -> None:
+        t = self.topo
+        ex = self.ex
+        ctx, dl, _ = self._ctxs.pop(0)
+        if t.is_last:
+            grads = [dl]
+        else:
+            if self._next_bwd is None:
+                self._prepost_bwd()
+            _, pending = self._next_bwd
+            self._next_bwd = None
+            grads = list(pending.wait())
+            self._prepost_bwd()
+        accumulate = self._accum > 0
+        final = (self._accum + 1) == self.update_interval
+        gin = ex.backward(ctx, grads, accumulate=accumulate, final=final)
+        if not t.is_first:
+            self.p2p.send(self.routing.next_bwd_send_peer(), [g for g in gin], "bwd")
+        self._accum += 1
+        if final:
+            self._optimizer_step()
+            self._accum = 0
+        self.bwd_id += 1
+
+    def _optimizer_step(self) -> None:
+        ex = self.ex
+        st = ex.store
+        if self.fdp is not None:
+            self.fdp.finish_step()             # fused all-reduce+SGD already ran per bucket
+            return
+        if self.replica_group is not None:
+            dist.all_reduce(st.g_flat, group=self.replica_group)   # averaged via grad_scale
+        nxt = st.next_version()
+        st.sgd_step(out_version=nxt)
+        st.advance_version()
+
+    # ------------------------------------------------------------------ full 1F1B epoch
+    def run_epoch(self, loader: Optional[Iterator] = None, num_iterations: Optional[int] = None,
+                  on_forward=None) -> None:
+        """``warmup`` forwards, 1F1B steady state, drain
+        (``main_with_runtime.py:432-494``)."""
+        n = num_iterations
+        self.train(n)
+        it = iter(loader) if loader is not None else None
+        for op, i in one_f_one_b(n, self.warmup):
+            if op == F:
+                if self.topo.is_first:
+                    x, y = next(it)
+                    stats = self.run_forward(x, y)
+                else:
+                    stats = self.run_forward()
+                if on_forward is not None:
+                    on_forward(i, stats)
+            else:
+                self.run_backward()
+        self.p2p.flush()
+
+    def run_eval(self, loader: Optional[Iterator], num_iterations: int, on_forward=None) -> None:
+        self.eval(num_iterations)
+        it = iter(loader) if loader is not None else None
+        for i in range(num_iterations):
+            if self.topo.is_first:
+                x, y = next(it)
+                stats = self.run_forward(x, y)
+            else:
+                stats = self.run_forward()
+            if on_forward is not None:
+                on_forward(i, stats)
+        self.p2p.flush()
+
+    # ------------------------------------------------------------------ checkpoints
+    def state_dict(self) -> Dict[str, object]:
+        """Per-stage checkpoint payload (reference ``checkpoint.<stage>.pth.tar``,
+        ``main_with_runtime.py:392-403,580-584``).  Unlike the reference, the optimizer's
+        fp32 master + momentum are saved, so a resumed run continues bit-identically."""
+        st = self.ex.store
+        return {"stage": self.topo.stage, "state_dict": self.ex.state_dict(),
+                "master": st.master.detach().cpu().clone(), "momentum": st.mom.detach().cpu().clone(),
+                "hyper": st.hyper.detach().cpu().clone()}
+
+    def load_state_dict(self, sd: Dict[str, object]) -> None:
+        self.ex.load_state_dict(sd["state_dict"])
+        st = self.ex.store
+        if "master" in sd and sd["master"].numel() == st.master.numel():
+            st.master.copy_(sd["master"].to(st.device))
+            st.mom.copy_(sd["momentum"].to(st.device))
+            for wf in st.w_flat:
+                if not st.shard_optimizer:
+                    wf.copy_(st.master.to(st.dtype))
+
+    def set_lr(self, lr: float) -> None:
+        self.ex.store.set_lr(lr * self.cfg.lr_scale(self.topo.stage))

@@ -1,0 +1,159 @@
+"""PipeDream runtime on the CPU/Gloo fake transport: schedules, routing, weight-stashing
+semantics, and multi-process end-to-end equivalences."""
+import glob
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from ddlbench_b200.engine import StageExecutor
+from ddlbench_b200.models import build_model
+from ddlbench_b200.parallel.pipedream.config import PipelineConfig, RankTopology
+from ddlbench_b200.parallel.pipedream.schedule import (MessagingCursor, one_f_one_b, validate)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_PORT = [29600]
+
+
+def _launch(reps, tmp_path, extra_env=None, iters=6, timeout=420):
+    n = sum(reps)
+    env = dict(os.environ)
+    env.update({"PD_REPS": ",".join(map(str, reps)), "PD_OUT": str(tmp_path), "PD_CPU": "1",
+                "PD_ITERS": str(iters), "OMP_NUM_THREADS": "2"})
+    env.update(extra_env or {})
+    _PORT[0] += 1
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_PORT[0]),
+           os.path.join(ROOT, "tests", "pipedream_worker.py")]
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    return [torch.load(f) for f in sorted(glob.glob(os.path.join(str(tmp_path), "rank*.pt")))]
+
+
+def test_warmup_formula_and_confs():
+    cfg = PipelineConfig.straight(4)
+    assert [cfg.warmup(s) for s in range(4)] == [3, 2, 1, 0]
+    assert cfg.module_to_stage_map == [0, 1, 2, 3, 3]
+    h = PipelineConfig.hybrid(PipelineConfig.parse_stage_to_num_ranks("0:3,1:1"))
+    assert h.stage_to_rank_map == {0: [0, 1, 2], 1: [3]} and [h.warmup(0), h.warmup(1)] == [1, 0]
+    assert h.lr_scale(1) == pytest.approx(1 / 3)
+    d = PipelineConfig.data_parallel(3, 4)
+    assert d.warmup(0) == 0 and d.num_stages == 1
+    rt = PipelineConfig.from_json(h.to_dict())
+    assert rt.stage_to_rank_map == h.stage_to_rank_map
+    depth = PipelineConfig.from_json({"module_to_stage_map": [0, 1, 1],
+                                      "stage_to_rank_map": {"0": [0], "1": [1]},
+                                      "stage_to_depth_map": {"0": 5, "1": 0}})
+    assert depth.warmup(0) == 5
+    t = RankTopology.of(h, 1)
+    assert (t.stage, t.rank_in_stage, t.next_ranks, t.prev_ranks) == (0, 1, [3], [])
+
+
+def test_one_f_one_b_order():
+    seq = one_f_one_b(5, 2)
+    assert seq[:3] == [("F", 0), ("F", 1), ("F", 2)] and seq[3] == ("B", 0)
+    assert [i for op, i in seq if op == "B"] == list(range(5))
+    assert one_f_one_b(3, 0) == [("F", 0), ("B", 0), ("F", 1), ("B", 1), ("F", 2), ("B", 2)]
+
+
+def test_messaging_cursor_when_previous_stage_is_smaller():
+    # 4 replicas fed by 2: the case the reference's `>` -> `>=` fix is about
+    seqs = [[MessagingCursor(r, 4, 2).take() for _ in range(1)] for r in range(4)]
+    assert seqs == [[0], [1], [1], [1]]
+    c = MessagingCursor(0, 2, 4)
+    assert [c.take() for _ in range(4)] == [0, 2, 1, 3]
+
+
+@pytest.mark.parametrize("reps", [[1, 1, 1, 1], [2, 1], [1, 2], [3, 1], [2, 2, 1], [4, 2, 1, 1],
+                                  [2, 4], [7, 3, 6], [1, 1, 2, 4], [4, 2, 2]])
+def test_routing_is_deadlock_free(reps):
+    validate(PipelineConfig.hybrid(reps), 48)
+
+
+def test_weight_stashing_semantics():
+    """Idea of pipedream-fork/runtime/tests/backprop/sgd_with_stashing.py: forward three
+    minibatches with the same weights, then interleave backward/step.  With V versions the
+    first V backwards see the weights their forward saw (input-gradients equal those of a
+    fresh model); later ones see stepped weights."""
+    torch.manual_seed(0)
+    m = build_model("vgg11", "mnist")
+    x = torch.randn(4, 1, 28, 28)
+    t = torch.randint(0, 10, (4,))
+
+    def input_grads(versions):
+        ex = StageExecutor.from_model(m, device="cpu", dtype=torch.float32, versions=versions,
+                                      lr=0.5, momentum=0.0, first_stage=False)
+        ctxs = []
+        for _ in range(3):
+            o, c = ex.forward([x], version=ex.store.latest, need_input_grad=True)
+            s, d = ex.loss(o[0], t)
+            ctxs.append((c, d))
+        grads = []
+        for c, d in ctxs:
+            # backward against the version recorded at forward time — unless it was recycled
+            if (ex.store.latest - c.version) >= versions:
+                c.version = ex.store.latest
+            grads.append(ex.backward(c, [d])[0].clone())
+            ex.store.sgd_step(out_version=ex.store.next_version())
+            ex.store.advance_version()
+        return grads
+
+    g1, g2, g3 = input_grads(1), input_grads(2), input_grads(3)
+    assert not torch.allclose(g1[0], g1[1])                 # V=1: second backward sees new weights
+    assert torch.allclose(g2[0], g2[1]) and not torch.allclose(g2[1], g2[2])
+    assert torch.allclose(g3[0], g3[1]) and torch.allclose(g3[1], g3[2])
+    assert torch.allclose(g1[0], g3[0])
+
+
+def test_no_input_pipelining_equals_sequential_sgd(tmp_path):
+    """warm-up 0, one weight version == plain model-parallel == single-process SGD."""
+    res = _launch([1, 1], tmp_path, {"PD_NOPIPE": "1"}, iters=4)
+    torch.manual_seed(0)
+    model = build_model("resnet18", "cifar10")
+    ex = StageExecutor.from_model(model, device="cpu", dtype=torch.float32, lr=0.05, momentum=0.9,
+                                  weight_decay=1e-4)
+    g = torch.Generator().manual_seed(100)
+    losses = []
+    for _ in range(4):
+        x, y = torch.randn(8, 3, 32, 32, generator=g), torch.randint(0, 10, (8,), generator=g)
+        o, c = ex.forward([x])
+        s, d = ex.loss(o[0], y)
+        ex.backward(c, [d])
+        ex.store.sgd_step()
+        losses.append(float(s[0]))
+    ref = ex.state_dict()
+    assert all(r["warmup"] == 0 and r["versions"] == 1 for r in res)
+    pipe_losses = [r for r in res if r["losses"]][0]["losses"]
+    assert pipe_losses == pytest.approx(losses, rel=5e-3, abs=5e-3)  # fp32 summation order differs with thread count
+    for r in res:
+        for k, v in r["state"].items():
+            assert torch.allclose(v.float(), ref[k].float(), atol=5e-3, rtol=5e-2), k
+
+
+def test_1f1b_two_stage_runs_with_stashing(tmp_path):
+    res = _launch([1, 1], tmp_path, iters=6)
+    s0 = [r for r in res if r["stage"] == 0][0]
+    s1 = [r for r in res if r["stage"] == 1][0]
+    assert (s0["warmup"], s0["versions"]) == (1, 2) and (s1["warmup"], s1["versions"]) == (0, 1)
+    assert len(s1["losses"]) == 6 and all(l == l for l in s1["losses"])
+    assert s0["bytes_sent"] > 0 and s1["bytes_sent"] > 0
+
+
+def test_hybrid_replicated_first_stage(tmp_path):
+    res = _launch([2, 1], tmp_path, iters=4)
+    reps = [r for r in res if r["stage"] == 0]
+    assert len(reps) == 2
+    for k in reps[0]["state"]:
+        if "running_" in k:
+            continue   # BatchNorm statistics are local to a replica (as with DDP in the reference)
+        assert torch.allclose(reps[0]["state"][k], reps[1]["state"][k], atol=1e-6), k
+    last = [r for r in res if r["stage"] == 1][0]
+    assert len(last["losses"]) == 8   # 4 per first-stage replica x 2 replicas
+
+
+def test_macrobatch_mode(tmp_path):
+    res = _launch([1, 1], tmp_path, {"PD_MACRO": "1"}, iters=6)
+    s0 = [r for r in res if r["stage"] == 0][0]
+    assert s0["versions"] <= 2
