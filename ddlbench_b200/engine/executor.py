@@ -64,6 +64,9 @@ class StageExecutor:
             for i in op.inputs:
                 self._last_op_of_value[i] = idx
         self.xent_ws: Optional[ops.XentWorkspace] = None
+        # optional per-op timer with begin(id) -> handle / end(handle) (utils.layer_profiler);
+        # ids are 2*op_index for forward, 2*op_index+1 for backward
+        self.profiler = None
 
     # ------------------------------------------------------------------ helpers
     @classmethod
@@ -94,9 +97,14 @@ class StageExecutor:
         vals: Dict[str, torch.Tensor] = dict(zip(plan.in_names, inputs))
         keep = set(plan.out_names)
         E.TCGEN05["conv1x1"] = E.TCGEN05["linear"] = self.tcgen05
+        prof = self.profiler
         for idx, op in enumerate(plan.ops):
             xs = [vals[i] for i in op.inputs]
+            if prof is not None:
+                h = prof.begin(2 * idx)
             vals[op.output] = op.forward(P, B, xs, ctx.saved[idx], training)
+            if prof is not None:
+                prof.end(h)
             for i in op.inputs:
                 if self._last_op_of_value.get(i) == idx and i not in keep:
                     vals.pop(i, None)
@@ -131,7 +139,11 @@ class StageExecutor:
                         G[p].zero_()
             else:
                 need = [(i not in in_set) or ctx.need_input_grad for i in op.inputs]
+                if self.profiler is not None:
+                    h = self.profiler.begin(2 * idx + 1)
                 dxs = op.backward(P, G, dys, ctx.saved[idx], accumulate, need)
+                if self.profiler is not None:
+                    self.profiler.end(h)
                 for i, dx in zip(op.inputs, dxs):
                     if dx is not None:
                         grads.setdefault(i, []).append(dx)

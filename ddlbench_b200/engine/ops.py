@@ -24,6 +24,9 @@ aten = torch.ops.aten
 Ctx = Dict[str, object]
 # set by the executor: route 1x1 convs / FC through the tcgen05 GEMM kernels
 TCGEN05 = {"conv1x1": False, "linear": False}
+# 0.0 while a forward is being RE-computed (GPipe checkpointing) so BatchNorm running
+# statistics are not updated twice for the same micro-batch
+BN_MOMENTUM_SCALE = [1.0]
 
 
 def _write(dst: torch.Tensor, src: torch.Tensor, accumulate: bool) -> None:
@@ -148,8 +151,8 @@ class ConvBnAct(Op, _ConvMixin):
         fuse_stats = training and self.ws is not None and self._is_gemm(x)
         c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums if fuse_stats else None)
         y, stat = ops.bn_forward(c, res, P[self.k_g], P[self.k_b], B[self.k_rm], B[self.k_rv],
-                                 self.eps, self.momentum, self.act, self.ws, stats_ready=fused,
-                                 training=training)
+                                 self.eps, self.momentum * BN_MOMENTUM_SCALE[0], self.act, self.ws,
+                                 stats_ready=fused, training=training)
         if training:
             ctx["x"], ctx["c"], ctx["stat"] = x, c, stat
             ctx["y"] = y if self.act != ACT_NONE else None

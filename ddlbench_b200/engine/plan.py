@@ -95,6 +95,7 @@ def compile_plan(model: LayerGraphModel, start: int = 0, stop: Optional[int] = N
             continue
         n = nodes[i]
         m = n.op
+        before = set(used)
         used.add(i)
         if isinstance(m, nn.Conv2d):
             j = sole_next(i)
@@ -162,5 +163,6 @@ def compile_plan(model: LayerGraphModel, start: int = 0, stop: Optional[int] = N
             out.append(E.AddAct(n.name, list(n.inputs), n.name, _act_of(m)))
         else:
             out.append(E.ModuleOp(n.name, list(n.inputs), n.name, m, pname(n)))
+        out[-1].node_ids = sorted(used - before)   # layer-graph nodes this op covers
         i += 1
     return Plan(out, list(in_names), list(out_names), model.arch, model.input_shape)

@@ -45,7 +45,8 @@ def main():
     losses = []
     rt.run_epoch(iter(data) if topo.is_first else None, n,
                  on_forward=lambda i, s: losses.append(float(s[0])) if s is not None else None)
-    rt.run_eval(iter(data) if topo.is_first else None, min(n, 2))
+    ne = cfg.num_iterations(topo.stage, 2)
+    rt.run_eval(iter(data) if topo.is_first else None, ne)
     sd = rt.ex.state_dict()
     torch.save({"rank": rank, "stage": topo.stage, "losses": losses, "state": sd,
                 "warmup": rt.warmup, "versions": rt.ex.store.versions,
