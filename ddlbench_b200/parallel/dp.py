@@ -263,10 +263,10 @@ class FusedDataParallel:
         st = self.ex.store
         w = st.w_flat[st.latest]
         full = w.float()
-        dist.broadcast(full, src=dist.get_global_rank(self.ctx.group, root)
-                       if self.ctx.group is not None else root, group=self.ctx.group)
+        src = dist.get_global_rank(self.ctx.group, root) if self.ctx.group is not None else root
+        dist.broadcast(full, src=src, group=self.ctx.group)
         st.load_full_master(full)
         for k in sorted(self.ex.buffers):
-            dist.broadcast(self.ex.buffers[k], src=root, group=self.ctx.group)
+            dist.broadcast(self.ex.buffers[k], src=src, group=self.ctx.group)
         torch.cuda.synchronize(st.device)
         dist.barrier(self.ctx.group)
