@@ -130,6 +130,14 @@ class StageExecutor:
         lay = self.store.layout
         remaining = list(self._bucket_sizes)
         in_set = set(plan.in_names)
+        side = self._wgrad_stream()
+        E.WGRAD_OVERLAP["stream"] = side
+
+        def join_side():
+            if side is not None and E.WGRAD_OVERLAP["keep"]:
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                E.WGRAD_OVERLAP["keep"].clear()
+
         for idx in range(len(plan.ops) - 1, -1, -1):
             op = plan.ops[idx]
             dys = grads.pop(op.output, None)
@@ -153,7 +161,10 @@ class StageExecutor:
                     b = lay.bucket_of[p]
                     remaining[b] -= 1
                     if remaining[b] == 0:
+                        join_side()            # the bucket's weight gradients must have landed
                         self.on_bucket_ready(b)
+        join_side()
+        E.WGRAD_OVERLAP["stream"] = None
         out: List[Optional[torch.Tensor]] = []
         for name in plan.in_names:
             gl = grads.get(name)
@@ -165,6 +176,14 @@ class StageExecutor:
                     g = g + extra
                 out.append(g)
         return out
+
+    def _wgrad_stream(self):
+        """Side stream for weight-gradient kernels (GPU only; ``overlap_wgrad`` attribute)."""
+        if self.device.type != "cuda" or not getattr(self, "overlap_wgrad", True):
+            return None
+        if getattr(self, "_wg_stream", None) is None:
+            self._wg_stream = torch.cuda.Stream(device=self.device)
+        return self._wg_stream
 
     # ------------------------------------------------------------------ loss (last stage)
     def loss(self, logits: torch.Tensor, target: torch.Tensor, smoothing: float = 0.0,

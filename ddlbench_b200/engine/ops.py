@@ -27,6 +27,9 @@ TCGEN05 = {"conv1x1": False, "linear": False}
 # 0.0 while a forward is being RE-computed (GPipe checkpointing) so BatchNorm running
 # statistics are not updated twice for the same micro-batch
 BN_MOMENTUM_SCALE = [1.0]
+# side stream for weight-gradient kernels (set by the executor during backward) and the
+# operands that must outlive it
+WGRAD_OVERLAP = {"stream": None, "keep": []}
 
 
 def _write(dst: torch.Tensor, src: torch.Tensor, accumulate: bool) -> None:
@@ -93,23 +96,41 @@ class _ConvMixin:
                 x.dtype == torch.bfloat16 and ci % 8 == 0 and co % 8 == 0 and
                 x.is_contiguous(memory_format=torch.channels_last))
 
-    def _conv_fwd(self, x, w, bias=None, col_sums=None, relu=False):
+    def _conv_fwd(self, x, w, bias=None, col_sums=None, relu=False, bn_finalize=None):
         """Returns (y, stats_fused)."""
         if self._is_gemm(x):
             n, ci, h, wd = x.shape
             co = self.wshape[0]
             a = x.permute(0, 2, 3, 1).reshape(n * h * wd, ci)
-            d = ops.gemm_tn(a, w.reshape(co, ci), col_sums=col_sums, bias=bias, relu=relu)
+            d = ops.gemm_tn(a, w.reshape(co, ci), col_sums=col_sums, bias=bias, relu=relu,
+                            bn_finalize=bn_finalize)
             return d.view(n, h, wd, co).permute(0, 3, 1, 2), col_sums is not None
         y = aten.convolution(x, w, None, self.stride, self.padding, self.dilation, False, [0, 0],
                              self.groups)
         return y, False
 
-    def _conv_bwd(self, dy, x, w, need_dx: bool):
-        dx, dw, _ = aten.convolution_backward(dy, x, w, None, self.stride, self.padding,
-                                              self.dilation, False, [0, 0], self.groups,
-                                              [need_dx, True, False])
-        return dx, dw
+    def _conv_bwd(self, dy, x, w, need_dx: bool, gw: torch.Tensor, accumulate: bool):
+        """Data gradient (returned) and weight gradient (written into ``gw``).  With a side
+        stream configured (``WGRAD_OVERLAP``) the weight-gradient kernel — which nothing
+        needs before the optimizer — runs concurrently with the rest of backward: at the
+        benchmark's batch size every kernel fills only a fraction of the 148 SMs."""
+        side = WGRAD_OVERLAP["stream"] if dy.is_cuda else None
+        args = (None, self.stride, self.padding, self.dilation, False, [0, 0], self.groups)
+        if side is None:
+            dx, dw, _ = aten.convolution_backward(dy, x, w, *args, [need_dx, True, False])
+            _write(gw, dw, accumulate)
+            return dx
+        main = torch.cuda.current_stream(dy.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        dx = aten.convolution_backward(dy, x, w, *args, [True, False, False])[0] if need_dx else None
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            dw = aten.convolution_backward(dy, x, w, *args, [False, True, False])[1]
+            _write(gw, dw, accumulate)
+        # keep the operands alive until the streams are joined (executor.backward)
+        WGRAD_OVERLAP["keep"].append((dy, x, dw))
+        return dx
 
 
 class ConvBnAct(Op, _ConvMixin):
@@ -149,10 +170,18 @@ class ConvBnAct(Op, _ConvMixin):
         x = xs[0]
         res = xs[1] if self.has_res else None
         fuse_stats = training and self.ws is not None and self._is_gemm(x)
-        c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums if fuse_stats else None)
+        mom = self.momentum * BN_MOMENTUM_SCALE[0]
+        stat_ready = None
+        if fuse_stats:
+            # statistics AND their finalize ride in the GEMM epilogue (last CTA)
+            stat_ready = torch.empty(2 * self.channels, dtype=torch.float32, device=x.device)
+            fin = (self.ws.counter[32:33], stat_ready, B[self.k_rm], B[self.k_rv], self.eps, mom)
+            c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums, bn_finalize=fin)
+        else:
+            c, fused = self._conv_fwd(x, P[self.k_w])
         y, stat = ops.bn_forward(c, res, P[self.k_g], P[self.k_b], B[self.k_rm], B[self.k_rv],
-                                 self.eps, self.momentum * BN_MOMENTUM_SCALE[0], self.act, self.ws,
-                                 stats_ready=fused, training=training)
+                                 self.eps, mom, self.act, self.ws, stats_ready=fused,
+                                 training=training, stat_ready=stat_ready)
         if training:
             ctx["x"], ctx["c"], ctx["stat"] = x, c, stat
             ctx["y"] = y if self.act != ACT_NONE else None
@@ -166,8 +195,7 @@ class ConvBnAct(Op, _ConvMixin):
         dc, dz = ops.bn_backward(dys[0], dy2, ctx["y"], ctx["c"], ctx["stat"], P[self.k_g],
                                  self.act, self.has_res and need[1], G[self.k_g], G[self.k_b],
                                  accumulate, self.ws)
-        dx, dw = self._conv_bwd(dc, ctx["x"], P[self.k_w], need[0])
-        _write(G[self.k_w], dw, accumulate)
+        dx = self._conv_bwd(dc, ctx["x"], P[self.k_w], need[0], G[self.k_w], accumulate)
         return [dx, dz] if self.has_res else [dx]
 
 
@@ -221,8 +249,7 @@ class ConvBiasAct(Op, _ConvMixin):
             dz = dys[0]
         if self.has_bias:
             ops.bias_grad_(dz, G[self.k_b], accumulate, self.ws)
-        dx, dw = self._conv_bwd(dz, ctx["x"], P[self.k_w], need[0])
-        _write(G[self.k_w], dw, accumulate)
+        dx = self._conv_bwd(dz, ctx["x"], P[self.k_w], need[0], G[self.k_w], accumulate)
         return [dx]
 
 
@@ -284,15 +311,23 @@ class MaxPool(Op):
         self.p, self.d, self.ceil = _pair(m.padding), _pair(m.dilation), bool(m.ceil_mode)
 
     def forward(self, P, B, xs, ctx, training):
-        y, idx = aten.max_pool2d_with_indices(xs[0], self.k, self.s, self.p, self.d, self.ceil)
+        x = xs[0]
+        if ops.maxpool_supported(x, self.k, self.s, self.p, self.d, self.ceil):
+            y, idx = ops.maxpool_fwd(x, self.k[0], self.s[0], self.p[0], want_idx=training)
+            if training:
+                ctx["native"], ctx["idx"], ctx["shape"] = True, idx, tuple(x.shape)
+            return y
+        y, idx = aten.max_pool2d_with_indices(x, self.k, self.s, self.p, self.d, self.ceil)
         if training:
-            ctx["x"], ctx["idx"] = xs[0], idx
+            ctx["native"], ctx["x"], ctx["idx"] = False, x, idx
         return y
 
     def backward(self, P, G, dys, ctx, accumulate, need):
         dy = _sum_grads(dys)
         if not need[0]:
             return [None]
+        if ctx["native"]:
+            return [ops.maxpool_bwd(dy, ctx["idx"], ctx["shape"], self.k[0], self.s[0], self.p[0])]
         return [aten.max_pool2d_with_indices_backward(dy, ctx["x"], self.k, self.s, self.p, self.d,
                                                       self.ceil, ctx["idx"])]
 

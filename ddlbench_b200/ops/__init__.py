@@ -151,7 +151,7 @@ class BnWorkspace:
 
 def bn_forward(x, res, gamma, beta, running_mean, running_var, eps: float, momentum: float,
                act: int, ws: Optional[BnWorkspace] = None, stats_ready: bool = False,
-               training: bool = True):
+               training: bool = True, stat_ready: Optional[torch.Tensor] = None):
     """y = act(BN(x) [+ res]).  Returns (y, stat[2, C]).  ``stats_ready``: the producer
     (tcgen05 GEMM epilogue) already accumulated sum / sum-of-squares into ``ws.sums``."""
     M, C = _mc(x)
@@ -167,8 +167,11 @@ def bn_forward(x, res, gamma, beta, running_mean, running_var, eps: float, momen
         e = ext()
         if ws is None:
             ws = BnWorkspace(C, x.device)
-        stat = torch.empty(2 * C, dtype=torch.float32, device=x.device)
-        if stats_ready:
+        stat = stat_ready if stat_ready is not None else \
+            torch.empty(2 * C, dtype=torch.float32, device=x.device)
+        if stat_ready is not None:
+            _count(-1)      # (mean, invstd) were finalized inside the producing GEMM
+        elif stats_ready:
             e.bn_finalize(ws.sums, stat, running_mean, running_var, M, C, eps, momentum)
         else:
             e.bn_stats(x, ws.sums, ws.counter, stat, running_mean, running_var, M, C, eps, momentum)
@@ -310,6 +313,32 @@ def global_avg_pool_bwd(dy: torch.Tensor, shape) -> torch.Tensor:
     return (dy.float() / (h * w)).to(dy.dtype).view(n, c, 1, 1).expand(n, c, h, w).contiguous()
 
 
+def maxpool_supported(x: torch.Tensor, k, s, p, dilation, ceil_mode) -> bool:
+    return (_nhwc_ok(x) and x.dim() == 4 and k[0] == k[1] and s[0] == s[1] and p[0] == p[1] and
+            list(dilation) == [1, 1] and not ceil_mode and 1 <= k[0] <= 15)
+
+
+def maxpool_fwd(x: torch.Tensor, k: int, s: int, p: int, want_idx: bool = True):
+    """NHWC bf16 max-pool; returns (y, idx) with idx = arg-max position inside the window."""
+    n, c, h, w = x.shape
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    y = torch.empty((n, c, ho, wo), dtype=x.dtype, device=x.device,
+                    memory_format=torch.channels_last)
+    idx = torch.empty((n, c, ho, wo), dtype=torch.uint8, device=x.device,
+                      memory_format=torch.channels_last) if want_idx else None
+    ext().maxpool_fwd(x, y, idx, k, s, p)
+    _count()
+    return y, idx
+
+
+def maxpool_bwd(dy: torch.Tensor, idx: torch.Tensor, in_shape, k: int, s: int, p: int):
+    dx = torch.empty(tuple(in_shape), dtype=dy.dtype, device=dy.device,
+                     memory_format=torch.channels_last)
+    ext().maxpool_bwd(dy.contiguous(memory_format=torch.channels_last), idx, dx, k, s, p)
+    _count()
+    return dx
+
+
 # ------------------------------------------------------------------------------- GEMM
 def gemm_tn_supported(a: torch.Tensor, b: torch.Tensor) -> bool:
     return (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and
@@ -320,14 +349,20 @@ def gemm_tn_supported(a: torch.Tensor, b: torch.Tensor) -> bool:
 
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, col_sums: Optional[torch.Tensor] = None,
             bias: Optional[torch.Tensor] = None, relu: bool = False,
-            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, bn_finalize=None) -> torch.Tensor:
     """D[M, N] = A[M, K] @ B[N, K]^T on the tcgen05 tensor cores (csrc/gemm_tcgen05.cu).
     ``col_sums`` (the [R, 2, N] fp32 replicated BN workspace, zero on entry) receives the
-    per-column sum / sum-of-squares of D spread over its R replicas."""
+    per-column sum / sum-of-squares of D spread over its R replicas.  ``bn_finalize`` =
+    (ticket, stat_out[2N], running_mean, running_var, eps, momentum): the last CTA also turns
+    the sums into (mean, invstd), updates the running statistics and re-zeroes the workspace."""
     if gemm_tn_supported(a, b):
         if out is None:
             out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.bfloat16, device=a.device)
-        ext().gemm_bf16_tn(a, b, out, col_sums, bias, relu)
+        if bn_finalize is not None and col_sums is not None:
+            tk, st, rm, rv, eps, mom = bn_finalize
+            ext().gemm_bf16_tn(a, b, out, col_sums, bias, relu, tk, st, rm, rv, float(eps), float(mom))
+        else:
+            ext().gemm_bf16_tn(a, b, out, col_sums, bias, relu, None, None, None, None, 0.0, 0.0)
         _count()
         return out
     d = a.float() @ b.float().t()

@@ -72,13 +72,27 @@ int ddl_set_mask(const int64_t* lengths, void* mask, int T, int B, cudaStream_t 
 int ddl_gap_fwd(const void* x, void* y, int N, int HW, int C, cudaStream_t st);
 int ddl_gap_bwd(const void* dy, void* dx, int N, int HW, int C, int sms, cudaStream_t st);
 
+// ---- pool.cu
+int ddl_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, int Ho, int Wo,
+                    int k, int s, int p, int sms, cudaStream_t st);
+int ddl_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, int Ho,
+                    int Wo, int k, int s, int p, int sms, cudaStream_t st);
+
 // ---- gemm_tcgen05.cu  (TMA + tcgen05/TMEM GEMM; see the file header)
 // D[M,N] = A[M,K] * B[N,K]^T  (both K-major bf16), fp32 accumulate in TMEM, bf16 output.
 // Optional epilogue: per-column (output-channel) sum / sum-of-squares into col_sums[2][N]
 // (BatchNorm statistics), optional bias[N] add and ReLU.
+// `fin` (nullable): also finalize the BatchNorm statistics in the last CTA of the grid.
+typedef struct DdlBnFinalize {
+  unsigned int* ticket;   // grid arrival counter, zero on entry, self-resetting
+  float* stat_out;        // [2][N] (mean, invstd)
+  float* running_mean;    // [N] or NULL
+  float* running_var;     // [N] or NULL
+  float eps, momentum;
+} DdlBnFinalize;
 int ddl_gemm_bf16_tn(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb,
-                     int ldd, float* col_sums, const void* bias, int relu, int sms,
-                     cudaStream_t st);
+                     int ldd, float* col_sums, const void* bias, int relu,
+                     const DdlBnFinalize* fin, int sms, cudaStream_t st);
 // D[M,N] (+)= A^T B with A stored [K,M] (M contiguous) and B stored [K,N] (N contiguous):
 // both operands MN-major (weight gradient: A = dY[pixels, Cout], B = X[pixels, Cin]).
 // Split-K over `splits` CTAs per tile with fp32 atomics into D32 when splits > 1.

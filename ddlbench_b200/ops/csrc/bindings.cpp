@@ -199,18 +199,39 @@ void gap_bwd(at::Tensor dy, at::Tensor dx, int64_t N, int64_t HW, int64_t C) {
         "gap_bwd");
 }
 
+void maxpool_fwd(at::Tensor x, at::Tensor y, c10::optional<at::Tensor> idx, int64_t k, int64_t s,
+                 int64_t p) {
+  c10::cuda::CUDAGuard g(x.device());
+  check(ddl_maxpool_fwd(x.data_ptr(), y.data_ptr(), optr(idx), (int)x.size(0), (int)x.size(2),
+                        (int)x.size(3), (int)x.size(1), (int)y.size(2), (int)y.size(3), (int)k,
+                        (int)s, (int)p, sm_count(), cur_stream()),
+        "maxpool_fwd");
+}
+void maxpool_bwd(at::Tensor dy, at::Tensor idx, at::Tensor dx, int64_t k, int64_t s, int64_t p) {
+  c10::cuda::CUDAGuard g(dy.device());
+  check(ddl_maxpool_bwd(dy.data_ptr(), idx.data_ptr(), dx.data_ptr(), (int)dx.size(0),
+                        (int)dx.size(2), (int)dx.size(3), (int)dx.size(1), (int)dy.size(2),
+                        (int)dy.size(3), (int)k, (int)s, (int)p, sm_count(), cur_stream()),
+        "maxpool_bwd");
+}
+
 // ------------------------------------------------------------------------------ GEMM
 void gemm_bf16_tn(at::Tensor A, at::Tensor B, at::Tensor D, c10::optional<at::Tensor> col_sums,
-                  c10::optional<at::Tensor> bias, bool relu) {
+                  c10::optional<at::Tensor> bias, bool relu, c10::optional<at::Tensor> ticket,
+                  c10::optional<at::Tensor> stat_out, c10::optional<at::Tensor> rmean,
+                  c10::optional<at::Tensor> rvar, double eps, double momentum) {
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && D.dim() == 2 && is_bf16(A) && is_bf16(B) &&
               is_bf16(D));
   TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1 && D.stride(1) == 1);
   const int M = (int)A.size(0), K = (int)A.size(1), N = (int)B.size(0);
   TORCH_CHECK(B.size(1) == K && D.size(0) == M && D.size(1) == N);
   c10::cuda::CUDAGuard g(A.device());
+  DdlBnFinalize fin{(unsigned int*)optr(ticket), (float*)optr(stat_out), (float*)optr(rmean),
+                    (float*)optr(rvar), (float)eps, (float)momentum};
+  const bool use_fin = fin.ticket != nullptr && fin.stat_out != nullptr;
   check(ddl_gemm_bf16_tn(A.data_ptr(), B.data_ptr(), D.data_ptr(), M, N, K, (int)A.stride(0),
                          (int)B.stride(0), (int)D.stride(0), (float*)optr(col_sums), optr(bias),
-                         relu, sm_count(), cur_stream()),
+                         relu, use_fin ? &fin : nullptr, sm_count(), cur_stream()),
         "gemm_bf16_tn");
 }
 void gemm_bf16_nt_mn(at::Tensor A, at::Tensor B, at::Tensor D, int64_t splits,
@@ -514,6 +535,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_mask", &set_mask);
   m.def("gap_fwd", &gap_fwd);
   m.def("gap_bwd", &gap_bwd);
+  m.def("maxpool_fwd", &maxpool_fwd);
+  m.def("maxpool_bwd", &maxpool_bwd);
   m.def("gemm_bf16_tn", &gemm_bf16_tn);
   m.def("gemm_bf16_nt_mn", &gemm_bf16_nt_mn);
   m.def("gemm_info", &gemm_info);

@@ -144,7 +144,7 @@ __device__ __forceinline__ void finalize_stats(float s, float q, int c, int C, i
 
 // --------------------------------------------------------------------------- forward
 // sums: [R][2][C] fp32 (sum, sumsq), zero on entry, zero again on exit.
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, 4)
 bn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums,
                 unsigned int* __restrict__ counter, float* __restrict__ stat_out,
                 float* __restrict__ running_mean, float* __restrict__ running_var, int64_t M,
@@ -214,7 +214,7 @@ __global__ void bn_finalize_kernel(float* __restrict__ sums, float* __restrict__
 
 // y = act((x - mean) * invstd * gamma + beta [+ res])
 template <typename PT>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, 4)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                 __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
                 const PT* __restrict__ gamma, const PT* __restrict__ beta, int64_t M, int C,
@@ -280,7 +280,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 // sums[0][c] += sum dz ; sums[1][c] += sum dz * xhat ; optionally materialise dz.
 // Last CTA: coef[3][C] = {gamma*invstd, sum_dz/M, sum_dz_xhat/M}, dgamma/dbeta written.
 template <typename PT, typename GT>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, 4)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
                      const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
                      __nv_bfloat16* __restrict__ dz_out, const float* __restrict__ stat,
@@ -291,67 +291,45 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   __shared__ float red[16][kBnThreads];
   const int cv_total = C >> 3;
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
-  float v[16], mean[8], istd[8];
+  float v[16], mean[8];
 #pragma unroll
   for (int k = 0; k < 16; ++k) v[k] = 0.f;
   if (cv < cv_total) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      mean[k] = stat[cv * 8 + k];
-      istd[k] = stat[C + cv * 8 + k];
-    }
+    for (int k = 0; k < 8; ++k) mean[k] = stat[cv * 8 + k];   // invstd is applied once, at finalize
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     int64_t r1 = r0 + rows_per_block;
     if (r1 > M) r1 = M;
     const int step = blockDim.y;
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 2 * step) {
-      const bool two = (r + step) < r1;
+    // one row per trip: its 3-4 independent 16-byte loads are issued back to back; occupancy
+    // (4 CTAs/SM at <= 64 registers) supplies the rest of the memory-level parallelism
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += step) {
       const int64_t o0 = r * C + (int64_t)cv * 8;
-      const int64_t o1 = two ? (r + step) * C + (int64_t)cv * 8 : o0;
-      float d0[8], d1[8], x0[8], x1[8];
-      load8(dy + o0, d0);
-      load8(dy + o1, d1);
-      {  // x is re-read by bn_bwd_apply: ordinary (cacheable) load
-        int4 b0 = *reinterpret_cast<const int4*>(x + o0);
-        int4 b1 = *reinterpret_cast<const int4*>(x + o1);
-        unpack8(*reinterpret_cast<bf16x8*>(&b0), x0);
-        unpack8(*reinterpret_cast<bf16x8*>(&b1), x1);
-      }
+      int4 rd = ld_stream(dy + o0);
+      int4 rx = *reinterpret_cast<const int4*>(x + o0);  // re-read by bn_bwd_apply: cacheable
+      int4 r2, ry;
+      if (dy2) r2 = ld_stream(dy2 + o0);
+      if (act) ry = ld_stream(y + o0);
+      float d0[8], x0[8];
+      unpack8(*reinterpret_cast<bf16x8*>(&rd), d0);
       if (dy2) {  // gradient fan-in (block output feeds the next conv AND the next skip)
-        float e0[8], e1[8];
-        load8(dy2 + o0, e0);
-        load8(dy2 + o1, e1);
+        float e0[8];
+        unpack8(*reinterpret_cast<bf16x8*>(&r2), e0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          d0[k] += e0[k];
-          d1[k] += e1[k];
-        }
+        for (int k = 0; k < 8; ++k) d0[k] += e0[k];
       }
       if (act) {
-        float y0[8], y1[8];
-        load8(y + o0, y0);
-        load8(y + o1, y1);
+        float y0[8];
+        unpack8(*reinterpret_cast<bf16x8*>(&ry), y0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          d0[k] *= act_mask(y0[k], act);
-          d1[k] *= act_mask(y1[k], act);
-        }
+        for (int k = 0; k < 8; ++k) d0[k] *= act_mask(y0[k], act);
       }
-      if (dz_out) {
-        *reinterpret_cast<bf16x8*>(dz_out + o0) = pack8(d0);
-        if (two) *reinterpret_cast<bf16x8*>(dz_out + o1) = pack8(d1);
-      }
+      if (dz_out) *reinterpret_cast<bf16x8*>(dz_out + o0) = pack8(d0);
+      unpack8(*reinterpret_cast<bf16x8*>(&rx), x0);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         v[k] += d0[k];
-        v[8 + k] = fmaf(d0[k], (x0[k] - mean[k]) * istd[k], v[8 + k]);
-      }
-      if (two) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          v[k] += d1[k];
-          v[8 + k] = fmaf(d1[k], (x1[k] - mean[k]) * istd[k], v[8 + k]);
-        }
+        v[8 + k] = fmaf(d0[k], x0[k] - mean[k], v[8 + k]);
       }
     }
   }
@@ -365,6 +343,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       const int c = c0 + i;
       float sdz, sdzx;
       gather_and_clear(sums, C, c, sdz, sdzx);
+      sdzx *= stat[C + c];                       // sum dz * xhat
       coef[c] = to_f(gamma[c]) * stat[C + c];
       coef[C + c] = sdz * inv_m;
       coef[2 * C + c] = sdzx * inv_m;
@@ -380,7 +359,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 }
 
 // dx = coef0 * (dz - coef1 - xhat * coef2); dz is read from dz_in, or rebuilt from dy & y
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, 4)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz_in, const __nv_bfloat16* __restrict__ dy,
                     const __nv_bfloat16* __restrict__ dy2, const __nv_bfloat16* __restrict__ y,
                     const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dx,
@@ -389,15 +368,16 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz_in, const __nv_bfloat16
   const int cv_total = C >> 3;
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv >= cv_total) return;
-  float mean[8], istd[8], c0[8], c1[8], c2[8];
+  // dx = c0*(d - c1 - (x-mean)*istd*c2) = A*d + Bx*x + K  (3 coefficients per channel)
+  float A[8], Bx[8], K[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = cv * 8 + k;
-    mean[k] = stat[c];
-    istd[k] = stat[C + c];
-    c0[k] = coef[c];
-    c1[k] = coef[C + c];
-    c2[k] = coef[2 * C + c];
+    const float mean = stat[c], istd = stat[C + c];
+    const float c0 = coef[c], c1 = coef[C + c], c2 = coef[2 * C + c];
+    A[k] = c0;
+    Bx[k] = -c0 * istd * c2;
+    K[k] = c0 * (mean * istd * c2 - c1);
   }
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
@@ -439,8 +419,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz_in, const __nv_bfloat16
     load8(x + o1, x1);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      d0[k] = c0[k] * (d0[k] - c1[k] - (x0[k] - mean[k]) * istd[k] * c2[k]);
-      d1[k] = c0[k] * (d1[k] - c1[k] - (x1[k] - mean[k]) * istd[k] * c2[k]);
+      d0[k] = fmaf(A[k], d0[k], fmaf(Bx[k], x0[k], K[k]));
+      d1[k] = fmaf(A[k], d1[k], fmaf(Bx[k], x1[k], K[k]));
     }
     *reinterpret_cast<bf16x8*>(dx + o0) = pack8(d0);
     if (two) *reinterpret_cast<bf16x8*>(dx + o1) = pack8(d1);
@@ -491,7 +471,7 @@ act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
 
 // per-channel sum over rows of an NHWC bf16 tensor (bias gradient); last CTA writes `out`.
 template <typename GT>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, 4)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums,
               unsigned int* __restrict__ counter, GT* __restrict__ out, int accumulate, int64_t M,
               int C, int rows_per_block) {
@@ -536,7 +516,7 @@ extern "C" int ddl_bn_stats(const void* x, float* sums, unsigned int* counter, f
                             float* running_mean, float* running_var, int64_t M, int C, float eps,
                             float momentum, int sms, cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 3, 8);
+  BnDims d = bn_dims(M, C, sms, 4, 4);
   bn_stats_kernel<<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
       (const bf16*)x, sums, counter, stat, running_mean, running_var, M, C, d.rows_per_block, eps,
       momentum);
@@ -554,7 +534,7 @@ extern "C" int ddl_bn_apply(const void* x, const void* res, void* y, const float
                             const void* gamma, const void* beta, int param_is_bf16, int64_t M,
                             int C, int act, int sms, cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 6, 4);
+  BnDims d = bn_dims(M, C, sms, 8, 2);
   if (param_is_bf16)
     bn_apply_kernel<bf16><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
         (const bf16*)x, (const bf16*)res, (bf16*)y, stat, (const bf16*)gamma, (const bf16*)beta, M,
@@ -573,7 +553,7 @@ extern "C" int ddl_bn_bwd_reduce(const void* dy, const void* dy2, const void* y,
                                  int accumulate, int64_t M, int C, int act, int sms,
                                  cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 3, 8);
+  BnDims d = bn_dims(M, C, sms, 4, 4);
 #define L(PT, GT)                                                                              \
   bn_bwd_reduce_kernel<PT, GT><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(                 \
       (const bf16*)dy, (const bf16*)dy2, (const bf16*)y, (const bf16*)x, (bf16*)dz_out, stat,   \
@@ -591,7 +571,7 @@ extern "C" int ddl_bn_bwd_apply(const void* dz_in, const void* dy, const void* d
                                 const void* x, void* dx, const float* stat, const float* coef,
                                 int64_t M, int C, int act, int sms, cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 6, 4);
+  BnDims d = bn_dims(M, C, sms, 8, 2);
   bn_bwd_apply_kernel<<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
       (const bf16*)dz_in, (const bf16*)dy, (const bf16*)dy2, (const bf16*)y, (const bf16*)x,
       (bf16*)dx, stat, coef, M, C, d.rows_per_block, act);
@@ -630,7 +610,7 @@ extern "C" int ddl_colsum(const void* x, float* sums, unsigned int* counter, voi
                           int out_is_bf16, int accumulate, int64_t M, int C, int sms,
                           cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 3, 8);
+  BnDims d = bn_dims(M, C, sms, 4, 4);
   if (out_is_bf16)
     colsum_kernel<bf16><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
         (const bf16*)x, sums, counter, (bf16*)out, accumulate, M, C, d.rows_per_block);

@@ -33,7 +33,6 @@ namespace gemm {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 3;
 constexpr int kThreads = 192;  // 6 warps
 constexpr long long kSpinCycles = 4000000000LL;  // ~2 s: a protocol bug traps, never hangs
 
@@ -164,9 +163,39 @@ struct EpilogueParams {
   const __nv_bfloat16* bias;  // [N] or null
   int relu;
   int M, N, K;
+  // Optional fused BatchNorm finalize: the LAST CTA of the grid turns the partial sums into
+  // (mean, invstd), updates the running statistics and re-zeroes the workspace, so the
+  // BatchNorm that follows a 1x1 convolution needs no statistics kernel at all.
+  unsigned int* ticket;       // grid-wide arrival counter (self-resetting), or null
+  float* stat_out;            // [2][N] mean, invstd
+  float* running_mean;        // [N] or null
+  float* running_var;         // [N] or null
+  float eps, momentum;
 };
 
-template <int BLOCK_N>
+__device__ __forceinline__ void bn_finalize_channel(const EpilogueParams& ep, int c) {
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int r = 0; r < DDL_BN_REPLICAS; ++r) {
+    float* p = ep.col_sums + (size_t)r * 2 * ep.N;
+    s += __ldcg(p + c);
+    q += __ldcg(p + ep.N + c);
+    p[c] = 0.f;
+    p[ep.N + c] = 0.f;
+  }
+  const float inv_m = 1.f / (float)ep.M;
+  const float mean = s * inv_m;
+  const float var = fmaxf(fmaf(-mean, mean, q * inv_m), 0.f);
+  ep.stat_out[c] = mean;
+  ep.stat_out[ep.N + c] = rsqrtf(var + ep.eps);
+  if (ep.running_mean) {
+    const float unbiased = ep.M > 1 ? var * ((float)ep.M / (float)(ep.M - 1)) : var;
+    ep.running_mean[c] = fmaf(ep.momentum, mean - ep.running_mean[c], ep.running_mean[c]);
+    ep.running_var[c] = fmaf(ep.momentum, unbiased - ep.running_var[c], ep.running_var[c]);
+  }
+}
+
+template <int BLOCK_N, int kStages>
 struct SmemLayout {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;       // 16 KB
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;       // 8/16 KB
@@ -181,12 +210,16 @@ struct SmemLayout {
   static constexpr int kDynamic = kTotal + 1024;              // slack for 1024-B alignment
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 1)
+// kStages is chosen from K on the host: the 1x1 convolutions of the first ResNet stages have
+// K = 64..256 (1-4 k-blocks), where a short ring frees shared memory for more co-resident CTAs
+// (ncu on the first version: 2 CTAs/SM, 16% warps active, one long load->MMA->epilogue chain
+// per CTA; the kernel is latency-bound, so more CTAs in flight is what hides it).
+template <int BLOCK_N, int kStages>
+__global__ void __launch_bounds__(kThreads, (kStages <= 2) ? 4 : 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
                     const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_d, EpilogueParams ep) {
-  using L = SmemLayout<BLOCK_N>;
+  using L = SmemLayout<BLOCK_N, kStages>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -333,6 +366,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
         atomicAdd(&cs[ep.N + col + 1], q1);
       }
     }
+    if (ep.col_sums && ep.ticket) {
+      // last CTA to arrive finalizes the statistics of all N channels
+      __shared__ bool is_last;
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        const unsigned int t = atomicAdd(ep.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) *ep.ticket = 0u;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (is_last) {
+        __threadfence();
+        for (int c = et; c < ep.N; c += 128) bn_finalize_channel(ep, c);
+      }
+    }
     if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
@@ -377,10 +426,11 @@ static int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t 
   return r == CUDA_SUCCESS ? 0 : -3;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int kStages>
 static int launch_tn(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb,
-                     int ldd, float* col_sums, const void* bias, int relu, cudaStream_t st) {
-  using L = SmemLayout<BLOCK_N>;
+                     int ldd, float* col_sums, const void* bias, int relu, const DdlBnFinalize* fin,
+                     cudaStream_t st) {
+  using L = SmemLayout<BLOCK_N, kStages>;
   CUtensorMap ma, mb, md;
   int rc;
   if ((rc = make_map_2d(&ma, A, M, K, lda, BLOCK_K, BLOCK_M))) return rc;
@@ -388,14 +438,23 @@ static int launch_tn(const void* A, const void* B, void* D, int M, int N, int K,
   if ((rc = make_map_2d(&md, D, M, N, ldd, 64, BLOCK_M))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, kStages>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  EpilogueParams ep{col_sums, (const __nv_bfloat16*)bias, relu, M, N, K};
+  EpilogueParams ep{col_sums, (const __nv_bfloat16*)bias, relu, M, N, K,
+                    nullptr, nullptr, nullptr, nullptr, 0.f, 0.f};
+  if (fin && col_sums) {
+    ep.ticket = fin->ticket;
+    ep.stat_out = fin->stat_out;
+    ep.running_mean = fin->running_mean;
+    ep.running_var = fin->running_var;
+    ep.eps = fin->eps;
+    ep.momentum = fin->momentum;
+  }
   const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
-  gemm_bf16_tn_kernel<BLOCK_N><<<tiles, kThreads, L::kDynamic, st>>>(ma, mb, md, ep);
+  gemm_bf16_tn_kernel<BLOCK_N, kStages><<<tiles, kThreads, L::kDynamic, st>>>(ma, mb, md, ep);
   return (int)cudaGetLastError();
 }
 
@@ -404,7 +463,7 @@ static int launch_tn(const void* A, const void* B, void* D, int M, int N, int K,
 
 extern "C" int ddl_gemm_bf16_tn(const void* A, const void* B, void* D, int M, int N, int K,
                                 int lda, int ldb, int ldd, float* col_sums, const void* bias,
-                                int relu, int sms, cudaStream_t st) {
+                                int relu, const DdlBnFinalize* fin, int sms, cudaStream_t st) {
   using namespace ddl::gemm;
   (void)sms;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
@@ -412,8 +471,17 @@ extern "C" int ddl_gemm_bf16_tn(const void* A, const void* B, void* D, int M, in
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
        reinterpret_cast<uintptr_t>(D)) & 15)
     return -1;
-  if (N <= 64) return launch_tn<64>(A, B, D, M, N, K, lda, ldb, ldd, col_sums, bias, relu, st);
-  return launch_tn<128>(A, B, D, M, N, K, lda, ldb, ldd, col_sums, bias, relu, st);
+#define DDL_GEMM_ARGS A, B, D, M, N, K, lda, ldb, ldd, col_sums, bias, relu, fin, st
+  const int kb = (K + BLOCK_K - 1) / BLOCK_K;
+  if (N <= 64) {
+    if (kb <= 1) return launch_tn<64, 1>(DDL_GEMM_ARGS);
+    if (kb <= 2) return launch_tn<64, 2>(DDL_GEMM_ARGS);
+    return launch_tn<64, 4>(DDL_GEMM_ARGS);
+  }
+  if (kb <= 1) return launch_tn<128, 1>(DDL_GEMM_ARGS);
+  if (kb <= 2) return launch_tn<128, 2>(DDL_GEMM_ARGS);
+  return launch_tn<128, 3>(DDL_GEMM_ARGS);
+#undef DDL_GEMM_ARGS
 }
 
 extern "C" int ddl_gemm_bf16_nt_mn(const void*, const void*, void*, int, int, int, int, int, int,
@@ -424,7 +492,7 @@ extern "C" int ddl_gemm_bf16_nt_mn(const void*, const void*, void*, int, int, in
 extern "C" int ddl_gemm_selftest_info(char* buf, int len) {
   using namespace ddl::gemm;
   snprintf(buf, len,
-           "tcgen05 bf16 TN GEMM: BLOCK_M=%d BLOCK_K=%d stages=%d smem(N=128)=%d B smem(N=64)=%d B",
-           BLOCK_M, BLOCK_K, kStages, SmemLayout<128>::kDynamic, SmemLayout<64>::kDynamic);
+           "tcgen05 bf16 TN GEMM: BLOCK_M=%d BLOCK_K=%d stages=1..4 smem(N=128,3st)=%d B smem(N=128,1st)=%d B",
+           BLOCK_M, BLOCK_K, SmemLayout<128, 3>::kDynamic, SmemLayout<128, 1>::kDynamic);
   return 0;
 }

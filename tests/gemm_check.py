@@ -19,6 +19,24 @@ def check(M, N, K, stats=False, bias=False, relu=False, seed=0):
     assert ops.gemm_tn_supported(a, b), (M, N, K)
     d = ops.gemm_tn(a, b, col_sums=sums, bias=bias_t, relu=relu)
     torch.cuda.synchronize()
+    if stats:
+        # same GEMM with the fused BatchNorm finalize (last CTA): (mean, invstd) + running stats
+        sums2 = torch.zeros_like(sums)
+        ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+        stat = torch.empty(2 * N, device="cuda")
+        rm, rv = torch.zeros(N, device="cuda"), torch.ones(N, device="cuda")
+        for _ in range(2):
+            d2 = ops.gemm_tn(a, b, col_sums=sums2, bn_finalize=(ticket, stat, rm, rv, 1e-5, 0.1))
+        torch.cuda.synchronize()
+        df2 = d2.float()
+        mean_ref, var_ref = df2.mean(0), df2.var(0, unbiased=False)
+        fin_ok = (stat[:N] - mean_ref).abs().max().item() < 2e-2 * max(1.0, mean_ref.abs().max().item()) \
+            and ((stat[N:] - torch.rsqrt(var_ref + 1e-5)).abs() / torch.rsqrt(var_ref + 1e-5)).max().item() < 2e-2 \
+            and sums2.abs().max().item() == 0.0 and int(ticket.item()) == 0 \
+            and (rm - 0.19 * mean_ref).abs().max().item() < 2e-2 * max(1.0, mean_ref.abs().max().item())
+        if not fin_ok:
+            print("  fused BN finalize FAILED", (stat[:N] - mean_ref).abs().max().item(), sums2.abs().max().item(), int(ticket.item()))
+            return False
     ref = a.float() @ b.float().t()
     if bias:
         ref = ref + bias_t.float()

@@ -166,6 +166,22 @@ def test_global_avg_pool():
                                rtol=2e-2, atol=1e-3)
 
 
+@pytest.mark.parametrize("shape,k,s,p", [((8, 64, 112, 112), 3, 2, 1), ((4, 128, 32, 32), 2, 2, 0),
+                                          ((2, 16, 9, 13), 3, 2, 1), ((2, 8, 7, 7), 3, 1, 1)])
+def test_maxpool(shape, k, s, p):
+    torch.manual_seed(4)
+    x = _nhwc(*shape)
+    assert ops.maxpool_supported(x, [k, k], [s, s], [p, p], [1, 1], False)
+    y, idx = ops.maxpool_fwd(x, k, s, p)
+    y_ref, i_ref = torch.ops.aten.max_pool2d_with_indices(x.float(), [k, k], [s, s], [p, p], [1, 1], False)
+    assert torch.equal(y.float(), y_ref)
+    dy = torch.randn_like(y)
+    dx = ops.maxpool_bwd(dy, idx, x.shape, k, s, p)
+    dx_ref = torch.ops.aten.max_pool2d_with_indices_backward(dy.float(), x.float(), [k, k], [s, s],
+                                                             [p, p], [1, 1], False, i_ref)
+    torch.testing.assert_close(dx.float(), dx_ref, rtol=2e-2, atol=2e-2)
+
+
 def test_l2norm():
     x = torch.randn(100003, device=DEV).to(torch.bfloat16)
     torch.testing.assert_close(ops.l2norm(x)[0], x.float().norm(), rtol=1e-3, atol=1e-3)
