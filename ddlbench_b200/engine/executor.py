@@ -179,7 +179,7 @@ class StageExecutor:
 
     def _wgrad_stream(self):
         """Side stream for weight-gradient kernels (GPU only; ``overlap_wgrad`` attribute)."""
-        if self.device.type != "cuda" or not getattr(self, "overlap_wgrad", True):
+        if self.device.type != "cuda" or not getattr(self, "overlap_wgrad", E.OVERLAP_WGRAD_DEFAULT):
             return None
         if getattr(self, "_wg_stream", None) is None:
             self._wg_stream = torch.cuda.Stream(device=self.device)

@@ -30,6 +30,9 @@ BN_MOMENTUM_SCALE = [1.0]
 # side stream for weight-gradient kernels (set by the executor during backward) and the
 # operands that must outlive it
 WGRAD_OVERLAP = {"stream": None, "keep": []}
+import os as _os
+FUSE_BN_FINALIZE = _os.environ.get("DDLB_FUSE_FINALIZE", "0") == "1"
+OVERLAP_WGRAD_DEFAULT = _os.environ.get("DDLB_WGRAD_OVERLAP", "1") == "1"
 
 
 def _write(dst: torch.Tensor, src: torch.Tensor, accumulate: bool) -> None:
@@ -172,11 +175,15 @@ class ConvBnAct(Op, _ConvMixin):
         fuse_stats = training and self.ws is not None and self._is_gemm(x)
         mom = self.momentum * BN_MOMENTUM_SCALE[0]
         stat_ready = None
-        if fuse_stats:
-            # statistics AND their finalize ride in the GEMM epilogue (last CTA)
+        if fuse_stats and FUSE_BN_FINALIZE:
+            # statistics AND their finalize ride in the GEMM epilogue (last CTA).  Measured
+            # slower than a separate 4 us finalize launch (the last CTA gathers R*2*N values
+            # with 128 threads and every CTA pays a fence + ticket), so this is off by default.
             stat_ready = torch.empty(2 * self.channels, dtype=torch.float32, device=x.device)
             fin = (self.ws.counter[32:33], stat_ready, B[self.k_rm], B[self.k_rv], self.eps, mom)
             c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums, bn_finalize=fin)
+        elif fuse_stats:
+            c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums)
         else:
             c, fused = self._conv_fwd(x, P[self.k_w])
         y, stat = ops.bn_forward(c, res, P[self.k_g], P[self.k_b], B[self.k_rm], B[self.k_rv],

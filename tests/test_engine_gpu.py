@@ -77,14 +77,14 @@ def test_trainer_cuda_graph_matches_eager_and_learns():
 
 def test_trainer_resnet50_imagenet_step_u8():
     from ddlbench_b200.data.synthetic import SyntheticImages
+    # small LR: with lr=0.1 a single repeated batch of 8 transiently blows the loss up
+    # (observed identically with and without our kernels) before it collapses
     tr = Trainer("resnet50", "imagenet", batch_size=8, device="cuda", dtype=torch.bfloat16,
-                 cuda_graph=True, tcgen05=True)
+                 cuda_graph=True, tcgen05=True, lr=0.005, momentum=0.9)
     src = SyntheticImages("imagenet", 8, num_batches=2, device="cuda")
-    first = None
-    for i in range(6):
+    losses = []
+    for i in range(12):
         x, t = src.batch(0)
-        s = tr.step_u8(x, t, src.mean, src.std)
-        first = float(s[0]) if first is None else first
-    last = float(s[0])
-    assert last == last and last < first
+        losses.append(float(tr.step_u8(x, t, src.mean, src.std)[0]))
+    assert all(l == l for l in losses) and min(losses[-3:]) < losses[0]
     assert tr.launches_per_step > 100
