@@ -1,0 +1,124 @@
+"""Auxiliary tools: tracer, inference / flat partitioners, log post-processing, driver YAML,
+activation logger, sparsity analysis, layer summary."""
+import os
+import pickle
+
+import pytest
+import torch
+import torch.nn as nn
+
+from ddlbench_b200 import driver
+from ddlbench_b200.models import build_model
+from ddlbench_b200.partition import flat_optimizer, inference_optimizer
+from ddlbench_b200.partition.graph import Graph, Node
+from ddlbench_b200.partition.tracer import to_layer_graph, trace_to_graph
+from ddlbench_b200.utils import process_output, sparsity, summary
+from ddlbench_b200.utils.activation_logger import ActivationAndGradientLogger
+
+
+class Block(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.c1 = nn.Conv2d(3, 8, 3, padding=1)
+        self.r = nn.ReLU()
+        self.c2 = nn.Conv2d(8, 8, 3, padding=1)
+        self.pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Linear(8, 4)
+
+    def forward(self, x):
+        y = self.r(self.c1(x))
+        y = self.c2(y) + y
+        return self.fc(torch.flatten(self.pool(y), 1))
+
+
+def test_fx_tracer_builds_graph_and_layer_graph():
+    m = Block().eval()
+    g = trace_to_graph(m)
+    descs = [n.node_desc for n in g.nodes.values()]
+    assert descs[0] == "Input0" and any(d.startswith("Conv2d(3, 8") for d in descs)
+    assert "Add()" in descs and any(d.startswith("View") for d in descs)
+    add = next(n for n in g.nodes.values() if n.node_desc == "Add()")
+    assert len(g.in_edges[add.node_id]) == 2
+    lg = to_layer_graph(m, (3, 8, 8), 4).eval()
+    x = torch.randn(2, 3, 8, 8)
+    with torch.no_grad():
+        assert torch.allclose(lg(x), m(x), atol=1e-6)
+
+
+def _chain(costs):
+    g = Graph()
+    prev = None
+    for i, c in enumerate(costs):
+        n = Node("node%d" % i, "L%d()" % i, c * 1000, 0.0, 1e3, 1e3)
+        g.add_node(n)
+        if prev is not None:
+            g.add_edge(prev, n)
+        prev = n
+    return g
+
+
+def test_inference_optimizer_meets_throughput_constraint():
+    g = _chain([1.0, 1.0, 1.0, 1.0])
+    t, lat, splits, reps = inference_optimizer.main(4, None, 1.5, 1e12, graph=g, out=lambda *a: None)
+    assert t is not None and t <= 1.5 and lat >= 4.0 - 1e-9
+    t2, lat2, _, _ = inference_optimizer.main(1, None, 1.5, 1e12, graph=_chain([1.0] * 4),
+                                              out=lambda *a: None)
+    assert t2 is None          # one worker cannot sustain an input every 1.5 s
+
+
+def test_flat_optimizer_on_csv_profile(tmp_path):
+    p = tmp_path / "prof.csv"
+    p.write_text("layer,fwd,bwd,act,param\n" + "\n".join("L%d,%f,%f,1000,1000" % (i, c, c)
+                                                          for i, c in enumerate([1, 2, 3, 4, 5, 6])))
+    rows = flat_optimizer.read_profile_csv(str(p))
+    assert len(rows) == 6
+    t, ends, reps = flat_optimizer.optimize_chain(rows, 3, 1e12, straight_pipeline=True)
+    assert ends[-1] == 6 and reps == [1, 1, 1]
+    assert t == pytest.approx(0.018, rel=1e-6)      # 2,4,6 | 8,10 | 12 ms -> max 18 ms
+    g = flat_optimizer.convert_profile_to_graph(rows)
+    assert len(g.nodes) == 6 and len(flat_optimizer.compress_graph_branches(g).nodes) == 1
+
+
+def test_process_output_table():
+    log = ["Epoch 0: 36.0 seconds", " * Prec@1 10.000 Prec@5 50.000",
+           "device-timed | 1000.000 samples/sec (all 4 GPUs, max over ranks) | 1.0 ms/step",
+           "Epoch 1: 72.0 seconds", " * Prec@1 20.000 Prec@5 60.000"]
+    parsed = process_output.parse(log)
+    assert parsed["top1"] == [10.0, 20.0] and parsed["epoch_hours"] == [0.01, 0.02]
+    tbl = process_output.table(parsed).splitlines()
+    assert tbl[0].startswith("Epoch#") and tbl[2].split("\t")[1] == "0.030"
+
+
+def test_driver_yaml_to_command():
+    conf = driver.load("configs/driver/resnet50_8hybrid.yml")
+    cmd = driver.build_command(conf)
+    assert "--nproc-per-node=8" in cmd and "resnet50" in cmd and "pipedream" in cmd
+    assert driver.arch_of("models.vgg16.gpus=4") == "vgg16"
+    with pytest.raises(ValueError):
+        import yaml, tempfile
+        with tempfile.NamedTemporaryFile("w", suffix=".yml", delete=False) as f:
+            yaml.safe_dump({"module": "x"}, f)
+        driver.load(f.name)
+
+
+def test_activation_logger_and_sparsity(tmp_path):
+    m = Block()
+    lg = ActivationAndGradientLogger(str(tmp_path))
+    lg.hook_modules(m)
+    m(torch.randn(2, 3, 8, 8)).sum().backward()
+    lg.dump(0)
+    lg.unhook_modules()
+    acts = pickle.load(open(tmp_path / "0" / "activations.pkl", "rb"))
+    assert "r" in acts and "fc" in acts
+    sp = sparsity.measure_sparsity(str(tmp_path / "0" / "activations.pkl"))
+    assert 0.2 < sp["r"][0.0] < 0.8            # ReLU output is about half zeros
+    cr = sparsity.measure_compression_ratio(str(tmp_path / "0" / "activations.pkl"))
+    assert 0.1 < cr["r"] < 1.0      # zero-run-length coding shrinks a ReLU output
+    assert sparsity.extract_reduce_times(["allreduce[2] start=1.5 end=2.0"]) == [(2, 0.5)]
+
+
+def test_network_summary_counts_parameters():
+    m = build_model("resnet18", "cifar10")
+    text, total, trainable = summary.summary(m)
+    assert total == sum(p.numel() for p in m.parameters()) == trainable
+    assert "Conv2d-1" in text and "Total params" in text
