@@ -1,0 +1,178 @@
+"""Real-data input mode (``run.sh -s``): the ``DATADIR/<SET>/{train,val}/class_k/*.JPEG`` tree.
+
+The reference reads this tree with torchvision ``ImageFolder`` + ``DataLoader(num_workers=
+CORES_GPU, pin_memory=True, shuffle=True)`` and per-sample CPU transforms producing fp32 CHW
+tensors (``benchmark/imagenet/imagenet_pytorch.py:68-110``, ``cifar10_pytorch.py:164-186``,
+``mnist_pytorch.py:136-150`` incl. the grayscale loader).  Here the loader's product is the
+same thing the synthetic source yields — a PINNED uint8 [B, H, W, C] batch + int64 labels — so
+everything downstream (double-buffered H2D copy stream, fused u8->bf16 normalise kernel,
+captured step) is shared.  Decode runs in a thread pool (PIL releases the GIL inside libjpeg)
+with ``prefetch`` batches in flight; ``gpu_decode=True`` ships the compressed bytes instead and
+decodes with nvJPEG on the device (``torchvision.io.decode_jpeg(device=cuda)``).
+
+Sharding for data parallelism follows ``DistributedSampler(num_replicas, rank)`` semantics
+(``imagenet_horovod.py:113-123``): a per-epoch seeded permutation, padded to a multiple of the
+world size, strided by rank.
+"""
+from __future__ import annotations
+
+import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ..models import DATASETS
+from .synthetic import MEAN_STD
+
+_EXT = (".jpeg", ".jpg", ".png", ".ppm", ".bmp")
+
+
+def scan_tree(root: str) -> Tuple[List[Tuple[str, int]], List[str]]:
+    """(path, class index) samples + sorted class names — ImageFolder's contract."""
+    classes = sorted(d.name for d in os.scandir(root) if d.is_dir())
+    samples = []
+    for ci, c in enumerate(classes):
+        for dirpath, _, files in sorted(os.walk(os.path.join(root, c))):
+            for f in sorted(files):
+                if f.lower().endswith(_EXT):
+                    samples.append((os.path.join(dirpath, f), ci))
+    if not samples:
+        raise FileNotFoundError("no images under %s" % root)
+    return samples, classes
+
+
+class JpegFolder:
+    """Drop-in for ``SyntheticImages`` backed by an image tree."""
+
+    def __init__(self, datadir: str, dataset: str, batch_size: int, split: str = "train",
+                 shuffle: bool = True, seed: int = 1, rank: int = 0, world: int = 1,
+                 workers: Optional[int] = None, pinned: bool = False, augment: Optional[bool] = None,
+                 prefetch: int = 3, gpu_decode: bool = False, device="cpu"):
+        c, hw, ncls, _ = DATASETS[dataset]
+        name = {"highres": "HIGHRES", "imagenet": "IMAGENET", "cifar10": "CIFAR10",
+                "mnist": "MNIST"}[dataset]
+        self.root = os.path.join(datadir, name, split)
+        self.samples, self.classes = scan_tree(self.root)
+        self.dataset, self.batch_size, self.split = dataset, batch_size, split
+        self.channels, self.size, self.num_classes = c, hw, ncls
+        self.shape = (batch_size, hw, hw, c)
+        self.mean, self.std = MEAN_STD[dataset]
+        self.shuffle, self.seed, self.rank, self.world = shuffle, seed, rank, world
+        self.augment = (split == "train") if augment is None else augment
+        self.pinned = pinned and torch.cuda.is_available()
+        self.gpu_decode = gpu_decode and torch.cuda.is_available()
+        self.device = torch.device(device)
+        self.pool = ThreadPoolExecutor(max_workers=workers or min(32, os.cpu_count() or 4))
+        self.prefetch = max(1, prefetch)
+        self.epoch = 0
+        self._lock = threading.Lock()
+        self._pending: Dict[int, object] = {}
+        self._order = self._make_order()
+        self.length = len(self._order) // batch_size           # drop_last
+        if self.length == 0:
+            raise ValueError("batch size %d exceeds the %d samples of this shard"
+                             % (batch_size, len(self._order)))
+
+    # ---------------------------------------------------------------- sampling
+    def _make_order(self) -> np.ndarray:
+        n = len(self.samples)
+        idx = (np.random.RandomState(self.seed + self.epoch).permutation(n) if self.shuffle
+               else np.arange(n))
+        if self.world > 1:
+            pad = (-n) % self.world
+            idx = np.concatenate([idx, idx[:pad]])[self.rank::self.world]
+        return idx
+
+    def set_epoch(self, epoch: int) -> None:
+        with self._lock:
+            self.epoch = epoch
+            self._order = self._make_order()
+            for f in self._pending.values():
+                f.cancel()
+            self._pending.clear()
+
+    def __len__(self) -> int:
+        return self.length
+
+    # ---------------------------------------------------------------- decode
+    def _load_one(self, path: str, rng: np.random.RandomState) -> np.ndarray:
+        from PIL import Image
+        with Image.open(path) as im:
+            im = im.convert("L" if self.channels == 1 else "RGB")
+            s = self.size
+            if self.dataset in ("imagenet", "highres"):
+                if self.augment and self.dataset == "imagenet":
+                    # RandomResizedCrop(224) + horizontal flip
+                    w, h = im.size
+                    area = w * h * rng.uniform(0.08, 1.0)
+                    ar = np.exp(rng.uniform(np.log(3 / 4), np.log(4 / 3)))
+                    cw = int(min(w, max(1, round(np.sqrt(area * ar)))))
+                    ch = int(min(h, max(1, round(np.sqrt(area / ar)))))
+                    x0, y0 = rng.randint(0, w - cw + 1), rng.randint(0, h - ch + 1)
+                    im = im.resize((s, s), Image.BILINEAR, box=(x0, y0, x0 + cw, y0 + ch))
+                elif im.size != (s, s):
+                    # Resize(256/224*s) + CenterCrop(s)
+                    w, h = im.size
+                    r = (s * 256 // 224) / min(w, h)
+                    im = im.resize((max(s, round(w * r)), max(s, round(h * r))), Image.BILINEAR)
+                    w, h = im.size
+                    im = im.crop(((w - s) // 2, (h - s) // 2, (w - s) // 2 + s, (h - s) // 2 + s))
+            elif im.size != (s, s):
+                im = im.resize((s, s), Image.BILINEAR)
+            a = np.asarray(im, dtype=np.uint8)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        if self.augment:
+            if self.dataset == "cifar10":                      # RandomCrop(32, padding=4)
+                p = np.zeros((s + 8, s + 8, a.shape[2]), np.uint8)
+                p[4:4 + s, 4:4 + s] = a
+                y0, x0 = rng.randint(0, 9), rng.randint(0, 9)
+                a = p[y0:y0 + s, x0:x0 + s]
+            if self.dataset != "mnist" and rng.rand() < 0.5:
+                a = a[:, ::-1]
+        return np.ascontiguousarray(a)
+
+    def _make_batch(self, i: int, order: np.ndarray, epoch: int):
+        sel = order[(i % self.length) * self.batch_size:(i % self.length + 1) * self.batch_size]
+        labels = torch.tensor([self.samples[j][1] for j in sel], dtype=torch.int64)
+        if self.gpu_decode:
+            from torchvision.io import ImageReadMode, decode_jpeg, read_file
+            raw = [read_file(self.samples[j][0]) for j in sel]
+            mode = ImageReadMode.GRAY if self.channels == 1 else ImageReadMode.RGB
+            dec = decode_jpeg(raw, device=self.device, mode=mode)
+            img = torch.stack([d.permute(1, 2, 0) for d in dec]).contiguous()
+            return img, labels.to(self.device, non_blocking=True)
+        img = torch.empty(self.shape, dtype=torch.uint8)
+        if self.pinned:
+            img, labels = img.pin_memory(), labels.pin_memory()
+        out = img.numpy()
+        for k, j in enumerate(sel):
+            rng = np.random.RandomState((self.seed * 1000003 + epoch * 7919 + int(j)) & 0x7FFFFFFF)
+            out[k] = self._load_one(self.samples[j][0], rng)
+        return img, labels
+
+    def _submit(self, i: int) -> None:
+        if i not in self._pending:
+            self._pending[i] = self.pool.submit(self._make_batch, i, self._order, self.epoch)
+
+    def batch(self, i: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        with self._lock:
+            for k in range(i, i + self.prefetch):
+                self._submit(k)
+            fut = self._pending.pop(i)
+            for k in [k for k in self._pending if k < i]:
+                self._pending.pop(k).cancel()
+        return fut.result()
+
+    def __iter__(self):
+        for i in range(self.length):
+            yield self.batch(i)
+
+    def bytes_per_step(self) -> int:
+        return int(np.prod(self.shape)) + self.batch_size * 8
+
+    def close(self) -> None:
+        self.pool.shutdown(wait=False, cancel_futures=True)

@@ -122,10 +122,12 @@ def run(cfg: RunConfig, group=None, verbose: bool = True) -> Dict[str, float]:
                       allreduce=cfg.allreduce, tcgen05=cfg.fused and use_cuda, seed=cfg.seed,
                       group=group)
     pinned = cfg.data_mode == "pinned" and use_cuda
-    train_src = SyntheticImages(cfg.benchmark, cfg.batch_size, num_batches=4,
-                                device=("cpu" if pinned else device), pinned=pinned,
-                                seed=cfg.seed + rank)
-    steps = len(train_src) // world if distributed else len(train_src)
+    from ..data import make_source
+    train_src = make_source(cfg, cfg.batch_size, device, rank, world, "train", pinned=pinned)
+    real = not isinstance(train_src, SyntheticImages)
+    val_src = make_source(cfg, cfg.batch_size, device, rank, world, "val") if real else train_src
+    # the image-tree source is already sharded per rank; the synthetic one models the full set
+    steps = len(train_src) if real else (len(train_src) // world if distributed else len(train_src))
     if cfg.steps_per_epoch:
         steps = min(steps, cfg.steps_per_epoch)
     val_steps = cfg.eval_steps if cfg.eval_steps is not None else max(1, steps // 10)
@@ -138,6 +140,8 @@ def run(cfg: RunConfig, group=None, verbose: bool = True) -> Dict[str, float]:
         timer.start()
         loss_sum = torch.zeros(1, device=device)
         data_trained = 0
+        if real:
+            train_src.set_epoch(epoch)
         pre.i_issue = 0
         pre.issue()
         for i in range(steps):
@@ -155,7 +159,7 @@ def run(cfg: RunConfig, group=None, verbose: bool = True) -> Dict[str, float]:
         ms = timer.stop()
         tock = time.time()
         train_loss = float(loss_sum.item()) / max(data_trained, 1)
-        vloss, vacc = evaluate(trainer, train_src, val_steps, cfg, say)
+        vloss, vacc = evaluate(trainer, val_src, min(val_steps, len(val_src)), cfg, say)
         t = tock - tick
         thr = data_trained / max(t, 1e-9)
         ms_max = max_over_ranks(ms, device, group)
@@ -165,7 +169,7 @@ def run(cfg: RunConfig, group=None, verbose: bool = True) -> Dict[str, float]:
         throughputs.append(thr)
         elapsed.append(t)
         valid_acc = vacc
-    vloss, valid_acc = evaluate(trainer, train_src, val_steps, cfg, lambda *a, **k: None)
+    vloss, valid_acc = evaluate(trainer, val_src, min(val_steps, len(val_src)), cfg, lambda *a, **k: None)
     if cfg.framework == "horovod":
         from ..parallel import dp
         vloss = float(dp.allreduce(torch.tensor(vloss), name="avg_loss"))

@@ -75,7 +75,8 @@ def run_gpipe(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
                  momentum=cfg.momentum, weight_decay=cfg.weight_decay, tcgen05=cfg.fused)
     pipe.set_micro_batch(micro)
     first, last = rank == 0, rank == parts - 1 or world == 1
-    src = SyntheticImages(cfg.benchmark, batch, num_batches=2, device=device, seed=cfg.seed)
+    from ..data import make_source
+    src = make_source(cfg, batch, device, 0, 1, "train", num_batches=2)
     steps = len(src)
     if cfg.steps_per_epoch:
         steps = min(steps, cfg.steps_per_epoch)
@@ -189,9 +190,10 @@ def run_pipedream(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
                       macrobatch=cfg.extra.get("macrobatch") == "1", tcgen05=cfg.fused,
                       verbose=verbose)
     topo = rt.topo
-    src = SyntheticImages(cfg.benchmark, cfg.batch_size, num_batches=2, device=device,
-                          seed=cfg.seed + topo.rank_in_stage)
-    loader_size = len(src) // pcfg.replicas(0)
+    from ..data import make_source
+    src = make_source(cfg, cfg.batch_size, device, topo.rank_in_stage, pcfg.replicas(0), "train",
+                      num_batches=2)
+    loader_size = len(src) if hasattr(src, "set_epoch") else len(src) // pcfg.replicas(0)
     if cfg.steps_per_epoch:
         loader_size = min(loader_size, cfg.steps_per_epoch)
     n = pcfg.num_iterations(topo.stage, loader_size)

@@ -164,6 +164,8 @@ class StageRuntime:
         self._next_fwd = None
         self._next_bwd = None
         self.loss_stats: Optional[torch.Tensor] = None
+        from .stats import RuntimeStats
+        self.forward_stats, self.backward_stats = RuntimeStats(True), RuntimeStats(False)
         self.training = True
         self.verbose = verbose
         self._accum = 0
@@ -216,9 +218,12 @@ class StageRuntime:
             self._next_fwd = None
             bufs = pending.wait()
             xs, target = list(bufs[:-1]), bufs[-1]
+            self.forward_stats.received(bufs)
             self._prepost_fwd()               # overlap the next transfer with this compute
         version = ex.store.latest
+        tok = self.forward_stats.begin_compute(self.device)
         outs, ctx = ex.forward(xs, training=self.training, version=version)
+        self.forward_stats.end_compute(tok)
         stats = None
         dl = None
         if t.is_last:
@@ -227,6 +232,7 @@ class StageRuntime:
             self.loss_stats = stats
         else:
             self.p2p.send(self.routing.fwd_send_peer(self.fwd_id), list(outs) + [target], "fwd")
+            self.forward_stats.sent(list(outs) + [target])
         if self.training:
             self._ctxs.append((ctx, dl, None))
         self.fwd_id += 1
@@ -245,12 +251,16 @@ class StageRuntime:
             _, pending = self._next_bwd
             self._next_bwd = None
             grads = list(pending.wait())
+            self.backward_stats.received(grads)
             self._prepost_bwd()
         accumulate = self._accum > 0
         final = (self._accum + 1) == self.update_interval
+        tok = self.backward_stats.begin_compute(self.device)
         gin = ex.backward(ctx, grads, accumulate=accumulate, final=final)
+        self.backward_stats.end_compute(tok)
         if not t.is_first:
             self.p2p.send(self.routing.next_bwd_send_peer(), [g for g in gin], "bwd")
+            self.backward_stats.sent(gin)
         self._accum += 1
         if final:
             self._optimizer_step()

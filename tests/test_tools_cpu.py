@@ -122,3 +122,55 @@ def test_network_summary_counts_parameters():
     text, total, trainable = summary.summary(m)
     assert total == sum(p.numel() for p in m.parameters()) == trainable
     assert "Conv2d-1" in text and "Total params" in text
+
+
+def test_launcher_passes_ranks_and_propagates_failure(tmp_path):
+    import subprocess
+    import sys
+    script = tmp_path / "child.py"
+    script.write_text(
+        "import argparse, os, sys\n"
+        "ap = argparse.ArgumentParser(); ap.add_argument('--rank', type=int)\n"
+        "ap.add_argument('--local_rank', type=int); ap.add_argument('--fail', type=int, default=-1)\n"
+        "a = ap.parse_args()\n"
+        "assert int(os.environ['RANK']) == a.rank and os.environ['WORLD_SIZE'] == '3'\n"
+        "open(os.path.join(os.path.dirname(__file__), 'r%d' % a.rank), 'w').write(str(a.local_rank))\n"
+        "sys.exit(7 if a.rank == a.fail else 0)\n")
+    cmd = [sys.executable, "-m", "ddlbench_b200.launch", "--nproc_per_node", "3", "--pid-file",
+           str(tmp_path / "pids"), str(script)]
+    assert subprocess.run(cmd, timeout=120).returncode == 0
+    assert sorted(p.name for p in tmp_path.glob("r*")) == ["r0", "r1", "r2"]
+    assert len(open(tmp_path / "pids").read().split()) == 3
+    assert subprocess.run(cmd + ["--fail", "1"], timeout=120).returncode == 7
+    assert subprocess.run([sys.executable, "-m", "ddlbench_b200.launch", "--terminate",
+                           str(tmp_path / "pids")], timeout=60).returncode == 0
+
+
+def test_threadsafe_queue_and_counter():
+    import threading
+    from ddlbench_b200.utils.threadsafe import Counter, Queue
+    q, c = Queue(maxsize=2), Counter(4)
+
+    def prod():
+        for i in range(4):
+            q.add(i)
+            c.decrement()
+    t = threading.Thread(target=prod)
+    t.start()
+    got = [q.remove(timeout=5) for _ in range(4)]
+    c.wait(timeout=5)
+    t.join()
+    assert got == [0, 1, 2, 3] and c.count == 0 and len(q) == 0
+
+
+def test_runtime_stats_format():
+    from ddlbench_b200.parallel.pipedream.stats import RuntimeStats
+    st = RuntimeStats(forward=True)
+    st.sent([torch.zeros(10, dtype=torch.float32)])
+    tok = st.begin_compute("cpu")
+    st.end_compute(tok)
+    lines = []
+    st.print_stats(out=lines.append)
+    assert lines[0] == "Forward Stats:" and "\t send_tensors_size 40.000 bytes" in lines
+    st.reset_stats()
+    assert st.stats["send_tensors_size"] == 0
