@@ -57,7 +57,13 @@ def build_model(arch: str, dataset: str = "imagenet") -> LayerGraphModel:
     elif arch == "mobilenetv2":
         m = build_mobilenetv2(arch, style=style, in_channels=c, num_classes=ncls, input_hw=hw)
     else:
-        raise ValueError(f"unknown architecture {arch!r}; choose from {ARCHS}")
+        from .extra import EXTRA_BUILDERS
+        if arch not in EXTRA_BUILDERS:
+            raise ValueError(f"unknown architecture {arch!r}; choose from "
+                             f"{ARCHS + tuple(EXTRA_BUILDERS)}")
+        if style != "imagenet":
+            raise ValueError(f"{arch} is defined for ImageNet-shaped inputs only")
+        m = EXTRA_BUILDERS[arch](arch, in_channels=c, num_classes=ncls, input_hw=hw)
     m.dataset = dataset
     return m
 

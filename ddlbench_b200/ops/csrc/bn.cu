@@ -57,6 +57,28 @@ static inline BnDims bn_dims(int64_t M, int C, int sms, int waves, int min_rows_
   return d;
 }
 
+// Mapping for the REDUCING kernels (statistics, backward sums, bias gradient): a block is one
+// warp of channel vectors wide (<= 256 channels) and 8 row lanes deep, the grid is
+// (row splits, channel slabs).  The number of partial-sum atomics is gx*gy*cvb*NV/4; with the
+// full-width mapping above a 2048-channel layer issued 1.6 M scalar atomics for 6 MB of data
+// (ncu: 31 us, 0.4 TB/s), this one 75 K vector atomics.
+static inline BnDims bn_dims_reduce(int64_t M, int C, int sms, int waves, int min_rows_per_lane) {
+  BnDims d;
+  const int cv = C / 8;
+  d.cvb = cv < 32 ? cv : 32;
+  d.rl = kBnThreads / d.cvb;
+  d.gy = (cv + d.cvb - 1) / d.cvb;
+  int64_t target = (int64_t)sms * waves / d.gy;
+  if (target < 1) target = 1;
+  int64_t max_useful = (M + (int64_t)d.rl * min_rows_per_lane - 1) / ((int64_t)d.rl * min_rows_per_lane);
+  if (target > max_useful) target = max_useful;
+  if (target < 1) target = 1;
+  d.gx = (int)target;
+  d.rows_per_block = (int)((M + d.gx - 1) / d.gx);
+  d.gx = (int)((M + d.rows_per_block - 1) / d.rows_per_block);
+  return d;
+}
+
 // act: 0 none, 1 relu, 2 relu6
 __device__ __forceinline__ float act_fwd(float v, int act) {
   if (act == 1) return fmaxf(v, 0.f);
@@ -85,15 +107,23 @@ __device__ __forceinline__ void block_reduce_to_workspace(const float* vals, flo
   for (int k = 0; k < NV; ++k) red[k][tid] = vals[k];
   __syncthreads();
   const int nthreads = blockDim.x * blockDim.y;
-  const int nout = blockDim.x * NV;
+  const int nout = blockDim.x * (NV / 4);
   float* dst = sums + (size_t)rep * 2 * C;
+  // one 16-byte vector atomic (red.global.add.v4.f32, sm_90+) per 4 adjacent channels:
+  // a quarter of the L2 atomic transactions of the scalar form
   for (int o = tid; o < nout; o += nthreads) {
-    const int tx = o % blockDim.x, k = o / blockDim.x;
+    const int tx = o % blockDim.x, k0 = (o / blockDim.x) * 4;
     const int c_vec = blockIdx.y * blockDim.x + tx;
     if (c_vec >= cv_total) continue;
-    float acc = 0.f;
-    for (int ty = 0; ty < blockDim.y; ++ty) acc += red[k][ty * blockDim.x + tx];
-    atomicAdd(&dst[(k >> 3) * C + c_vec * 8 + (k & 7)], acc);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ty = 0; ty < blockDim.y; ++ty) {
+      const int t = ty * blockDim.x + tx;
+      acc.x += red[k0][t];
+      acc.y += red[k0 + 1][t];
+      acc.z += red[k0 + 2][t];
+      acc.w += red[k0 + 3][t];
+    }
+    atomicAdd(reinterpret_cast<float4*>(&dst[(k0 >> 3) * C + c_vec * 8 + (k0 & 7)]), acc);
   }
 }
 
@@ -516,7 +546,7 @@ extern "C" int ddl_bn_stats(const void* x, float* sums, unsigned int* counter, f
                             float* running_mean, float* running_var, int64_t M, int C, float eps,
                             float momentum, int sms, cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 4, 4);
+  BnDims d = bn_dims_reduce(M, C, sms, 4, 4);
   bn_stats_kernel<<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
       (const bf16*)x, sums, counter, stat, running_mean, running_var, M, C, d.rows_per_block, eps,
       momentum);
@@ -553,7 +583,7 @@ extern "C" int ddl_bn_bwd_reduce(const void* dy, const void* dy2, const void* y,
                                  int accumulate, int64_t M, int C, int act, int sms,
                                  cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 4, 4);
+  BnDims d = bn_dims_reduce(M, C, sms, 4, 4);
 #define L(PT, GT)                                                                              \
   bn_bwd_reduce_kernel<PT, GT><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(                 \
       (const bf16*)dy, (const bf16*)dy2, (const bf16*)y, (const bf16*)x, (bf16*)dz_out, stat,   \
@@ -610,7 +640,7 @@ extern "C" int ddl_colsum(const void* x, float* sums, unsigned int* counter, voi
                           int out_is_bf16, int accumulate, int64_t M, int C, int sms,
                           cudaStream_t st) {
   if (C % 8) return -1;
-  BnDims d = bn_dims(M, C, sms, 4, 4);
+  BnDims d = bn_dims_reduce(M, C, sms, 4, 4);
   if (out_is_bf16)
     colsum_kernel<bf16><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
         (const bf16*)x, sums, counter, (bf16*)out, accumulate, M, C, d.rows_per_block);
