@@ -21,6 +21,8 @@ import torch
 from . import reference as ref
 from .reference import ACT_NONE, ACT_RELU, ACT_RELU6
 
+ACT_BITMASK = 0x100   # flag or-ed into `act`: the `y` argument of the BN backward kernels is a bitmask
+
 _ext = None
 _ext_err: Optional[BaseException] = None
 _lock = threading.Lock()
@@ -151,15 +153,17 @@ class BnWorkspace:
 
 def bn_forward(x, res, gamma, beta, running_mean, running_var, eps: float, momentum: float,
                act: int, ws: Optional[BnWorkspace] = None, stats_ready: bool = False,
-               training: bool = True, stat_ready: Optional[torch.Tensor] = None):
-    """y = act(BN(x) [+ res]).  Returns (y, stat[2, C]).  ``stats_ready``: the producer
+               training: bool = True, stat_ready: Optional[torch.Tensor] = None,
+               mask_out: Optional[torch.Tensor] = None):
+    """y = act(BN(x) [+ res]).  Returns (y, stat[2, C]).  ``mask_out`` (uint8, numel/8): receives
+    the activation derivative as one bit per element for ``bn_backward(mask=...)``.  ``stats_ready``: the producer
     (tcgen05 GEMM epilogue) already accumulated sum / sum-of-squares into ``ws.sums``."""
     M, C = _mc(x)
     if not training:
         stat = torch.stack([running_mean.float(), torch.rsqrt(running_var.float() + eps)])
         if _nhwc_ok(x):
             y = torch.empty_like(x)
-            ext().bn_apply(x, res, y, stat.contiguous(), gamma, beta, M, C, act)
+            ext().bn_apply(x, res, y, stat.contiguous(), gamma, beta, None, M, C, act)
             _count()
             return y, stat
         return ref.bn_apply(x, res, stat, gamma, beta, act), stat
@@ -176,7 +180,7 @@ def bn_forward(x, res, gamma, beta, running_mean, running_var, eps: float, momen
         else:
             e.bn_stats(x, ws.sums, ws.counter, stat, running_mean, running_var, M, C, eps, momentum)
         y = torch.empty_like(x)
-        e.bn_apply(x, res, y, stat, gamma, beta, M, C, act)
+        e.bn_apply(x, res, y, stat, gamma, beta, mask_out, M, C, act)
         _count(2)
         return y, stat.view(2, C)
     stat = ref.bn_stat(x, eps)
@@ -186,8 +190,9 @@ def bn_forward(x, res, gamma, beta, running_mean, running_var, eps: float, momen
 
 
 def bn_backward(dy, dy2, y, x, stat, gamma, act: int, want_dz: bool, dgamma_out, dbeta_out,
-                accumulate: bool = False, ws: Optional[BnWorkspace] = None):
-    """Backward of ``bn_forward``.  Writes dgamma/dbeta into the given (flat-buffer) views.
+                accumulate: bool = False, ws: Optional[BnWorkspace] = None,
+                mask: Optional[torch.Tensor] = None):
+    """Backward of ``bn_forward``.  ``mask``: the bitmask ``bn_forward`` wrote (read instead of y).  Writes dgamma/dbeta into the given (flat-buffer) views.
     Returns (dx, dz) where dz (if requested) is the gradient flowing to the residual input."""
     M, C = _mc(x)
     if _nhwc_ok(x):
@@ -197,6 +202,8 @@ def bn_backward(dy, dy2, y, x, stat, gamma, act: int, want_dz: bool, dgamma_out,
         stat_f = stat.reshape(-1)
         dz = torch.empty_like(x) if want_dz else None
         yy = y if act != ACT_NONE else None
+        if mask is not None and act != ACT_NONE:
+            yy, act = mask, act | ACT_BITMASK
         e.bn_bwd_reduce(dy, dy2, yy, x, dz, stat_f, ws.sums, ws.counter, gamma, ws.coef,
                         dgamma_out, dbeta_out, accumulate, M, C, act)
         dx = torch.empty_like(x)

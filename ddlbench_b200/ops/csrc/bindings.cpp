@@ -99,11 +99,13 @@ void bn_finalize(at::Tensor sums, at::Tensor stat, c10::optional<at::Tensor> rme
         "bn_finalize");
 }
 void bn_apply(at::Tensor x, c10::optional<at::Tensor> res, at::Tensor y, at::Tensor stat,
-              at::Tensor gamma, at::Tensor beta, int64_t M, int64_t C, int64_t act) {
+              at::Tensor gamma, at::Tensor beta, c10::optional<at::Tensor> mask_out, int64_t M,
+              int64_t C, int64_t act) {
   c10::cuda::CUDAGuard g(x.device());
+  TORCH_CHECK(!mask_out.has_value() || mask_out->numel() * 8 >= M * C, "activation mask too small");
   check(ddl_bn_apply(x.data_ptr(), optr(res), y.data_ptr(), stat.data_ptr<float>(),
-                     gamma.data_ptr(), beta.data_ptr(), is_bf16(gamma), M, (int)C, (int)act,
-                     sm_count(), cur_stream()),
+                     gamma.data_ptr(), beta.data_ptr(), is_bf16(gamma), optr(mask_out), M, (int)C,
+                     (int)act, sm_count(), cur_stream()),
         "bn_apply");
 }
 void bn_bwd_reduce(at::Tensor dy, c10::optional<at::Tensor> dy2, c10::optional<at::Tensor> y,

@@ -96,6 +96,20 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
   unpack8(*reinterpret_cast<bf16x8*>(&raw), f);
 }
 
+// The activation derivative as ONE BIT per element (bit k of byte [row][c/8] = act'(y[c+k]) != 0),
+// written by bn_apply and read by the two backward kernels instead of the 16x larger y: the
+// backward is bandwidth-bound on the big layers (ncu: 5.5 TB/s), so bytes are time.  The bit is
+// derived from the ROUNDED bf16 output so it equals act_mask(y) exactly.
+__device__ __forceinline__ uint8_t act_bits(const bf16x8& p, int act) {
+  float q[8];
+  unpack8(p, q);
+  unsigned m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m |= (act_mask(q[k], act) != 0.f ? 1u : 0u) << k;
+  return (uint8_t)m;
+}
+constexpr int kActBitmask = 0x100;  // flag in `act`: the `y` argument points to such a bitmask
+
 // block-level reduction of NV (8 or 16) per-thread values over the row lanes, then one
 // atomicAdd per (value, channel) into replica `rep` of the workspace.
 template <int NV>
@@ -179,6 +193,7 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums,
                 unsigned int* __restrict__ counter, float* __restrict__ stat_out,
                 float* __restrict__ running_mean, float* __restrict__ running_var, int64_t M,
                 int C, int rows_per_block, float eps, float momentum) {
+  pdl_enter();
   __shared__ float red[16][kBnThreads];
   const int cv_total = C >> 3;
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
@@ -235,6 +250,7 @@ __global__ void bn_finalize_kernel(float* __restrict__ sums, float* __restrict__
                                    float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int64_t M, int C, float eps,
                                    float momentum) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s, q;
@@ -247,8 +263,9 @@ template <typename PT>
 __global__ void __launch_bounds__(kBnThreads, 4)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                 __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
-                const PT* __restrict__ gamma, const PT* __restrict__ beta, int64_t M, int C,
-                int rows_per_block, int act) {
+                const PT* __restrict__ gamma, const PT* __restrict__ beta,
+                uint8_t* __restrict__ mask_out, int64_t M, int C, int rows_per_block, int act) {
+  pdl_enter();
   const int cv_total = C >> 3;
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv >= cv_total) return;
@@ -286,8 +303,13 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
         f1[k] = act_fwd(fmaf(f1[k], sc[k], sh[k]), act);
       }
     }
-    *reinterpret_cast<bf16x8*>(y + o0) = pack8(f0);  // stays in L2: the next conv reads it
-    *reinterpret_cast<bf16x8*>(y + o1) = pack8(f1);
+    const bf16x8 p0 = pack8(f0), p1 = pack8(f1);
+    *reinterpret_cast<bf16x8*>(y + o0) = p0;  // stays in L2: the next conv reads it
+    *reinterpret_cast<bf16x8*>(y + o1) = p1;
+    if (mask_out) {
+      mask_out[r * cv_total + cv] = act_bits(p0, act);
+      mask_out[(r + step) * cv_total + cv] = act_bits(p1, act);
+    }
   }
   for (; r < r1; r += step) {
     const int64_t off = r * C + (int64_t)cv * 8;
@@ -302,7 +324,9 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = act_fwd(fmaf(f[k], sc[k], sh[k]), act);
     }
-    *reinterpret_cast<bf16x8*>(y + off) = pack8(f);
+    const bf16x8 p = pack8(f);
+    *reinterpret_cast<bf16x8*>(y + off) = p;
+    if (mask_out) mask_out[r * cv_total + cv] = act_bits(p, act);
   }
 }
 
@@ -317,8 +341,11 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      float* __restrict__ sums, unsigned int* __restrict__ counter,
                      const PT* __restrict__ gamma, float* __restrict__ coef,
                      GT* __restrict__ dgamma, GT* __restrict__ dbeta, int accumulate, int64_t M,
-                     int C, int rows_per_block, int act) {
+                     int C, int rows_per_block, int act_flags) {
+  pdl_enter();
   __shared__ float red[16][kBnThreads];
+  const bool bitmask = (act_flags & kActBitmask) != 0;
+  const int act = act_flags & 0xff;
   const int cv_total = C >> 3;
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   float v[16], mean[8];
@@ -338,8 +365,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       int4 rd = ld_stream(dy + o0);
       int4 rx = *reinterpret_cast<const int4*>(x + o0);  // re-read by bn_bwd_apply: cacheable
       int4 r2, ry;
+      unsigned mb = 0;
       if (dy2) r2 = ld_stream(dy2 + o0);
-      if (act) ry = ld_stream(y + o0);
+      if (bitmask) mb = reinterpret_cast<const uint8_t*>(y)[r * cv_total + cv];
+      else if (act) ry = ld_stream(y + o0);
       float d0[8], x0[8];
       unpack8(*reinterpret_cast<bf16x8*>(&rd), d0);
       if (dy2) {  // gradient fan-in (block output feeds the next conv AND the next skip)
@@ -348,7 +377,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 #pragma unroll
         for (int k = 0; k < 8; ++k) d0[k] += e0[k];
       }
-      if (act) {
+      if (bitmask) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d0[k] = (mb >> k) & 1u ? d0[k] : 0.f;
+      } else if (act) {
         float y0[8];
         unpack8(*reinterpret_cast<bf16x8*>(&ry), y0);
 #pragma unroll
@@ -394,7 +426,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz_in, const __nv_bfloat16
                     const __nv_bfloat16* __restrict__ dy2, const __nv_bfloat16* __restrict__ y,
                     const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dx,
                     const float* __restrict__ stat, const float* __restrict__ coef, int64_t M, int C,
-                    int rows_per_block, int act) {
+                    int rows_per_block, int act_flags) {
+  pdl_enter();
+  const bool bitmask = (act_flags & kActBitmask) != 0;
+  const int act = act_flags & 0xff;
   const int cv_total = C >> 3;
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv >= cv_total) return;
@@ -434,7 +469,16 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz_in, const __nv_bfloat16
           d1[k] += e1[k];
         }
       }
-      if (act) {
+      if (bitmask) {
+        const uint8_t* mk = reinterpret_cast<const uint8_t*>(y);
+        const unsigned m0 = mk[r * cv_total + cv];
+        const unsigned m1 = mk[(two ? r + step : r) * cv_total + cv];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          d0[k] = (m0 >> k) & 1u ? d0[k] : 0.f;
+          d1[k] = (m1 >> k) & 1u ? d1[k] : 0.f;
+        }
+      } else if (act) {
         float y0[8], y1[8];
         load8(y + o0, y0);
         load8(y + o1, y1);
@@ -463,6 +507,7 @@ template <typename PT>
 __global__ void __launch_bounds__(256)
 bias_act_kernel(const __nv_bfloat16* __restrict__ x, const PT* __restrict__ bias,
                 __nv_bfloat16* __restrict__ y, int64_t nvec, int cv_total, int act) {
+  pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
     const int cv = (int)(v % cv_total);
@@ -479,6 +524,7 @@ __global__ void __launch_bounds__(256)
 act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
                const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dz, int64_t nvec,
                int act) {
+  pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
     float d[8];
@@ -505,6 +551,7 @@ __global__ void __launch_bounds__(kBnThreads, 4)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums,
               unsigned int* __restrict__ counter, GT* __restrict__ out, int accumulate, int64_t M,
               int C, int rows_per_block) {
+  pdl_enter();
   __shared__ float red[16][kBnThreads];
   const int cv_total = C >> 3;
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
@@ -547,7 +594,7 @@ extern "C" int ddl_bn_stats(const void* x, float* sums, unsigned int* counter, f
                             float momentum, int sms, cudaStream_t st) {
   if (C % 8) return -1;
   BnDims d = bn_dims_reduce(M, C, sms, 4, 4);
-  bn_stats_kernel<<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
+  launch_pdl(bn_stats_kernel, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st, 
       (const bf16*)x, sums, counter, stat, running_mean, running_var, M, C, d.rows_per_block, eps,
       momentum);
   return (int)cudaGetLastError();
@@ -555,24 +602,24 @@ extern "C" int ddl_bn_stats(const void* x, float* sums, unsigned int* counter, f
 
 extern "C" int ddl_bn_finalize(float* sums, float* stat, float* running_mean, float* running_var,
                                int64_t M, int C, float eps, float momentum, cudaStream_t st) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, stat, running_mean, running_var, M, C,
+  launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, st, sums, stat, running_mean, running_var, M, C,
                                                      eps, momentum);
   return (int)cudaGetLastError();
 }
 
 extern "C" int ddl_bn_apply(const void* x, const void* res, void* y, const float* stat,
-                            const void* gamma, const void* beta, int param_is_bf16, int64_t M,
-                            int C, int act, int sms, cudaStream_t st) {
+                            const void* gamma, const void* beta, int param_is_bf16, void* mask_out,
+                            int64_t M, int C, int act, int sms, cudaStream_t st) {
   if (C % 8) return -1;
   BnDims d = bn_dims(M, C, sms, 8, 2);
   if (param_is_bf16)
-    bn_apply_kernel<bf16><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
-        (const bf16*)x, (const bf16*)res, (bf16*)y, stat, (const bf16*)gamma, (const bf16*)beta, M,
-        C, d.rows_per_block, act);
+    launch_pdl(bn_apply_kernel<bf16>, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st, 
+        (const bf16*)x, (const bf16*)res, (bf16*)y, stat, (const bf16*)gamma, (const bf16*)beta,
+        (uint8_t*)mask_out, M, C, d.rows_per_block, act);
   else
-    bn_apply_kernel<float><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
+    launch_pdl(bn_apply_kernel<float>, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st, 
         (const bf16*)x, (const bf16*)res, (bf16*)y, stat, (const float*)gamma, (const float*)beta,
-        M, C, d.rows_per_block, act);
+        (uint8_t*)mask_out, M, C, d.rows_per_block, act);
   return (int)cudaGetLastError();
 }
 
@@ -585,7 +632,7 @@ extern "C" int ddl_bn_bwd_reduce(const void* dy, const void* dy2, const void* y,
   if (C % 8) return -1;
   BnDims d = bn_dims_reduce(M, C, sms, 4, 4);
 #define L(PT, GT)                                                                              \
-  bn_bwd_reduce_kernel<PT, GT><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(                 \
+  launch_pdl((bn_bwd_reduce_kernel<PT, GT>), dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st,                  \
       (const bf16*)dy, (const bf16*)dy2, (const bf16*)y, (const bf16*)x, (bf16*)dz_out, stat,   \
       sums, counter, (const PT*)gamma, coef, (GT*)dgamma, (GT*)dbeta, accumulate, M, C,         \
       d.rows_per_block, act)
@@ -602,7 +649,7 @@ extern "C" int ddl_bn_bwd_apply(const void* dz_in, const void* dy, const void* d
                                 int64_t M, int C, int act, int sms, cudaStream_t st) {
   if (C % 8) return -1;
   BnDims d = bn_dims(M, C, sms, 8, 2);
-  bn_bwd_apply_kernel<<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
+  launch_pdl(bn_bwd_apply_kernel, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st, 
       (const bf16*)dz_in, (const bf16*)dy, (const bf16*)dy2, (const bf16*)y, (const bf16*)x,
       (bf16*)dx, stat, coef, M, C, d.rows_per_block, act);
   return (int)cudaGetLastError();
@@ -616,10 +663,10 @@ extern "C" int ddl_bias_act(const void* x, const void* bias, int bias_is_bf16, v
   if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
   if (blocks < 1) blocks = 1;
   if (bias_is_bf16)
-    bias_act_kernel<bf16><<<(int)blocks, 256, 0, st>>>((const bf16*)x, (const bf16*)bias, (bf16*)y,
+    launch_pdl(bias_act_kernel<bf16>, dim3((int)blocks), dim3(256), 0, st, (const bf16*)x, (const bf16*)bias, (bf16*)y,
                                                        nvec, C / 8, act);
   else
-    bias_act_kernel<float><<<(int)blocks, 256, 0, st>>>((const bf16*)x, (const float*)bias,
+    launch_pdl(bias_act_kernel<float>, dim3((int)blocks), dim3(256), 0, st, (const bf16*)x, (const float*)bias,
                                                         (bf16*)y, nvec, C / 8, act);
   return (int)cudaGetLastError();
 }
@@ -631,7 +678,7 @@ extern "C" int ddl_act_bwd(const void* dy, const void* dy2, const void* y, void*
   int64_t blocks = (nvec + 255) / 256;
   if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
   if (blocks < 1) blocks = 1;
-  act_bwd_kernel<<<(int)blocks, 256, 0, st>>>((const bf16*)dy, (const bf16*)dy2, (const bf16*)y,
+  launch_pdl(act_bwd_kernel, dim3((int)blocks), dim3(256), 0, st, (const bf16*)dy, (const bf16*)dy2, (const bf16*)y,
                                               (bf16*)dz, nvec, act);
   return (int)cudaGetLastError();
 }
@@ -642,10 +689,10 @@ extern "C" int ddl_colsum(const void* x, float* sums, unsigned int* counter, voi
   if (C % 8) return -1;
   BnDims d = bn_dims_reduce(M, C, sms, 4, 4);
   if (out_is_bf16)
-    colsum_kernel<bf16><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
+    launch_pdl(colsum_kernel<bf16>, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st, 
         (const bf16*)x, sums, counter, (bf16*)out, accumulate, M, C, d.rows_per_block);
   else
-    colsum_kernel<float><<<dim3(d.gx, d.gy), dim3(d.cvb, d.rl), 0, st>>>(
+    launch_pdl(colsum_kernel<float>, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st, 
         (const bf16*)x, sums, counter, (float*)out, accumulate, M, C, d.rows_per_block);
   return (int)cudaGetLastError();
 }

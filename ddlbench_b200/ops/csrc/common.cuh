@@ -88,4 +88,52 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   return v;
 }
 
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A training step at batch 32 is ~250 short kernels
+// in one stream/graph; with ordinary stream order each boundary costs the full launch +
+// scheduling latency AFTER the previous grid has drained.  Every kernel here
+//   * calls pdl_trigger() first: the next grid in the stream may be scheduled as soon as all
+//     CTAs of this one are resident (its launch latency and prologue overlap our tail), and
+//   * calls pdl_wait() before its first access to global memory: that blocks until the
+//     preceding grid has completed and its writes are visible.
+// Because every participating kernel waits before touching memory and cannot complete before
+// its own wait returns, completion order is still the stream order (transitively).  Kernels
+// launched without the attribute (cuDNN, NCCL) are ordinary full dependencies either way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_enter() {
+  pdl_trigger();
+  pdl_wait();
+}
+
+}  // namespace ddl
+
+// Host side: launch with the programmatic-stream-serialization attribute (DDLB_PDL=0 turns it
+// off; works under stream capture, the edge becomes a programmatic graph dependency).
+#include <cstdlib>
+namespace ddl {
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("DDLB_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 }  // namespace ddl

@@ -236,6 +236,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
   const int tile_n = blockIdx.x % tiles_n;
   const int num_k_blocks = (ep.K + BLOCK_K - 1) / BLOCK_K;
 
+  pdl_trigger();   // the next kernel's launch + prologue may overlap this grid's tail
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -252,6 +253,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // barrier init, TMEM allocation and descriptor prefetch above overlap the previous grid;
+  // from here on we read its output
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -454,8 +458,9 @@ static int launch_tn(const void* A, const void* B, void* D, int M, int N, int K,
     ep.momentum = fin->momentum;
   }
   const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
-  gemm_bf16_tn_kernel<BLOCK_N, kStages><<<tiles, kThreads, L::kDynamic, st>>>(ma, mb, md, ep);
-  return (int)cudaGetLastError();
+  cudaError_t err = launch_pdl((gemm_bf16_tn_kernel<BLOCK_N, kStages>), dim3(tiles), dim3(kThreads),
+                               (size_t)L::kDynamic, st, ma, mb, md, ep);
+  return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
 }
 
 }  // namespace gemm

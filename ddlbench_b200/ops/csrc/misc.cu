@@ -14,6 +14,7 @@ namespace ddl {
 __global__ void __launch_bounds__(256)
 u8_to_bf16_norm_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out,
                        int64_t n, int C, float4 scale, float4 shift) {
+  pdl_enter();
   // out = in * scale[c] + shift[c]   with scale = 1/(255*std), shift = -mean/std
   const float sc[4] = {scale.x, scale.y, scale.z, scale.w};
   const float sh[4] = {shift.x, shift.y, shift.z, shift.w};
@@ -53,6 +54,7 @@ template <int VEC_BYTES>
 __global__ void __launch_bounds__(256)
 revert_varlen_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                      const int64_t* __restrict__ lengths, int T, int B, int64_t row_bytes) {
+  pdl_enter();
   const int64_t vec_per_row = row_bytes / VEC_BYTES;
   const int64_t total = (int64_t)T * B * vec_per_row;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -83,6 +85,7 @@ revert_varlen_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
 // (pack_utils.cpp:13-31, `set_mask_cpp`).
 __global__ void set_mask_kernel(const int64_t* __restrict__ lengths, uint8_t* __restrict__ mask,
                                 int T, int B) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T * B) return;
   const int b = i % B, t = i / B;
@@ -96,6 +99,7 @@ __global__ void set_mask_kernel(const int64_t* __restrict__ lengths, uint8_t* __
 // looping over all rows: 32 CTAs, 17 us for 6 MB).
 __global__ void __launch_bounds__(256)
 gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int HW, int C) {
+  pdl_enter();
   __shared__ float red[8][8][33];
   const int n = blockIdx.x;
   const int cv_total = C >> 3;
@@ -132,6 +136,7 @@ gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ 
 __global__ void __launch_bounds__(256)
 gap_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int64_t nvec,
                int HW, int C) {
+  pdl_enter();
   const int cv_total = C >> 3;
   const float inv = 1.f / (float)HW;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -166,7 +171,7 @@ extern "C" int ddl_u8_to_bf16_norm(const void* in, void* out, int64_t n, int C, 
     sc[c] = 1.f / (255.f * stdv[c]);
     sh[c] = -mean[c] / stdv[c];
   }
-  u8_to_bf16_norm_kernel<<<cap_blocks(n / 16 + 1, 256, sms, 16), 256, 0, st>>>(
+  launch_pdl(u8_to_bf16_norm_kernel, dim3(cap_blocks(n / 16 + 1, 256, sms, 16)), dim3(256), 0, st, 
       (const uint8_t*)in, (__nv_bfloat16*)out, n, C, make_float4(sc[0], sc[1], sc[2], sc[3]),
       make_float4(sh[0], sh[1], sh[2], sh[3]));
   return (int)cudaGetLastError();
@@ -177,8 +182,8 @@ extern "C" int ddl_revert_varlen(const void* in, void* out, const int64_t* lengt
   if (T <= 0 || B <= 0 || row_bytes <= 0) return 0;
   const bool aligned = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
 #define L(V)                                                                                  \
-  revert_varlen_kernel<V><<<cap_blocks((int64_t)T * B * (row_bytes / V), 256, sms, 16), 256, 0, \
-                            st>>>((const uint8_t*)in, (uint8_t*)out, lengths, T, B, row_bytes)
+  launch_pdl(revert_varlen_kernel<V>, dim3(cap_blocks((int64_t)T * B * (row_bytes / V), 256, sms, 16)), dim3(256), 0, \
+                            st, (const uint8_t*)in, (uint8_t*)out, lengths, T, B, row_bytes)
   if (row_bytes % 16 == 0 && aligned) L(16);
   else if (row_bytes % 4 == 0) L(4);
   else if (row_bytes % 2 == 0) L(2);
@@ -189,13 +194,13 @@ extern "C" int ddl_revert_varlen(const void* in, void* out, const int64_t* lengt
 
 extern "C" int ddl_set_mask(const int64_t* lengths, void* mask, int T, int B, cudaStream_t st) {
   if (T * B <= 0) return 0;
-  set_mask_kernel<<<(T * B + 255) / 256, 256, 0, st>>>(lengths, (uint8_t*)mask, T, B);
+  launch_pdl(set_mask_kernel, dim3((T * B + 255) / 256), dim3(256), 0, st, lengths, (uint8_t*)mask, T, B);
   return (int)cudaGetLastError();
 }
 
 extern "C" int ddl_gap_fwd(const void* x, void* y, int N, int HW, int C, cudaStream_t st) {
   if (C % 8) return -1;
-  gap_fwd_kernel<<<dim3(N, (C / 8 + 31) / 32), dim3(32, 8), 0, st>>>(
+  launch_pdl(gap_fwd_kernel, dim3(dim3(N, (C / 8 + 31) / 32)), dim3(dim3(32, 8)), 0, st, 
       (const __nv_bfloat16*)x, (__nv_bfloat16*)y, HW, C);
   return (int)cudaGetLastError();
 }
@@ -204,7 +209,7 @@ extern "C" int ddl_gap_bwd(const void* dy, void* dx, int N, int HW, int C, int s
                            cudaStream_t st) {
   if (C % 8) return -1;
   const int64_t nvec = (int64_t)N * HW * (C / 8);
-  gap_bwd_kernel<<<cap_blocks(nvec, 256, sms, 16), 256, 0, st>>>(
+  launch_pdl(gap_bwd_kernel, dim3(cap_blocks(nvec, 256, sms, 16)), dim3(256), 0, st, 
       (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec, HW, C);
   return (int)cudaGetLastError();
 }

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                    uint8_t* __restrict__ idx, int N, int H, int W, int C, int Ho, int Wo, int k,
                    int s, int p) {
+  pdl_enter();
   // blockIdx.y = (n, ho) row of the output; x-dimension = (wo, channel-vector): 32-bit index
   // math only (64-bit div/mod per thread made the first version 4x slower than the copy time)
   const int cv_total = C >> 3;
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                    __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo,
                    int k, int s, int p) {
+  pdl_enter();
   const int cv_total = C >> 3;
   const int row_items = W * cv_total;
   for (int rowid = blockIdx.y; rowid < N * H; rowid += gridDim.y) {
@@ -114,7 +116,7 @@ extern "C" int ddl_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, 
   const int row_items = Wo * (C / 8);
   dim3 grid((row_items + 255) / 256, N * Ho > 65535 ? 65535 : N * Ho);
   (void)sms;
-  maxpool_fwd_kernel<<<grid, 256, 0, st>>>(
+  launch_pdl(maxpool_fwd_kernel, dim3(grid), dim3(256), 0, st, 
       (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)idx, N, H, W, C, Ho, Wo, k, s, p);
   return (int)cudaGetLastError();
 }
@@ -126,7 +128,7 @@ extern "C" int ddl_maxpool_bwd(const void* dy, const void* idx, void* dx, int N,
   const int row_items = W * (C / 8);
   dim3 grid((row_items + 255) / 256, N * H > 65535 ? 65535 : N * H);
   (void)sms;
-  maxpool_bwd_kernel<<<grid, 256, 0, st>>>(
+  launch_pdl(maxpool_bwd_kernel, dim3(grid), dim3(256), 0, st, 
       (const __nv_bfloat16*)dy, (const uint8_t*)idx, (__nv_bfloat16*)dx, N, H, W, C, Ho, Wo, k, s,
       p);
   return (int)cudaGetLastError();

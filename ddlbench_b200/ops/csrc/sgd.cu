@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(256)
 sgd_flat_kernel(float* __restrict__ master, float* __restrict__ mom,
                 const GradT* __restrict__ grad, WT* __restrict__ w_out,
                 WT* __restrict__ w_out2, const float* __restrict__ hyper, int64_t n) {
+  pdl_enter();
   const float lr = hyper[0], mu = hyper[1], wd = hyper[2], gs = hyper[3];
   const int64_t nvec = n >> 3;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -87,6 +88,7 @@ sgd_flat_kernel(float* __restrict__ master, float* __restrict__ mom,
 // (pipedream-fork/profiler/translation/seq2seq/utils.py:209-219).
 template <typename T>
 __global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ x, float* out, int64_t n) {
+  pdl_enter();
   float acc = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -123,16 +125,16 @@ extern "C" int ddl_sgd_flat(void* master, void* mom, const void* grad, int grad_
   float* M = (float*)master;
   float* V = (float*)mom;
   if (grad_is_bf16 && w_is_bf16)
-    sgd_flat_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>(
+    launch_pdl((sgd_flat_kernel<__nv_bfloat16, __nv_bfloat16>), dim3(grid), dim3(256), 0, stream, 
         M, V, (const __nv_bfloat16*)grad, (__nv_bfloat16*)w_out, (__nv_bfloat16*)w_out2, hyper, n);
   else if (grad_is_bf16 && !w_is_bf16)
-    sgd_flat_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>(
+    launch_pdl((sgd_flat_kernel<__nv_bfloat16, float>), dim3(grid), dim3(256), 0, stream, 
         M, V, (const __nv_bfloat16*)grad, (float*)w_out, (float*)w_out2, hyper, n);
   else if (!grad_is_bf16 && w_is_bf16)
-    sgd_flat_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>(
+    launch_pdl((sgd_flat_kernel<float, __nv_bfloat16>), dim3(grid), dim3(256), 0, stream, 
         M, V, (const float*)grad, (__nv_bfloat16*)w_out, (__nv_bfloat16*)w_out2, hyper, n);
   else
-    sgd_flat_kernel<float, float><<<grid, 256, 0, stream>>>(
+    launch_pdl((sgd_flat_kernel<float, float>), dim3(grid), dim3(256), 0, stream, 
         M, V, (const float*)grad, (float*)w_out, (float*)w_out2, hyper, n);
   return (int)cudaGetLastError();
 }
@@ -143,8 +145,8 @@ extern "C" int ddl_sumsq(const void* x, int is_bf16, float* out, int64_t n, int 
   if (n <= 0) return 0;
   int grid = grid_for(n, sms);
   if (is_bf16)
-    sumsq_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, out, n);
+    launch_pdl(sumsq_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, out, n);
   else
-    sumsq_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, out, n);
+    launch_pdl(sumsq_kernel<float>, dim3(grid), dim3(256), 0, stream, (const float*)x, out, n);
   return (int)cudaGetLastError();
 }

@@ -46,6 +46,7 @@ xent_fwd_bwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ ta
                     T* __restrict__ dlogits, float* __restrict__ row_stats,
                     float* __restrict__ out, unsigned int* __restrict__ ticket, int rows,
                     int C, float smoothing, float grad_scale) {
+  pdl_enter();
   extern __shared__ float row[];
   __shared__ float red[BLOCK / 32];
   __shared__ bool is_last;
@@ -127,7 +128,7 @@ extern "C" int ddl_xent(const void* logits, int is_bf16, const int64_t* target, 
   const bool cache = (size_t)C * sizeof(float) <= 48 * 1024;
   const size_t smem = cache ? (size_t)C * sizeof(float) : 0;
 #define LAUNCH(T, CACHE)                                                                      \
-  xent_fwd_bwd_kernel<T, BLOCK, CACHE><<<rows, BLOCK, smem, stream>>>(                        \
+  launch_pdl((xent_fwd_bwd_kernel<T, BLOCK, CACHE>), dim3(rows), dim3(BLOCK), smem, stream,                         \
       (const T*)logits, target, (T*)dlogits, row_stats, out, ticket, rows, C, smoothing,      \
       grad_scale)
   if (is_bf16) {

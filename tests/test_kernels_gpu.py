@@ -103,6 +103,23 @@ def test_bn_forward_backward(n, c, h, w, act, has_res):
     if has_res:
         errz = (dz.float() - dz_r.float()).abs()
         assert (errz > 0.05).float().mean().item() < 2e-3
+    if act:
+        # 1-bit activation mask written by the forward: same backward as with y, bit for bit
+        mask = torch.zeros(x.numel() // 8, dtype=torch.uint8, device=DEV)
+        y2, stat2 = ops.bn_forward(x, res, gamma, beta, rm, rv, 1e-5, 0.1, act, ws, mask_out=mask)
+        bits = ((mask.view(-1, 1) >> torch.arange(8, device=DEV, dtype=torch.uint8)) & 1).bool()
+        yf = y2.permute(0, 2, 3, 1).reshape(-1).float()
+        expect = (yf > 0) & (yf < 6) if act == 2 else yf > 0
+        assert torch.equal(bits.view(-1), expect)
+        dg1, db1, dg2, db2 = (torch.empty_like(dg) for _ in range(4))
+        dx1, dz1 = ops.bn_backward(dy, dy2, y2, x, stat2, gamma, act, has_res, dg1, db1, False, ws)
+        dx2, dz2 = ops.bn_backward(dy, dy2, y2, x, stat2, gamma, act, has_res, dg2, db2, False, ws,
+                                   mask=mask)
+        # identical up to the (non-deterministic) order of the partial-sum atomics
+        assert (dx2.float() - dx1.float()).abs().max().item() <= \
+            2e-2 * max(dx1.float().abs().max().item(), 1e-3)
+        if has_res:
+            assert torch.equal(dz2, dz1)
 
 
 def test_bn_eval_mode():
