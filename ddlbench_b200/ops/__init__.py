@@ -138,6 +138,11 @@ def _nhwc_ok(x: torch.Tensor) -> bool:
             (x.dim() == 2 or x.is_contiguous(memory_format=torch.channels_last)))
 
 
+# Single-pass cluster kernels (csrc/bn_cluster.cu).  Per kernel they beat the two-kernel path on
+# the 7x7/14x14 layers (ncu: 10-14 us vs 15-24 us) but inside the training graph the step time is
+# unchanged: 8/16-CTA clusters need whole-GPC slots and stop overlapping with the weight-gradient
+# kernels on the side stream.  Off by default; DDLB_BN_CLUSTER=1 enables them.
+BN_CLUSTER_FUSED = os.environ.get("DDLB_BN_CLUSTER", "0") == "1"
 BN_REPLICAS = 8  # must match DDL_BN_REPLICAS (csrc/common.cuh); checked at first use
 
 
@@ -173,6 +178,13 @@ def bn_forward(x, res, gamma, beta, running_mean, running_var, eps: float, momen
             ws = BnWorkspace(C, x.device)
         stat = stat_ready if stat_ready is not None else \
             torch.empty(2 * C, dtype=torch.float32, device=x.device)
+        if stat_ready is None and not stats_ready and BN_CLUSTER_FUSED:
+            # single pass on a thread-block cluster (statistics + apply, x read once)
+            y = torch.empty_like(x)
+            if e.bn_fwd_fused(x, res, y, mask_out, stat, running_mean, running_var, gamma, beta,
+                              M, C, eps, momentum, act):
+                _count()
+                return y, stat.view(2, C)
         if stat_ready is not None:
             _count(-1)      # (mean, invstd) were finalized inside the producing GEMM
         elif stats_ready:
@@ -204,6 +216,13 @@ def bn_backward(dy, dy2, y, x, stat, gamma, act: int, want_dz: bool, dgamma_out,
         yy = y if act != ACT_NONE else None
         if mask is not None and act != ACT_NONE:
             yy, act = mask, act | ACT_BITMASK
+        if BN_CLUSTER_FUSED:
+            # single pass on a thread-block cluster when a channel slab fits in its shared memory
+            dx = torch.empty_like(x)
+            if e.bn_bwd_fused(dy, dy2, yy, x, dz, dx, stat_f, gamma, dgamma_out, dbeta_out,
+                              accumulate, M, C, act):
+                _count()
+                return dx, dz
         e.bn_bwd_reduce(dy, dy2, yy, x, dz, stat_f, ws.sums, ws.counter, gamma, ws.coef,
                         dgamma_out, dbeta_out, accumulate, M, C, act)
         dx = torch.empty_like(x)

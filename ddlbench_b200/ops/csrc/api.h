@@ -37,6 +37,15 @@ int ddl_bn_bwd_reduce(const void* dy, const void* dy2, const void* y, const void
 int ddl_bn_bwd_apply(const void* dz_in, const void* dy, const void* dy2, const void* y, const void* x, void* dx,
                      const float* stat, const float* coef, int64_t M, int C, int act, int sms,
                      cudaStream_t st);
+int ddl_bn_bwd_fused(const void* dy, const void* dy2, const void* ymask, const void* x, void* dz_out,
+                     void* dx, const float* stat, const void* gamma, int param_is_bf16, void* dgamma,
+                     void* dbeta, int grad_is_bf16, int accumulate, int64_t M, int C, int act_flags,
+                     int sms, cudaStream_t st);
+int ddl_bn_fwd_fused(const void* x, const void* res, void* y, void* mask_out, float* stat_out,
+                     float* running_mean, float* running_var, const void* gamma, const void* beta,
+                     int param_is_bf16, int64_t M, int C, float eps, float momentum, int act, int sms,
+                     cudaStream_t st);
+int ddl_bn_cluster_plan(int64_t M, int C, int tiles, int sms, int* rows_per_cta, int64_t* smem);
 int ddl_bias_act(const void* x, const void* bias, int bias_is_bf16, void* y, int64_t M, int C,
                  int act, int sms, cudaStream_t st);
 int ddl_act_bwd(const void* dy, const void* dy2, const void* y, void* dz, int64_t n, int act,

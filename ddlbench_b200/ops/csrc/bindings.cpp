@@ -132,6 +132,40 @@ void bn_bwd_apply(c10::optional<at::Tensor> dz_in, c10::optional<at::Tensor> dy,
                          sm_count(), cur_stream()),
         "bn_bwd_apply");
 }
+// cluster-fused single-pass forms; return false when the layer does not fit (caller falls back)
+bool bn_bwd_fused(at::Tensor dy, c10::optional<at::Tensor> dy2, c10::optional<at::Tensor> ymask,
+                  at::Tensor x, c10::optional<at::Tensor> dz_out, at::Tensor dx, at::Tensor stat,
+                  at::Tensor gamma, at::Tensor dgamma, at::Tensor dbeta, bool accumulate, int64_t M,
+                  int64_t C, int64_t act_flags) {
+  c10::cuda::CUDAGuard g(x.device());
+  const int rc = ddl_bn_bwd_fused(dy.data_ptr(), optr(dy2), optr(ymask), x.data_ptr(), optr(dz_out),
+                                  dx.data_ptr(), stat.data_ptr<float>(), gamma.data_ptr(),
+                                  is_bf16(gamma), dgamma.data_ptr(), dbeta.data_ptr(),
+                                  is_bf16(dgamma), accumulate, M, (int)C, (int)act_flags, sm_count(),
+                                  cur_stream());
+  if (rc == -12345) return false;
+  check(rc, "bn_bwd_fused");
+  return true;
+}
+bool bn_fwd_fused(at::Tensor x, c10::optional<at::Tensor> res, at::Tensor y,
+                  c10::optional<at::Tensor> mask_out, at::Tensor stat,
+                  c10::optional<at::Tensor> rmean, c10::optional<at::Tensor> rvar, at::Tensor gamma,
+                  at::Tensor beta, int64_t M, int64_t C, double eps, double mom, int64_t act) {
+  c10::cuda::CUDAGuard g(x.device());
+  const int rc = ddl_bn_fwd_fused(x.data_ptr(), optr(res), y.data_ptr(), optr(mask_out),
+                                  stat.data_ptr<float>(), (float*)optr(rmean), (float*)optr(rvar),
+                                  gamma.data_ptr(), beta.data_ptr(), is_bf16(gamma), M, (int)C,
+                                  (float)eps, (float)mom, (int)act, sm_count(), cur_stream());
+  if (rc == -12345) return false;
+  check(rc, "bn_fwd_fused");
+  return true;
+}
+std::vector<int64_t> bn_cluster_plan(int64_t M, int64_t C, int64_t tiles) {
+  int rows = 0;
+  int64_t smem = 0;
+  const int r = ddl_bn_cluster_plan(M, (int)C, (int)tiles, sm_count(), &rows, &smem);
+  return {r & 0xff, (r >> 8) & 0xff, (r >> 16) & 1, rows, smem};
+}
 void bias_act(at::Tensor x, c10::optional<at::Tensor> bias, at::Tensor y, int64_t M, int64_t C,
               int64_t act) {
   c10::cuda::CUDAGuard g(x.device());
@@ -528,6 +562,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_apply", &bn_apply);
   m.def("bn_bwd_reduce", &bn_bwd_reduce);
   m.def("bn_bwd_apply", &bn_bwd_apply);
+  m.def("bn_bwd_fused", &bn_bwd_fused);
+  m.def("bn_fwd_fused", &bn_fwd_fused);
+  m.def("bn_cluster_plan", &bn_cluster_plan);
   m.def("bias_act", &bias_act);
   m.def("act_bwd", &act_bwd);
   m.def("colsum", &colsum);

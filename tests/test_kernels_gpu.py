@@ -65,7 +65,11 @@ def test_xent(rows, C, dtype, smoothing):
                                      (2, 960, 7, 7), (3, 1280, 5, 5), (16, 8, 9, 11)])
 @pytest.mark.parametrize("act", [0, 1, 2])
 @pytest.mark.parametrize("has_res", [False, True])
-def test_bn_forward_backward(n, c, h, w, act, has_res):
+@pytest.mark.parametrize("fused", [False, True])
+def test_bn_forward_backward(n, c, h, w, act, has_res, fused, monkeypatch):
+    # fused=True: single-pass cluster kernels (where a channel slab fits in a cluster's shared
+    # memory; (32, 64, 56, 56) does not and exercises the fallback), False: two-kernel path
+    monkeypatch.setattr(ops, "BN_CLUSTER_FUSED", fused)
     torch.manual_seed(2)
     x = _nhwc(n, c, h, w, scale=1.5, shift=0.3)
     res = _nhwc(n, c, h, w) if has_res else None
@@ -120,6 +124,52 @@ def test_bn_forward_backward(n, c, h, w, act, has_res):
             2e-2 * max(dx1.float().abs().max().item(), 1e-3)
         if has_res:
             assert torch.equal(dz2, dz1)
+
+
+@pytest.mark.parametrize("m,c,tiles,ok", [(32 * 14 * 14, 1024, 2, True), (32 * 7 * 7, 2048, 2, True),
+                                          (32 * 28 * 28, 128, 2, True), (32 * 28 * 28, 512, 1, True),
+                                          (32 * 56 * 56, 64, 2, False), (32 * 112 * 112, 64, 1, False)])
+def test_bn_cluster_plan(m, c, tiles, ok):
+    sv, cl, good, rows, smem = ops.ext().bn_cluster_plan(m, c, tiles)
+    assert ok or not good            # 56x56 / 112x112 slabs can never fit a cluster
+    if good:
+        assert sv in (4, 8, 16) and cl in (1, 2, 4, 8, 16) and rows * cl >= m
+        assert smem <= 227 * 1024 and rows * sv * 16 * tiles <= smem
+
+
+@pytest.mark.parametrize("n,c,h,w", [(32, 1024, 14, 14), (32, 128, 28, 28), (32, 512, 28, 28)])
+def test_bn_cluster_large_layers(n, c, h, w, monkeypatch):
+    """ResNet-50 layer2/3 shapes at the benchmark batch: cluster path vs fp32 reference."""
+    monkeypatch.setattr(ops, "BN_CLUSTER_FUSED", True)
+    torch.manual_seed(4)
+    x = _nhwc(n, c, h, w, scale=1.3, shift=-0.2)
+    res = _nhwc(n, c, h, w)
+    gamma = (torch.rand(c, device=DEV) + 0.5).to(torch.bfloat16)
+    beta = (torch.randn(c, device=DEV) * 0.2).to(torch.bfloat16)
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    mask = torch.zeros(x.numel() // 8, dtype=torch.uint8, device=DEV)
+    before = ops.launches
+    y, stat = ops.bn_forward(x, res, gamma, beta, rm, rv, 1e-5, 0.1, 1, ops.BnWorkspace(c, DEV),
+                             mask_out=mask)
+    fits = ops.ext().bn_cluster_plan(n * h * w, c, 2)[2]       # x and res tiles
+    assert ops.launches - before == (1 if fits else 2)          # one kernel, not stats + apply
+    stat_ref = ref.bn_stat(x, 1e-5)
+    y_ref = ref.bn_apply(x, res, stat_ref, gamma, beta, 1)
+    torch.testing.assert_close(stat.view(2, c), stat_ref, rtol=2e-3, atol=1e-3)
+    torch.testing.assert_close(y.float(), y_ref.float(), rtol=2e-2, atol=2e-2)
+    dy, dy2 = _nhwc(n, c, h, w), _nhwc(n, c, h, w)
+    dg = torch.empty(c, device=DEV, dtype=torch.bfloat16)
+    db = torch.empty(c, device=DEV, dtype=torch.bfloat16)
+    before = ops.launches
+    dx, dz = ops.bn_backward(dy, dy2, y, x, stat, gamma, 1, True, dg, db, False, None, mask=mask)
+    fits = ops.ext().bn_cluster_plan(n * h * w, c, 3)[2]       # dy, dy2 and x tiles
+    assert ops.launches - before == (1 if fits else 2)
+    dx_r, dz_r, dg_r, db_r = ref.bn_backward(dy, dy2, y, x, stat_ref, gamma, 1, True)
+    torch.testing.assert_close(dg.float(), dg_r, rtol=3e-2, atol=3e-2 * max(dg_r.abs().max().item(), 1))
+    torch.testing.assert_close(db.float(), db_r, rtol=3e-2, atol=3e-2 * max(db_r.abs().max().item(), 1))
+    assert torch.equal(dz.float(), dz_r.to(torch.bfloat16).float())
+    err = (dx.float() - dx_r.float()).abs()
+    assert (err > 0.05 * max(dx_r.float().abs().max().item(), 1e-3)).float().mean().item() < 2e-3
 
 
 def test_bn_eval_mode():
