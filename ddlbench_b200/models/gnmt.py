@@ -241,6 +241,13 @@ class GNMT(nn.Module):
                     prev.output_names.append(name)
                     if name not in prev.input_names and not any(name in o for _, _, _, o in prev.spec):
                         prev.input_names.append(name)
+        # the wire format of a boundary is the producer's output order
+        for k in range(1, len(stages)):
+            prev_out = stages[k - 1].output_names
+            extra = [x for x in prev_out if x not in stages[k].input_names]
+            assert not [x for x in stages[k].input_names if x not in prev_out]
+            stages[k].pass_through = extra            # received but neither read nor forwarded
+            stages[k].input_names = list(prev_out)
         return stages
 
     def profile_graph(self, times_ms: Optional[Dict[str, Tuple[float, float]]] = None):
