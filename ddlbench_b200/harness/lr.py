@@ -9,6 +9,10 @@
 """
 from __future__ import annotations
 
+import math
+
+import torch
+
 from ..config import RunConfig
 
 
@@ -52,3 +56,37 @@ def pipedream_lr(base_lr: float, policy: str, epoch: int, total_epochs: int, ste
     if policy == "exponential":
         return stage_base * (0.97 ** epoch)
     return stage_base
+
+
+class WarmupMultiStepLR(torch.optim.lr_scheduler.LRScheduler):
+    """GNMT learning-rate policy (``profiler/translation/seq2seq/train/lr_scheduler.py:6-47``):
+    exponential warm-up over ``warmup_steps`` iterations (from 1% of the base rate), then the
+    base rate until ``remain_steps``, then a decay by ``decay_factor`` every ``decay_interval``
+    iterations, at most ``decay_steps`` times."""
+
+    def __init__(self, optimizer, iterations: int, warmup_steps: int = 200, remain_steps=0.666,
+                 decay_interval=None, decay_steps: int = 4, decay_factor: float = 0.5, last_epoch=-1):
+        def _abs(v):
+            return int(v * iterations) if isinstance(v, float) else int(v)
+        self.warmup_steps = _abs(warmup_steps)
+        self.remain_steps = _abs(remain_steps)
+        if decay_interval is None:
+            left = max(iterations - self.remain_steps, 0)
+            decay_interval = max(left // max(decay_steps, 1), 1)
+        self.decay_interval = _abs(decay_interval)
+        self.decay_steps, self.decay_factor = decay_steps, decay_factor
+        if self.warmup_steps > self.remain_steps:
+            self.warmup_steps = self.remain_steps
+        super().__init__(optimizer, last_epoch)
+
+    def factor(self, step: int) -> float:
+        if step <= self.warmup_steps and self.warmup_steps > 0:
+            return math.exp(math.log(0.01) / self.warmup_steps * (self.warmup_steps - step))
+        if step >= self.remain_steps:
+            n = min((step - self.remain_steps) // self.decay_interval + 1, self.decay_steps)
+            return self.decay_factor ** n
+        return 1.0
+
+    def get_lr(self):
+        f = self.factor(self.last_epoch)
+        return [base * f for base in self.base_lrs]

@@ -214,6 +214,8 @@ class FusedDataParallel:
         self.comm_stream = torch.cuda.Stream(device=st.device) if overlap else None
         self._ev_pool: List[torch.cuda.Event] = []
         self._launched = 0
+        self.log_reduce_times = os.environ.get("DDLB_LOG_REDUCE_TIMES", "0") == "1"
+        self._reduce_events = []
         executor.on_bucket_ready = self._on_bucket
         # average over ranks folded into grad_scale
         st.set_grad_scale(1.0 / ctx.world)
@@ -241,6 +243,10 @@ class FusedDataParallel:
             ev = torch.cuda.Event()
             ev.record(main)
             self.comm_stream.wait_event(ev)
+        log = self.log_reduce_times and not torch.cuda.is_current_stream_capturing()
+        if log:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
         with torch.cuda.stream(stream):
             self.ops.ext().ar_sgd_twoshot(
                 self.g_sym.ptrs, wsym.ptrs, self.ctx.flags.ptrs, self.g_sym.mc_ptr, wsym.mc_ptr,
@@ -248,6 +254,9 @@ class FusedDataParallel:
                 self.ctx.status, bucket.offset, bucket.length // st.world, st.rank, self.blocks,
                 use_mm)
             self.ops._count()
+        if log:
+            e1.record(stream)
+            self._reduce_events.append((b, bucket.length, e0, e1))
         self._launched += 1
 
     def finish_step(self) -> None:
@@ -256,6 +265,23 @@ class FusedDataParallel:
             ev = torch.cuda.Event()
             ev.record(self.comm_stream)
             torch.cuda.current_stream(self.ex.store.device).wait_event(ev)
+        if self._reduce_events:
+            self.flush_reduce_log()
+
+    def flush_reduce_log(self, out=print) -> None:
+        """Per-bucket all-reduce timing lines (``DDLB_LOG_REDUCE_TIMES=1``, eager mode only) —
+        the information the reference gets from its patched DDP's ``log_reduce_times=True``
+        (``profiler/image_classification/main.py:248-249``), parsed by
+        ``utils.sparsity.extract_reduce_times``.  Times are device times relative to the first
+        bucket of the step, in seconds."""
+        evs, self._reduce_events = self._reduce_events, []
+        if not evs:
+            return
+        evs[-1][3].synchronize()
+        base = evs[0][2]
+        for b, n, e0, e1 in evs:
+            out("allreduce[%d] start=%.6f end=%.6f elements=%d" % (
+                b, base.elapsed_time(e0) / 1e3, base.elapsed_time(e1) / 1e3, n))
 
     def broadcast_from(self, root: int = 0) -> None:
         """Make every rank start from rank ``root``'s weights (hvd.broadcast_parameters) and

@@ -49,13 +49,47 @@ def table(parsed: Dict[str, list]) -> str:
     return "\n".join(out)
 
 
+def parse_gnmt(lines: List[str]) -> Dict[str, list]:
+    """GNMT logs (``runtime/scripts/process_output_gnmt.py``): epoch times plus the BLEU score
+    reported after each epoch (``Epoch <e>: BLEU <v>``) and the last training loss."""
+    epoch_time, bleu, loss = [], [], []
+    last_loss = float("nan")
+    for ln in lines:
+        m = re.search(r"Epoch (\d+): ([\d.]+) seconds", ln)
+        if m:
+            epoch_time.append(float(m.group(2)) / 3600.0)
+            loss.append(last_loss)
+            continue
+        m = re.search(r"BLEU\s*=?\s*([\d.]+)", ln)
+        if m:
+            bleu.append(float(m.group(1)))
+            continue
+        m = re.search(r"Loss ([\d.]+)", ln)
+        if m:
+            last_loss = float(m.group(1))
+    return {"epoch_hours": epoch_time, "bleu": bleu, "loss": loss}
+
+
+def table_gnmt(parsed: Dict[str, list]) -> str:
+    out = ["Epoch#\tRuntime\tBLEU\tLoss\tEpoch"]
+    run = 0.0
+    for i, t in enumerate(parsed["epoch_hours"]):
+        run += t
+        b = parsed["bleu"][i] if i < len(parsed["bleu"]) else float("nan")
+        out.append("%d\t%.3f\t%.2f\t%.4f\t%.3f" % (i, run, b, parsed["loss"][i], t))
+    return "\n".join(out)
+
+
 def main(argv=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
+    gnmt = "--gnmt" in argv
+    argv = [x for x in argv if x != "--gnmt"]
     if len(argv) != 1:
-        print("python -m ddlbench_b200.utils.process_output <output.log>")
+        print("python -m ddlbench_b200.utils.process_output [--gnmt] <output.log>")
         return 1
     with open(argv[0]) as f:
-        print(table(parse([ln.rstrip("\n") for ln in f])))
+        lines = [ln.rstrip("\n") for ln in f]
+    print(table_gnmt(parse_gnmt(lines)) if gnmt else table(parse(lines)))
     return 0
 
 

@@ -174,3 +174,68 @@ def test_runtime_stats_format():
     assert lines[0] == "Forward Stats:" and "\t send_tensors_size 40.000 bytes" in lines
     st.reset_stats()
     assert st.stats["send_tensors_size"] == 0
+
+
+def test_gnmt_lr_schedule_and_fp_optimizers():
+    from ddlbench_b200.harness.lr import WarmupMultiStepLR
+    from ddlbench_b200.utils.fp_optimizer import Fp16Optimizer, Fp32Optimizer, flat_grad_norm
+    m = nn.Linear(4, 4)
+    opt = torch.optim.SGD(m.parameters(), lr=1.0)
+    sch = WarmupMultiStepLR(opt, iterations=100, warmup_steps=10, remain_steps=60, decay_interval=10,
+                            decay_steps=3, decay_factor=0.5)
+    lrs = []
+    for _ in range(100):
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sch.step()
+    assert abs(lrs[0] - 0.01) < 1e-6 and lrs[5] < lrs[9] < 1.0 + 1e-9 and lrs[30] == 1.0
+    assert lrs[60] == 0.5 and lrs[70] == 0.25 and lrs[99] == 0.125
+    # fp32 wrapper clips to the requested norm
+    w = Fp32Optimizer(m, grad_clip=0.1)
+    loss = (m(torch.ones(2, 4)) * 100).sum()
+    norm = w.step(loss, torch.optim.SGD(m.parameters(), lr=0.0))
+    assert norm > 0.1
+    # bf16 model + fp32 master copy stays in sync
+    mb = nn.Linear(4, 4).to(torch.bfloat16)
+    w16 = Fp16Optimizer(mb, grad_clip=5.0)
+    o16 = torch.optim.SGD(w16.fp32_params, lr=0.1)
+    before = mb.weight.detach().clone()
+    w16.step(mb(torch.ones(2, 4, dtype=torch.bfloat16)).float().sum(), o16)
+    assert not torch.equal(before, mb.weight) and w16.master.dtype == torch.float32
+    assert flat_grad_norm(mb.parameters()) == 0.0
+
+
+def test_gnmt_partition_tools_and_log_table(tmp_path):
+    from ddlbench_b200.models.gnmt import GNMT
+    from ddlbench_b200.partition import gnmt_tools
+    m = GNMT(vocab_size=64, hidden_size=16, num_layers=4)
+    times = gnmt_tools.profile_gnmt(m, batch_size=2, seq_len=4, iters=1)
+    assert set(times) == {name for name, _, _, _ in m.spec} and all(f >= 0 for f, _ in times.values())
+    cuts, reps = gnmt_tools.partition(m, 4, times, batch_size=2, seq_len=4, bandwidth=1e12, straight=True)
+    assert cuts[-1] == len(m.spec) and len(cuts) == len(reps) and sum(reps) <= 4
+    stages = m.split(len(cuts), cuts)
+    assert sum(len(s.spec) for s in stages) == len(m.spec)
+    d = gnmt_tools.write_confs(str(tmp_path), "gnmt", m, cuts, reps)
+    import json
+    conf = json.load(open(os.path.join(d, "hybrid_conf.json")))
+    assert len(conf["module_to_stage_map"]) == len(m.spec) + 1 and conf["cuts"] == cuts
+    assert os.path.exists(os.path.join(d, "mp_conf.json")) and os.path.exists(os.path.join(d, "dp_conf.json"))
+    parsed = process_output.parse_gnmt(["Epoch: [0][0/5]\tTime 0.1\tLoss 9.5000", "Epoch 0: 36.0 seconds",
+                                        "Epoch 0: BLEU 12.50"])
+    assert parsed["bleu"] == [12.5] and parsed["loss"] == [9.5]
+    assert process_output.table_gnmt(parsed).splitlines()[1].split("\t")[2] == "12.50"
+
+
+def test_imagenet_subset_tool(tmp_path):
+    import subprocess
+    import sys
+    src = tmp_path / "src"
+    for split in ("train", "val"):
+        for c in ("n01", "n02", "n03"):
+            (src / split / c).mkdir(parents=True)
+            for i in range(3):
+                (src / split / c / ("%d.JPEG" % i)).write_bytes(b"x")
+    r = subprocess.run([sys.executable, "tools/imagenet_subset.py", str(src), str(tmp_path / "dst"),
+                        "--classes", "2", "--per-class", "2"], capture_output=True, text=True)
+    assert r.returncode == 0 and "copied 8 files of 2 classes" in r.stdout
+    assert len(os.listdir(tmp_path / "dst" / "train")) == 2
