@@ -35,6 +35,8 @@ def parse(argv=None):
     ap.add_argument("--no-rank-args", action="store_true",
                     help="do not append --rank/--local_rank (env contract only)")
     ap.add_argument("--terminate", metavar="PIDFILE", default=None)
+    ap.add_argument("-m", "--module", action="store_true",
+                    help="training_script is a module name (python -m)")
     ap.add_argument("training_script", nargs="?")
     ap.add_argument("training_script_args", nargs=argparse.REMAINDER)
     return ap.parse_args(argv)
@@ -86,7 +88,8 @@ def main(argv=None) -> int:
         env = dict(os.environ, MASTER_ADDR=a.master_addr, MASTER_PORT=str(a.master_port),
                    WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(local),
                    LOCAL_WORLD_SIZE=str(a.nproc_per_node))
-        cmd = [sys.executable, "-u", a.training_script] + list(a.training_script_args)
+        cmd = [sys.executable, "-u"] + (["-m"] if a.module else []) + [a.training_script] + \
+            list(a.training_script_args)
         if not a.no_rank_args:
             cmd += ["--rank", str(rank), "--local_rank", str(local)]
         procs.append(subprocess.Popen(cmd, env=env))
