@@ -473,6 +473,81 @@ class AddAct(Op):
         return [dz if n else None for n in need]
 
 
+class BnAct(Op):
+    """y = act(BN(x)) for a BatchNorm that does not directly follow a convolution
+    (pre-activation blocks: DenseNet, NASNet).  Same kernels as ``ConvBnAct``."""
+    kind = "bn_act"
+
+    def __init__(self, name, inputs, output, bn: nn.BatchNorm2d, act: int, bn_name: str):
+        super().__init__(name, inputs, output)
+        self.act = act
+        self.eps, self.momentum = bn.eps, (bn.momentum if bn.momentum is not None else 0.1)
+        self.channels = bn.num_features
+        self.k_g, self.k_b = bn_name + ".weight", bn_name + ".bias"
+        self.k_rm, self.k_rv = bn_name + ".running_mean", bn_name + ".running_var"
+        self.params = [self.k_g, self.k_b]
+        self._init = {self.k_g: bn.weight.detach().float(), self.k_b: bn.bias.detach().float()}
+        self._bufs = {self.k_rm: bn.running_mean.detach().float().clone(),
+                      self.k_rv: bn.running_var.detach().float().clone()}
+        self.ws: Optional[ops.BnWorkspace] = None
+
+    def param_specs(self):
+        from .store import ParamSpec
+        return [ParamSpec(self.k_g, (self.channels,), self._init[self.k_g], False, self.order),
+                ParamSpec(self.k_b, (self.channels,), self._init[self.k_b], False, self.order)]
+
+    def buffers(self):
+        return self._bufs
+
+    def to_device(self, device):
+        if torch.device(device).type == "cuda":
+            self.ws = ops.BnWorkspace(self.channels, device)
+
+    def forward(self, P, B, xs, ctx, training):
+        x = xs[0]
+        mom = self.momentum * BN_MOMENTUM_SCALE[0]
+        mask = None
+        if training and self.act != ACT_NONE and ACT_BITMASK_ON and ops._nhwc_ok(x):
+            mask = torch.empty(x.numel() // 8, dtype=torch.uint8, device=x.device)
+        y, stat = ops.bn_forward(x, None, P[self.k_g], P[self.k_b], B[self.k_rm], B[self.k_rv],
+                                 self.eps, mom, self.act, self.ws, training=training, mask_out=mask)
+        if training:
+            ctx["x"], ctx["stat"], ctx["mask"] = x, stat, mask
+            ctx["y"] = y if self.act != ACT_NONE else None
+        return y
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        dy2 = dys[1] if len(dys) > 1 else None
+        if len(dys) > 2:
+            dys = [_sum_grads(dys[:-1]), dys[-1]]
+            dy2 = dys[1]
+        dx, _ = ops.bn_backward(dys[0], dy2, ctx["y"], ctx["x"], ctx["stat"], P[self.k_g], self.act,
+                                False, G[self.k_g], G[self.k_b], accumulate, self.ws,
+                                mask=ctx.get("mask"))
+        return [dx]
+
+
+class ConcatOp(Op):
+    """Channel concatenation (DenseNet / Inception / SqueezeNet / NASNet joins)."""
+    kind = "concat"
+
+    def __init__(self, name, inputs, output, dim: int = 1):
+        super().__init__(name, inputs, output)
+        self.dim = dim
+
+    def forward(self, P, B, xs, ctx, training):
+        if training:
+            ctx["sizes"] = [x.shape[self.dim] for x in xs]
+            ctx["cl"] = xs[0].dim() == 4 and xs[0].is_contiguous(memory_format=torch.channels_last)
+        return torch.cat(list(xs), dim=self.dim)
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        dy = _sum_grads(dys)
+        parts = torch.split(dy, ctx["sizes"], dim=self.dim)
+        fmt = torch.channels_last if ctx["cl"] else torch.contiguous_format
+        return [p.contiguous(memory_format=fmt) if n else None for p, n in zip(parts, need)]
+
+
 class ModuleOp(Op):
     """Fallback: any ``nn.Module`` runs under a local autograd tape, with its parameters
     aliased to views of the flat store.  Keeps the engine complete for arbitrary layers

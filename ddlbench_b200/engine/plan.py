@@ -159,6 +159,16 @@ def compile_plan(model: LayerGraphModel, start: int = 0, stop: Optional[int] = N
                 act, last = _act_of(nodes[j].op), j
                 used.add(j)
             out.append(E.AddAct(n.name, list(n.inputs), nodes[last].name, act))
+        elif isinstance(m, nn.BatchNorm2d) and m.track_running_stats and len(n.inputs) == 1:
+            act, last = ACT_NONE, i
+            j = sole_next(i)
+            if j is not None and _act_of(nodes[j].op) is not None and \
+                    nodes[j].inputs == (n.name,):
+                act, last = _act_of(nodes[j].op), j
+                used.add(j)
+            out.append(E.BnAct(n.name, [n.inputs[0]], nodes[last].name, m, act, pname(n)))
+        elif type(m).__name__ == "Concat" and hasattr(m, "dim"):
+            out.append(E.ConcatOp(n.name, list(n.inputs), n.name, m.dim))
         elif _act_of(m) is not None and len(n.inputs) == 1:
             out.append(E.AddAct(n.name, list(n.inputs), n.name, _act_of(m)))
         else:

@@ -123,3 +123,40 @@ def test_stage_split_equals_whole():
         assert torch.allclose(s0.store.g_views[name], whole.store.g_views[name], atol=1e-5), name
     for name in s1.store.layout.entries:
         assert torch.allclose(s1.store.g_views[name], whole.store.g_views[name], atol=1e-5), name
+
+
+@pytest.mark.parametrize("arch,hw", [("squeezenet1_1", 48), ("densenet121", 32), ("mobilenet", 32)])
+def test_engine_runs_extra_zoo(arch, hw):
+    """Concat joins and pre-activation BatchNorm (``ConcatOp`` / ``BnAct``) against autograd."""
+    from ddlbench_b200.models.extra import EXTRA_BUILDERS
+    torch.manual_seed(0)
+    m = EXTRA_BUILDERS[arch](arch, num_classes=10, input_hw=hw).double().train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    ex = StageExecutor.from_model(m, device="cpu", dtype=torch.float64, lr=0.1, momentum=0.9,
+                                  weight_decay=1e-4)
+    kinds = {op.kind for op in ex.plan.ops}
+    assert "module" not in kinds                       # nothing falls back to the autograd op
+    for name, p in m.named_parameters():
+        ex.store.weights()[name].copy_(p.detach())
+    x = torch.randn(4, 3, hw, hw, dtype=torch.float64)
+    t = torch.randint(0, 10, (4,))
+    y = m(x)
+    F.cross_entropy(y, t).backward()
+    outs, ctx = ex.forward([ex.prepare_input(x)])
+    _, d = ex.loss(outs[0], t)
+    ex.backward(ctx, [d])
+    assert torch.allclose(outs[0], y, atol=1e-8)
+    assert _global_rel_err(ex, m) < 1e-6
+
+
+def test_extra_zoo_parameter_counts():
+    from ddlbench_b200.models import build_model
+    want = {"densenet121": 7978856, "densenet161": 28681000, "squeezenet1_0": 1248424,
+            "squeezenet1_1": 1235496, "resnext50": 25028904, "inception_v3": 23834568,
+            "mobilenet": 4231976}          # torchvision's counts (mobilenet: Howard et al. 4.2 M)
+    for arch, n in want.items():
+        assert sum(p.numel() for p in build_model(arch, "imagenet").parameters()) == n, arch
+    nas = build_model("nasnetamobile", "imagenet")
+    assert 5.0e6 < sum(p.numel() for p in nas.parameters()) < 5.6e6      # 5.3 M in the paper
