@@ -1,0 +1,94 @@
+"""run.sh flag parsing / expansion, environment contract, and golden log lines (the formats the
+reference's post-processing greps for — SURVEY.md §5.5)."""
+import re
+
+import torch
+import torch.distributed as dist
+
+from ddlbench_b200 import cli
+from ddlbench_b200.config import BATCH_SIZES, RunConfig
+from ddlbench_b200.harness import logfmt
+
+
+def _expand(argv):
+    return cli.expand(cli.build_parser().parse_args(argv))
+
+
+def test_run_sh_defaults_and_all_expansion():
+    cfgs = _expand([])
+    # defaults: mnist / pytorch / 1 GPU / log interval 25 / all six benchmark models / synthetic
+    assert [c.arch for c in cfgs] == ["resnet18", "resnet50", "resnet152", "vgg11", "vgg16", "mobilenetv2"]
+    assert {c.benchmark for c in cfgs} == {"mnist"} and {c.framework for c in cfgs} == {"pytorch"}
+    assert cfgs[0].log_interval == 25 and cfgs[0].synthetic and cfgs[0].gpus == 1
+    every = _expand(["-b", "all", "-f", "all", "-m", "all"])
+    # 4 frameworks x 4 data sets x 6 models, minus resnet152 under pipedream (disabled in `all`)
+    assert len(every) == 4 * 4 * 6 - 4
+    assert not [c for c in every if c.framework == "pipedream" and c.arch == "resnet152"]
+    assert [c.arch for c in _expand(["-m", "exp2"])] == ["resnet50", "vgg16", "mobilenetv2"]
+    # an explicit request for the disabled pair is honoured here
+    assert len(_expand(["-f", "pipedream", "-m", "resnet152", "-b", "imagenet"])) == 1
+    # -s (real data) has no HIGHRES set
+    assert {c.benchmark for c in _expand(["-b", "all", "-s", "-m", "vgg11"])} == {"mnist", "cifar10", "imagenet"}
+    # multi-node `all` keeps only the multi-node frameworks
+    assert {c.framework for c in _expand(["-f", "all", "-n", "2", "-m", "vgg11"])} == {"horovod", "pipedream"}
+
+
+def test_flags_reach_the_run_config_and_env_contract():
+    (c,) = _expand(["-b", "imagenet", "-f", "pipedream", "-g", "8", "-p", "5", "-m", "resnet50",
+                    "--stages", "4x2", "--epochs", "2", "--steps", "7", "--macrobatch"])
+    assert (c.gpus, c.log_interval, c.epochs, c.steps_per_epoch) == (8, 5, 2, 7)
+    assert c.extra["stages"] == "4x2" and c.extra["macrobatch"] == "1"
+    assert c.batch_size == BATCH_SIZES[("imagenet", "pipedream")]["resnet50"] if isinstance(
+        BATCH_SIZES.get(("imagenet", "pipedream")), dict) else c.batch_size > 0
+    env = c.export_env()
+    assert env["LOGINTER"] == "5" and "CORES_GPU" in env and "DATADIR" in env
+    assert re.match(r"pipedream - imagenet - resnet50 - batch=\d+", c.header())
+    back = cli._cfg_to_argv(c, cli.build_parser().parse_args(["-f", "pipedream"]))
+    assert "--stages" in back and "4x2" in back and "--macrobatch" in back
+
+
+def test_golden_log_lines():
+    assert logfmt.creating_model("resnet50") == "=> creating model 'resnet50'"
+    assert re.fullmatch(r"train \| 1/3 epoch \(40%\) \| 1234\.568 samples/sec \(estimated\) \| "
+                        r"mem \(GB\): \d+\.\d{3} \(\d+\.\d{3}\) / \d+\.\d{3}",
+                        logfmt.train_progress(1, 3, 40.0, 1234.5678))
+    assert logfmt.valid_progress(97.0, 10.0) == "valid | 97% | 10.000 samples/sec (estimated)"
+    assert logfmt.epoch_summary(2, 3, 0.5, 100.0, 0.25, 0.9) == \
+        "2/3 epoch | train loss:0.500 100.000 samples/sec | valid loss:0.250 accuracy:0.900"
+    assert logfmt.final_summary(0.91234, 100.0, 12.5) == \
+        "valid accuracy: 0.9123 | 100.000 samples/sec, 12.500 sec/epoch (average)"
+    assert logfmt.test_set(0.1234, 98.5) == "\nTEST SET: Average loss: 0.1234, Accuracy: 98.50%\n"
+    line = logfmt.pd_train(0, 5, 60, 0.1, 0.2, 0.001, 1.5, 2.5, 6.9, 7.0, 1.0, 2.0, 3.0, 4.0)
+    assert line == ("Epoch: [0][5/60]\tTime: 0.100 (0.200)\tEpoch time [hr]: 0.001 (0.001)\t"
+                    "Memory: 1.500 (2.500)\tLoss: 6.9000 (7.0000)\tPrec@1: 1.000 (2.000)\t"
+                    "Prec@5: 3.000 (4.000)")
+    assert logfmt.pd_train_nonlast(0, 5, 60, 1.5, 2.5) == "Epoch: [0][5/60]\tMemory: 1.500 (2.500)"
+    assert logfmt.pd_test(0, 1, 4, 0.1, 0.1, 0.0, 0.0, 1.0, 1.0, 5.0, 5.0, 9.0, 9.0).startswith("Test: [0][1/4]\tTime: 0.100")
+    assert logfmt.pd_prec(12.5, 50.0) == " * Prec@1 12.500 Prec@5 50.000"
+    assert logfmt.pd_epoch_time(3, 12.3456) == "Epoch 3: 12.346 seconds"
+    assert logfmt.pd_lr(1, 100, 0.01) == "Epoch: 1 Step 100 \tLearning rate: 0.010000"
+    # the post-processing regexes of the reference find what they look for
+    assert re.search(r"Epoch (\d+): ([\d.]+) seconds", logfmt.pd_epoch_time(3, 12.3456))
+    assert re.search(r"\* Prec@1 ([\d.]+) Prec@5 ([\d.]+)", logfmt.pd_prec(12.5, 50.0))
+
+
+def test_hvd_allreduce_equals_serial_sum_single_process():
+    """hvd API on a 1-rank gloo group: average / sum semantics and the optimizer wrapper."""
+    from ddlbench_b200.parallel import dp
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29631", rank=0, world_size=1)
+    try:
+        x = torch.arange(6.0)
+        assert torch.equal(dp.allreduce(x.clone(), name="x"), x)
+        assert dp.size() == 1 and dp.rank() == 0 and dp.local_rank() == 0
+        m = torch.nn.Linear(3, 2)
+        opt = dp.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.1),
+                                      named_parameters=m.named_parameters())
+        dp.broadcast_parameters(m.state_dict(), root_rank=0)
+        dp.broadcast_optimizer_state(opt, root_rank=0)
+        before = m.weight.detach().clone()
+        m(torch.ones(1, 3)).sum().backward()
+        opt.step()
+        assert not torch.equal(before, m.weight)
+    finally:
+        dist.destroy_process_group()
