@@ -33,6 +33,8 @@ WGRAD_OVERLAP = {"stream": None, "keep": []}
 import os as _os
 FUSE_BN_FINALIZE = _os.environ.get("DDLB_FUSE_FINALIZE", "0") == "1"
 ACT_BITMASK_ON = _os.environ.get("DDLB_ACT_BITMASK", "1") == "1"
+# tcgen05 implicit-GEMM for the 3x3 convolutions (csrc/conv_tcgen05.cu): opt-in until validated
+CONV3X3_TCGEN05 = _os.environ.get("DDLB_CONV3X3_TCGEN05", "0") == "1"
 OVERLAP_WGRAD_DEFAULT = _os.environ.get("DDLB_WGRAD_OVERLAP", "1") == "1"
 
 
@@ -100,6 +102,10 @@ class _ConvMixin:
                 x.dtype == torch.bfloat16 and ci % 8 == 0 and co % 8 == 0 and
                 x.is_contiguous(memory_format=torch.channels_last))
 
+    def _is_conv_tc(self, x: torch.Tensor, w: torch.Tensor) -> bool:
+        return CONV3X3_TCGEN05 and TCGEN05["conv1x1"] and ops.conv_tn_supported(
+            x, w, self.stride, self.padding, self.dilation, self.groups)
+
     def _conv_fwd(self, x, w, bias=None, col_sums=None, relu=False, bn_finalize=None):
         """Returns (y, stats_fused)."""
         if self._is_gemm(x):
@@ -109,6 +115,10 @@ class _ConvMixin:
             d = ops.gemm_tn(a, w.reshape(co, ci), col_sums=col_sums, bias=bias, relu=relu,
                             bn_finalize=bn_finalize)
             return d.view(n, h, wd, co).permute(0, 3, 1, 2), col_sums is not None
+        if self._is_conv_tc(x, w):
+            y = ops.conv_tn(x, w, col_sums=col_sums, bias=bias, relu=relu)
+            if y is not None:
+                return y, col_sums is not None
         y = aten.convolution(x, w, None, self.stride, self.padding, self.dilation, False, [0, 0],
                              self.groups)
         return y, False
@@ -173,7 +183,8 @@ class ConvBnAct(Op, _ConvMixin):
     def forward(self, P, B, xs, ctx, training):
         x = xs[0]
         res = xs[1] if self.has_res else None
-        fuse_stats = training and self.ws is not None and self._is_gemm(x)
+        fuse_stats = training and self.ws is not None and \
+            (self._is_gemm(x) or self._is_conv_tc(x, P[self.k_w]))
         mom = self.momentum * BN_MOMENTUM_SCALE[0]
         stat_ready = None
         if fuse_stats and FUSE_BN_FINALIZE:

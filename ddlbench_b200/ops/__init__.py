@@ -408,4 +408,29 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, col_sums: Optional[torch.Tensor] =
     return d
 
 
+def conv_tn_supported(x: torch.Tensor, w: torch.Tensor, stride, padding, dilation, groups) -> bool:
+    """Shapes the tcgen05 implicit-GEMM convolution (csrc/conv_tcgen05.cu) takes: stride 1, odd
+    kernel with "same" padding, no groups/dilation, Cin % 64 == 0, Cout % 64 == 0, bf16 NHWC."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.dim() == 4):
+        return False
+    co, ci, kh, kw = w.shape
+    return (list(stride) == [1, 1] and list(dilation) == [1, 1] and groups == 1 and kh % 2 == 1 and
+            kw % 2 == 1 and kh * kw > 1 and list(padding) == [kh // 2, kw // 2] and ci % 64 == 0 and
+            co % 64 == 0 and x.is_contiguous(memory_format=torch.channels_last) and
+            w.is_contiguous(memory_format=torch.channels_last))
+
+
+def conv_tn(x: torch.Tensor, w: torch.Tensor, col_sums: Optional[torch.Tensor] = None,
+            bias: Optional[torch.Tensor] = None, relu: bool = False) -> Optional[torch.Tensor]:
+    """y = conv2d(x, w) (stride 1, same padding) with optional fused bias/ReLU and BatchNorm
+    partial sums, on the tensor cores.  Returns None if the kernel declines the shape."""
+    co, ci, kh, kw = w.shape
+    y = torch.empty((x.shape[0], co, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device,
+                    memory_format=torch.channels_last)
+    if ext().conv_bf16_nhwc(x, w, y, kh // 2, kw // 2, col_sums, bias, relu):
+        _count()
+        return y
+    return None
+
+
 __all__ = [n for n in dir() if not n.startswith("_")]

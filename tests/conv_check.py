@@ -1,0 +1,84 @@
+"""Stand-alone correctness + timing check of the tcgen05 implicit-GEMM convolution (run under a
+timeout by tests/test_kernels_gpu.py when DDLB_TEST_CONV_TCGEN05=1, or directly under gpurun)."""
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ddlbench_b200 import ops  # noqa: E402
+
+
+def check(n, ci, co, hw, k, stats=False, bias=False, relu=False, seed=0):
+    torch.manual_seed(seed)
+    x = (torch.randn(n, ci, hw, hw, device="cuda") * 0.5).to(torch.bfloat16).contiguous(
+        memory_format=torch.channels_last)
+    w = (torch.randn(co, ci, k, k, device="cuda") * (1.0 / (k * k * ci) ** 0.5)).to(
+        torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(co, device="cuda").to(torch.bfloat16) if bias else None
+    sums = torch.zeros(ops.BN_REPLICAS * 2 * co, device="cuda") if stats else None
+    assert ops.conv_tn_supported(x, w, [1, 1], [k // 2, k // 2], [1, 1], 1), (n, ci, co, hw, k)
+    y = ops.conv_tn(x, w, col_sums=sums, bias=b, relu=relu)
+    torch.cuda.synchronize()
+    if y is None:
+        print("conv declined", (n, ci, co, hw, k))
+        return False
+    ref = F.conv2d(x.float(), w.float(), b.float() if bias else None, padding=k // 2)
+    if relu:
+        ref = torch.relu(ref)
+    err = (y.float() - ref).abs().max().item()
+    tol = 0.02 * max(ref.abs().max().item(), 1.0)
+    ok = err <= tol and y.is_contiguous(memory_format=torch.channels_last)
+    if stats:
+        yf = y.float()
+        tot = sums.view(ops.BN_REPLICAS, 2, co).sum(0)
+        s_ref, q_ref = yf.sum((0, 2, 3)), (yf * yf).sum((0, 2, 3))
+        ok = ok and (tot[0] - s_ref).abs().max().item() <= 1e-2 * max(s_ref.abs().max().item(), 1.0) + 0.5 \
+            and (tot[1] - q_ref).abs().max().item() <= 1e-2 * q_ref.abs().max().item() + 0.5
+    print(f"conv n={n} ci={ci} co={co} hw={hw} k={k} stats={stats} bias={bias} relu={relu}: "
+          f"max_err={err:.4f} tol={tol:.4f} {'OK' if ok else 'FAIL'}", flush=True)
+    return ok
+
+
+def bench(n, ci, co, hw, k=3, iters=20):
+    x = torch.randn(n, ci, hw, hw, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(co, ci, k, k, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    out = {}
+    for name, fn in (("tcgen05", lambda: ops.conv_tn(x, w)),
+                     ("cudnn", lambda: F.conv2d(x, w, padding=k // 2))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name + "_us"] = round(e0.elapsed_time(e1) / iters * 1e3, 1)
+    out["shape"] = [n, ci, co, hw, k]
+    out["tflops_tcgen05"] = round(2.0 * n * hw * hw * co * ci * k * k / out["tcgen05_us"] / 1e6, 1)
+    return out
+
+
+def main():
+    ok = True
+    # ResNet-50 3x3 layers at the benchmark batch, a padded-edge case per box shape, 5x5
+    for args in [(32, 64, 64, 56, 3), (32, 128, 128, 28, 3), (32, 256, 256, 14, 3), (32, 512, 512, 7, 3),
+                 (3, 64, 64, 9, 3), (5, 128, 192, 13, 3), (2, 64, 128, 10, 5), (1, 64, 64, 1, 3)]:
+        ok &= check(*args)
+    ok &= check(32, 256, 256, 14, 3, stats=True)
+    ok &= check(7, 64, 64, 11, 3, stats=True, bias=True, relu=True)
+    if ok and os.environ.get("BENCH", "1") == "1":
+        res = [bench(32, 64, 64, 56), bench(32, 128, 128, 28), bench(32, 256, 256, 14), bench(32, 512, 512, 7)]
+        for r in res:
+            print(json.dumps(r))
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(res, open("gpurun_out/conv_bench.json", "w"), indent=1)
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
