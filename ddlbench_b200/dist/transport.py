@@ -22,6 +22,7 @@ Two backends behind one interface:
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -86,6 +87,7 @@ class DistP2P:
         self._inflight_sends: List[Tuple[object, torch.Tensor]] = []
         self.bytes_sent = 0
         self.bytes_received = 0
+        self.poison = os.environ.get("DDLB_DEBUG_POISON", "0") == "1"
 
     def _group(self, src: int, dst: int):
         return self.groups.get(src, dst) if self.groups is not None else None
@@ -104,6 +106,11 @@ class DistP2P:
         slot = self._slot[key]
         self._slot[key] = (slot + 1) % len(self._bufs[key])
         bufs = self._bufs[key][slot]
+        if self.poison:
+            # debug mode: a consumer that reads a ring slot before its transfer completed (or a
+            # slot that was recycled too early) sees NaN / a sentinel instead of stale, plausible data
+            for b in bufs:
+                b.fill_(float("nan") if b.is_floating_point() else -1)
         works = []
         g = self._group(src, self.rank)
         if self.gpu:

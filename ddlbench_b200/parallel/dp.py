@@ -45,7 +45,11 @@ def init(backend: Optional[str] = None, group=None) -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         lr = int(os.environ.get("LOCAL_RANK", os.environ["RANK"]))
-        kw = {}
+        # watchdog: a rank that dies leaves its peers blocked in a collective; they give up after
+        # DDLB_DIST_TIMEOUT_S seconds (default 30 min; the reference sets 120 min,
+        # runtime/communication.py:41-43) and the launcher then stops the rest of the job
+        import datetime
+        kw = {"timeout": datetime.timedelta(seconds=float(os.environ.get("DDLB_DIST_TIMEOUT_S", "1800")))}
         if backend == "nccl":
             torch.cuda.set_device(lr)
             kw["device_id"] = torch.device("cuda", lr)

@@ -239,3 +239,23 @@ def test_imagenet_subset_tool(tmp_path):
                         "--classes", "2", "--per-class", "2"], capture_output=True, text=True)
     assert r.returncode == 0 and "copied 8 files of 2 classes" in r.stdout
     assert len(os.listdir(tmp_path / "dst" / "train")) == 2
+
+
+def test_step_timeline_chrome_trace(tmp_path):
+    import json
+    from ddlbench_b200.engine import StageExecutor
+    from ddlbench_b200.utils.timeline import StepTimeline
+    m = build_model("resnet18", "cifar10")
+    ex = StageExecutor.from_model(m, device="cpu", dtype=torch.float32)
+    tl = StepTimeline(ex)
+    with tl:
+        outs, ctx = ex.forward([torch.randn(2, 3, 32, 32)])
+        _, d = ex.loss(outs[0], torch.tensor([1, 2]))
+        ex.backward(ctx, [d])
+    assert ex.profiler is None
+    spans = tl.spans()
+    assert len(spans) == 2 * len(ex.plan.ops) and all(dur >= 0 for _, _, dur in spans)
+    trace = json.load(open(tl.save(str(tmp_path / "t.json"))))
+    names = [e["name"] for e in trace["traceEvents"] if e["ph"] == "X"]
+    assert any(n.startswith("fwd conv_bn_act") for n in names) and any(n.startswith("bwd ") for n in names)
+    assert "ms" in tl.table(5).splitlines()[0]
