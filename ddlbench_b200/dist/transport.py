@@ -8,17 +8,19 @@ each message = an int32 shape message + payload, ``tensor.detach().clone()`` on 
 Here shapes are static (known from a dry run), so a message is one transfer into a
 PRE-ALLOCATED ring of receive buffers; receives are pre-posted one step ahead on a
 communication stream so the transfer overlaps the stage's compute; there are no helper threads.
-Two backends behind one interface:
 
-* ``DistP2P`` — ``torch.distributed`` isend/irecv: NCCL p2p over NVLink on GPUs, Gloo on CPU
-  (the fake transport that lets the schedules run under pytest on a GPU-less box).  Every
-  (pair, direction) gets its own 2-rank process group so an outstanding receive can never
-  block a send in the other direction (the reference needs the same property and creates a
-  group per pair *per tensor*).
-* ``SymmP2P`` — our own kernels over symmetric memory: the producer stores the tensor straight
-  into the consumer's ring slot and raises a sequence flag (``p2p_put``), the consumer's stream
-  waits on the flag (``p2p_wait``); consumption is acknowledged by a flag in the other
-  direction.  No NCCL stream, no host involvement.
+``DistP2P`` — ``torch.distributed`` isend/irecv: NCCL p2p over NVLink on GPUs, Gloo on CPU (the
+fake transport that lets the schedules run under pytest on a GPU-less box).  Every
+(pair, direction) gets its own 2-rank process group so an outstanding receive can never block a
+send in the other direction (the reference needs the same property and creates a group per pair
+*per tensor*).  NCCL's rendezvous gives the back-pressure the reference implements with "ack"
+tokens.
+
+The building blocks of a transport that bypasses NCCL exist as kernels — ``p2p_put`` (store the
+tensor straight into the consumer's symmetric-memory slot over NVLink, then raise a sequence
+flag) and ``p2p_wait`` (the consumer's stream spins on the flag), ``ops/csrc/allreduce.cu`` — and
+are measured by ``bench/p2p_bandwidth.py``; wiring them in as a second backend (it needs a
+consumer->producer acknowledgement for ring reuse) is an open item.
 """
 from __future__ import annotations
 

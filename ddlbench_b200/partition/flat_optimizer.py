@@ -67,8 +67,6 @@ def optimize_chain(rows, num_machines: int, bandwidth: float, memory_size: float
                 for mp in range(1, (1 if straight_pipeline else m) + 1):
                     if k > 0 and m - mp < 1:
                         continue
-                    if k == 0 and mp != m and straight_pipeline is False and m - mp != 0:
-                        pass
                     prev = A[k][m - mp][0] if k > 0 else 0.0
                     if prev == INF:
                         continue
