@@ -35,6 +35,8 @@ FUSE_BN_FINALIZE = _os.environ.get("DDLB_FUSE_FINALIZE", "0") == "1"
 ACT_BITMASK_ON = _os.environ.get("DDLB_ACT_BITMASK", "1") == "1"
 # tcgen05 implicit-GEMM for the 3x3 convolutions (csrc/conv_tcgen05.cu): opt-in until validated
 CONV3X3_TCGEN05 = _os.environ.get("DDLB_CONV3X3_TCGEN05", "0") == "1"
+# first convolution (3 input channels) as im2col + tcgen05 GEMM (csrc/im2col.cu): opt-in until validated
+STEM_IM2COL = _os.environ.get("DDLB_STEM_IM2COL", "0") == "1"
 OVERLAP_WGRAD_DEFAULT = _os.environ.get("DDLB_WGRAD_OVERLAP", "1") == "1"
 
 
@@ -102,6 +104,26 @@ class _ConvMixin:
                 x.dtype == torch.bfloat16 and ci % 8 == 0 and co % 8 == 0 and
                 x.is_contiguous(memory_format=torch.channels_last))
 
+    def _is_stem_gemm(self, x: torch.Tensor) -> bool:
+        """Few-channel first convolution (7x7/s2 on RGB, 3x3 on RGB/grey) as patch matrix + GEMM."""
+        co, ci, kh, kw = self.wshape
+        return (STEM_IM2COL and TCGEN05["conv1x1"] and ci <= 4 and kh * kw > 1 and
+                self.groups == 1 and self.dilation == [1, 1] and self.stride[0] == self.stride[1] and
+                self.padding[0] == self.padding[1] and kh == kw and co % 8 == 0 and x.is_cuda and
+                x.dtype == torch.bfloat16 and x.dim() == 4 and
+                x.is_contiguous(memory_format=torch.channels_last) and
+                kh * (x.shape[3] + 2 * self.padding[0]) * ci * 2 <= 48 * 1024)
+
+    def _stem_weight_matrix(self, w: torch.Tensor, kpad: int) -> torch.Tensor:
+        co, ci, kh, kw = self.wshape
+        wm = getattr(self, "_wm", None)
+        if wm is None or wm.device != w.device or wm.shape[1] != kpad:
+            wm = torch.zeros((co, kpad), dtype=w.dtype, device=w.device)
+            if not torch.cuda.is_current_stream_capturing():
+                self._wm = wm          # padded columns stay zero; only [:, :k] is rewritten
+        wm[:, :kh * kw * ci].copy_(w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci))
+        return wm
+
     def _is_conv_tc(self, x: torch.Tensor, w: torch.Tensor) -> bool:
         return CONV3X3_TCGEN05 and TCGEN05["conv1x1"] and ops.conv_tn_supported(
             x, w, self.stride, self.padding, self.dilation, self.groups)
@@ -115,6 +137,15 @@ class _ConvMixin:
             d = ops.gemm_tn(a, w.reshape(co, ci), col_sums=col_sums, bias=bias, relu=relu,
                             bn_finalize=bn_finalize)
             return d.view(n, h, wd, co).permute(0, 3, 1, 2), col_sums is not None
+        if self._is_stem_gemm(x):
+            n, ci, h, wd = x.shape
+            co, _, kh, kw = self.wshape
+            a = ops.im2col_rows(x, kh, kw, self.stride[0], self.padding[0])
+            oh = (h + 2 * self.padding[0] - kh) // self.stride[0] + 1
+            ow = (wd + 2 * self.padding[1] - kw) // self.stride[1] + 1
+            d = ops.gemm_tn(a, self._stem_weight_matrix(w, a.shape[1]), col_sums=col_sums, bias=bias,
+                            relu=relu, bn_finalize=bn_finalize)
+            return d.view(n, oh, ow, co).permute(0, 3, 1, 2), col_sums is not None
         if self._is_conv_tc(x, w):
             y = ops.conv_tn(x, w, col_sums=col_sums, bias=bias, relu=relu)
             if y is not None:
@@ -184,7 +215,7 @@ class ConvBnAct(Op, _ConvMixin):
         x = xs[0]
         res = xs[1] if self.has_res else None
         fuse_stats = training and self.ws is not None and \
-            (self._is_gemm(x) or self._is_conv_tc(x, P[self.k_w]))
+            (self._is_gemm(x) or self._is_stem_gemm(x) or self._is_conv_tc(x, P[self.k_w]))
         mom = self.momentum * BN_MOMENTUM_SCALE[0]
         stat_ready = None
         if fuse_stats and FUSE_BN_FINALIZE:

@@ -408,6 +408,22 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, col_sums: Optional[torch.Tensor] =
     return d
 
 
+def im2col_rows(x: torch.Tensor, kh: int, kw: int, stride: int, pad: int) -> torch.Tensor:
+    """[N, C, H, W] -> patch matrix [N*OH*OW, roundup(kh*kw*C, 8)] with K ordered (kh, kw, c) — the
+    A operand that turns a few-channel first convolution into a tensor-core GEMM
+    (csrc/im2col.cu)."""
+    n, c, h, w = x.shape
+    oh, ow = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+    k = kh * kw * c
+    kpad = (k + 7) // 8 * 8
+    if x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last):
+        a = torch.empty((n * oh * ow, kpad), dtype=x.dtype, device=x.device)
+        if ext().im2col_rows(x, a, kh, kw, stride, pad):
+            _count()
+            return a
+    return ref.im2col_rows(x, kh, kw, stride, pad)
+
+
 def conv_tn_supported(x: torch.Tensor, w: torch.Tensor, stride, padding, dilation, groups) -> bool:
     """Shapes the tcgen05 implicit-GEMM convolution (csrc/conv_tcgen05.cu) takes: stride 1, odd
     kernel with "same" padding, no groups/dilation, Cin % 64 == 0, Cout % 64 == 0, bf16 NHWC."""

@@ -290,6 +290,21 @@ bool conv_bf16_nhwc(at::Tensor x, at::Tensor w, at::Tensor y, int64_t pad_h, int
   check(rc, "conv_bf16_nhwc");
   return true;
 }
+// x: [N, C, H, W] channels_last bf16 -> a: [N*OH*OW, Kpad] patch matrix (K order kh, kw, c)
+bool im2col_rows(at::Tensor x, at::Tensor a, int64_t KH, int64_t KW, int64_t stride, int64_t pad) {
+  TORCH_CHECK(x.dim() == 4 && is_bf16(x) && is_bf16(a) && a.dim() == 2 && a.is_contiguous());
+  TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast), "im2col_rows: channels_last input");
+  const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
+  const int OH = (H + 2 * (int)pad - (int)KH) / (int)stride + 1;
+  const int OW = (W + 2 * (int)pad - (int)KW) / (int)stride + 1;
+  TORCH_CHECK(a.size(0) == (int64_t)N * OH * OW, "im2col_rows: bad output rows");
+  c10::cuda::CUDAGuard g(x.device());
+  const int rc = ddl_im2col_rows(x.data_ptr(), a.data_ptr(), N, H, W, C, (int)KH, (int)KW,
+                                 (int)stride, (int)pad, (int)a.size(1), cur_stream());
+  if (rc == -1) return false;
+  check(rc, "im2col_rows");
+  return true;
+}
 void gemm_bf16_nt_mn(at::Tensor A, at::Tensor B, at::Tensor D, int64_t splits,
                      c10::optional<at::Tensor> workspace) {
   // A: [K, M], B: [K, N], D: [M, N]
@@ -599,6 +614,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16_tn", &gemm_bf16_tn);
   m.def("gemm_bf16_nt_mn", &gemm_bf16_nt_mn);
   m.def("conv_bf16_nhwc", &conv_bf16_nhwc);
+  m.def("im2col_rows", &im2col_rows);
   m.def("gemm_info", &gemm_info);
   m.def("ar_sgd_twoshot", &ar_sgd_twoshot);
   m.def("ar_twoshot", &ar_twoshot);

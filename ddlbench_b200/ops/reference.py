@@ -158,3 +158,17 @@ def set_mask(lengths: torch.Tensor, T: int) -> torch.Tensor:
 
 def global_avg_pool(x: torch.Tensor) -> torch.Tensor:
     return _up(x).mean(dim=(2, 3)).to(x.dtype)
+
+
+def im2col_rows(x, kh: int, kw: int, stride: int, pad: int):
+    """Patch matrix with K ordered (kh, kw, c), zero-padded to a multiple of 8 columns."""
+    import torch.nn.functional as F
+    n, c, h, w = x.shape
+    cols = F.unfold(_up(x), (kh, kw), padding=pad, stride=stride)            # [N, c*kh*kw, L]
+    L = cols.shape[-1]
+    cols = cols.view(n, c, kh * kw, L).permute(0, 3, 2, 1).reshape(n * L, kh * kw * c)
+    k = kh * kw * c
+    kpad = (k + 7) // 8 * 8
+    out = cols.new_zeros((n * L, kpad))
+    out[:, :k] = cols
+    return out.to(x.dtype)

@@ -275,3 +275,23 @@ def test_tcgen05_conv3x3():
     sys.stdout.write(p.stdout[-4000:])
     sys.stderr.write(p.stderr[-4000:])
     assert p.returncode == 0, "tcgen05 convolution check failed"
+
+
+@pytest.mark.skipif(os.environ.get("DDLB_TEST_CONV_TCGEN05") != "1",
+                    reason="opt-in: kernel not yet validated on hardware")
+@pytest.mark.parametrize("n,c,hw,k,s,p", [(4, 3, 224, 7, 2, 3), (2, 3, 32, 3, 1, 1), (3, 1, 28, 3, 1, 1),
+                                          (2, 3, 37, 7, 2, 3)])
+def test_im2col_rows_and_stem_gemm(n, c, hw, k, s, p):
+    torch.manual_seed(0)
+    x = torch.randn(n, c, hw, hw, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    a = ops.im2col_rows(x, k, k, s, p)
+    a_ref = ref.im2col_rows(x, k, k, s, p)
+    assert a.shape == a_ref.shape and torch.equal(a.float(), a_ref.float().to(a.device))
+    w = (torch.randn(64, c, k, k, device=DEV) * 0.1).to(torch.bfloat16)
+    wm = torch.zeros(64, a.shape[1], device=DEV, dtype=torch.bfloat16)
+    wm[:, :k * k * c] = w.permute(0, 2, 3, 1).reshape(64, -1)
+    y = ops.gemm_tn(a, wm)
+    oh = (hw + 2 * p - k) // s + 1
+    y_ref = torch.nn.functional.conv2d(x.float(), w.float(), stride=s, padding=p)
+    err = (y.float().view(n, oh, oh, 64).permute(0, 3, 1, 2) - y_ref).abs().max().item()
+    assert err < 0.03 * max(1.0, y_ref.abs().max().item())
