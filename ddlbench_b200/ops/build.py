@@ -123,6 +123,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
                 "-lcudart", f"-Wl,-rpath,{torch_lib}", f"-Wl,-rpath,{Path(home, 'lib64')}"]
         _run(cmd, verbose)
         stamp.write_text(link_tag)
+    # drop objects of older source revisions (the cache is keyed by content hash, so they only
+    # accumulate and inflate the snapshot that travels to the GPU box)
+    keep = {o.name for o in objs}
+    for old in BUILD.glob("*.o"):
+        if old.name not in keep:
+            try:
+                old.unlink()
+            except OSError:
+                pass
     return out
 
 
