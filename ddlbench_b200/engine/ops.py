@@ -37,6 +37,7 @@ ACT_BITMASK_ON = _os.environ.get("DDLB_ACT_BITMASK", "1") == "1"
 CONV3X3_TCGEN05 = _os.environ.get("DDLB_CONV3X3_TCGEN05", "0") == "1"
 # first convolution (3 input channels) as im2col + tcgen05 GEMM (csrc/im2col.cu): opt-in until validated
 STEM_IM2COL = _os.environ.get("DDLB_STEM_IM2COL", "0") == "1"
+CONV3X3_DGRAD = CONV3X3_TCGEN05 and _os.environ.get("DDLB_CONV3X3_DGRAD", "0") == "1"
 OVERLAP_WGRAD_DEFAULT = _os.environ.get("DDLB_WGRAD_OVERLAP", "1") == "1"
 
 
@@ -161,14 +162,23 @@ class _ConvMixin:
         benchmark's batch size every kernel fills only a fraction of the 148 SMs."""
         side = WGRAD_OVERLAP["stream"] if dy.is_cuda else None
         args = (None, self.stride, self.padding, self.dilation, False, [0, 0], self.groups)
+        dx_tc = None
+        if need_dx and CONV3X3_DGRAD and self._is_conv_tc(x, w) and \
+                dy.is_contiguous(memory_format=torch.channels_last):
+            # data gradient of a stride-1 "same" convolution = the same convolution of dy with the
+            # spatially flipped, channel-transposed filter: reuse the tcgen05 kernel
+            wt = w.flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=torch.channels_last)
+            dx_tc = ops.conv_tn(dy, wt)
+        lib_dx = need_dx and dx_tc is None
         if side is None:
-            dx, dw, _ = aten.convolution_backward(dy, x, w, *args, [need_dx, True, False])
+            dx, dw, _ = aten.convolution_backward(dy, x, w, *args, [lib_dx, True, False])
             _write(gw, dw, accumulate)
-            return dx
+            return dx_tc if dx_tc is not None else dx
         main = torch.cuda.current_stream(dy.device)
         ev = torch.cuda.Event()
         ev.record(main)
-        dx = aten.convolution_backward(dy, x, w, *args, [True, False, False])[0] if need_dx else None
+        dx = dx_tc if dx_tc is not None else (
+            aten.convolution_backward(dy, x, w, *args, [True, False, False])[0] if lib_dx else None)
         with torch.cuda.stream(side):
             side.wait_event(ev)
             dw = aten.convolution_backward(dy, x, w, *args, [False, True, False])[1]
