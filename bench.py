@@ -189,6 +189,13 @@ def run_ours(args) -> dict:
         "launches_per_step_in_graph": int(trainer.launches_per_step),
         "peak_mem_gb": round(mem_gb, 3),
     }
+    if rank == 0:
+        try:   # informational; must never break the measurement
+            from ddlbench_b200.models import build_model
+            from ddlbench_b200.utils.cost import roofline
+            out["roofline"] = roofline(build_model(ARCH, DATASET), PER_GPU_BATCH, ms_step)
+        except Exception as e:  # pragma: no cover
+            out["roofline"] = {"error": str(e)[:200]}
     if n > 1:
         dist.barrier()
         dp.shutdown()

@@ -259,3 +259,13 @@ def test_step_timeline_chrome_trace(tmp_path):
     names = [e["name"] for e in trace["traceEvents"] if e["ph"] == "X"]
     assert any(n.startswith("fwd conv_bn_act") for n in names) and any(n.startswith("bwd ") for n in names)
     assert "ms" in tl.table(5).splitlines()[0]
+
+
+def test_roofline_cost_model():
+    from ddlbench_b200.utils.cost import model_cost, roofline
+    m = build_model("resnet50", "imagenet")
+    c = model_cost(m, 2)
+    assert abs(c["forward_flops"] / 2 / 2 - 4.09e9) < 0.05e9          # 4.09 GMACs per image
+    r = roofline(m, 32, 4.64)
+    assert r["step_gflop"] > 700 and "of " in r["tensor_frac"] and r["peaks"]["hbm_gbs"] > 1000
+    assert m.training                                                 # mode restored
