@@ -6,10 +6,13 @@ learning_rate_policy, weight_decay, epochs, config_file, print_frequency, no_inp
 verbose_frequency, lr_warmup, synthetic_data, recompute, macrobatch``.  ``machines`` is the
 reference's ``['host:gpu', ...]`` list: its length is the number of workers.
 
-Differences by design: workers are local processes started through ``torch.distributed.run``
-(one per entry of ``machines``; the host part is recorded but all GPUs of an NVSwitch box are
-local), there is no docker/ssh layer, and ``module`` (``models.<arch>.gpus=<N>``) selects the
-architecture — stage modules are sliced from the layer graph instead of being imported.
+Differences by design: when every entry of ``machines`` names the same host (the normal case:
+all GPUs of an NVSwitch box) the workers are local processes started through
+``torch.distributed.run``; with several hosts one ``ddlbench_b200.launch`` per host is started
+over ``ssh -n`` (the reference's fan-out, ``driver.py:313-356``, minus docker), all pointing at
+the first host as rendezvous.  ``module`` (``models.<arch>.gpus=<N>``) selects the architecture —
+stage modules are sliced from the layer graph instead of being imported; ``model_type:
+translation`` starts the GNMT harness.
 The launcher writes ``<log_directory>/<timestamp>/{config.yml, machinefile, output.log}`` and
 records the git commit like the reference (``driver.py:73-100``).
 """
@@ -70,6 +73,62 @@ def build_command(conf: Dict, resume: str = "", dataset: str = "imagenet", port:
     return cmd
 
 
+def hosts_of(conf: Dict) -> "Dict[str, int]":
+    """host -> number of workers, in first-appearance order (entries are ``host:gpu``)."""
+    out: Dict[str, int] = {}
+    for m in conf["machines"]:
+        h = str(m).split(":")[0]
+        out[h] = out.get(h, 0) + 1
+    return out
+
+
+def worker_args(conf: Dict, resume: str = "", dataset: str = "imagenet") -> List[str]:
+    """Module + arguments every worker runs (after the launcher part of the command)."""
+    n = len(conf["machines"])
+    if conf.get("model_type") == "translation":
+        args = ["ddlbench_b200.harness.translation", "--stages", str(n)]
+        if "gnmt_large" in conf["module"]:
+            args += ["--num-layers", "8"]
+        for key, flag in (("batch_size", "--batch-size"), ("epochs", "--epochs"),
+                          ("learning_rate", "--lr"), ("print_frequency", "--print-freq")):
+            if conf.get(key):
+                args += [flag, str(conf[key])]
+        if conf.get("data_dir") and conf["data_dir"] != "synthetic":
+            args += ["--data-dir", str(conf["data_dir"])]
+        if resume:
+            args += ["--checkpoint-dir", resume]
+        return args
+    return build_command(conf, resume, dataset)[build_command(conf, resume, dataset).index("ddlbench_b200.cli"):]
+
+
+def build_node_commands(conf: Dict, resume: str = "", dataset: str = "imagenet",
+                        port: int = 29450, repo: str = "") -> "List[tuple]":
+    """[(host, argv)] — one entry for a single-host run, one ``ssh`` command per host otherwise."""
+    hosts = hosts_of(conf)
+    wargs = worker_args(conf, resume, dataset)
+    names = list(hosts)
+    if len(names) == 1:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               "--nproc-per-node=%d" % hosts[names[0]], "--master-addr", "127.0.0.1",
+               "--master-port", str(port), "-m"] + wargs
+        return [(names[0], cmd)]
+    per = set(hosts.values())
+    if len(per) != 1:
+        raise ValueError("every host must run the same number of workers, got %s" % hosts)
+    repo = repo or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if "-g" in wargs:                       # cli workers: GPUs per node + number of nodes
+        wargs[wargs.index("-g") + 1] = str(hosts[names[0]])
+        wargs += ["-n", str(len(names))]
+    out = []
+    for i, h in enumerate(names):
+        inner = ("cd %s && python -m ddlbench_b200.launch --nnodes %d --node_rank %d "
+                 "--nproc_per_node %d --master_addr %s --master_port %d --no-rank-args "
+                 "--pid-file driver_node%d.pids -m %s" % (
+                     repo, len(names), i, hosts[h], names[0], port, i, " ".join(wargs)))
+        out.append((h, ["ssh", "-n", h, "-o", "StrictHostKeyChecking=no", inner]))
+    return out
+
+
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--config_file", required=True, help="Path to configuration file")
@@ -81,9 +140,11 @@ def main(argv=None) -> int:
     conf = load(a.config_file)
     out_dir = os.path.join(conf["log_directory"],
                            datetime.datetime.now().isoformat().split(".")[0].replace(":", "-"))
-    cmd = build_command(conf, a.resume, a.dataset)
+    nodes = build_node_commands(conf, a.resume, a.dataset)
+    cmd = nodes[0][1]
     if a.dry_run:
-        print(" ".join(cmd))
+        for _, c in nodes:
+            print(" ".join(c))
         return 0
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, "config.yml"), "w") as f:
@@ -101,12 +162,16 @@ def main(argv=None) -> int:
     with open(os.path.join(out_dir, "output.log"), "w") as log:
         log.write("git commit: %s\ncommand: %s\n" % (commit, " ".join(cmd)))
         log.flush()
+        others = [subprocess.Popen(c, stdout=open(os.path.join(out_dir, "output_%s.log" % h), "w"),
+                                   stderr=subprocess.STDOUT, env=env) for h, c in nodes[1:]]
         p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
         for line in p.stdout:
             log.write(line)
             if not a.quiet:
                 sys.stdout.write(line)
         p.wait()
+        for o in others:
+            o.wait()
     print("output in %s" % out_dir)
     return p.returncode
 

@@ -269,3 +269,12 @@ def test_roofline_cost_model():
     r = roofline(m, 32, 4.64)
     assert r["step_gflop"] > 700 and "of " in r["tensor_frac"] and r["peaks"]["hbm_gbs"] > 1000
     assert m.training                                                 # mode restored
+
+
+def test_driver_multi_host_and_translation_commands():
+    two = driver.build_node_commands(driver.load("configs/driver/resnet50_16hybrid_2nodes.yml"))
+    assert [h for h, _ in two] == ["node0", "node1"] and all(c[0] == "ssh" for _, c in two)
+    assert "--node_rank 1" in two[1][1][-1] and "--master_addr node0" in two[1][1][-1]
+    assert "-g 8" in two[0][1][-1] and "-n 2" in two[0][1][-1]
+    (host, cmd), = driver.build_node_commands(driver.load("configs/driver/gnmt_4pipedream.yml"))
+    assert "ddlbench_b200.harness.translation" in cmd and cmd[cmd.index("--stages") + 1] == "4"
