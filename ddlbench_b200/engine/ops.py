@@ -37,6 +37,8 @@ ACT_BITMASK_ON = _os.environ.get("DDLB_ACT_BITMASK", "1") == "1"
 CONV3X3_TCGEN05 = _os.environ.get("DDLB_CONV3X3_TCGEN05", "0") == "1"
 # first convolution (3 input channels) as im2col + tcgen05 GEMM (csrc/im2col.cu): opt-in until validated
 STEM_IM2COL = _os.environ.get("DDLB_STEM_IM2COL", "0") == "1"
+# weight gradient of 1x1 convolutions / linear layers on tcgen05 (csrc/gemm_wgrad_tcgen05.cu): opt-in
+WGRAD_TCGEN05 = _os.environ.get("DDLB_WGRAD_TCGEN05", "0") == "1"
 CONV3X3_DGRAD = CONV3X3_TCGEN05 and _os.environ.get("DDLB_CONV3X3_DGRAD", "0") == "1"
 OVERLAP_WGRAD_DEFAULT = _os.environ.get("DDLB_WGRAD_OVERLAP", "1") == "1"
 
@@ -181,7 +183,13 @@ class _ConvMixin:
             aten.convolution_backward(dy, x, w, *args, [True, False, False])[0] if lib_dx else None)
         with torch.cuda.stream(side):
             side.wait_event(ev)
-            dw = aten.convolution_backward(dy, x, w, *args, [False, True, False])[1]
+            if WGRAD_TCGEN05 and self._is_gemm(x) and dy.is_contiguous(memory_format=torch.channels_last):
+                n, ci, h, wd = x.shape
+                co = self.wshape[0]
+                dw = ops.gemm_nt_mn(dy.permute(0, 2, 3, 1).reshape(n * h * wd, co),
+                                    x.permute(0, 2, 3, 1).reshape(n * h * wd, ci)).view(co, ci, 1, 1)
+            else:
+                dw = aten.convolution_backward(dy, x, w, *args, [False, True, False])[1]
             _write(gw, dw, accumulate)
         # keep the operands alive until the streams are joined (executor.backward)
         WGRAD_OVERLAP["keep"].append((dy, x, dw))

@@ -408,6 +408,28 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, col_sums: Optional[torch.Tensor] =
     return d
 
 
+def gemm_nt_mn_supported(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and
+            b.dim() == 2 and a.shape[0] == b.shape[0] and a.stride(1) == 1 and b.stride(1) == 1 and
+            a.shape[1] % 8 == 0 and b.shape[1] % 8 == 0 and a.stride(0) % 8 == 0 and
+            b.stride(0) % 8 == 0 and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0)
+
+
+def gemm_nt_mn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
+               splits: int = 0) -> torch.Tensor:
+    """out[M, N] (fp32) += a[K, M]^T @ b[K, N] — the weight-gradient GEMM (reduction over the slow
+    dimension of both operands, csrc/gemm_wgrad_tcgen05.cu).  ``out`` is zero-initialised when
+    omitted; ``splits`` = k-splits per output tile (0: fill the machine)."""
+    if out is None:
+        out = torch.zeros((a.shape[1], b.shape[1]), dtype=torch.float32, device=a.device)
+    if gemm_nt_mn_supported(a, b) and out.dtype == torch.float32 and out.stride(1) == 1:
+        ext().gemm_bf16_nt_mn(a, b, out, splits, None)
+        _count()
+        return out
+    out.add_(a.float().t() @ b.float())
+    return out
+
+
 def im2col_rows(x: torch.Tensor, kh: int, kw: int, stride: int, pad: int) -> torch.Tensor:
     """[N, C, H, W] -> patch matrix [N*OH*OW, roundup(kh*kw*C, 8)] with K ordered (kh, kw, c) — the
     A operand that turns a few-channel first convolution into a tensor-core GEMM

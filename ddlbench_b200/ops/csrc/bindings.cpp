@@ -307,8 +307,9 @@ bool im2col_rows(at::Tensor x, at::Tensor a, int64_t KH, int64_t KW, int64_t str
 }
 void gemm_bf16_nt_mn(at::Tensor A, at::Tensor B, at::Tensor D, int64_t splits,
                      c10::optional<at::Tensor> workspace) {
-  // A: [K, M], B: [K, N], D: [M, N]
+  // A: [K, M], B: [K, N], D: [M, N] fp32, accumulated into (D += A^T B)
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && D.dim() == 2 && is_bf16(A) && is_bf16(B));
+  TORCH_CHECK(D.scalar_type() == at::kFloat, "gemm_bf16_nt_mn accumulates into an fp32 matrix");
   TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1 && D.stride(1) == 1);
   const int K = (int)A.size(0), M = (int)A.size(1), N = (int)B.size(1);
   TORCH_CHECK(B.size(0) == K && D.size(0) == M && D.size(1) == N);

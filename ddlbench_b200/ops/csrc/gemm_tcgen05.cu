@@ -329,11 +329,6 @@ extern "C" int ddl_gemm_bf16_tn(const void* A, const void* B, void* D, int M, in
 #undef DDL_GEMM_ARGS
 }
 
-extern "C" int ddl_gemm_bf16_nt_mn(const void*, const void*, void*, int, int, int, int, int, int,
-                                   int, int, float*, int, cudaStream_t) {
-  return -4;  // weight-gradient (MN-major) variant: see gemm_wgrad.cu once enabled
-}
-
 extern "C" int ddl_gemm_selftest_info(char* buf, int len) {
   using namespace ddl::gemm;
   snprintf(buf, len,

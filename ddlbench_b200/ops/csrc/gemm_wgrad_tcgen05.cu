@@ -1,0 +1,242 @@
+// Weight-gradient GEMM on the tcgen05 tensor cores: both operands MN-major.
+//
+//     D[M, N] += A^T B        A = dY [K = pixels, M = Cout],  B = X [K = pixels, N = Cin]
+//
+// (the weight gradient of a 1x1 convolution / linear layer in NHWC: the reduction runs over the
+// pixel index, which is the SLOW dimension of both operands.)  Nothing is transposed in memory:
+// a TMA box of 64 pixel rows x 64 channels lands in shared memory as 64 rows of 128 bytes, and
+// the MMA consumes it through an MN-MAJOR shared-memory descriptor (instruction-descriptor bits
+// a_major = b_major = 1): canonical SWIZZLE_128B MN-major layout ((8,8,m),(8,k)) — 64 contiguous
+// channels per row, rows 128 B apart, 8-row groups SBO = 1024 B apart, 64-channel atoms LBO apart
+// (here one 8 KB TMA box each).  One k-block = 64 pixels = 4 MMAs of K = 16 (the descriptor start
+// address advances by 16 rows = 2048 B per MMA).
+//
+// K (= batch*H*W, 10^3..10^5) is far larger than M*N/(128*128) tiles can cover, so the grid is
+// (tiles_m * tiles_n) x splits and every CTA adds its fp32 partial tile into D with 16-byte
+// vector atomics straight from the TMEM read-out (no shared-memory staging, no second pass).
+//
+// STATUS: opt-in (DDLB_WGRAD_TCGEN05=1).  Written after round 1's GPU minutes were spent: it
+// compiles for sm_100a but has not run on hardware.  The one assumption that cannot be checked
+// offline is which of LBO / SBO addresses the MN direction for MN-major SWIZZLE_128B operands;
+// `desc_variant` (env DDLB_WGRAD_DESC_VARIANT) swaps them for bring-up.
+#include <cuda.h>
+#include <cstdio>
+
+#include "api.h"
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace ddl {
+namespace gemm {
+
+constexpr int kMnBox = 64;                       // channels per TMA box (128 B) and pixels per k-block
+constexpr int kMnBoxBytes = kMnBox * 128;        // 8 KB
+
+// MN-major SWIZZLE_128B descriptor: lbo = byte stride between 64-element MN atoms, sbo = byte
+// stride between 8-row K groups.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo,
+                                                            uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct WgradParams {
+  float* D;          // [M, N] fp32, accumulated into
+  int M, N, K, ldd;
+  int kb_per_split;  // k-blocks (of 64 rows) per CTA
+  int desc_variant;  // 0: (LBO = MN atom stride, SBO = K group stride); 1: swapped
+};
+
+template <int BLOCK_N, int kStages>
+struct WgradSmem {
+  static constexpr int kABytes = (BLOCK_M / kMnBox) * kMnBoxBytes;   // 16 KB
+  static constexpr int kBBytes = (BLOCK_N / kMnBox) * kMnBoxBytes;   // 8/16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  static constexpr int kBarOffset = kRingBytes;
+  static constexpr int kTmemPtrOffset = kBarOffset + (2 * kStages + 1) * 8;
+  static constexpr int kTotal = kTmemPtrOffset + 16;
+  static constexpr int kDynamic = kTotal + 1024;
+};
+
+template <int BLOCK_N, int kStages>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_mn_kernel(const __grid_constant__ CUtensorMap map_a,
+                    const __grid_constant__ CUtensorMap map_b, WgradParams wp) {
+  using L = WgradSmem<BLOCK_N, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = (wp.N + BLOCK_N - 1) / BLOCK_N;
+  const int tile = blockIdx.x;
+  const int tile_m = tile / tiles_n, tile_n = tile % tiles_n;
+  const int total_kb = (wp.K + kMnBox - 1) / kMnBox;
+  const int kb0 = blockIdx.y * wp.kb_per_split;
+  int kb1 = kb0 + wp.kb_per_split;
+  if (kb1 > total_kb) kb1 = total_kb;
+  const int num_k_blocks = kb1 - kb0;            // >= 1 by construction of the grid
+
+  pdl_trigger();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      for (int i = 0; i < num_k_blocks; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        const int krow = (kb0 + i) * kMnBox;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = smem + s * L::kStageBytes;
+        uint8_t* b_dst = a_dst + L::kABytes;
+        mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
+#pragma unroll
+        for (int j = 0; j < BLOCK_M / kMnBox; ++j)
+          tma_load_2d(a_dst + j * kMnBoxBytes, &map_a, &full_bar[s],
+                      tile_m * BLOCK_M + j * kMnBox, krow);
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / kMnBox; ++j)
+          tma_load_2d(b_dst + j * kMnBoxBytes, &map_b, &full_bar[s],
+                      tile_n * BLOCK_N + j * kMnBox, krow);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 1, 1);   // both MN-major
+    const uint32_t mn_stride = kMnBoxBytes, kgrp_stride = 1024;
+    const uint32_t lbo = wp.desc_variant ? kgrp_stride : mn_stride;
+    const uint32_t sbo = wp.desc_variant ? mn_stride : kgrp_stride;
+    for (int i = 0; i < num_k_blocks; ++i) {
+      const int s = i % kStages;
+      const uint32_t ph = (i / kStages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+        const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < kMnBox / UMMA_K; ++k) {
+          // 16 pixel rows per MMA: +2048 B inside every 8 KB box
+          const uint64_t adesc = make_mnmajor_sw128_desc(a_addr + k * (UMMA_K * 128), lbo, sbo);
+          const uint64_t bdesc = make_mnmajor_sw128_desc(b_addr + k * (UMMA_K * 128), lbo, sbo);
+          umma_f16(tmem_base, adesc, bdesc, idesc, (i | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+        if (i == num_k_blocks - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (128 thr)
+    const int quad = warp & 3;
+    const int row = tile_m * BLOCK_M + quad * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * 32), r);
+      const int col0 = tile_n * BLOCK_N + cb * 32;
+      if (row < wp.M) {
+        float* dst = wp.D + (size_t)row * wp.ldd + col0;
+        if (col0 + 32 <= wp.N && (wp.ldd & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            atomicAdd(reinterpret_cast<float4*>(dst + 4 * j),
+                      make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < wp.N) atomicAdd(dst + j, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BLOCK_N);
+  }
+}
+
+template <int BLOCK_N, int kStages>
+static int launch_mn(const void* A, const void* B, float* D, int M, int N, int K, int lda, int ldb,
+                     int ldd, int splits, int variant, cudaStream_t st) {
+  using L = WgradSmem<BLOCK_N, kStages>;
+  CUtensorMap ma, mb;
+  int rc;
+  // A: [K rows, M cols], box = 64 columns x 64 rows
+  if ((rc = make_map_2d(&ma, A, K, M, lda, kMnBox, kMnBox))) return rc;
+  if ((rc = make_map_2d(&mb, B, K, N, ldb, kMnBox, kMnBox))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_mn_kernel<BLOCK_N, kStages>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int total_kb = (K + kMnBox - 1) / kMnBox;
+  if (splits < 1) splits = 1;
+  if (splits > total_kb) splits = total_kb;
+  int per = (total_kb + splits - 1) / splits;
+  splits = (total_kb + per - 1) / per;            // no empty CTAs
+  WgradParams wp{D, M, N, K, ldd, per, variant};
+  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  cudaError_t err = launch_pdl((gemm_bf16_mn_kernel<BLOCK_N, kStages>), dim3(tiles, splits),
+                               dim3(kThreads), (size_t)L::kDynamic, st, ma, mb, wp);
+  return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
+}
+
+}  // namespace gemm
+}  // namespace ddl
+
+// D (fp32 [M, N], leading dimension ldd) += A^T B.  `splits` <= 0 picks enough k-splits to put
+// about two CTAs on every SM.  Only fp32 accumulation targets are supported (out_is_bf16 and
+// workspace are accepted for interface stability and must be 0 / null).
+extern "C" int ddl_gemm_bf16_nt_mn(const void* A, const void* B, void* D, int M, int N, int K,
+                                   int lda, int ldb, int ldd, int out_is_bf16, int splits,
+                                   float* workspace, int sms, cudaStream_t st) {
+  using namespace ddl::gemm;
+  (void)workspace;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (out_is_bf16) return -1;
+  if ((lda % 8) || (ldb % 8) || (M % 8) || (N % 8)) return -1;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) return -1;
+  static const int variant = [] {
+    const char* e = std::getenv("DDLB_WGRAD_DESC_VARIANT");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  const int bn = N <= 64 ? 64 : 128;
+  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
+  if (splits <= 0) splits = (2 * sms + tiles - 1) / tiles;
+  if (bn == 64) return launch_mn<64, 4>(A, B, (float*)D, M, N, K, lda, ldb, ldd, splits, variant, st);
+  return launch_mn<128, 4>(A, B, (float*)D, M, N, K, lda, ldb, ldd, splits, variant, st);
+}

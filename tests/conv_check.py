@@ -42,6 +42,24 @@ def check(n, ci, co, hw, k, stats=False, bias=False, relu=False, seed=0):
     return ok
 
 
+def check_wgrad(K, M, N, splits=0, seed=0):
+    """D[M, N] = A[K, M]^T B[K, N] (MN-major operands, split-K fp32 atomics)."""
+    torch.manual_seed(seed)
+    a = (torch.randn(K, M, device="cuda") * 0.5).to(torch.bfloat16)
+    b = (torch.randn(K, N, device="cuda") * 0.5).to(torch.bfloat16)
+    assert ops.gemm_nt_mn_supported(a, b)
+    d = ops.gemm_nt_mn(a, b, splits=splits)
+    d = ops.gemm_nt_mn(a, b, out=d, splits=splits)          # accumulates: 2x
+    torch.cuda.synchronize()
+    ref = 2.0 * (a.float().t() @ b.float())
+    err = (d - ref).abs().max().item()
+    tol = 0.02 * max(ref.abs().max().item(), 1.0)
+    ok = err <= tol
+    print(f"wgrad K={K} M={M} N={N} splits={splits}: max_err={err:.4f} tol={tol:.4f} "
+          f"{'OK' if ok else 'FAIL'} (desc variant {os.environ.get('DDLB_WGRAD_DESC_VARIANT', '0')})", flush=True)
+    return ok
+
+
 def bench(n, ci, co, hw, k=3, iters=20):
     x = torch.randn(n, ci, hw, hw, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     w = torch.randn(co, ci, k, k, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
@@ -71,6 +89,11 @@ def main():
         ok &= check(*args)
     ok &= check(32, 256, 256, 14, 3, stats=True)
     ok &= check(7, 64, 64, 11, 3, stats=True, bias=True, relu=True)
+    if os.environ.get("CHECK_WGRAD", "1") == "1":
+        for args in [(64, 128, 64), (128, 128, 128), (6272, 256, 1024), (100352, 64, 256), (1000, 72, 200),
+                     (200, 136, 64)]:
+            ok &= check_wgrad(*args)
+        ok &= check_wgrad(4096, 256, 128, splits=1)
     if ok and os.environ.get("BENCH", "1") == "1":
         res = [bench(32, 64, 64, 56), bench(32, 128, 128, 28), bench(32, 256, 256, 14), bench(32, 512, 512, 7)]
         for r in res:
