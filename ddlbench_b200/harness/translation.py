@@ -182,8 +182,8 @@ def main(argv=None) -> Dict[str, float]:
                 ntok += int((target != PAD).sum()) + int(sl.sum())
                 if i % a.print_freq == 0 and rank == 0:
                     print("Epoch: [%d][%d/%d]\tTime %.3f\tLoss %.4f\tTok/s %.0f" % (
-                        epoch, i, steps, time.time() - t0, float(loss), ntok / max(time.time() - t0, 1e-9)))
-            out["train_loss"] = float(loss)
+                        epoch, i, steps, time.time() - t0, float(loss.detach()), ntok / max(time.time() - t0, 1e-9)))
+            out["train_loss"] = float(loss.detach())
             out["tokens_per_sec"] = ntok * dp / max(time.time() - t0, 1e-9)
             if rank == 0:
                 print("Epoch %d: %.3f seconds" % (epoch, time.time() - t0))
