@@ -11,6 +11,8 @@ loss read-back overlap the previous / next replay.
 """
 from __future__ import annotations
 
+import os
+
 import time
 from typing import Dict, List, Optional, Tuple
 
@@ -68,6 +70,15 @@ class Trainer:
                 dist.broadcast(full, src=0, group=group)
                 self.ex.store.load_full_master(full.clone())
         self.group = group
+        # opt-in: per-bucket SGD on a side stream while backward is still running (single GPU).
+        # The optimizer is 85 us (1.8 %) at the end of the ResNet-50 step; overlapped, only the
+        # last bucket's update stays on the critical path.  Off until measured on hardware.
+        self._sgd_overlap = (os.environ.get("DDLB_SGD_OVERLAP", "0") == "1" and self.fdp is None
+                             and not self.distributed)
+        self._sgd_stream = torch.cuda.Stream(device=self.device) if (self._sgd_overlap and on_gpu) else None
+        self._sgd_buckets_done = 0
+        if self._sgd_overlap:
+            self.ex.on_bucket_ready = self._sgd_bucket
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_x: Optional[torch.Tensor] = None
         self.static_t: Optional[torch.Tensor] = None
@@ -87,10 +98,32 @@ class Trainer:
             self._update_baseline()
         return stats
 
+    def _sgd_bucket(self, b: int) -> None:
+        """Bucket ``b`` has its final gradients (and its weights are no longer read by this
+        backward): update it now, off the critical path."""
+        st = self.ex.store
+        if self._sgd_stream is None:
+            st.sgd_step(bucket=b)
+        else:
+            main = torch.cuda.current_stream(self.device)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self._sgd_stream):
+                self._sgd_stream.wait_event(ev)
+                st.sgd_step(bucket=b)
+        self._sgd_buckets_done += 1
+
     def _update_baseline(self) -> None:
         """Non-fused update: (NCCL all-reduce of the flat gradient buffer, then) fused SGD."""
         if self.distributed:
             dist.all_reduce(self.ex.store.g_flat, group=self.group)
+        if self._sgd_overlap:
+            # every bucket was updated as it became ready; just join the side stream
+            assert self._sgd_buckets_done == len(self.ex.store.layout.buckets), "a bucket was not updated"
+            self._sgd_buckets_done = 0
+            if self._sgd_stream is not None:
+                torch.cuda.current_stream(self.device).wait_stream(self._sgd_stream)
+            return
         self.ex.store.sgd_step()
 
     @property

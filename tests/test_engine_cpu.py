@@ -160,3 +160,20 @@ def test_extra_zoo_parameter_counts():
         assert sum(p.numel() for p in build_model(arch, "imagenet").parameters()) == n, arch
     nas = build_model("nasnetamobile", "imagenet")
     assert 5.0e6 < sum(p.numel() for p in nas.parameters()) < 5.6e6      # 5.3 M in the paper
+
+
+def test_per_bucket_sgd_overlap_equals_single_update(monkeypatch):
+    """DDLB_SGD_OVERLAP: updating bucket by bucket from the bucket-ready hook == one flat update."""
+    from ddlbench_b200.harness import Trainer
+    x = torch.randn(4, 1, 28, 28)
+    t = torch.randint(0, 10, (4,))
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("DDLB_SGD_OVERLAP", flag)
+        tr = Trainer("resnet18", "mnist", batch_size=4, device="cpu", dtype=torch.float32, lr=0.05,
+                     momentum=0.9, weight_decay=1e-4, cuda_graph=False, seed=7, bucket_elems=1 << 18)
+        assert len(tr.ex.store.layout.buckets) > 3
+        for _ in range(3):
+            tr.step(x, t)
+        res[flag] = tr.ex.store.master.clone()
+    assert torch.equal(res["0"], res["1"])
