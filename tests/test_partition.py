@@ -184,3 +184,52 @@ def test_profile_partition_codegen_round_trip(tmp_path):
     assert torch.allclose(env[mods[-2][2][-1]], y, atol=1e-5)
     full = pkg.full_model()
     assert sum(p.numel() for p in full.parameters()) == sum(p.numel() for p in m.parameters())
+
+
+def test_pipeline_simulator_matches_steady_state_bounds():
+    from ddlbench_b200.partition.simulate import chrome_trace, simulate_1f1b, simulate_gpipe
+    # balanced straight pipeline: steady state = one stage's forward+backward per minibatch
+    r = simulate_1f1b([1.0] * 4, [2.0] * 4, minibatches=64)
+    assert abs(r["steady_ms_per_minibatch"] - 3.0) < 1e-6 and r["bound_ms"] == 3.0
+    assert r["bubble_fraction"]["3.0"] < 0.06 and len(r["spans"]) == 2 * 4 * 64
+    # the slowest stage sets the pace
+    r = simulate_1f1b([1, 1, 3, 1], [2, 2, 5, 2], minibatches=64)
+    assert abs(r["steady_ms_per_minibatch"] - 8.0) < 1e-6
+    # replicating the slow stage helps, but strict 1F1B with the runtime's warm-up depths does
+    # not reach the partitioner's bound (max_s (f+b)/replicas = 4.0): the in-flight depth is too
+    # small to cover the replicated stage's latency — exactly what the simulator is for
+    r2 = simulate_1f1b([1, 1, 3, 1], [2, 2, 5, 2], replicas=[1, 1, 2, 1], minibatches=64)
+    assert r2["bound_ms"] == 4.0 and 4.0 - 1e-9 <= r2["steady_ms_per_minibatch"] < 8.0
+    # GPipe: (m + S - 1) slots of fwd then bwd(+recompute); bubble = (S-1)/(m+S-1) without comm
+    g = simulate_gpipe([1.0] * 4, [2.0] * 4, microbatches=8, recompute=False)
+    assert abs(g["makespan_ms"] - (8 + 3) * 3.0) < 1e-6
+    assert abs(g["bubble_fraction"]["0"] - 3.0 / 11.0) < 1e-6
+    assert len(chrome_trace(g["spans"])["traceEvents"]) == 2 * 4 * 8
+
+
+def test_simulator_agrees_with_partitioner_objective():
+    """The optimizer's 'time per stage in pipeline' is the simulator's steady state for the
+    partition it emits (straight pipeline, free communication)."""
+    from ddlbench_b200.partition import optimizer
+    from ddlbench_b200.partition.graph import Graph, Node
+    from ddlbench_b200.partition.simulate import simulate_1f1b
+    costs = [3, 1, 4, 1, 5, 9, 2, 6]
+    g = Graph()
+    prev = None
+    for i, c in enumerate(costs):
+        n = Node("node%d" % i, "L%d()" % i, c, 2.0 * c, 1.0, 1.0)
+        g.add_node(n)
+        if prev is not None:
+            g.add_edge(prev, n)
+        prev = n
+    pp, _, reps, gr = optimizer.main([4], None, [1e15], straight_pipeline=True, graph=g,
+                                     out=lambda *a, **k: None, print_configuration=False)
+    stage_t = {}
+    for n in gr.nodes.values():
+        stage_t.setdefault(n.stage_id, [0.0, 0.0])
+        stage_t[n.stage_id][0] += n.forward_compute_time
+        stage_t[n.stage_id][1] += n.backward_compute_time
+    fwd = [stage_t[s][0] for s in sorted(stage_t)]
+    bwd = [stage_t[s][1] for s in sorted(stage_t)]
+    r = simulate_1f1b(fwd, bwd, minibatches=96)
+    assert abs(r["steady_ms_per_minibatch"] - pp * 1e3) < 1e-6
