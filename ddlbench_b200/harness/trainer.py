@@ -141,6 +141,9 @@ class Trainer:
             return self._step_eager(self.ex.prepare_input(x), target)
         if self.graph is None:
             self._capture(x, target)
+            if not self.cuda_graph:          # capture failed: eager from now on
+                self.steps_done += 1
+                return self._step_eager(self.ex.prepare_input(x), target)
         if x.data_ptr() != self.static_x.data_ptr():
             self.static_x.copy_(x, non_blocking=True)
         if target.data_ptr() != self.static_t.data_ptr():
@@ -155,6 +158,8 @@ class Trainer:
         if self.cuda_graph:
             if self.graph is None:
                 self._capture(ops.normalize_u8(x_u8, mean, std, dtype=self.dtype), target)
+                if not self.cuda_graph:
+                    return self.step(ops.normalize_u8(x_u8, mean, std, dtype=self.dtype), target)
             ops.normalize_u8(x_u8, mean, std, dtype=self.dtype, out=self.static_x)
             self.static_t.copy_(target, non_blocking=True)
             self._replay()
@@ -181,16 +186,47 @@ class Trainer:
         torch.cuda.synchronize(self.device)
         if self.distributed:
             dist.barrier(self.group)
-        before = ops.launches
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.static_stats = self._step_eager(self.static_x, self.static_t,
-                                                 update=not self._nccl_outside_graph)
-        self.launches_per_step = ops.launches - before
-        self.graph = g
+        # Capture.  If it fails (all ranks decide together), retry once without programmatic
+        # dependent launch, and as a last resort stay in eager mode — a benchmark run must
+        # degrade, not die.
+        ok = self._try_capture()
+        if not ok and ops.ext().set_pdl(False):
+            print("[trainer] graph capture failed; retrying without programmatic dependent launch",
+                  flush=True)
+            ok = self._try_capture()
+        if not ok:
+            print("[trainer] graph capture failed; continuing in eager mode", flush=True)
+            self.cuda_graph = False
+            self.graph = None
         torch.cuda.synchronize(self.device)
         if self.distributed:
             dist.barrier(self.group)
+
+    def _try_capture(self) -> bool:
+        before = ops.launches
+        g = torch.cuda.CUDAGraph()
+        failed = 0
+        try:
+            with torch.cuda.graph(g):
+                self.static_stats = self._step_eager(self.static_x, self.static_t,
+                                                     update=not self._nccl_outside_graph)
+        except Exception as e:  # noqa: BLE001
+            print("[trainer] capture error: %s" % str(e).splitlines()[0][:200], flush=True)
+            failed = 1
+            try:
+                torch.cuda.synchronize(self.device)
+            except Exception:  # noqa: BLE001
+                pass
+        if self.distributed:
+            flag = torch.tensor([failed], device=self.device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            failed = int(flag.item())
+        if failed:
+            self._sgd_buckets_done = 0
+            return False
+        self.launches_per_step = ops.launches - before
+        self.graph = g
+        return True
 
     # ------------------------------------------------------------------ evaluation
     @torch.no_grad()

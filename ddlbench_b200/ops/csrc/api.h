@@ -114,6 +114,7 @@ int ddl_gemm_bf16_nt_mn(const void* A, const void* B, void* D, int M, int N, int
                         int ldb, int ldd, int out_is_bf16, int splits, float* workspace, int sms,
                         cudaStream_t st);
 int ddl_gemm_selftest_info(char* buf, int len);
+int ddl_set_pdl(int on);
 
 #ifdef __cplusplus
 }

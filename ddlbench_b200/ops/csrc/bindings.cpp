@@ -617,6 +617,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_bf16_nhwc", &conv_bf16_nhwc);
   m.def("im2col_rows", &im2col_rows);
   m.def("gemm_info", &gemm_info);
+  m.def("set_pdl", [](bool on) { return ddl_set_pdl(on ? 1 : 0) != 0; },
+        "enable / disable programmatic dependent launch for our kernels; returns the previous setting");
   m.def("ar_sgd_twoshot", &ar_sgd_twoshot);
   m.def("ar_twoshot", &ar_twoshot);
   m.def("ar_oneshot", &ar_oneshot);

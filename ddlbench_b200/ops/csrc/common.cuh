@@ -114,13 +114,17 @@ __device__ __forceinline__ void pdl_enter() {
 // off; works under stream capture, the edge becomes a programmatic graph dependency).
 #include <cstdlib>
 namespace ddl {
-inline bool pdl_enabled() {
-  static const bool on = [] {
+// One flag for the whole extension (an inline function's static local is a single object across
+// translation units); initialised from DDLB_PDL, switchable at run time (ddl_set_pdl) so a caller
+// can retry a failed graph capture without programmatic edges.
+inline int& pdl_flag() {
+  static int on = [] {
     const char* e = std::getenv("DDLB_PDL");
-    return !(e && e[0] == '0');
+    return (e && e[0] == '0') ? 0 : 1;
   }();
   return on;
 }
+inline bool pdl_enabled() { return pdl_flag() != 0; }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                               cudaStream_t st, Args... args) {

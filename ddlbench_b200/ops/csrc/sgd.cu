@@ -150,3 +150,10 @@ extern "C" int ddl_sumsq(const void* x, int is_bf16, float* out, int64_t n, int 
     launch_pdl(sumsq_kernel<float>, dim3(grid), dim3(256), 0, stream, (const float*)x, out, n);
   return (int)cudaGetLastError();
 }
+
+// run-time switch for programmatic dependent launch (see common.cuh); returns the previous value
+extern "C" int ddl_set_pdl(int on) {
+  const int prev = ddl::pdl_flag();
+  ddl::pdl_flag() = on ? 1 : 0;
+  return prev;
+}
