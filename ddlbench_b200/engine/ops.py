@@ -12,6 +12,7 @@ Parameter gradients are written straight into views of the flat gradient buffer
 """
 from __future__ import annotations
 
+import os as _os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -30,8 +31,11 @@ BN_MOMENTUM_SCALE = [1.0]
 # side stream for weight-gradient kernels (set by the executor during backward) and the
 # operands that must outlive it
 WGRAD_OVERLAP = {"stream": None, "keep": []}
-import os as _os
+
+# ---- switches; read once at import
+# BN finalize inside the GEMM epilogue (measured slower than a separate 4 us launch)
 FUSE_BN_FINALIZE = _os.environ.get("DDLB_FUSE_FINALIZE", "0") == "1"
+# BN backward reads the 1-bit activation mask written by the forward instead of y
 ACT_BITMASK_ON = _os.environ.get("DDLB_ACT_BITMASK", "1") == "1"
 # tcgen05 implicit-GEMM for the 3x3 convolutions (csrc/conv_tcgen05.cu): opt-in until validated
 CONV3X3_TCGEN05 = _os.environ.get("DDLB_CONV3X3_TCGEN05", "0") == "1"
@@ -39,7 +43,9 @@ CONV3X3_TCGEN05 = _os.environ.get("DDLB_CONV3X3_TCGEN05", "0") == "1"
 STEM_IM2COL = _os.environ.get("DDLB_STEM_IM2COL", "0") == "1"
 # weight gradient of 1x1 convolutions / linear layers on tcgen05 (csrc/gemm_wgrad_tcgen05.cu): opt-in
 WGRAD_TCGEN05 = _os.environ.get("DDLB_WGRAD_TCGEN05", "0") == "1"
+# data gradient of those 3x3 convolutions through the same kernel (flipped, transposed filter)
 CONV3X3_DGRAD = CONV3X3_TCGEN05 and _os.environ.get("DDLB_CONV3X3_DGRAD", "0") == "1"
+# weight-gradient kernels on a side stream during backward
 OVERLAP_WGRAD_DEFAULT = _os.environ.get("DDLB_WGRAD_OVERLAP", "1") == "1"
 
 
