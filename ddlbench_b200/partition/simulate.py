@@ -20,7 +20,7 @@ from ..parallel.pipedream.schedule import B as OP_B, F as OP_F, fill_drain, one_
 
 
 def simulate_1f1b(fwd: Sequence[float], bwd: Sequence[float], replicas: Optional[Sequence[int]] = None,
-                  comm: float = 0.0, minibatches: int = 64) -> Dict[str, object]:
+                  comm: float = 0.0, minibatches: int = 64, extra_warmup: int = 0) -> Dict[str, object]:
     """``fwd[s]`` / ``bwd[s]``: ms per minibatch on ONE replica of stage s.  Minibatch m is served
     by replica ``m % replicas[s]`` of every stage (the runtime's round-robin routing)."""
     S = len(fwd)
@@ -31,7 +31,7 @@ def simulate_1f1b(fwd: Sequence[float], bwd: Sequence[float], replicas: Optional
     warm = []
     for s in range(S):
         w = num_ranks - 1 - sum(replicas[:s])
-        warm.append(max(0, w // replicas[s]))
+        warm.append(max(0, w // replicas[s]) + extra_warmup)
     f_done: Dict[Tuple[int, int], float] = {}      # (stage, minibatch) -> time forward finished
     b_done: Dict[Tuple[int, int], float] = {}
     free = {(s, r): 0.0 for s in range(S) for r in range(replicas[s])}
@@ -129,6 +129,8 @@ def cli(argv=None) -> int:
     ap.add_argument("--comm", type=float, default=0.0)
     ap.add_argument("-n", "--minibatches", type=int, default=64)
     ap.add_argument("--gpipe", type=int, default=0, help="simulate GPipe with this many micro-batches")
+    ap.add_argument("--extra-warmup", type=int, default=0,
+                    help="additional in-flight minibatches per stage (hides transfer latency)")
     ap.add_argument("--trace", default=None, help="write a Chrome trace JSON here")
     a = ap.parse_args(argv)
     fwd = [float(x) for x in a.fwd.split(",")]
@@ -137,7 +139,7 @@ def cli(argv=None) -> int:
         res = simulate_gpipe(fwd, bwd, a.gpipe, a.comm)
     else:
         reps = [int(x) for x in a.replicas.split(",")] if a.replicas else None
-        res = simulate_1f1b(fwd, bwd, reps, a.comm, a.minibatches)
+        res = simulate_1f1b(fwd, bwd, reps, a.comm, a.minibatches, a.extra_warmup)
     spans = res.pop("spans")
     if a.trace:
         json.dump(chrome_trace(spans), open(a.trace, "w"))
