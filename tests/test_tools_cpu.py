@@ -278,3 +278,35 @@ def test_driver_multi_host_and_translation_commands():
     assert "-g 8" in two[0][1][-1] and "-n 2" in two[0][1][-1]
     (host, cmd), = driver.build_node_commands(driver.load("configs/driver/gnmt_4pipedream.yml"))
     assert "ddlbench_b200.harness.translation" in cmd and cmd[cmd.index("--stages") + 1] == "4"
+
+
+def test_launcher_terminate_stops_exactly_the_recorded_pids(tmp_path):
+    """``launch.py --terminate <pidfile>`` signals the recorded children only (the reference's
+    ``terminate_runtime.py`` runs ``pkill -f`` on every machine)."""
+    import signal
+    import subprocess
+    import sys
+    import time
+    script = tmp_path / "sleeper.py"
+    script.write_text("import time, sys\ntime.sleep(120)\n")
+    pidfile = tmp_path / "pids"
+    launcher = subprocess.Popen([sys.executable, "-m", "ddlbench_b200.launch", "--nproc_per_node", "2",
+                                 "--no-rank-args", "--pid-file", str(pidfile), str(script)])
+    bystander = subprocess.Popen([sys.executable, str(script)])     # same command line, not ours
+    try:
+        for _ in range(100):
+            if pidfile.exists() and len(pidfile.read_text().split()) == 2:
+                break
+            time.sleep(0.1)
+        pids = [int(p) for p in pidfile.read_text().split()]
+        assert len(pids) == 2 and bystander.pid not in pids
+        r = subprocess.run([sys.executable, "-m", "ddlbench_b200.launch", "--terminate", str(pidfile)],
+                           capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0 and "Done Terminating" in r.stdout
+        assert launcher.wait(timeout=30) != 0            # its children were terminated
+        assert bystander.poll() is None                  # an unrelated process with the same name lives on
+    finally:
+        bystander.kill()
+        bystander.wait()
+        if launcher.poll() is None:
+            launcher.kill()
