@@ -616,6 +616,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16_nt_mn", &gemm_bf16_nt_mn);
   m.def("conv_bf16_nhwc", &conv_bf16_nhwc);
   m.def("im2col_rows", &im2col_rows);
+  m.def("conv_box", [](int64_t nb, int64_t h, int64_t w) {
+    int b[3];
+    ddl_conv_box((int)nb, (int)h, (int)w, b);
+    return std::vector<int64_t>{b[0], b[1], b[2]};
+  });
   m.def("gemm_info", &gemm_info);
   m.def("set_pdl", [](bool on) { return ddl_set_pdl(on ? 1 : 0) != 0; },
         "enable / disable programmatic dependent launch for our kernels; returns the previous setting");

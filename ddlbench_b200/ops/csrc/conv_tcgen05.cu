@@ -303,3 +303,8 @@ extern "C" int ddl_conv_bf16_nhwc(const void* x, const void* w, void* y, int NB,
   if (narrow) return launch_conv<64, 4>(x, w, y, cp, st);
   return launch_conv<128, 3>(x, w, y, cp, st);
 }
+
+// Tile box chosen for an [NB, H, W] output (host-only; exposed for tests): {TW, TH, TN}.
+extern "C" void ddl_conv_box(int NB, int H, int W, int* out3) {
+  ddl::gemm::choose_box(NB, H, W, &out3[0], &out3[1], &out3[2]);
+}

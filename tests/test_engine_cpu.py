@@ -177,3 +177,87 @@ def test_per_bucket_sgd_overlap_equals_single_update(monkeypatch):
             tr.step(x, t)
         res[flag] = tr.ex.store.master.clone()
     assert torch.equal(res["0"], res["1"])
+
+
+@pytest.mark.parametrize("nb,ci,co,hw,k", [(3, 64, 64, 9, 3), (2, 64, 128, 7, 3), (5, 64, 64, 14, 3),
+                                           (2, 128, 64, 10, 5)])
+def test_conv_tcgen05_tiling_logic_emulated(nb, ci, co, hw, k):
+    """Host-side emulation of csrc/conv_tcgen05.cu: same tile boxes (from the C++ chooser), same
+    (tap, channel-slice) K loop, same shifted / zero-filled input boxes, same row -> pixel
+    mapping and clipped stores — must reproduce conv2d.  (Checks the algorithm the kernel
+    implements; the tensor-core descriptors themselves need the GPU test.)"""
+    import torch.nn.functional as Fn
+    from ddlbench_b200 import ops
+    ext = ops.load_ext(build_if_missing=False)
+    TW, TH, TN = ext.conv_box(nb, hw, hw)
+    assert TW * TH * TN == 128
+    torch.manual_seed(0)
+    x = torch.randn(nb, hw, hw, ci, dtype=torch.float64)                  # NHWC
+    w = torch.randn(co, k, k, ci, dtype=torch.float64)                    # KRSC
+    wmat = w.reshape(co, k * k * ci)
+    pad = k // 2
+    BLOCK_N, BLOCK_K = 64, 64
+    y = torch.zeros(nb, hw, hw, co, dtype=torch.float64)
+    tiles_w, tiles_h, tiles_nb = -(-hw // TW), -(-hw // TH), -(-nb // TN)
+
+    def box(t, n0, h0, w0, c0):           # 4-D TMA load with zero fill outside the tensor
+        out = torch.zeros(TN, TH, TW, BLOCK_K, dtype=torch.float64)
+        for a in range(TN):
+            for b in range(TH):
+                for c in range(TW):
+                    n, h, ww = n0 + a, h0 + b, w0 + c
+                    if 0 <= n < nb and 0 <= h < hw and 0 <= ww < hw:
+                        out[a, b, c] = t[n, h, ww, c0:c0 + BLOCK_K]
+        return out.reshape(128, BLOCK_K)  # row = (ln * TH + lh) * TW + lw
+
+    for tile_pix in range(tiles_w * tiles_h * tiles_nb):
+        w0 = (tile_pix % tiles_w) * TW
+        h0 = ((tile_pix // tiles_w) % tiles_h) * TH
+        n0 = (tile_pix // (tiles_w * tiles_h)) * TN
+        for tile_n in range(co // BLOCK_N):
+            acc = torch.zeros(128, BLOCK_N, dtype=torch.float64)
+            for kb in range(k * k * (ci // BLOCK_K)):
+                tap, cb = divmod(kb, ci // BLOCK_K)
+                kh, kw = divmod(tap, k)
+                a = box(x, n0, h0 + kh - pad, w0 + kw - pad, cb * BLOCK_K)
+                bmat = wmat[tile_n * BLOCK_N:(tile_n + 1) * BLOCK_N,
+                            tap * ci + cb * BLOCK_K: tap * ci + (cb + 1) * BLOCK_K]
+                acc += a @ bmat.t()
+            for row in range(128):
+                lw, lh, ln = row % TW, (row // TW) % TH, row // (TW * TH)
+                if w0 + lw < hw and h0 + lh < hw and n0 + ln < nb:       # clipped store
+                    y[n0 + ln, h0 + lh, w0 + lw, tile_n * BLOCK_N:(tile_n + 1) * BLOCK_N] = acc[row]
+    ref = Fn.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), padding=pad).permute(0, 2, 3, 1)
+    torch.testing.assert_close(y, ref, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("n,c,hw,k,s,p", [(2, 3, 20, 7, 2, 3), (1, 3, 9, 3, 1, 1), (2, 1, 12, 3, 1, 1)])
+def test_im2col_kernel_index_math_emulated(n, c, hw, k, s, p):
+    """The staging / gather arithmetic of csrc/im2col.cu (rows[] fill, k -> (kh, rem), base offset)
+    replayed on the host against the reference patch matrix."""
+    from ddlbench_b200.ops import reference as ref
+    torch.manual_seed(0)
+    x = torch.randn(n, c, hw, hw)
+    xh = x.permute(0, 2, 3, 1).contiguous().reshape(-1)                 # NHWC flat
+    H = W = hw
+    OH = (H + 2 * p - k) // s + 1
+    OW = (W + 2 * p - k) // s + 1
+    K, R = k * k * c, k * c
+    kpad = (K + 7) // 8 * 8
+    rowlen = (W + 2 * p) * c
+    out = torch.zeros(n * OH * OW, kpad)
+    for blk in range(n * OH):
+        nn_, oh = divmod(blk, OH)
+        ih0 = oh * s - p
+        rows = torch.zeros(k * rowlen)
+        for i in range(k * rowlen):
+            kh, j = divmod(i, rowlen)
+            ih, iwc = ih0 + kh, j - p * c
+            if 0 <= ih < H and 0 <= iwc < W * c:
+                rows[i] = xh[(nn_ * H + ih) * W * c + iwc]
+        for ow in range(OW):
+            base = ow * s * c
+            for kk in range(kpad):
+                if kk < K:
+                    out[(nn_ * OH + oh) * OW + ow, kk] = rows[(kk // R) * rowlen + base + (kk % R)]
+    torch.testing.assert_close(out, ref.im2col_rows(x, k, k, s, p))
