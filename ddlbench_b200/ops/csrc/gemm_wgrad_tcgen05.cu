@@ -16,9 +16,11 @@
 // vector atomics straight from the TMEM read-out (no shared-memory staging, no second pass).
 //
 // STATUS: opt-in (DDLB_WGRAD_TCGEN05=1).  Written after round 1's GPU minutes were spent: it
-// compiles for sm_100a but has not run on hardware.  The one assumption that cannot be checked
-// offline is which of LBO / SBO addresses the MN direction for MN-major SWIZZLE_128B operands;
-// `desc_variant` (env DDLB_WGRAD_DESC_VARIANT) swaps them for bring-up.
+// compiles for sm_100a but has not run on hardware.  LBO = stride between 64-element MN atoms,
+// SBO = stride between 8-row K groups follows the canonical Major-MN SWIZZLE_128B layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units documented in CUTLASS
+// (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>); `desc_variant`
+// (env DDLB_WGRAD_DESC_VARIANT=1) swaps the two for bring-up should the hardware disagree.
 #include <cuda.h>
 #include <cstdio>
 
