@@ -156,7 +156,8 @@ class _ConvMixin:
                             relu=relu, bn_finalize=bn_finalize)
             return d.view(n, oh, ow, co).permute(0, 3, 1, 2), col_sums is not None
         if self._is_conv_tc(x, w):
-            y = ops.conv_tn(x, w, col_sums=col_sums, bias=bias, relu=relu)
+            y = ops.conv_tn(x, w, col_sums=col_sums, bias=bias, relu=relu, stride=self.stride[0],
+                            padding=self.padding)
             if y is not None:
                 return y, col_sums is not None
         y = aten.convolution(x, w, None, self.stride, self.padding, self.dilation, False, [0, 0],
@@ -171,7 +172,9 @@ class _ConvMixin:
         side = WGRAD_OVERLAP["stream"] if dy.is_cuda else None
         args = (None, self.stride, self.padding, self.dilation, False, [0, 0], self.groups)
         dx_tc = None
-        if need_dx and CONV3X3_DGRAD and self._is_conv_tc(x, w) and \
+        if need_dx and CONV3X3_DGRAD and self._is_conv_tc(x, w) and self.stride == [1, 1] and \
+                self.padding == [self.wshape[2] // 2, self.wshape[3] // 2] and \
+                self.wshape[2] % 2 == 1 and self.wshape[3] % 2 == 1 and \
                 dy.is_contiguous(memory_format=torch.channels_last):
             # data gradient of a stride-1 "same" convolution = the same convolution of dy with the
             # spatially flipped, channel-transposed filter: reuse the tcgen05 kernel

@@ -447,25 +447,34 @@ def im2col_rows(x: torch.Tensor, kh: int, kw: int, stride: int, pad: int) -> tor
 
 
 def conv_tn_supported(x: torch.Tensor, w: torch.Tensor, stride, padding, dilation, groups) -> bool:
-    """Shapes the tcgen05 implicit-GEMM convolution (csrc/conv_tcgen05.cu) takes: stride 1, odd
-    kernel with "same" padding, no groups/dilation, Cin % 64 == 0, Cout % 64 == 0, bf16 NHWC."""
+    """Shapes the tcgen05 implicit-GEMM convolution (csrc/conv_tcgen05.cu) takes: stride 1 or 2,
+    no groups/dilation, Cin % 64 == 0, Cout % 64 == 0, bf16 NHWC (1x1 stride-1 convolutions are
+    plain GEMMs and go through ``gemm_tn`` instead)."""
     if not (x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.dim() == 4):
         return False
     co, ci, kh, kw = w.shape
-    return (list(stride) == [1, 1] and list(dilation) == [1, 1] and groups == 1 and kh % 2 == 1 and
-            kw % 2 == 1 and kh * kw > 1 and list(padding) == [kh // 2, kw // 2] and ci % 64 == 0 and
-            co % 64 == 0 and x.is_contiguous(memory_format=torch.channels_last) and
-            w.is_contiguous(memory_format=torch.channels_last))
+    st = list(stride)
+    return (st[0] == st[1] and st[0] in (1, 2) and list(dilation) == [1, 1] and groups == 1 and
+            (kh * kw > 1 or st[0] == 2) and kh <= 7 and kw <= 7 and ci % 64 == 0 and co % 64 == 0 and
+            x.is_contiguous(memory_format=torch.channels_last) and
+            (w.is_contiguous(memory_format=torch.channels_last) or kh * kw == 1))
 
 
 def conv_tn(x: torch.Tensor, w: torch.Tensor, col_sums: Optional[torch.Tensor] = None,
-            bias: Optional[torch.Tensor] = None, relu: bool = False) -> Optional[torch.Tensor]:
-    """y = conv2d(x, w) (stride 1, same padding) with optional fused bias/ReLU and BatchNorm
-    partial sums, on the tensor cores.  Returns None if the kernel declines the shape."""
+            bias: Optional[torch.Tensor] = None, relu: bool = False, stride: int = 1,
+            padding: Optional[Sequence[int]] = None) -> Optional[torch.Tensor]:
+    """y = conv2d(x, w, stride, padding) with optional fused bias/ReLU and BatchNorm partial
+    sums, on the tensor cores.  ``padding`` defaults to "same" (k // 2).  Returns None if the
+    kernel declines the shape."""
     co, ci, kh, kw = w.shape
-    y = torch.empty((x.shape[0], co, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device,
+    ph, pw = (kh // 2, kw // 2) if padding is None else (int(padding[0]), int(padding[1]))
+    oh = (x.shape[2] + 2 * ph - kh) // stride + 1
+    ow = (x.shape[3] + 2 * pw - kw) // stride + 1
+    y = torch.empty((x.shape[0], co, oh, ow), dtype=x.dtype, device=x.device,
                     memory_format=torch.channels_last)
-    if ext().conv_bf16_nhwc(x, w, y, kh // 2, kw // 2, col_sums, bias, relu):
+    if kh * kw == 1 and not w.is_contiguous(memory_format=torch.channels_last):
+        w = w.contiguous(memory_format=torch.channels_last)
+    if ext().conv_bf16_nhwc(x, w, y, ph, pw, stride, col_sums, bias, relu):
         _count()
         return y
     return None

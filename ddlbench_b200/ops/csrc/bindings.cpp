@@ -273,19 +273,21 @@ void gemm_bf16_tn(at::Tensor A, at::Tensor B, at::Tensor D, c10::optional<at::Te
 // x: [N, Cin, H, W] channels_last; w: [Cout, Cin, KH, KW] channels_last (KRSC in memory);
 // y: [N, Cout, H, W] channels_last.  Returns false for unsupported shapes.
 bool conv_bf16_nhwc(at::Tensor x, at::Tensor w, at::Tensor y, int64_t pad_h, int64_t pad_w,
-                    c10::optional<at::Tensor> col_sums, c10::optional<at::Tensor> bias, bool relu) {
+                    int64_t stride, c10::optional<at::Tensor> col_sums, c10::optional<at::Tensor> bias, bool relu) {
   TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && y.dim() == 4 && is_bf16(x) && is_bf16(w) && is_bf16(y));
   TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast) &&
               w.is_contiguous(at::MemoryFormat::ChannelsLast) &&
               y.is_contiguous(at::MemoryFormat::ChannelsLast), "conv_bf16_nhwc: channels_last operands");
   const int NB = (int)x.size(0), Cin = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
   const int Cout = (int)w.size(0), KH = (int)w.size(2), KW = (int)w.size(3);
-  TORCH_CHECK(w.size(1) == Cin && y.size(0) == NB && y.size(1) == Cout && y.size(2) == H &&
-              y.size(3) == W);
+  const int OH = (H + 2 * (int)pad_h - KH) / (int)stride + 1;
+  const int OW = (W + 2 * (int)pad_w - KW) / (int)stride + 1;
+  TORCH_CHECK(w.size(1) == Cin && y.size(0) == NB && y.size(1) == Cout && y.size(2) == OH &&
+              y.size(3) == OW, "conv_bf16_nhwc: output shape");
   c10::cuda::CUDAGuard g(x.device());
   const int rc = ddl_conv_bf16_nhwc(x.data_ptr(), w.data_ptr(), y.data_ptr(), NB, H, W, Cin, Cout, KH,
-                                    KW, (int)pad_h, (int)pad_w, (float*)optr(col_sums), optr(bias),
-                                    relu, sm_count(), cur_stream());
+                                    KW, (int)pad_h, (int)pad_w, (int)stride, (float*)optr(col_sums),
+                                    optr(bias), relu, sm_count(), cur_stream());
   if (rc == -1) return false;
   check(rc, "conv_bf16_nhwc");
   return true;

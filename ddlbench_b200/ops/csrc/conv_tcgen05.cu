@@ -35,7 +35,8 @@ struct ConvParams {
   float* col_sums;            // [R][2][Cout] replicated partial sums, or null
   const __nv_bfloat16* bias;  // [Cout] or null
   int relu;
-  int NB, H, W, Cin, Cout;
+  int NB, H, W, Cin, Cout;    // H, W: INPUT height / width
+  int OH, OW, stride;         // output height / width, convolution stride (1 or 2)
   int KH, KW, pad_h, pad_w;
   int TW, TH, TN;             // pixel box of one tile (TW*TH*TN == 128)
   int tiles_w, tiles_h, tiles_nb;
@@ -114,8 +115,8 @@ conv_bf16_nhwc_kernel(const __grid_constant__ CUtensorMap map_x,
         uint8_t* b_dst = a_dst + L::kABytes;
         mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
         // input box shifted by the tap offset; the halo is zero-filled by the TMA unit
-        tma_load_4d(a_dst, &map_x, &full_bar[s], cb * BLOCK_K, w0 + kw - cp.pad_w,
-                    h0 + kh - cp.pad_h, n0);
+        tma_load_4d(a_dst, &map_x, &full_bar[s], cb * BLOCK_K, w0 * cp.stride + kw - cp.pad_w,
+                    h0 * cp.stride + kh - cp.pad_h, n0);
         tma_load_2d(b_dst, &map_w, &full_bar[s], tap * cp.Cin + cb * BLOCK_K, tile_n * BLOCK_N);
       }
     }
@@ -148,7 +149,7 @@ conv_bf16_nhwc_kernel(const __grid_constant__ CUtensorMap map_x,
     const int row = quad * 32 + lane;       // pixel of the tile held by this thread
     // which pixel is it, and is it inside the image?
     const int lw = row % cp.TW, lh = (row / cp.TW) % cp.TH, ln = row / (cp.TW * cp.TH);
-    const bool valid = (w0 + lw < cp.W) && (h0 + lh < cp.H) && (n0 + ln < cp.NB);
+    const bool valid = (w0 + lw < cp.OW) && (h0 + lh < cp.OH) && (n0 + ln < cp.NB);
     for (int i = et; i < BLOCK_N; i += 128) {
       const int col = tile_n * BLOCK_N + i;
       bias_s[i] = (cp.bias && col < cp.Cout) ? __bfloat162float(cp.bias[col]) : 0.f;
@@ -253,10 +254,12 @@ static int launch_conv(const void* x, const void* w, void* y, ConvParams cp, cud
   using L = ConvSmem<BLOCK_N, kStages>;
   CUtensorMap mx, mw, my;
   int rc;
-  if ((rc = make_map_nhwc(&mx, x, cp.NB, cp.H, cp.W, cp.Cin, BLOCK_K, cp.TW, cp.TH, cp.TN))) return rc;
+  if ((rc = make_map_nhwc(&mx, x, cp.NB, cp.H, cp.W, cp.Cin, BLOCK_K, cp.TW, cp.TH, cp.TN,
+                          cp.stride)))
+    return rc;
   const int64_t kdim = (int64_t)cp.KH * cp.KW * cp.Cin;
   if ((rc = make_map_2d(&mw, w, cp.Cout, kdim, kdim, BLOCK_K, BLOCK_N))) return rc;
-  if ((rc = make_map_nhwc(&my, y, cp.NB, cp.H, cp.W, cp.Cout, 64, cp.TW, cp.TH, cp.TN))) return rc;
+  if ((rc = make_map_nhwc(&my, y, cp.NB, cp.OH, cp.OW, cp.Cout, 64, cp.TW, cp.TH, cp.TN))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_bf16_nhwc_kernel<BLOCK_N, kStages>,
@@ -273,17 +276,21 @@ static int launch_conv(const void* x, const void* w, void* y, ConvParams cp, cud
 }  // namespace gemm
 }  // namespace ddl
 
-// x: [NB, H, W, Cin] bf16 NHWC; w: [Cout, KH, KW, Cin] bf16 (KRSC); y: [NB, H, W, Cout].
-// Stride 1, dilation 1, output size == input size (pad = (k-1)/2, odd k).  Returns -1 for
-// unsupported shapes (the caller falls back to the library convolution).
+// x: [NB, H, W, Cin] bf16 NHWC; w: [Cout, KH, KW, Cin] bf16 (KRSC); y: [NB, OH, OW, Cout] with
+// OH = (H + 2*pad_h - KH) / stride + 1.  Stride 1 or 2 (strided input sampling by the TMA unit),
+// dilation 1.  Returns -1 for unsupported shapes (the caller falls back to the library).
 extern "C" int ddl_conv_bf16_nhwc(const void* x, const void* w, void* y, int NB, int H, int W,
                                   int Cin, int Cout, int KH, int KW, int pad_h, int pad_w,
-                                  float* col_sums, const void* bias, int relu, int sms,
+                                  int stride, float* col_sums, const void* bias, int relu, int sms,
                                   cudaStream_t st) {
   using namespace ddl::gemm;
   if (NB <= 0 || H <= 0 || W <= 0) return 0;
   if (Cin % BLOCK_K || Cout % 64 || KH < 1 || KW < 1 || KH > 7 || KW > 7) return -1;
-  if (2 * pad_h != KH - 1 || 2 * pad_w != KW - 1) return -1;
+  if ((stride != 1 && stride != 2) || pad_h < 0 || pad_w < 0 || pad_h >= KH + stride ||
+      pad_w >= KW + stride)
+    return -1;
+  const int OH = (H + 2 * pad_h - KH) / stride + 1, OW = (W + 2 * pad_w - KW) / stride + 1;
+  if (OH <= 0 || OW <= 0) return -1;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) |
        reinterpret_cast<uintptr_t>(y)) & 15)
     return -1;
@@ -292,10 +299,12 @@ extern "C" int ddl_conv_bf16_nhwc(const void* x, const void* w, void* y, int NB,
   cp.bias = (const __nv_bfloat16*)bias;
   cp.relu = relu;
   cp.NB = NB; cp.H = H; cp.W = W; cp.Cin = Cin; cp.Cout = Cout;
+  cp.OH = OH; cp.OW = OW; cp.stride = stride;
   cp.KH = KH; cp.KW = KW; cp.pad_h = pad_h; cp.pad_w = pad_w;
-  choose_box(NB, H, W, &cp.TW, &cp.TH, &cp.TN);
-  cp.tiles_w = (W + cp.TW - 1) / cp.TW;
-  cp.tiles_h = (H + cp.TH - 1) / cp.TH;
+  choose_box(NB, OH, OW, &cp.TW, &cp.TH, &cp.TN);
+  if (cp.TW * stride > 256 || cp.TH * stride > 256) return -1;
+  cp.tiles_w = (OW + cp.TW - 1) / cp.TW;
+  cp.tiles_h = (OH + cp.TH - 1) / cp.TH;
   cp.tiles_nb = (NB + cp.TN - 1) / cp.TN;
   const int pix_tiles = cp.tiles_w * cp.tiles_h * cp.tiles_nb;
   // narrow N tiles when the grid would not fill the machine (7x7 / 14x14 layers)

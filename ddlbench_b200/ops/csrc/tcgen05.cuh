@@ -192,15 +192,20 @@ static inline int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, i
   return r == CUDA_SUCCESS ? 0 : -3;
 }
 
-// 4-D bf16 NHWC tensor [N, H, W, C] (dense), box = {box_c, box_w, box_h, box_n}
+// 4-D bf16 NHWC tensor [N, H, W, C] (dense), box = {box_c, box_w, box_h, box_n} ELEMENTS
+// LOADED; `step` > 1 samples every step-th pixel along W and H (a strided convolution's input):
+// the driver wants boxDim = elements * step for those dimensions (cuda.h, cuTensorMapEncodeTiled).
 static inline int make_map_nhwc(CUtensorMap* map, const void* ptr, int64_t N, int64_t H, int64_t W,
-                                int64_t C, int box_c, int box_w, int box_h, int box_n) {
+                                int64_t C, int box_c, int box_w, int box_h, int box_n,
+                                int step = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return -2;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * step), (cuuint32_t)(box_h * step),
+                       (cuuint32_t)box_n};
+  cuuint32_t estr[4] = {1, (cuuint32_t)step, (cuuint32_t)step, 1};
+  if (box[1] > 256 || box[2] > 256) return -1;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

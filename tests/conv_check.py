@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ddlbench_b200 import ops  # noqa: E402
 
 
-def check(n, ci, co, hw, k, stats=False, bias=False, relu=False, seed=0):
+def check(n, ci, co, hw, k, stats=False, bias=False, relu=False, seed=0, stride=1):
     torch.manual_seed(seed)
     x = (torch.randn(n, ci, hw, hw, device="cuda") * 0.5).to(torch.bfloat16).contiguous(
         memory_format=torch.channels_last)
@@ -19,13 +19,13 @@ def check(n, ci, co, hw, k, stats=False, bias=False, relu=False, seed=0):
         torch.bfloat16).contiguous(memory_format=torch.channels_last)
     b = torch.randn(co, device="cuda").to(torch.bfloat16) if bias else None
     sums = torch.zeros(ops.BN_REPLICAS * 2 * co, device="cuda") if stats else None
-    assert ops.conv_tn_supported(x, w, [1, 1], [k // 2, k // 2], [1, 1], 1), (n, ci, co, hw, k)
-    y = ops.conv_tn(x, w, col_sums=sums, bias=b, relu=relu)
+    assert ops.conv_tn_supported(x, w, [stride, stride], [k // 2, k // 2], [1, 1], 1), (n, ci, co, hw, k)
+    y = ops.conv_tn(x, w, col_sums=sums, bias=b, relu=relu, stride=stride)
     torch.cuda.synchronize()
     if y is None:
         print("conv declined", (n, ci, co, hw, k))
         return False
-    ref = F.conv2d(x.float(), w.float(), b.float() if bias else None, padding=k // 2)
+    ref = F.conv2d(x.float(), w.float(), b.float() if bias else None, stride=stride, padding=k // 2)
     if relu:
         ref = torch.relu(ref)
     err = (y.float() - ref).abs().max().item()
@@ -37,7 +37,7 @@ def check(n, ci, co, hw, k, stats=False, bias=False, relu=False, seed=0):
         s_ref, q_ref = yf.sum((0, 2, 3)), (yf * yf).sum((0, 2, 3))
         ok = ok and (tot[0] - s_ref).abs().max().item() <= 1e-2 * max(s_ref.abs().max().item(), 1.0) + 0.5 \
             and (tot[1] - q_ref).abs().max().item() <= 1e-2 * q_ref.abs().max().item() + 0.5
-    print(f"conv n={n} ci={ci} co={co} hw={hw} k={k} stats={stats} bias={bias} relu={relu}: "
+    print(f"conv n={n} ci={ci} co={co} hw={hw} k={k} stride={stride} stats={stats} bias={bias} relu={relu}: "
           f"max_err={err:.4f} tol={tol:.4f} {'OK' if ok else 'FAIL'}", flush=True)
     return ok
 
@@ -88,6 +88,10 @@ def main():
                  (3, 64, 64, 9, 3), (5, 128, 192, 13, 3), (2, 64, 128, 10, 5), (1, 64, 64, 1, 3)]:
         ok &= check(*args)
     ok &= check(32, 256, 256, 14, 3, stats=True)
+    # strided: ResNet-50's 3x3/s2 and 1x1/s2 (downsample) layers, odd sizes
+    for args in [(32, 128, 128, 56, 3), (32, 256, 512, 56, 1), (4, 64, 64, 15, 3), (3, 128, 64, 9, 1)]:
+        ok &= check(*args, stride=2)
+    ok &= check(8, 256, 256, 28, 3, stats=True, stride=2)
     ok &= check(7, 64, 64, 11, 3, stats=True, bias=True, relu=True)
     if os.environ.get("CHECK_WGRAD", "1") == "1":
         for args in [(64, 128, 64), (128, 128, 128), (6272, 256, 1024), (100352, 64, 256), (1000, 72, 200),

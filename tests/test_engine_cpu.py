@@ -179,9 +179,11 @@ def test_per_bucket_sgd_overlap_equals_single_update(monkeypatch):
     assert torch.equal(res["0"], res["1"])
 
 
-@pytest.mark.parametrize("nb,ci,co,hw,k", [(3, 64, 64, 9, 3), (2, 64, 128, 7, 3), (5, 64, 64, 14, 3),
-                                           (2, 128, 64, 10, 5)])
-def test_conv_tcgen05_tiling_logic_emulated(nb, ci, co, hw, k):
+@pytest.mark.parametrize("nb,ci,co,hw,k,stride", [(3, 64, 64, 9, 3, 1), (2, 64, 128, 7, 3, 1),
+                                                  (5, 64, 64, 14, 3, 1), (2, 128, 64, 10, 5, 1),
+                                                  (3, 64, 64, 14, 3, 2), (2, 64, 128, 9, 1, 2),
+                                                  (2, 64, 64, 8, 3, 2)])
+def test_conv_tcgen05_tiling_logic_emulated(nb, ci, co, hw, k, stride):
     """Host-side emulation of csrc/conv_tcgen05.cu: same tile boxes (from the C++ chooser), same
     (tap, channel-slice) K loop, same shifted / zero-filled input boxes, same row -> pixel
     mapping and clipped stores — must reproduce conv2d.  (Checks the algorithm the kernel
@@ -189,23 +191,25 @@ def test_conv_tcgen05_tiling_logic_emulated(nb, ci, co, hw, k):
     import torch.nn.functional as Fn
     from ddlbench_b200 import ops
     ext = ops.load_ext(build_if_missing=False)
-    TW, TH, TN = ext.conv_box(nb, hw, hw)
+    pad = k // 2
+    ohw = (hw + 2 * pad - k) // stride + 1
+    TW, TH, TN = ext.conv_box(nb, ohw, ohw)
     assert TW * TH * TN == 128
     torch.manual_seed(0)
     x = torch.randn(nb, hw, hw, ci, dtype=torch.float64)                  # NHWC
     w = torch.randn(co, k, k, ci, dtype=torch.float64)                    # KRSC
     wmat = w.reshape(co, k * k * ci)
-    pad = k // 2
     BLOCK_N, BLOCK_K = 64, 64
-    y = torch.zeros(nb, hw, hw, co, dtype=torch.float64)
-    tiles_w, tiles_h, tiles_nb = -(-hw // TW), -(-hw // TH), -(-nb // TN)
+    y = torch.zeros(nb, ohw, ohw, co, dtype=torch.float64)
+    tiles_w, tiles_h, tiles_nb = -(-ohw // TW), -(-ohw // TH), -(-nb // TN)
 
     def box(t, n0, h0, w0, c0):           # 4-D TMA load with zero fill outside the tensor
         out = torch.zeros(TN, TH, TW, BLOCK_K, dtype=torch.float64)
         for a in range(TN):
             for b in range(TH):
                 for c in range(TW):
-                    n, h, ww = n0 + a, h0 + b, w0 + c
+                    # element strides of the tensor map: every `stride`-th pixel from the start
+                    n, h, ww = n0 + a, h0 + b * stride, w0 + c * stride
                     if 0 <= n < nb and 0 <= h < hw and 0 <= ww < hw:
                         out[a, b, c] = t[n, h, ww, c0:c0 + BLOCK_K]
         return out.reshape(128, BLOCK_K)  # row = (ln * TH + lh) * TW + lw
@@ -219,15 +223,16 @@ def test_conv_tcgen05_tiling_logic_emulated(nb, ci, co, hw, k):
             for kb in range(k * k * (ci // BLOCK_K)):
                 tap, cb = divmod(kb, ci // BLOCK_K)
                 kh, kw = divmod(tap, k)
-                a = box(x, n0, h0 + kh - pad, w0 + kw - pad, cb * BLOCK_K)
+                a = box(x, n0, h0 * stride + kh - pad, w0 * stride + kw - pad, cb * BLOCK_K)
                 bmat = wmat[tile_n * BLOCK_N:(tile_n + 1) * BLOCK_N,
                             tap * ci + cb * BLOCK_K: tap * ci + (cb + 1) * BLOCK_K]
                 acc += a @ bmat.t()
             for row in range(128):
                 lw, lh, ln = row % TW, (row // TW) % TH, row // (TW * TH)
-                if w0 + lw < hw and h0 + lh < hw and n0 + ln < nb:       # clipped store
+                if w0 + lw < ohw and h0 + lh < ohw and n0 + ln < nb:     # clipped store
                     y[n0 + ln, h0 + lh, w0 + lw, tile_n * BLOCK_N:(tile_n + 1) * BLOCK_N] = acc[row]
-    ref = Fn.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), padding=pad).permute(0, 2, 3, 1)
+    ref = Fn.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), stride=stride,
+                    padding=pad).permute(0, 2, 3, 1)
     torch.testing.assert_close(y, ref, rtol=1e-10, atol=1e-10)
 
 
