@@ -1,7 +1,11 @@
-// Implicit-GEMM convolution (KH x KW, stride 1, "same"-style padding) on the tcgen05 tensor
-// cores for NHWC bf16 activations — the 3x3 convolutions of ResNet / VGG:
+// Implicit-GEMM convolution (KH x KW, stride 1 or 2, any padding) on the tcgen05 tensor cores
+// for NHWC bf16 activations — the 3x3 convolutions of ResNet / VGG and the strided 3x3 / 1x1
+// (downsample) layers:
 //
-//     Y[n, h, w, :] = sum_{kh, kw}  X[n, h + kh - ph, w + kw - pw, :] * Wt[:, kh, kw, :]^T
+//     Y[n, h, w, :] = sum_{kh, kw}  X[n, s*h + kh - ph, s*w + kw - pw, :] * Wt[:, kh, kw, :]^T
+//
+// For stride 2 the input tensor map carries element strides {1, 2, 2, 1}: the TMA unit samples
+// every second pixel of the shifted box, so the strided case costs nothing extra.
 //
 // (reference: cuDNN library kernels chosen by PyTorch; BatchNorm statistics are a separate pass.)
 //
