@@ -137,8 +137,9 @@ class _ConvMixin:
         return CONV3X3_TCGEN05 and TCGEN05["conv1x1"] and ops.conv_tn_supported(
             x, w, self.stride, self.padding, self.dilation, self.groups)
 
-    def _conv_fwd(self, x, w, bias=None, col_sums=None, relu=False, bn_finalize=None):
-        """Returns (y, stats_fused)."""
+    def _conv_fwd(self, x, w, bias=None, col_sums=None, relu=False, bn_finalize=None, ctx=None):
+        """Returns (y, stats_fused).  ``ctx``: the op's saved-tensor dict (the stem path keeps its
+        patch matrix there for the weight gradient)."""
         if self._is_gemm(x):
             n, ci, h, wd = x.shape
             co = self.wshape[0]
@@ -150,6 +151,8 @@ class _ConvMixin:
             n, ci, h, wd = x.shape
             co, _, kh, kw = self.wshape
             a = ops.im2col_rows(x, kh, kw, self.stride[0], self.padding[0])
+            if ctx is not None and WGRAD_TCGEN05:
+                ctx["patch"] = a
             oh = (h + 2 * self.padding[0] - kh) // self.stride[0] + 1
             ow = (wd + 2 * self.padding[1] - kw) // self.stride[1] + 1
             d = ops.gemm_tn(a, self._stem_weight_matrix(w, a.shape[1]), col_sums=col_sums, bias=bias,
@@ -164,7 +167,7 @@ class _ConvMixin:
                              self.groups)
         return y, False
 
-    def _conv_bwd(self, dy, x, w, need_dx: bool, gw: torch.Tensor, accumulate: bool):
+    def _conv_bwd(self, dy, x, w, need_dx: bool, gw: torch.Tensor, accumulate: bool, patch=None):
         """Data gradient (returned) and weight gradient (written into ``gw``).  With a side
         stream configured (``WGRAD_OVERLAP``) the weight-gradient kernel — which nothing
         needs before the optimizer — runs concurrently with the rest of backward: at the
@@ -192,7 +195,13 @@ class _ConvMixin:
             aten.convolution_backward(dy, x, w, *args, [True, False, False])[0] if lib_dx else None)
         with torch.cuda.stream(side):
             side.wait_event(ev)
-            if WGRAD_TCGEN05 and self._is_gemm(x) and dy.is_contiguous(memory_format=torch.channels_last):
+            if patch is not None and dy.is_contiguous(memory_format=torch.channels_last):
+                # stem: dW[Cout, kh*kw*Cin (padded)] = dY^T @ patch matrix, then drop the padding
+                co, ci, kh, kw = self.wshape
+                n, _, oh, ow = dy.shape
+                dwm = ops.gemm_nt_mn(dy.permute(0, 2, 3, 1).reshape(n * oh * ow, co), patch)
+                dw = dwm[:, :kh * kw * ci].reshape(co, kh, kw, ci).permute(0, 3, 1, 2)
+            elif WGRAD_TCGEN05 and self._is_gemm(x) and dy.is_contiguous(memory_format=torch.channels_last):
                 n, ci, h, wd = x.shape
                 co = self.wshape[0]
                 dw = ops.gemm_nt_mn(dy.permute(0, 2, 3, 1).reshape(n * h * wd, co),
@@ -251,9 +260,9 @@ class ConvBnAct(Op, _ConvMixin):
             # with 128 threads and every CTA pays a fence + ticket), so this is off by default.
             stat_ready = torch.empty(2 * self.channels, dtype=torch.float32, device=x.device)
             fin = (self.ws.counter[32:33], stat_ready, B[self.k_rm], B[self.k_rv], self.eps, mom)
-            c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums, bn_finalize=fin)
+            c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums, bn_finalize=fin, ctx=ctx)
         elif fuse_stats:
-            c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums)
+            c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums, ctx=ctx)
         else:
             c, fused = self._conv_fwd(x, P[self.k_w])
         # 1 bit/element activation mask for the backward (read instead of y: 16x fewer bytes)
@@ -276,7 +285,8 @@ class ConvBnAct(Op, _ConvMixin):
         dc, dz = ops.bn_backward(dys[0], dy2, ctx["y"], ctx["c"], ctx["stat"], P[self.k_g],
                                  self.act, self.has_res and need[1], G[self.k_g], G[self.k_b],
                                  accumulate, self.ws, mask=ctx.get("mask"))
-        dx = self._conv_bwd(dc, ctx["x"], P[self.k_w], need[0], G[self.k_w], accumulate)
+        dx = self._conv_bwd(dc, ctx["x"], P[self.k_w], need[0], G[self.k_w], accumulate,
+                            patch=ctx.get("patch"))
         return [dx, dz] if self.has_res else [dx]
 
 
