@@ -201,6 +201,10 @@ class _ConvMixin:
                 n, _, oh, ow = dy.shape
                 dwm = ops.gemm_nt_mn(dy.permute(0, 2, 3, 1).reshape(n * oh * ow, co), patch)
                 dw = dwm[:, :kh * kw * ci].reshape(co, kh, kw, ci).permute(0, 3, 1, 2)
+            elif WGRAD_TCGEN05 and self._is_conv_tc(x, w) and \
+                    dy.is_contiguous(memory_format=torch.channels_last) and \
+                    (dw := ops.conv_wgrad(dy, x, self.wshape, self.stride[0], self.padding)) is not None:
+                pass        # 3x3 / strided convolutions: shifted-window MN-major kernel
             elif WGRAD_TCGEN05 and self._is_gemm(x) and dy.is_contiguous(memory_format=torch.channels_last):
                 n, ci, h, wd = x.shape
                 co = self.wshape[0]

@@ -480,4 +480,17 @@ def conv_tn(x: torch.Tensor, w: torch.Tensor, col_sums: Optional[torch.Tensor] =
     return None
 
 
+def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, wshape, stride: int = 1,
+               padding: Optional[Sequence[int]] = None) -> Optional[torch.Tensor]:
+    """Weight gradient [Cout, Cin, KH, KW] (fp32, KRSC memory) of a convolution from dy and x on
+    the tensor cores (csrc/gemm_wgrad_tcgen05.cu).  Returns None if the kernel declines."""
+    co, ci, kh, kw = wshape
+    ph, pw = (kh // 2, kw // 2) if padding is None else (int(padding[0]), int(padding[1]))
+    dw = torch.zeros((co, kh, kw, ci), dtype=torch.float32, device=x.device)
+    if ext().conv_wgrad_bf16_nhwc(dy, x, dw, ph, pw, stride):
+        _count()
+        return dw.permute(0, 3, 1, 2)
+    return None
+
+
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -41,6 +41,9 @@ int ddl_conv_bf16_nhwc(const void* x, const void* w, void* y, int NB, int H, int
                        int KH, int KW, int pad_h, int pad_w, int stride, float* col_sums,
                        const void* bias, int relu, int sms, cudaStream_t st);
 void ddl_conv_box(int NB, int H, int W, int* out3);
+int ddl_conv_wgrad_bf16_nhwc(const void* dy, const void* x, float* D, int NB, int H, int W, int Cin,
+                             int Cout, int KH, int KW, int pad_h, int pad_w, int stride, int sms,
+                             cudaStream_t st);
 int ddl_im2col_rows(const void* x, void* a, int N, int H, int W, int C, int KH, int KW, int stride,
                     int pad, int Kpad, cudaStream_t st);
 int ddl_bn_bwd_fused(const void* dy, const void* dy2, const void* ymask, const void* x, void* dz_out,

@@ -307,6 +307,25 @@ bool im2col_rows(at::Tensor x, at::Tensor a, int64_t KH, int64_t KW, int64_t str
   check(rc, "im2col_rows");
   return true;
 }
+// dW (fp32, [Cout, KH, KW, Cin] contiguous, accumulated into) from dy [N, Cout, OH, OW] and
+// x [N, Cin, H, W], both channels_last bf16.  Returns false for unsupported shapes.
+bool conv_wgrad_bf16_nhwc(at::Tensor dy, at::Tensor x, at::Tensor dw, int64_t pad_h, int64_t pad_w,
+                          int64_t stride) {
+  TORCH_CHECK(dy.dim() == 4 && x.dim() == 4 && dw.dim() == 4 && is_bf16(dy) && is_bf16(x));
+  TORCH_CHECK(dw.scalar_type() == at::kFloat && dw.is_contiguous(), "conv_wgrad: fp32 KRSC output");
+  TORCH_CHECK(dy.is_contiguous(at::MemoryFormat::ChannelsLast) &&
+              x.is_contiguous(at::MemoryFormat::ChannelsLast), "conv_wgrad: channels_last operands");
+  const int NB = (int)x.size(0), Cin = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
+  const int Cout = (int)dw.size(0), KH = (int)dw.size(1), KW = (int)dw.size(2);
+  TORCH_CHECK(dw.size(3) == Cin && dy.size(0) == NB && dy.size(1) == Cout);
+  c10::cuda::CUDAGuard g(x.device());
+  const int rc = ddl_conv_wgrad_bf16_nhwc(dy.data_ptr(), x.data_ptr(), dw.data_ptr<float>(), NB, H, W,
+                                          Cin, Cout, KH, KW, (int)pad_h, (int)pad_w, (int)stride,
+                                          sm_count(), cur_stream());
+  if (rc == -1) return false;
+  check(rc, "conv_wgrad_bf16_nhwc");
+  return true;
+}
 void gemm_bf16_nt_mn(at::Tensor A, at::Tensor B, at::Tensor D, int64_t splits,
                      c10::optional<at::Tensor> workspace) {
   // A: [K, M], B: [K, N], D: [M, N] fp32, accumulated into (D += A^T B)
@@ -617,6 +636,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16_tn", &gemm_bf16_tn);
   m.def("gemm_bf16_nt_mn", &gemm_bf16_nt_mn);
   m.def("conv_bf16_nhwc", &conv_bf16_nhwc);
+  m.def("conv_wgrad_bf16_nhwc", &conv_wgrad_bf16_nhwc);
   m.def("im2col_rows", &im2col_rows);
   m.def("conv_box", [](int64_t nb, int64_t h, int64_t w) {
     int b[3];

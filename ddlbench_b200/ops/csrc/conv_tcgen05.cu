@@ -230,29 +230,6 @@ conv_bf16_nhwc_kernel(const __grid_constant__ CUtensorMap map_x,
   }
 }
 
-// Pixel box of a tile: powers of two with TW*TH*TN == 128 that waste the fewest rows on the
-// right / bottom / batch edges (56x56 -> 8x8x2, 28x28 -> 4x4x8, 14x14 -> 16x2x4 (87.5 %),
-// 7x7 -> 8x1x16 (87.5 %)).
-static void choose_box(int NB, int H, int W, int* TW, int* TH, int* TN) {
-  double best = -1.0;
-  for (int tw = 1; tw <= 128; tw *= 2)
-    for (int th = 1; tw * th <= 128; th *= 2) {
-      const int tn = 128 / (tw * th);
-      if (tw > 64 || th > 64 || tn > 128) continue;
-      const double eff = ((double)W / (((W + tw - 1) / tw) * tw)) *
-                         ((double)H / (((H + th - 1) / th) * th)) *
-                         ((double)NB / (((NB + tn - 1) / tn) * tn));
-      // ties: wider rows (longer gmem runs), then taller boxes (halo rows shared in L2)
-      const double score = eff + 1e-3 * tw / 64.0 + 1e-4 * th / 64.0;
-      if (score > best) {
-        best = score;
-        *TW = tw;
-        *TH = th;
-        *TN = tn;
-      }
-    }
-}
-
 template <int BLOCK_N, int kStages>
 static int launch_conv(const void* x, const void* w, void* y, ConvParams cp, cudaStream_t st) {
   using L = ConvSmem<BLOCK_N, kStages>;
@@ -305,7 +282,7 @@ extern "C" int ddl_conv_bf16_nhwc(const void* x, const void* w, void* y, int NB,
   cp.NB = NB; cp.H = H; cp.W = W; cp.Cin = Cin; cp.Cout = Cout;
   cp.OH = OH; cp.OW = OW; cp.stride = stride;
   cp.KH = KH; cp.KW = KW; cp.pad_h = pad_h; cp.pad_w = pad_w;
-  choose_box(NB, OH, OW, &cp.TW, &cp.TH, &cp.TN);
+  choose_pixel_box(128, NB, OH, OW, &cp.TW, &cp.TH, &cp.TN);
   if (cp.TW * stride > 256 || cp.TH * stride > 256) return -1;
   cp.tiles_w = (OW + cp.TW - 1) / cp.TW;
   cp.tiles_h = (OH + cp.TH - 1) / cp.TH;
@@ -319,5 +296,5 @@ extern "C" int ddl_conv_bf16_nhwc(const void* x, const void* w, void* y, int NB,
 
 // Tile box chosen for an [NB, H, W] output (host-only; exposed for tests): {TW, TH, TN}.
 extern "C" void ddl_conv_box(int NB, int H, int W, int* out3) {
-  ddl::gemm::choose_box(NB, H, W, &out3[0], &out3[1], &out3[2]);
+  ddl::gemm::choose_pixel_box(128, NB, H, W, &out3[0], &out3[1], &out3[2]);
 }

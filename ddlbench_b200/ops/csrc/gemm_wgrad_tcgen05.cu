@@ -242,3 +242,195 @@ extern "C" int ddl_gemm_bf16_nt_mn(const void* A, const void* B, void* D, int M,
   if (bn == 64) return launch_mn<64, 4>(A, B, (float*)D, M, N, K, lda, ldb, ldd, splits, variant, st);
   return launch_mn<128, 4>(A, B, (float*)D, M, N, K, lda, ldb, ldd, splits, variant, st);
 }
+
+// =====================================================================================
+// Weight gradient of a KH x KW convolution (stride 1 or 2), same machinery:
+//
+//     dW[co][kh][kw][ci] += sum_{n,oh,ow} dY[n, oh, ow, co] * X[n, s*oh + kh - ph, s*ow + kw - pw, ci]
+//
+// One grid slice (blockIdx.z) per filter tap; the reduction runs over boxes of 64 output pixels
+// (TW x TH x TN): the dY box and the X box SHIFTED by the tap offset are both 4-D TMA loads
+// (the X tensor map carries the element strides of a strided convolution and zero-fills the
+// halo); both tiles are consumed MN-major.  Split-K over blockIdx.y, fp32 vector reductions into
+// the KRSC gradient matrix [Cout][KH*KW*Cin] at column offset tap*Cin.
+namespace ddl {
+namespace gemm {
+
+struct ConvWgradParams {
+  float* D;                    // [Cout][KH*KW*Cin] fp32, accumulated into
+  int Cout, Cin, ldd;          // ldd = KH*KW*Cin
+  int KW, pad_h, pad_w, stride;
+  int TW, TH, TN, tiles_w, tiles_h, total_tiles;
+  int tiles_per_split;
+};
+
+template <int BLOCK_N, int kStages>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy,
+                       const __grid_constant__ CUtensorMap map_x, ConvWgradParams wp) {
+  using L = WgradSmem<BLOCK_N, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = (wp.Cin + BLOCK_N - 1) / BLOCK_N;
+  const int tile_m = blockIdx.x / tiles_n, tile_n = blockIdx.x % tiles_n;
+  const int tap = blockIdx.z;
+  const int kh = tap / wp.KW, kw = tap % wp.KW;
+  const int t0 = blockIdx.y * wp.tiles_per_split;
+  int t1 = t0 + wp.tiles_per_split;
+  if (t1 > wp.total_tiles) t1 = wp.total_tiles;
+  const int num_k_blocks = t1 - t0;
+
+  pdl_trigger();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_x);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < num_k_blocks; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        const int pt = t0 + i;
+        const int w0 = (pt % wp.tiles_w) * wp.TW;
+        const int h0 = ((pt / wp.tiles_w) % wp.tiles_h) * wp.TH;
+        const int n0 = (pt / (wp.tiles_w * wp.tiles_h)) * wp.TN;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = smem + s * L::kStageBytes;
+        uint8_t* b_dst = a_dst + L::kABytes;
+        mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
+#pragma unroll
+        for (int j = 0; j < BLOCK_M / kMnBox; ++j)
+          tma_load_4d(a_dst + j * kMnBoxBytes, &map_dy, &full_bar[s],
+                      tile_m * BLOCK_M + j * kMnBox, w0, h0, n0);
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / kMnBox; ++j)
+          tma_load_4d(b_dst + j * kMnBoxBytes, &map_x, &full_bar[s],
+                      tile_n * BLOCK_N + j * kMnBox, w0 * wp.stride + kw - wp.pad_w,
+                      h0 * wp.stride + kh - wp.pad_h, n0);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 1, 1);
+    for (int i = 0; i < num_k_blocks; ++i) {
+      const int s = i % kStages;
+      const uint32_t ph = (i / kStages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+        const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < kMnBox / UMMA_K; ++k) {
+          const uint64_t adesc = make_mnmajor_sw128_desc(a_addr + k * (UMMA_K * 128), kMnBoxBytes, 1024);
+          const uint64_t bdesc = make_mnmajor_sw128_desc(b_addr + k * (UMMA_K * 128), kMnBoxBytes, 1024);
+          umma_f16(tmem_base, adesc, bdesc, idesc, (i | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+        if (i == num_k_blocks - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = tile_m * BLOCK_M + quad * 32 + lane;          // output channel
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * 32), r);
+      const int ci0 = tile_n * BLOCK_N + cb * 32;
+      if (row < wp.Cout && ci0 + 32 <= wp.Cin) {
+        float* dst = wp.D + (size_t)row * wp.ldd + (size_t)tap * wp.Cin + ci0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          atomicAdd(reinterpret_cast<float4*>(dst + 4 * j),
+                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BLOCK_N);
+  }
+}
+
+template <int BLOCK_N, int kStages>
+static int launch_conv_wgrad(const void* dy, const void* x, float* D, int NB, int H, int W, int OH,
+                             int OW, int Cin, int Cout, int KH, int KW, int pad_h, int pad_w,
+                             int stride, int sms, cudaStream_t st) {
+  using L = WgradSmem<BLOCK_N, kStages>;
+  ConvWgradParams wp{};
+  wp.D = D; wp.Cout = Cout; wp.Cin = Cin; wp.ldd = KH * KW * Cin;
+  wp.KW = KW; wp.pad_h = pad_h; wp.pad_w = pad_w; wp.stride = stride;
+  choose_pixel_box(kMnBox, NB, OH, OW, &wp.TW, &wp.TH, &wp.TN);
+  wp.tiles_w = (OW + wp.TW - 1) / wp.TW;
+  wp.tiles_h = (OH + wp.TH - 1) / wp.TH;
+  wp.total_tiles = wp.tiles_w * wp.tiles_h * ((NB + wp.TN - 1) / wp.TN);
+  CUtensorMap mdy, mx;
+  int rc;
+  if ((rc = make_map_nhwc(&mdy, dy, NB, OH, OW, Cout, kMnBox, wp.TW, wp.TH, wp.TN))) return rc;
+  if ((rc = make_map_nhwc(&mx, x, NB, H, W, Cin, kMnBox, wp.TW, wp.TH, wp.TN, stride))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_bf16_kernel<BLOCK_N, kStages>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int tiles = ((Cout + BLOCK_M - 1) / BLOCK_M) * ((Cin + BLOCK_N - 1) / BLOCK_N);
+  const int taps = KH * KW;
+  int splits = (2 * sms + tiles * taps - 1) / (tiles * taps);
+  if (splits < 1) splits = 1;
+  if (splits > wp.total_tiles) splits = wp.total_tiles;
+  wp.tiles_per_split = (wp.total_tiles + splits - 1) / splits;
+  splits = (wp.total_tiles + wp.tiles_per_split - 1) / wp.tiles_per_split;
+  cudaError_t err = launch_pdl((conv_wgrad_bf16_kernel<BLOCK_N, kStages>), dim3(tiles, splits, taps),
+                               dim3(kThreads), (size_t)L::kDynamic, st, mdy, mx, wp);
+  return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
+}
+
+}  // namespace gemm
+}  // namespace ddl
+
+// dy: [NB, OH, OW, Cout], x: [NB, H, W, Cin] bf16 NHWC; D: fp32 [Cout][KH][KW][Cin], accumulated.
+extern "C" int ddl_conv_wgrad_bf16_nhwc(const void* dy, const void* x, float* D, int NB, int H, int W,
+                                        int Cin, int Cout, int KH, int KW, int pad_h, int pad_w,
+                                        int stride, int sms, cudaStream_t st) {
+  using namespace ddl::gemm;
+  if (NB <= 0 || H <= 0 || W <= 0) return 0;
+  if (Cin % 64 || Cout % 64 || KH < 1 || KW < 1 || KH > 7 || KW > 7) return -1;
+  if (stride != 1 && stride != 2) return -1;
+  const int OH = (H + 2 * pad_h - KH) / stride + 1, OW = (W + 2 * pad_w - KW) / stride + 1;
+  if (OH <= 0 || OW <= 0) return -1;
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) |
+       reinterpret_cast<uintptr_t>(D)) & 15)
+    return -1;
+  if (Cin <= 64)
+    return launch_conv_wgrad<64, 4>(dy, x, D, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w, stride, sms, st);
+  return launch_conv_wgrad<128, 4>(dy, x, D, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w, stride, sms, st);
+}

@@ -212,5 +212,28 @@ static inline int make_map_nhwc(CUtensorMap* map, const void* ptr, int64_t N, in
   return r == CUDA_SUCCESS ? 0 : -3;
 }
 
+// Pixel box of a tile of `total` (128 or 64) output pixels: powers of two with TW*TH*TN == total
+// that waste the fewest rows on the right / bottom / batch edges (for 128: 56x56 -> 8x8x2,
+// 28x28 -> 4x4x8, 14x14 -> 2x2x32, 7x7 -> 8x1x16 (87.5 %)).
+static inline void choose_pixel_box(int total, int NB, int H, int W, int* TW, int* TH, int* TN) {
+  double best = -1.0;
+  for (int tw = 1; tw <= total; tw *= 2)
+    for (int th = 1; tw * th <= total; th *= 2) {
+      const int tn = total / (tw * th);
+      if (tw > 64 || th > 64 || tn > 128) continue;
+      const double eff = ((double)W / (((W + tw - 1) / tw) * tw)) *
+                         ((double)H / (((H + th - 1) / th) * th)) *
+                         ((double)NB / (((NB + tn - 1) / tn) * tn));
+      // ties: wider rows (longer gmem runs), then taller boxes (halo rows shared in L2)
+      const double score = eff + 1e-3 * tw / 64.0 + 1e-4 * th / 64.0;
+      if (score > best) {
+        best = score;
+        *TW = tw;
+        *TH = th;
+        *TN = tn;
+      }
+    }
+}
+
 }  // namespace gemm
 }  // namespace ddl

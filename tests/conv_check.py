@@ -60,6 +60,29 @@ def check_wgrad(K, M, N, splits=0, seed=0):
     return ok
 
 
+def check_conv_wgrad(n, ci, co, hw, k, stride=1, seed=0):
+    torch.manual_seed(seed)
+    pad = k // 2
+    x = (torch.randn(n, ci, hw, hw, device="cuda") * 0.5).to(torch.bfloat16).contiguous(
+        memory_format=torch.channels_last)
+    ohw = (hw + 2 * pad - k) // stride + 1
+    dy = (torch.randn(n, co, ohw, ohw, device="cuda") * 0.5).to(torch.bfloat16).contiguous(
+        memory_format=torch.channels_last)
+    dw = ops.conv_wgrad(dy, x, (co, ci, k, k), stride)
+    torch.cuda.synchronize()
+    if dw is None:
+        print("conv wgrad declined", (n, ci, co, hw, k, stride))
+        return False
+    w = torch.zeros(co, ci, k, k, device="cuda", requires_grad=True)
+    F.conv2d(x.float(), w, stride=stride, padding=pad).backward(dy.float())
+    err = (dw - w.grad).abs().max().item()
+    tol = 0.02 * max(w.grad.abs().max().item(), 1.0)
+    ok = err <= tol
+    print(f"conv wgrad n={n} ci={ci} co={co} hw={hw} k={k} stride={stride}: max_err={err:.4f} "
+          f"tol={tol:.4f} {'OK' if ok else 'FAIL'}", flush=True)
+    return ok
+
+
 def bench(n, ci, co, hw, k=3, iters=20):
     x = torch.randn(n, ci, hw, hw, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     w = torch.randn(co, ci, k, k, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
@@ -98,6 +121,9 @@ def main():
                      (200, 136, 64)]:
             ok &= check_wgrad(*args)
         ok &= check_wgrad(4096, 256, 128, splits=1)
+        for args in [(32, 64, 64, 56, 3), (32, 256, 256, 14, 3), (4, 128, 128, 15, 3, 2), (4, 256, 512, 14, 1, 2),
+                     (3, 64, 128, 9, 3)]:
+            ok &= check_conv_wgrad(*args)
     if ok and os.environ.get("BENCH", "1") == "1":
         res = [bench(32, 64, 64, 56), bench(32, 128, 128, 28), bench(32, 256, 256, 14), bench(32, 512, 512, 7)]
         for r in res:

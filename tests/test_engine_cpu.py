@@ -266,3 +266,57 @@ def test_im2col_kernel_index_math_emulated(n, c, hw, k, s, p):
                 if kk < K:
                     out[(nn_ * OH + oh) * OW + ow, kk] = rows[(kk // R) * rowlen + base + (kk % R)]
     torch.testing.assert_close(out, ref.im2col_rows(x, k, k, s, p))
+
+
+@pytest.mark.parametrize("nb,ci,co,hw,k,stride", [(3, 64, 64, 9, 3, 1), (2, 64, 128, 8, 3, 2),
+                                                  (2, 128, 64, 7, 1, 2)])
+def test_conv_wgrad_tcgen05_logic_emulated(nb, ci, co, hw, k, stride):
+    """Host emulation of conv_wgrad_bf16_kernel (csrc/gemm_wgrad_tcgen05.cu): per filter tap, the
+    reduction over 64-pixel boxes of dY and the tap-shifted (strided, zero-filled) X boxes must
+    give the weight gradient of conv2d."""
+    import torch.nn.functional as Fn
+    torch.manual_seed(0)
+    pad = k // 2
+    ohw = (hw + 2 * pad - k) // stride + 1
+    x = torch.randn(nb, hw, hw, ci, dtype=torch.float64)
+    dy = torch.randn(nb, ohw, ohw, co, dtype=torch.float64)
+    # same chooser as the C++ helper, for 64-pixel boxes (mirrors choose_pixel_box)
+    best, box = -1.0, None
+    tw = 1
+    while tw <= 64:
+        th = 1
+        while tw * th <= 64:
+            tn = 64 // (tw * th)
+            eff = (ohw / (-(-ohw // tw) * tw)) * (ohw / (-(-ohw // th) * th)) * (nb / (-(-nb // tn) * tn))
+            score = eff + 1e-3 * tw / 64.0 + 1e-4 * th / 64.0
+            if score > best:
+                best, box = score, (tw, th, tn)
+            th *= 2
+        tw *= 2
+    TW, TH, TN = box
+    tiles_w, tiles_h, tiles_nb = -(-ohw // TW), -(-ohw // TH), -(-nb // TN)
+
+    def load(t, size, n0, h0, w0, step):       # 4-D TMA box -> [64 pixels, C]
+        out = torch.zeros(TN, TH, TW, t.shape[3], dtype=torch.float64)
+        for a in range(TN):
+            for b in range(TH):
+                for c in range(TW):
+                    n, h, ww = n0 + a, h0 + b * step, w0 + c * step
+                    if 0 <= n < nb and 0 <= h < size and 0 <= ww < size:
+                        out[a, b, c] = t[n, h, ww]
+        return out.reshape(64, -1)
+
+    dw = torch.zeros(co, k, k, ci, dtype=torch.float64)
+    for tap in range(k * k):
+        kh, kw = divmod(tap, k)
+        for pt in range(tiles_w * tiles_h * tiles_nb):
+            w0 = (pt % tiles_w) * TW
+            h0 = ((pt // tiles_w) % tiles_h) * TH
+            n0 = (pt // (tiles_w * tiles_h)) * TN
+            a = load(dy, ohw, n0, h0, w0, 1)                                        # [64, Cout]
+            b = load(x, hw, n0, h0 * stride + kh - pad, w0 * stride + kw - pad, stride)   # [64, Cin]
+            dw[:, kh, kw, :] += a.t() @ b
+    xr = x.permute(0, 3, 1, 2)
+    wr = torch.zeros(co, ci, k, k, dtype=torch.float64, requires_grad=True)
+    Fn.conv2d(xr, wr, stride=stride, padding=pad).backward(dy.permute(0, 3, 1, 2))
+    torch.testing.assert_close(dw.permute(0, 3, 1, 2), wr.grad, rtol=1e-10, atol=1e-10)
