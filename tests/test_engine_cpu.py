@@ -125,7 +125,8 @@ def test_stage_split_equals_whole():
         assert torch.allclose(s1.store.g_views[name], whole.store.g_views[name], atol=1e-5), name
 
 
-@pytest.mark.parametrize("arch,hw", [("squeezenet1_1", 48), ("densenet121", 32), ("mobilenet", 32)])
+@pytest.mark.parametrize("arch,hw", [("squeezenet1_1", 48), ("densenet121", 32), ("mobilenet", 32),
+                                     ("inception_v3", 75)])
 def test_engine_runs_extra_zoo(arch, hw):
     """Concat joins and pre-activation BatchNorm (``ConcatOp`` / ``BnAct``) against autograd."""
     from ddlbench_b200.models.extra import EXTRA_BUILDERS
@@ -138,10 +139,11 @@ def test_engine_runs_extra_zoo(arch, hw):
                                   weight_decay=1e-4)
     kinds = {op.kind for op in ex.plan.ops}
     assert "module" not in kinds                       # nothing falls back to the autograd op
+    x_batch = 2 if arch == "inception_v3" else 4
     for name, p in m.named_parameters():
         ex.store.weights()[name].copy_(p.detach())
-    x = torch.randn(4, 3, hw, hw, dtype=torch.float64)
-    t = torch.randint(0, 10, (4,))
+    x = torch.randn(x_batch, 3, hw, hw, dtype=torch.float64)
+    t = torch.randint(0, 10, (x_batch,))
     y = m(x)
     F.cross_entropy(y, t).backward()
     outs, ctx = ex.forward([ex.prepare_input(x)])
