@@ -235,8 +235,22 @@ def run_pipedream(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
             else:
                 say(logfmt.pd_train_nonlast(epoch, i, n, mem_a, mem_c))
 
+        trace_dir = os.environ.get("DDLB_TIMELINE_DIR")
+        if trace_dir:
+            rt.forward_stats.reset_stats()
+            rt.backward_stats.reset_stats()
+            rt.forward_stats.spans, rt.backward_stats.spans = [], []
+            rt.forward_stats.keep_spans = rt.backward_stats.keep_spans = True
         rt.run_epoch(loader() if topo.is_first else None, n, on_forward=on_fwd)
         ms = timer.stop()
+        if trace_dir:
+            # one Chrome-trace file per rank: load them together to see the 1F1B interleaving
+            import json
+            from ..parallel.pipedream.stats import pipeline_trace
+            os.makedirs(trace_dir, exist_ok=True)
+            with open(os.path.join(trace_dir, "pipeline_e%d_rank%d.json" % (epoch, topo.rank)), "w") as f:
+                json.dump(pipeline_trace(rt.forward_stats, rt.backward_stats, topo.rank, topo.stage), f)
+            rt.forward_stats.keep_spans = rt.backward_stats.keep_spans = False
         sec = time.time() - t_epoch
         say(logfmt.pd_epoch_time(epoch, sec))
         ms_max = max_over_ranks(ms, device)

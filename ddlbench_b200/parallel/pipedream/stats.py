@@ -19,6 +19,9 @@ class RuntimeStats:
         self.forward = forward
         self.stats = {k: 0.0 for k in self.KEYS}
         self._events: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
+        # (start, end) of every pass for the timeline export: CUDA events or host seconds
+        self.spans: List[Tuple[object, object]] = []
+        self.keep_spans = False
 
     # -- compute time ---------------------------------------------------------------
     def begin_compute(self, device):
@@ -32,12 +35,17 @@ class RuntimeStats:
     def end_compute(self, token) -> None:
         if isinstance(token, float):
             import time
-            self.stats["compute_time"] += time.perf_counter() - token
+            now = time.perf_counter()
+            self.stats["compute_time"] += now - token
+            if self.keep_spans:
+                self.spans.append((token, now))
             return
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         self._events.append((token, e))
-        if len(self._events) > 4096:
+        if self.keep_spans:
+            self.spans.append((token, e))
+        if len(self._events) > 4096 and not self.keep_spans:
             self._resolve()
 
     def _resolve(self) -> None:
@@ -64,3 +72,25 @@ class RuntimeStats:
         self._events.clear()
         for k in self.stats:
             self.stats[k] = 0.0
+
+
+def pipeline_trace(forward: RuntimeStats, backward: RuntimeStats, rank: int, stage: int) -> dict:
+    """Chrome-trace events of one rank's forward / backward passes (``keep_spans`` must have been
+    set before the epoch): load the per-rank files together in Perfetto to see the 1F1B
+    interleaving and the bubbles.  Device spans are relative to the rank's first forward."""
+    events = []
+    spans = [("F", i, a, b) for i, (a, b) in enumerate(forward.spans)] + \
+            [("B", i, a, b) for i, (a, b) in enumerate(backward.spans)]
+    if not spans:
+        return {"traceEvents": []}
+    first = forward.spans[0][0] if forward.spans else backward.spans[0][0]
+    if not isinstance(first, float):
+        spans[-1][3].synchronize()
+    for kind, i, a, b in spans:
+        if isinstance(a, float):
+            ts, dur = (a - first) * 1e6, (b - a) * 1e6
+        else:
+            ts, dur = first.elapsed_time(a) * 1e3, a.elapsed_time(b) * 1e3
+        events.append({"name": "%s%d" % (kind, i), "ph": "X", "pid": stage, "tid": rank, "ts": ts,
+                       "dur": dur, "cat": "forward" if kind == "F" else "backward"})
+    return {"traceEvents": events, "displayTimeUnit": "ms"}
