@@ -92,3 +92,24 @@ def test_hvd_allreduce_equals_serial_sum_single_process():
         assert not torch.equal(before, m.weight)
     finally:
         dist.destroy_process_group()
+
+
+def test_run_sh_pipedream_plans_and_runs_on_cpu(tmp_path):
+    """run.sh front end -> profile -> partition -> generate -> 2-rank PipeDream run (Gloo)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = ["bash", os.path.join(root, "run", "run", "run.sh"), "-b", "mnist", "-f", "pipedream", "-g", "2",
+           "-m", "resnet18", "--steps", "4", "--epochs", "1", "--eval-steps", "1", "--device", "cpu",
+           "--workdir", str(tmp_path / "plan"), "--batch-size", "8", "--out", str(tmp_path / "out"),
+           "--master-port", "29733"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    text = r.stdout
+    assert re.search(r"Epoch 0: [\d.]+ seconds", text) and " * Prec@1 " in text
+    assert "device-timed |" in text
+    plan = tmp_path / "plan"
+    produced = [p.name for p in plan.rglob("*") if p.is_file()]
+    assert any(n == "graph.txt" for n in produced) and any(n.endswith("_conf.json") for n in produced)
+    outs = list((tmp_path / "out").glob("*/slurm.out"))
+    assert outs and "pipedream - mnist - resnet18" in outs[0].read_text()
