@@ -41,6 +41,8 @@ ACT_BITMASK_ON = _os.environ.get("DDLB_ACT_BITMASK", "1") == "1"
 CONV3X3_TCGEN05 = _os.environ.get("DDLB_CONV3X3_TCGEN05", "0") == "1"
 # first convolution (3 input channels) as im2col + tcgen05 GEMM (csrc/im2col.cu): opt-in until validated
 STEM_IM2COL = _os.environ.get("DDLB_STEM_IM2COL", "0") == "1"
+# hand-written depthwise 3x3 convolution (csrc/dwconv.cu): opt-in until validated
+DWCONV = _os.environ.get("DDLB_DWCONV", "0") == "1"
 # weight gradient of 1x1 convolutions / linear layers on tcgen05 (csrc/gemm_wgrad_tcgen05.cu): opt-in
 WGRAD_TCGEN05 = _os.environ.get("DDLB_WGRAD_TCGEN05", "0") == "1"
 # data gradient of those 3x3 convolutions through the same kernel (flipped, transposed filter)
@@ -158,6 +160,9 @@ class _ConvMixin:
             d = ops.gemm_tn(a, self._stem_weight_matrix(w, a.shape[1]), col_sums=col_sums, bias=bias,
                             relu=relu, bn_finalize=bn_finalize)
             return d.view(n, oh, ow, co).permute(0, 3, 1, 2), col_sums is not None
+        if DWCONV and ops.dwconv_supported(x, self.wshape, self.stride, self.padding, self.dilation,
+                                           self.groups) and bias is None and not relu:
+            return ops.dwconv_fwd(x, w, self.stride[0], self.padding[0]), False
         if self._is_conv_tc(x, w):
             y = ops.conv_tn(x, w, col_sums=col_sums, bias=bias, relu=relu, stride=self.stride[0],
                             padding=self.padding)
@@ -172,6 +177,11 @@ class _ConvMixin:
         stream configured (``WGRAD_OVERLAP``) the weight-gradient kernel — which nothing
         needs before the optimizer — runs concurrently with the rest of backward: at the
         benchmark's batch size every kernel fills only a fraction of the 148 SMs."""
+        if DWCONV and ops.dwconv_supported(x, self.wshape, self.stride, self.padding, self.dilation,
+                                           self.groups) and dy.is_contiguous(memory_format=torch.channels_last):
+            dx, dw = ops.dwconv_bwd(dy, x, w, self.stride[0], self.padding[0], need_dx)
+            _write(gw, dw, accumulate)
+            return dx
         side = WGRAD_OVERLAP["stream"] if dy.is_cuda else None
         args = (None, self.stride, self.padding, self.dilation, False, [0, 0], self.groups)
         dx_tc = None

@@ -493,4 +493,43 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, wshape, stride: int = 1,
     return None
 
 
+def dwconv_supported(x: torch.Tensor, wshape, stride, padding, dilation, groups) -> bool:
+    """Depthwise 3x3 (groups == channels), stride 1 or 2, bf16 NHWC (csrc/dwconv.cu)."""
+    co, cig, kh, kw = wshape
+    return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and groups == co == x.shape[1] and
+            cig == 1 and kh == 3 and kw == 3 and list(dilation) == [1, 1] and stride[0] == stride[1] and
+            stride[0] in (1, 2) and padding[0] == padding[1] and 0 <= padding[0] <= 2 and co % 8 == 0 and
+            x.is_contiguous(memory_format=torch.channels_last))
+
+
+def _dw_taps(w: torch.Tensor) -> torch.Tensor:
+    """[C, 1, 3, 3] -> tap-major [9, C] (the layout the kernels read with 16-byte vectors)."""
+    return w.reshape(w.shape[0], 9).t().contiguous()
+
+
+def dwconv_fwd(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.Tensor:
+    n, c, h, wd = x.shape
+    oh, ow = (h + 2 * pad - 3) // stride + 1, (wd + 2 * pad - 3) // stride + 1
+    y = torch.empty((n, c, oh, ow), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    assert ext().dwconv3x3(0, x, _dw_taps(w), y, h, wd, stride, pad)
+    _count()
+    return y
+
+
+def dwconv_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, stride: int, pad: int,
+               need_dx: bool = True):
+    """-> (dx or None, dw [C, 1, 3, 3] fp32)."""
+    n, c, h, wd = x.shape
+    e = ext()
+    dx = None
+    if need_dx:
+        dx = torch.empty_like(x)
+        assert e.dwconv3x3(1, dy, _dw_taps(w), dx, h, wd, stride, pad)
+        _count()
+    dwt = torch.zeros((9, c), dtype=torch.float32, device=x.device)
+    assert e.dwconv3x3(2, dy, x, dwt, h, wd, stride, pad)
+    _count()
+    return dx, dwt.t().reshape(c, 1, 3, 3)
+
+
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -40,6 +40,8 @@ int ddl_bn_bwd_apply(const void* dz_in, const void* dy, const void* dy2, const v
 int ddl_conv_bf16_nhwc(const void* x, const void* w, void* y, int NB, int H, int W, int Cin, int Cout,
                        int KH, int KW, int pad_h, int pad_w, int stride, float* col_sums,
                        const void* bias, int relu, int sms, cudaStream_t st);
+int ddl_dwconv3x3(int mode, const void* a, const void* b, void* out, int N, int H, int W, int C,
+                  int stride, int pad, int sms, cudaStream_t st);
 void ddl_conv_box(int NB, int H, int W, int* out3);
 int ddl_conv_wgrad_bf16_nhwc(const void* dy, const void* x, float* D, int NB, int H, int W, int Cin,
                              int Cout, int KH, int KW, int pad_h, int pad_w, int stride, int sms,

@@ -326,6 +326,19 @@ bool conv_wgrad_bf16_nhwc(at::Tensor dy, at::Tensor x, at::Tensor dw, int64_t pa
   check(rc, "conv_wgrad_bf16_nhwc");
   return true;
 }
+// depthwise 3x3: mode 0 forward (a = x, b = wt[9][C], out = y), 1 dgrad (a = dy, b = wt, out = dx,
+// whose shape gives H, W), 2 wgrad (a = dy, b = x, out = fp32 dw[9][C], accumulated)
+bool dwconv3x3(int64_t mode, at::Tensor a, at::Tensor b, at::Tensor out, int64_t H, int64_t W,
+               int64_t stride, int64_t pad) {
+  TORCH_CHECK(a.dim() == 4 && is_bf16(a) && a.is_contiguous(at::MemoryFormat::ChannelsLast));
+  const int N = (int)a.size(0), C = (int)a.size(1);
+  c10::cuda::CUDAGuard g(a.device());
+  const int rc = ddl_dwconv3x3((int)mode, a.data_ptr(), b.data_ptr(), out.data_ptr(), N, (int)H, (int)W, C,
+                               (int)stride, (int)pad, sm_count(), cur_stream());
+  if (rc == -1) return false;
+  check(rc, "dwconv3x3");
+  return true;
+}
 void gemm_bf16_nt_mn(at::Tensor A, at::Tensor B, at::Tensor D, int64_t splits,
                      c10::optional<at::Tensor> workspace) {
   // A: [K, M], B: [K, N], D: [M, N] fp32, accumulated into (D += A^T B)
@@ -638,6 +651,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_bf16_nhwc", &conv_bf16_nhwc);
   m.def("conv_wgrad_bf16_nhwc", &conv_wgrad_bf16_nhwc);
   m.def("im2col_rows", &im2col_rows);
+  m.def("dwconv3x3", &dwconv3x3);
   m.def("conv_box", [](int64_t nb, int64_t h, int64_t w) {
     int b[3];
     ddl_conv_box((int)nb, (int)h, (int)w, b);

@@ -322,3 +322,50 @@ def test_conv_wgrad_tcgen05_logic_emulated(nb, ci, co, hw, k, stride):
     wr = torch.zeros(co, ci, k, k, dtype=torch.float64, requires_grad=True)
     Fn.conv2d(xr, wr, stride=stride, padding=pad).backward(dy.permute(0, 3, 1, 2))
     torch.testing.assert_close(dw.permute(0, 3, 1, 2), wr.grad, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("hw,stride,pad", [(7, 1, 1), (8, 2, 1), (9, 2, 1)])
+def test_dwconv_kernel_index_math_emulated(hw, stride, pad):
+    """The tap / bounds / divisibility arithmetic of csrc/dwconv.cu (forward, dgrad, wgrad)
+    replayed on the host against autograd."""
+    import torch.nn.functional as Fn
+    torch.manual_seed(0)
+    n, c = 2, 8
+    x = torch.randn(n, c, hw, hw, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(c, 1, 3, 3, dtype=torch.float64, requires_grad=True)
+    y_ref = Fn.conv2d(x, w, stride=stride, padding=pad, groups=c)
+    dy = torch.randn_like(y_ref)
+    y_ref.backward(dy)
+    oh_n = ow_n = (hw + 2 * pad - 3) // stride + 1
+    wt = w.detach().reshape(c, 9).t()                       # [9, C] tap-major
+    xh, dyh = x.detach().permute(0, 2, 3, 1), dy.permute(0, 2, 3, 1)
+    y = torch.zeros(n, oh_n, ow_n, c, dtype=torch.float64)
+    dx = torch.zeros(n, hw, hw, c, dtype=torch.float64)
+    dw = torch.zeros(9, c, dtype=torch.float64)
+    for b in range(n):
+        for oh in range(oh_n):
+            for ow in range(ow_n):
+                for kh in range(3):
+                    ih = oh * stride - pad + kh
+                    if ih < 0 or ih >= hw:
+                        continue
+                    for kw in range(3):
+                        iw = ow * stride - pad + kw
+                        if iw < 0 or iw >= hw:
+                            continue
+                        y[b, oh, ow] += xh[b, ih, iw] * wt[kh * 3 + kw]
+                        dw[kh * 3 + kw] += dyh[b, oh, ow] * xh[b, ih, iw]
+        for ih in range(hw):
+            for iw in range(hw):
+                for kh in range(3):
+                    th = ih + pad - kh
+                    if th < 0 or th % stride or th // stride >= oh_n:
+                        continue
+                    for kw in range(3):
+                        tw = iw + pad - kw
+                        if tw < 0 or tw % stride or tw // stride >= ow_n:
+                            continue
+                        dx[b, ih, iw] += dyh[b, th // stride, tw // stride] * wt[kh * 3 + kw]
+    torch.testing.assert_close(y.permute(0, 3, 1, 2), y_ref.detach())
+    torch.testing.assert_close(dx.permute(0, 3, 1, 2), x.grad)
+    torch.testing.assert_close(dw.t().reshape(c, 1, 3, 3), w.grad)

@@ -295,3 +295,22 @@ def test_im2col_rows_and_stem_gemm(n, c, hw, k, s, p):
     y_ref = torch.nn.functional.conv2d(x.float(), w.float(), stride=s, padding=p)
     err = (y.float().view(n, oh, oh, 64).permute(0, 3, 1, 2) - y_ref).abs().max().item()
     assert err < 0.03 * max(1.0, y_ref.abs().max().item())
+
+
+@pytest.mark.skipif(os.environ.get("DDLB_TEST_CONV_TCGEN05") != "1",
+                    reason="opt-in: kernel not yet validated on hardware")
+@pytest.mark.parametrize("n,c,hw,stride", [(8, 96, 28, 1), (4, 144, 29, 2), (2, 32, 112, 2), (3, 960, 7, 1)])
+def test_dwconv3x3(n, c, hw, stride):
+    torch.manual_seed(0)
+    x = torch.randn(n, c, hw, hw, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(c, 1, 3, 3, device=DEV) * 0.3).to(torch.bfloat16)
+    assert ops.dwconv_supported(x, w.shape, [stride, stride], [1, 1], [1, 1], c)
+    y = ops.dwconv_fwd(x, w, stride, 1)
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    y_ref = torch.nn.functional.conv2d(xr, wr, stride=stride, padding=1, groups=c)
+    torch.testing.assert_close(y.float(), y_ref.detach(), rtol=2e-2, atol=2e-2)
+    dy = torch.randn_like(y_ref).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y_ref.backward(dy.float())
+    dx, dw = ops.dwconv_bwd(dy, x, w, stride, 1)
+    torch.testing.assert_close(dx.float(), xr.grad, rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(dw, wr.grad, rtol=2e-2, atol=2e-2 * max(1.0, wr.grad.abs().max().item()))
