@@ -10,7 +10,7 @@ O=gpurun_out/optin
 step() { echo "=== $*" | tee -a $O.log; }
 
 step "numerics: tcgen05 conv3x3 / stem im2col / wgrad (descriptor variant 0)"
-DDLB_TEST_CONV_TCGEN05=1 timeout 400 python -m pytest tests/test_kernels_gpu.py -x -q -k "im2col" 2>&1 | tail -3 | tee -a $O.log
+DDLB_TEST_CONV_TCGEN05=1 timeout 400 python -m pytest tests/test_kernels_gpu.py -q -k "im2col or dwconv3x3" 2>&1 | tail -3 | tee -a $O.log
 BENCH=0 CHECK_WGRAD=0 timeout 300 python tests/conv_check.py 2>&1 | tail -14 | tee -a $O.log
 for v in 0 1; do
   step "wgrad GEMM, DDLB_WGRAD_DESC_VARIANT=$v"
@@ -48,4 +48,19 @@ bench bn_cluster DDLB_BN_CLUSTER=1
 bench all_validated DDLB_STEM_IM2COL=1 DDLB_CONV3X3_TCGEN05=1 DDLB_SGD_OVERLAP=1
 bench all_tcgen05 DDLB_STEM_IM2COL=1 DDLB_CONV3X3_TCGEN05=1 DDLB_CONV3X3_DGRAD=1 DDLB_WGRAD_TCGEN05=1
 bench default_again DDLB_NONE=1
+step "MobileNetV2 (CIFAR-10 shape) with and without the depthwise kernels"
+for f in 0 1; do
+  DDLB_DWCONV=$f timeout 200 python - <<'PY' 2>&1 | tail -1 | tee -a $O.log
+import os, time, torch
+from ddlbench_b200.harness import Trainer
+tr = Trainer("mobilenetv2", "cifar10", batch_size=64, device="cuda", dtype=torch.bfloat16, cuda_graph=True, tcgen05=True)
+x = torch.randn(64, 3, 32, 32, device="cuda"); t = torch.randint(0, 10, (64,), device="cuda")
+for _ in range(5): tr.step(x, t)
+torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(30): s = tr.step(x, t)
+e1.record(); torch.cuda.synchronize()
+print("mobilenetv2 DDLB_DWCONV=%s: %.3f ms/step loss %.4f" % (os.environ.get("DDLB_DWCONV"), e0.elapsed_time(e1) / 30, float(s[0])))
+PY
+done
 step done
