@@ -231,7 +231,9 @@ extern "C" int ddl_gemm_bf16_nt_mn(const void* A, const void* B, void* D, int M,
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (out_is_bf16) return -1;
   if ((lda % 8) || (ldb % 8) || (M % 8) || (N % 8)) return -1;
-  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) return -1;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
+       reinterpret_cast<uintptr_t>(D)) & 15)
+    return -1;   // TMA sources and the 16-byte vector reductions into D need 16-byte alignment
   static const int variant = [] {
     const char* e = std::getenv("DDLB_WGRAD_DESC_VARIANT");
     return (e && e[0] == '1') ? 1 : 0;
