@@ -180,7 +180,8 @@ def run_ours(args) -> dict:
                    "l2": "no flush: per-step working set (weights+grads+master+activations, "
                          ">1 GB) exceeds the 126 MB L2 and inputs cycle over distinct batches",
                    "timing": "CUDA events on the launching stream, barrier+synchronize both "
-                             "sides, max over ranks"},
+                             "sides, max over ranks",
+                   "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("DDLB_")}},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": "images/sec",
                 "ms_per_step": round(ms_e2e, 4), "h2d_bytes_per_step": pre.h2d_bytes,
