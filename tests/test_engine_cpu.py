@@ -369,3 +369,21 @@ def test_dwconv_kernel_index_math_emulated(hw, stride, pad):
     torch.testing.assert_close(y.permute(0, 3, 1, 2), y_ref.detach())
     torch.testing.assert_close(dx.permute(0, 3, 1, 2), x.grad)
     torch.testing.assert_close(dw.t().reshape(c, 1, 3, 3), w.grad)
+
+
+def test_every_zoo_model_compiles_to_fused_ops_only():
+    """All reference architectures x data sets (and the extra zoo) map onto native engine ops:
+    nothing falls back to the autograd ``ModuleOp``."""
+    from ddlbench_b200.models.extra import EXTRA_ARCHS
+    from ddlbench_b200.models.zoo import ARCHS, DATASETS
+    for ds in DATASETS:
+        for arch in ARCHS:
+            plan = compile_plan(build_model(arch, ds))
+            kinds = {op.kind for op in plan.ops}
+            assert "module" not in kinds, (arch, ds, kinds)
+            assert plan.ops[0].kind in ("conv_bn_act", "conv_bias_act"), (arch, ds)
+    for arch in EXTRA_ARCHS:
+        if arch.startswith("nasnet"):
+            continue            # NASNet's pixel-shift crop is the one op served by ModuleOp
+        kinds = {op.kind for op in compile_plan(build_model(arch, "imagenet")).ops}
+        assert "module" not in kinds, (arch, kinds)
