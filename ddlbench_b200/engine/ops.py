@@ -641,6 +641,19 @@ class ConcatOp(Op):
         return [p.contiguous(memory_format=fmt) if n else None for p, n in zip(parts, need)]
 
 
+class ShiftCropOp(Op):
+    """One-pixel shift (drop the first row / column, zero-pad at the end): second path of
+    NASNet's factorised reduction."""
+    kind = "shift_crop"
+
+    def forward(self, P, B, xs, ctx, training):
+        return torch.nn.functional.pad(xs[0][:, :, 1:, 1:], (0, 1, 0, 1))
+
+    def backward(self, P, G, dys, ctx, accumulate, need):
+        dy = _sum_grads(dys)
+        return [torch.nn.functional.pad(dy[:, :, :-1, :-1], (1, 0, 1, 0))]
+
+
 class ModuleOp(Op):
     """Fallback: any ``nn.Module`` runs under a local autograd tape, with its parameters
     aliased to views of the flat store.  Keeps the engine complete for arbitrary layers

@@ -167,6 +167,8 @@ def compile_plan(model: LayerGraphModel, start: int = 0, stop: Optional[int] = N
                 act, last = _act_of(nodes[j].op), j
                 used.add(j)
             out.append(E.BnAct(n.name, [n.inputs[0]], nodes[last].name, m, act, pname(n)))
+        elif type(m).__name__ == "_ShiftCrop":
+            out.append(E.ShiftCropOp(n.name, [n.inputs[0]], n.name))
         elif type(m).__name__ == "Concat" and hasattr(m, "dim"):
             out.append(E.ConcatOp(n.name, list(n.inputs), n.name, m.dim))
         elif _act_of(m) is not None and len(n.inputs) == 1:

@@ -126,7 +126,7 @@ def test_stage_split_equals_whole():
 
 
 @pytest.mark.parametrize("arch,hw", [("squeezenet1_1", 48), ("densenet121", 32), ("mobilenet", 32),
-                                     ("inception_v3", 75)])
+                                     ("inception_v3", 75), ("nasnetamobile", 64)])
 def test_engine_runs_extra_zoo(arch, hw):
     """Concat joins and pre-activation BatchNorm (``ConcatOp`` / ``BnAct``) against autograd."""
     from ddlbench_b200.models.extra import EXTRA_BUILDERS
@@ -139,7 +139,7 @@ def test_engine_runs_extra_zoo(arch, hw):
                                   weight_decay=1e-4)
     kinds = {op.kind for op in ex.plan.ops}
     assert "module" not in kinds                       # nothing falls back to the autograd op
-    x_batch = 2 if arch == "inception_v3" else 4
+    x_batch = 2 if arch in ("inception_v3", "nasnetamobile") else 4
     for name, p in m.named_parameters():
         ex.store.weights()[name].copy_(p.detach())
     x = torch.randn(x_batch, 3, hw, hw, dtype=torch.float64)
@@ -383,7 +383,5 @@ def test_every_zoo_model_compiles_to_fused_ops_only():
             assert "module" not in kinds, (arch, ds, kinds)
             assert plan.ops[0].kind in ("conv_bn_act", "conv_bias_act"), (arch, ds)
     for arch in EXTRA_ARCHS:
-        if arch.startswith("nasnet"):
-            continue            # NASNet's pixel-shift crop is the one op served by ModuleOp
         kinds = {op.kind for op in compile_plan(build_model(arch, "imagenet")).ops}
         assert "module" not in kinds, (arch, kinds)
