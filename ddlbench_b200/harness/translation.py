@@ -45,6 +45,9 @@ def parse(argv=None):
     ap.add_argument("--optimizer", default="Adam", choices=["Adam", "SGD"])
     ap.add_argument("--smoothing", type=float, default=0.1)
     ap.add_argument("--grad-clip", type=float, default=5.0)
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="bf16: low-precision model + flat fp32 master weights (Fp16Optimizer)")
+    ap.add_argument("--warmup-steps", type=int, default=0, help="GNMT LR schedule: exponential warm-up")
     ap.add_argument("--stages", type=int, default=1)
     ap.add_argument("--beam-size", type=int, default=5)
     ap.add_argument("--eval-sentences", type=int, default=64)
@@ -158,7 +161,18 @@ def main(argv=None) -> Dict[str, float]:
     opt_args = {"lr": a.lr}
     if stages == 1:
         model.to(device)
-        opt = getattr(torch.optim, a.optimizer)(model.parameters(), **opt_args)
+        fp = None
+        if a.dtype == "bf16":
+            from ..utils.fp_optimizer import Fp16Optimizer
+            model.to(torch.bfloat16)
+            fp = Fp16Optimizer(model, grad_clip=a.grad_clip or float("inf"))
+            opt = getattr(torch.optim, a.optimizer)(fp.fp32_params, **opt_args)
+        else:
+            opt = getattr(torch.optim, a.optimizer)(model.parameters(), **opt_args)
+        sched = None
+        if a.warmup_steps:
+            from .lr import WarmupMultiStepLR
+            sched = WarmupMultiStepLR(opt, iterations=steps * a.epochs, warmup_steps=a.warmup_steps)
         for epoch in range(a.epochs):
             sampler.set_epoch(epoch)
             model.train()
@@ -170,15 +184,20 @@ def main(argv=None) -> Dict[str, float]:
                 src, sl, tin = (t.to(device, non_blocking=True) for t in inputs)
                 target = target.to(device, non_blocking=True)
                 loss = crit(model(src, sl, tin), target) / a.batch_size
-                opt.zero_grad(set_to_none=True)
-                loss.backward()
-                if dp > 1:
-                    for p_ in model.parameters():
-                        dist.all_reduce(p_.grad)
-                        p_.grad.div_(dp)
-                if a.grad_clip:
-                    nn.utils.clip_grad_norm_(model.parameters(), a.grad_clip)
-                opt.step()
+                if fp is not None and dp == 1:
+                    fp.step(loss, opt, sched)         # backward, clip on the fp32 master, update, copy back
+                else:
+                    opt.zero_grad(set_to_none=True)
+                    loss.backward()
+                    if dp > 1:
+                        for p_ in model.parameters():
+                            dist.all_reduce(p_.grad)
+                            p_.grad.div_(dp)
+                    if a.grad_clip:
+                        nn.utils.clip_grad_norm_(model.parameters(), a.grad_clip)
+                    opt.step()
+                    if sched is not None:
+                        sched.step()
                 ntok += int((target != PAD).sum()) + int(sl.sum())
                 if i % a.print_freq == 0 and rank == 0:
                     print("Epoch: [%d][%d/%d]\tTime %.3f\tLoss %.4f\tTok/s %.0f" % (

@@ -157,3 +157,13 @@ def test_gnmt_pipeline_1f1b_two_stages(tmp_path):
                             "--eval-sentences", "4", "--batch-size", "4",
                             "--checkpoint-dir", str(tmp_path / "ckpt")])
     assert "bleu" in out
+
+
+def test_translation_harness_bf16_master_weights_and_lr_schedule(tmp_path):
+    from ddlbench_b200.harness import translation
+    res = translation.main(["--data-dir", str(tmp_path / "data"), "--hidden", "32", "--num-layers", "2",
+                            "--batch-size", "16", "--max-len", "16", "--steps", "12", "--epochs", "1",
+                            "--lr", "0.01", "--device", "cpu", "--synthetic-sentences", "300",
+                            "--synthetic-vocab", "40", "--beam-size", "1", "--eval-sentences", "4",
+                            "--dtype", "bf16", "--warmup-steps", "4"])
+    assert res["train_loss"] == res["train_loss"] and res["train_loss"] > 0
