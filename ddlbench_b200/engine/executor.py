@@ -100,6 +100,12 @@ class StageExecutor:
         prof = self.profiler
         for idx, op in enumerate(plan.ops):
             xs = [vals[i] for i in op.inputs]
+            if E.PENDING_FOLD and not getattr(op, "folds_input", False):
+                # a deferred BatchNorm reached an op that cannot fold it: apply it the plain way
+                for x_ in xs:
+                    fold = E.PENDING_FOLD.pop(id(x_), None)
+                    if fold is not None:
+                        fold.materialize()
             if prof is not None:
                 h = prof.begin(2 * idx)
             vals[op.output] = op.forward(P, B, xs, ctx.saved[idx], training)
@@ -109,6 +115,11 @@ class StageExecutor:
                 if self._last_op_of_value.get(i) == idx and i not in keep:
                     vals.pop(i, None)
         outs = [vals[o] for o in plan.out_names]
+        if E.PENDING_FOLD:                   # nothing may leave the stage unwritten
+            for o in outs:
+                fold = E.PENDING_FOLD.pop(id(o), None)
+                if fold is not None:
+                    fold.materialize()
         if training:
             ctx.outputs = outs
         return outs, ctx

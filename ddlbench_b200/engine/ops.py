@@ -41,6 +41,10 @@ ACT_BITMASK_ON = _os.environ.get("DDLB_ACT_BITMASK", "1") == "1"
 CONV3X3_TCGEN05 = _os.environ.get("DDLB_CONV3X3_TCGEN05", "0") == "1"
 # first convolution (3 input channels) as im2col + tcgen05 GEMM (csrc/im2col.cu): opt-in until validated
 STEM_IM2COL = _os.environ.get("DDLB_STEM_IM2COL", "0") == "1"
+# BatchNorm application deferred into the consuming 1x1-convolution GEMM (opt-in, see
+# ops.gemm_tn_bnfold); pending (not yet written) outputs are tracked by object identity
+BN_FOLD = _os.environ.get("DDLB_BN_FOLD", "0") == "1"
+PENDING_FOLD: Dict[int, "ops.BnFold"] = {}
 # hand-written depthwise 3x3 convolution (csrc/dwconv.cu): opt-in until validated
 DWCONV = _os.environ.get("DDLB_DWCONV", "0") == "1"
 # weight gradient of 1x1 convolutions / linear layers on tcgen05 (csrc/gemm_wgrad_tcgen05.cu): opt-in
@@ -142,6 +146,14 @@ class _ConvMixin:
     def _conv_fwd(self, x, w, bias=None, col_sums=None, relu=False, bn_finalize=None, ctx=None):
         """Returns (y, stats_fused).  ``ctx``: the op's saved-tensor dict (the stem path keeps its
         patch matrix there for the weight gradient)."""
+        fold = PENDING_FOLD.pop(id(x), None) if PENDING_FOLD else None
+        if fold is not None and self._is_gemm(x):
+            n, ci, h, wd = x.shape
+            co = self.wshape[0]
+            d = ops.gemm_tn_bnfold(fold, w.reshape(co, ci), col_sums=col_sums, bias=bias, relu=relu)
+            return d.view(n, h, wd, co).permute(0, 3, 1, 2), col_sums is not None
+        if fold is not None:
+            fold.materialize()              # consumer cannot fold after all: plain application
         if self._is_gemm(x):
             n, ci, h, wd = x.shape
             co = self.wshape[0]
@@ -283,9 +295,17 @@ class ConvBnAct(Op, _ConvMixin):
         mask = None
         if training and self.act != ACT_NONE and ACT_BITMASK_ON and ops._nhwc_ok(c):
             mask = torch.empty(c.numel() // 8, dtype=torch.uint8, device=c.device)
-        y, stat = ops.bn_forward(c, res, P[self.k_g], P[self.k_b], B[self.k_rm], B[self.k_rv],
-                                 self.eps, mom, self.act, self.ws, stats_ready=fused,
-                                 training=training, stat_ready=stat_ready, mask_out=mask)
+        if getattr(self, "defer_apply", False) and stat_ready is None:
+            # the designated consumer (a 1x1-convolution GEMM) applies this BatchNorm while loading
+            # its operand and writes y / mask as a side effect
+            stat = ops.bn_statistics(c, B[self.k_rm], B[self.k_rv], self.eps, mom, self.ws,
+                                     stats_ready=fused, training=training)
+            y = torch.empty_like(c)
+            PENDING_FOLD[id(y)] = ops.BnFold(c, res, stat, P[self.k_g], P[self.k_b], self.act, y, mask)
+        else:
+            y, stat = ops.bn_forward(c, res, P[self.k_g], P[self.k_b], B[self.k_rm], B[self.k_rv],
+                                     self.eps, mom, self.act, self.ws, stats_ready=fused,
+                                     training=training, stat_ready=stat_ready, mask_out=mask)
         if training:
             ctx["x"], ctx["c"], ctx["stat"], ctx["mask"] = x, c, stat, mask
             ctx["y"] = y if self.act != ACT_NONE else None

@@ -177,4 +177,27 @@ def compile_plan(model: LayerGraphModel, start: int = 0, stop: Optional[int] = N
             out.append(E.ModuleOp(n.name, list(n.inputs), n.name, m, pname(n)))
         out[-1].node_ids = sorted(used - before)   # layer-graph nodes this op covers
         i += 1
+    if E.BN_FOLD:
+        _mark_bn_folds(out, set(out_names))
     return Plan(out, list(in_names), list(out_names), model.arch, model.input_shape)
+
+
+def _mark_bn_folds(ops_: List[E.Op], boundary: Set[str]) -> int:
+    """Defer the application of a conv+BN(+res)+act op into its FIRST consumer when that consumer
+    is a 1x1 / stride-1 convolution taking the value as its convolution input (it then runs as
+    the BN-fold GEMM).  Later consumers (skip connections) find the value already written."""
+    marked = 0
+    for i, p in enumerate(ops_):
+        if p.kind != "conv_bn_act" or p.output in boundary:
+            continue
+        first = next((q for q in ops_[i + 1:] if p.output in q.inputs), None)
+        if first is None or first.kind not in ("conv_bn_act", "conv_bias_act"):
+            continue
+        co, ci, kh, kw = first.wshape
+        if first.inputs[0] != p.output or (kh, kw) != (1, 1) or first.stride != [1, 1] or \
+                first.padding != [0, 0] or first.groups != 1 or ci % 8 or co % 8:
+            continue
+        p.defer_apply = True
+        first.folds_input = True
+        marked += 1
+    return marked

@@ -143,6 +143,9 @@ def _nhwc_ok(x: torch.Tensor) -> bool:
 # unchanged: 8/16-CTA clusters need whole-GPC slots and stop overlapping with the weight-gradient
 # kernels on the side stream.  Off by default; DDLB_BN_CLUSTER=1 enables them.
 BN_CLUSTER_FUSED = os.environ.get("DDLB_BN_CLUSTER", "0") == "1"
+# fused BN-fold GEMM kernel (csrc/gemm_bnfold_tcgen05.cu); without it a deferred BatchNorm is
+# applied by the ordinary kernel right before its consumer (same result, no saving)
+BNFOLD_KERNEL = os.environ.get("DDLB_BN_FOLD_KERNEL", "1") == "1"
 BN_REPLICAS = 8  # must match DDL_BN_REPLICAS (csrc/common.cuh); checked at first use
 
 
@@ -199,6 +202,74 @@ def bn_forward(x, res, gamma, beta, running_mean, running_var, eps: float, momen
     if running_mean is not None:
         ref.bn_update_running(stat, M, eps, momentum, running_mean, running_var)
     return ref.bn_apply(x, res, stat, gamma, beta, act), stat
+
+
+def bn_statistics(x, running_mean, running_var, eps: float, momentum: float,
+                  ws: Optional[BnWorkspace] = None, stats_ready: bool = False,
+                  training: bool = True) -> torch.Tensor:
+    """(mean, invstd) [2, C] of a BatchNorm WITHOUT applying it (the apply is folded into the
+    consumer, see ``gemm_tn_bnfold``); updates the running statistics like ``bn_forward``."""
+    M, C = _mc(x)
+    if not training:
+        return torch.stack([running_mean.float(), torch.rsqrt(running_var.float() + eps)])
+    if _nhwc_ok(x):
+        e = ext()
+        if ws is None:
+            ws = BnWorkspace(C, x.device)
+        stat = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+        if stats_ready:
+            e.bn_finalize(ws.sums, stat, running_mean, running_var, M, C, eps, momentum)
+        else:
+            e.bn_stats(x, ws.sums, ws.counter, stat, running_mean, running_var, M, C, eps, momentum)
+        _count()
+        return stat.view(2, C)
+    stat = ref.bn_stat(x, eps)
+    if running_mean is not None:
+        ref.bn_update_running(stat, M, eps, momentum, running_mean, running_var)
+    return stat
+
+
+class BnFold:
+    """A BatchNorm(+residual)+activation whose application is deferred into its consumer:
+    ``y`` (and ``mask``) are allocated but NOT yet written."""
+    __slots__ = ("c", "res", "stat", "gamma", "beta", "act", "y", "mask")
+
+    def __init__(self, c, res, stat, gamma, beta, act, y, mask):
+        self.c, self.res, self.stat, self.gamma, self.beta = c, res, stat, gamma, beta
+        self.act, self.y, self.mask = act, y, mask
+
+    def materialize(self) -> torch.Tensor:
+        """Plain (unfused) application: used when the consumer cannot fold."""
+        if _nhwc_ok(self.c):
+            M, C = _mc(self.c)
+            ext().bn_apply(self.c, self.res, self.y, self.stat.reshape(-1).contiguous(), self.gamma,
+                           self.beta, self.mask, M, C, self.act)
+            _count()
+        else:
+            self.y.copy_(ref.bn_apply(self.c, self.res, self.stat, self.gamma, self.beta, self.act))
+        return self.y
+
+
+def gemm_tn_bnfold(fold: BnFold, b: torch.Tensor, col_sums: Optional[torch.Tensor] = None,
+                   bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """D[M, N] = y @ b[N, K]^T with y = act(BN(c) [+ res]) computed ON THE WAY INTO the GEMM: the
+    kernel loads the raw ``c`` tile, rewrites it in shared memory, stores it to ``fold.y`` (which
+    the backward and any later consumer need) with its 1-bit mask, and feeds it to the tensor
+    cores (csrc/gemm_bnfold_tcgen05.cu) — the element-wise BatchNorm pass never runs."""
+    c = fold.c
+    n, k, h, w = c.shape
+    if BNFOLD_KERNEL and _nhwc_ok(c) and hasattr(ext(), "gemm_bf16_tn_bnfold"):
+        a2d = c.permute(0, 2, 3, 1).reshape(n * h * w, k)
+        y2d = fold.y.permute(0, 2, 3, 1).reshape(n * h * w, k)
+        r2d = fold.res.permute(0, 2, 3, 1).reshape(n * h * w, k) if fold.res is not None else None
+        out = torch.empty((n * h * w, b.shape[0]), dtype=c.dtype, device=c.device)
+        if ext().gemm_bf16_tn_bnfold(a2d, r2d, b, out, y2d, fold.mask, fold.stat.reshape(-1), fold.gamma,
+                                     fold.beta, fold.act, col_sums, bias, relu):
+            _count()
+            return out
+    y = fold.materialize()
+    a2d = y.permute(0, 2, 3, 1).reshape(n * h * w, k)
+    return gemm_tn(a2d, b, col_sums=col_sums, bias=bias, relu=relu)
 
 
 def bn_backward(dy, dy2, y, x, stat, gamma, act: int, want_dz: bool, dgamma_out, dbeta_out,
@@ -391,14 +462,15 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, col_sums: Optional[torch.Tensor] =
             ext().gemm_bf16_tn(a, b, out, col_sums, bias, relu, None, None, None, None, 0.0, 0.0)
         _count()
         return out
-    d = a.float() @ b.float().t()
+    up = torch.float32 if a.dtype in (torch.float16, torch.bfloat16) else a.dtype
+    d = a.to(up) @ b.to(up).t()
     if bias is not None:
-        d = d + bias.float()
+        d = d + bias.to(up)
     if relu:
         d = torch.relu(d)
     d = d.to(a.dtype)
     if col_sums is not None:
-        df = d.float()
+        df = d.to(col_sums.dtype)
         n = d.shape[1]
         col_sums[:n].add_(df.sum(0))
         col_sums[n:2 * n].add_((df * df).sum(0))

@@ -385,3 +385,46 @@ def test_every_zoo_model_compiles_to_fused_ops_only():
     for arch in EXTRA_ARCHS:
         kinds = {op.kind for op in compile_plan(build_model(arch, "imagenet")).ops}
         assert "module" not in kinds, (arch, kinds)
+
+
+def test_bn_fold_plan_and_executor_equivalence(monkeypatch):
+    """DDLB_BN_FOLD: BatchNorm applications deferred into the consuming 1x1-convolution GEMM.  On
+    the CPU the consumer materialises the value with the reference op, so this checks the plan
+    marking, the pending-value bookkeeping and the backward against autograd."""
+    from ddlbench_b200.engine import ops as E
+    from ddlbench_b200.engine.plan import compile_plan as cp
+    monkeypatch.setattr(E, "BN_FOLD", True)
+    torch.manual_seed(0)
+    m = build_model("resnet50", "cifar10").double().train()
+    plan = cp(m)
+    deferred = [op for op in plan.ops if getattr(op, "defer_apply", False)]
+    folding = [op for op in plan.ops if getattr(op, "folds_input", False)]
+    # per bottleneck: conv2's BN feeds conv3 (1x1), the block output feeds the next conv1 (1x1);
+    # conv1's BN feeds the 3x3 and the last block feeds the pooling head: not deferred; the CIFAR
+    # stem (no max-pool) feeds layer1.0.conv1 directly: deferred
+    assert len(deferred) == len(folding) == 16 + 15 + 1
+    assert all(op.wshape[2:] == (1, 1) for op in folding)
+    ex = StageExecutor(plan, device="cpu", dtype=torch.float64, lr=0.1, momentum=0.9, weight_decay=1e-4)
+    for name, p in m.named_parameters():
+        ex.store.weights()[name].copy_(p.detach())
+    x = torch.randn(4, 3, 32, 32, dtype=torch.float64)
+    t = torch.randint(0, 10, (4,))
+    y = m(x)
+    F.cross_entropy(y, t).backward()
+    outs, ctx = ex.forward([ex.prepare_input(x)])
+    assert not E.PENDING_FOLD                                   # every deferred value was written
+    _, d = ex.loss(outs[0], t)
+    ex.backward(ctx, [d])
+    assert torch.allclose(outs[0], y, atol=1e-9)
+    assert _global_rel_err(ex, m) < 1e-6
+    # a stage cut right after a deferred producer: the value must be written before it leaves
+    cut = next(i for i, n in enumerate(m.nodes) if n.name == "layer1.0.relu2") + 1
+    ex_a = StageExecutor(cp(m, 0, cut), device="cpu", dtype=torch.float64)
+    ex_b = StageExecutor(cp(m, cut, None), device="cpu", dtype=torch.float64, first_stage=False)
+    for name, p in m.named_parameters():
+        for e in (ex_a, ex_b):
+            if name in e.store.weights():
+                e.store.weights()[name].copy_(p.detach())
+    mid, _ = ex_a.forward([ex_a.prepare_input(x)])
+    out_b, _ = ex_b.forward(mid)
+    assert torch.allclose(out_b[0], y, atol=1e-9) and not E.PENDING_FOLD
