@@ -119,6 +119,10 @@ int ddl_gemm_bf16_tn(const void* A, const void* B, void* D, int M, int N, int K,
 int ddl_gemm_bf16_nt_mn(const void* A, const void* B, void* D, int M, int N, int K, int lda,
                         int ldb, int ldd, int out_is_bf16, int splits, float* workspace, int sms,
                         cudaStream_t st);
+int ddl_gemm_bf16_tn_bnfold(const void* C, const void* R, const void* B, void* D, void* Y, void* mask,
+                            int M, int N, int K, int ld, int ldb, int ldd, const float* stat,
+                            const void* gamma, const void* beta, int param_is_bf16, int act,
+                            float* col_sums, const void* bias, int relu, int sms, cudaStream_t st);
 int ddl_gemm_selftest_info(char* buf, int len);
 int ddl_set_pdl(int on);
 

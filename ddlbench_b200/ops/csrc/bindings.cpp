@@ -339,6 +339,33 @@ bool dwconv3x3(int64_t mode, at::Tensor a, at::Tensor b, at::Tensor out, int64_t
   check(rc, "dwconv3x3");
   return true;
 }
+// D = act(BN(C) [+ R]) @ B^T with Y = act(BN(C) [+ R]) (and its 1-bit mask) written as a side
+// effect.  C, R, Y: [M, K] views with the same leading dimension; returns false if declined.
+bool gemm_bf16_tn_bnfold(at::Tensor C, c10::optional<at::Tensor> R, at::Tensor B, at::Tensor D,
+                         at::Tensor Y, c10::optional<at::Tensor> mask, at::Tensor stat,
+                         at::Tensor gamma, at::Tensor beta, int64_t act,
+                         c10::optional<at::Tensor> col_sums, c10::optional<at::Tensor> bias,
+                         bool relu) {
+  TORCH_CHECK(C.dim() == 2 && B.dim() == 2 && D.dim() == 2 && Y.dim() == 2 && is_bf16(C) && is_bf16(B) &&
+              is_bf16(D) && is_bf16(Y));
+  TORCH_CHECK(C.stride(1) == 1 && B.stride(1) == 1 && D.stride(1) == 1 && Y.stride(1) == 1);
+  const int M = (int)C.size(0), K = (int)C.size(1), N = (int)B.size(0);
+  TORCH_CHECK(B.size(1) == K && D.size(0) == M && D.size(1) == N && Y.size(0) == M && Y.size(1) == K);
+  TORCH_CHECK(Y.stride(0) == C.stride(0), "bnfold: C and Y must share the leading dimension");
+  if (R.has_value() && R->defined())
+    TORCH_CHECK(R->stride(0) == C.stride(0) && R->size(0) == M && R->size(1) == K && is_bf16(*R));
+  TORCH_CHECK(stat.numel() >= 2 * K && stat.scalar_type() == at::kFloat && stat.is_contiguous());
+  c10::cuda::CUDAGuard g(C.device());
+  const int rc = ddl_gemm_bf16_tn_bnfold(C.data_ptr(), optr(R), B.data_ptr(), D.data_ptr(), Y.data_ptr(),
+                                         optr(mask), M, N, K, (int)C.stride(0), (int)B.stride(0),
+                                         (int)D.stride(0), stat.data_ptr<float>(), gamma.data_ptr(),
+                                         beta.data_ptr(), is_bf16(gamma), (int)act,
+                                         (float*)optr(col_sums), optr(bias), relu, sm_count(),
+                                         cur_stream());
+  if (rc == -1) return false;
+  check(rc, "gemm_bf16_tn_bnfold");
+  return true;
+}
 void gemm_bf16_nt_mn(at::Tensor A, at::Tensor B, at::Tensor D, int64_t splits,
                      c10::optional<at::Tensor> workspace) {
   // A: [K, M], B: [K, N], D: [M, N] fp32, accumulated into (D += A^T B)
@@ -648,6 +675,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("maxpool_bwd", &maxpool_bwd);
   m.def("gemm_bf16_tn", &gemm_bf16_tn);
   m.def("gemm_bf16_nt_mn", &gemm_bf16_nt_mn);
+  m.def("gemm_bf16_tn_bnfold", &gemm_bf16_tn_bnfold);
   m.def("conv_bf16_nhwc", &conv_bf16_nhwc);
   m.def("conv_wgrad_bf16_nhwc", &conv_wgrad_bf16_nhwc);
   m.def("im2col_rows", &im2col_rows);

@@ -83,6 +83,42 @@ def check_conv_wgrad(n, ci, co, hw, k, stride=1, seed=0):
     return ok
 
 
+def check_bnfold(n, k, co, hw, act=1, res=False, seed=0):
+    """D = act(BN(c) [+ res]) @ W^T with y / mask written by the same kernel, vs the two-step path."""
+    from ddlbench_b200.ops import reference as ref
+    torch.manual_seed(seed)
+    c = (torch.randn(n, k, hw, hw, device="cuda") * 1.5 + 0.3).to(torch.bfloat16).contiguous(
+        memory_format=torch.channels_last)
+    r = (torch.randn(n, k, hw, hw, device="cuda")).to(torch.bfloat16).contiguous(
+        memory_format=torch.channels_last) if res else None
+    gamma = (torch.rand(k, device="cuda") + 0.5).to(torch.bfloat16)
+    beta = (torch.randn(k, device="cuda") * 0.2).to(torch.bfloat16)
+    w = (torch.randn(co, k, device="cuda") * (1.0 / k ** 0.5)).to(torch.bfloat16)
+    stat = ref.bn_stat(c, 1e-5).contiguous()
+    y = torch.empty_like(c)
+    mask = torch.zeros(c.numel() // 8, dtype=torch.uint8, device="cuda")
+    sums = torch.zeros(ops.BN_REPLICAS * 2 * co, device="cuda")
+    fold = ops.BnFold(c, r, stat, gamma, beta, act, y, mask)
+    before = ops.launches
+    d = ops.gemm_tn_bnfold(fold, w, col_sums=sums)
+    torch.cuda.synchronize()
+    fused = ops.launches - before == 1
+    y_ref = ref.bn_apply(c, r, stat, gamma, beta, act)
+    d_ref = y_ref.permute(0, 2, 3, 1).reshape(-1, k).float() @ w.float().t()
+    err_y = (y.float() - y_ref.float()).abs().max().item()
+    err_d = (d.float() - d_ref).abs().max().item()
+    yf = y.permute(0, 2, 3, 1).reshape(-1).float()
+    bits = ((mask.view(-1, 1) >> torch.arange(8, device="cuda", dtype=torch.uint8)) & 1).bool().view(-1)
+    expect = (yf > 0) & (yf < 6) if act == 2 else (yf > 0 if act == 1 else torch.ones_like(yf, dtype=torch.bool))
+    tot = sums.view(ops.BN_REPLICAS, 2, co).sum(0)
+    ok = fused and err_y <= 0.03 * max(1.0, y_ref.float().abs().max().item()) and \
+        err_d <= 0.03 * max(1.0, d_ref.abs().max().item()) and bool(torch.equal(bits, expect)) and \
+        (tot[0] - d.float().sum(0)).abs().max().item() <= 1e-2 * max(d.float().sum(0).abs().max().item(), 1.0) + 0.5
+    print(f"bnfold n={n} k={k} co={co} hw={hw} act={act} res={res}: fused={fused} err_y={err_y:.4f} "
+          f"err_d={err_d:.4f} {'OK' if ok else 'FAIL'}", flush=True)
+    return ok
+
+
 def bench(n, ci, co, hw, k=3, iters=20):
     x = torch.randn(n, ci, hw, hw, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     w = torch.randn(co, ci, k, k, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
@@ -116,6 +152,10 @@ def main():
         ok &= check(*args, stride=2)
     ok &= check(8, 256, 256, 28, 3, stats=True, stride=2)
     ok &= check(7, 64, 64, 11, 3, stats=True, bias=True, relu=True)
+    if os.environ.get("CHECK_BNFOLD", "1") == "1":
+        for args in [(32, 64, 256, 56, 1, False), (32, 256, 64, 56, 1, True), (32, 512, 2048, 7, 1, False),
+                     (5, 128, 64, 9, 2, True), (3, 64, 136, 11, 0, False)]:
+            ok &= check_bnfold(*args)
     if os.environ.get("CHECK_WGRAD", "1") == "1":
         for args in [(64, 128, 64), (128, 128, 128), (6272, 256, 1024), (100352, 64, 256), (1000, 72, 200),
                      (200, 136, 64)]:
