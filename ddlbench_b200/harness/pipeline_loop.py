@@ -147,6 +147,23 @@ def plan_pipedream(cfg: RunConfig, model, world: int, device, dtype, out_dir: Op
     if out_dir:
         codegen.generate(gr, cfg.arch, os.path.join(out_dir, "models", cfg.arch, "gpus=%d" % world),
                          stage_to_num_ranks=reps)
+    # replay the runtime's 1F1B schedule with the profiled stage costs: the partitioner's
+    # objective is a steady-state bound, this is what the schedule can actually deliver
+    try:
+        from ..partition.simulate import simulate_1f1b
+        per_stage: Dict[int, list] = {}
+        for node in gr.nodes.values():
+            t = per_stage.setdefault(node.stage_id or 0, [0.0, 0.0])
+            t[0] += node.forward_compute_time
+            t[1] += node.backward_compute_time
+        order = sorted(per_stage)
+        sim = simulate_1f1b([per_stage[k][0] for k in order], [per_stage[k][1] for k in order],
+                            replicas=list(reps)[:len(order)], minibatches=64)
+        print("Simulated 1F1B steady state: %.3f ms per minibatch (bound %.3f ms), worst bubble %.0f%%"
+              % (sim["steady_ms_per_minibatch"], sim["bound_ms"],
+                 100.0 * max(sim["bubble_fraction"].values())), flush=True)
+    except Exception as e:  # noqa: BLE001 - advisory only
+        say("schedule simulation skipped: %s" % e)
     return stage_ids_from_graph(model, gr), reps
 
 
