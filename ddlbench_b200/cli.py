@@ -58,6 +58,12 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--straight", action="store_true", help="pipedream: no replication")
     p.add_argument("--no-input-pipelining", action="store_true")
     p.add_argument("--macrobatch", action="store_true")
+    # accepted for command-line parity with main_with_runtime.py; see the notes printed at start
+    p.add_argument("--recompute", action="store_true",
+                   help="pipedream: plumbed but a no-op in the reference (runtime.py:72-78) and here")
+    p.add_argument("--fp16", action="store_true",
+                   help="reference: apex fp16 + loss scale; here compute is bf16 with fp32 master weights already")
+    p.add_argument("--loss_scale", "--loss-scale", type=float, default=1.0, dest="loss_scale")
     p.add_argument("--config-path", default=None, help="pipedream: explicit *_conf.json")
     p.add_argument("--checkpoint-dir", default=None)
     p.add_argument("--workdir", default=None)
@@ -168,6 +174,10 @@ def main(argv=None) -> int:
     if args.nodes > 1 and args.framework in ("pytorch", "gpipe"):
         print("\n\nOnly Horovod and Pipedream support multi-node execution. Continuing with 1 node.\n\n")
         args.nodes = 1
+    if (args.fp16 or args.loss_scale != 1.0 or args.recompute) and not args.worker:
+        print("note: --fp16/--loss_scale/--recompute are accepted for command-line parity; compute is "
+              "bf16 with fp32 master weights (no loss scaling needed) and --recompute is a no-op as in "
+              "the reference runtime")
     cfgs = expand(args)
     if args.worker:
         assert len(cfgs) == 1
