@@ -59,6 +59,17 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--no-input-pipelining", action="store_true")
     p.add_argument("--macrobatch", action="store_true")
     # accepted for command-line parity with main_with_runtime.py; see the notes printed at start
+    # hyper-parameters of the reference scripts (argparse flags of benchmark/*/*.py and
+    # pipedream-fork/runtime/image_classification/main_with_runtime.py:29-104)
+    p.add_argument("--lr", "--learning-rate", type=float, default=None, dest="lr")
+    p.add_argument("--momentum", type=float, default=None)
+    p.add_argument("--wd", "--weight-decay", type=float, default=None, dest="wd")
+    p.add_argument("--lr_policy", "--lr-policy", default=None, dest="lr_policy",
+                   choices=["step", "polynomial", "exponential_decay"])
+    p.add_argument("--lr_warmup", "--lr-warmup", type=int, default=None, dest="lr_warmup",
+                   help="pipedream: warm-up epochs")
+    p.add_argument("--forward_only", "--forward-only", action="store_true", dest="forward_only",
+                   help="pipedream: evaluation passes only")
     p.add_argument("--recompute", action="store_true",
                    help="pipedream: plumbed but a no-op in the reference (runtime.py:72-78) and here")
     p.add_argument("--fp16", action="store_true",
@@ -103,12 +114,19 @@ def expand(args) -> List[RunConfig]:
                     extra["no_input_pipelining"] = "1"
                 if args.macrobatch:
                     extra["macrobatch"] = "1"
+                if args.lr_policy:
+                    extra["lr_policy"] = args.lr_policy
+                if args.lr_warmup is not None:
+                    extra["lr_warmup"] = str(args.lr_warmup)
+                if args.forward_only:
+                    extra["forward_only"] = "1"
                 kw = dict(benchmark=b, framework=fw, arch=m, gpus=args.gpus, nodes=args.nodes,
                           log_interval=args.loginterval, synthetic=not args.real_data,
                           device=args.device, allreduce=args.allreduce,
                           cuda_graph=not args.no_graph, steps_per_epoch=args.steps,
                           eval_steps=args.eval_steps, batch_size=args.batch_size,
-                          microbatches=args.microbatches, extra=extra)
+                          microbatches=args.microbatches, lr=args.lr, momentum=args.momentum,
+                          weight_decay=args.wd, extra=extra)
                 if args.epochs is not None:
                     kw["epochs"] = args.epochs
                 cfgs.append(RunConfig.from_env(**{k: v for k, v in kw.items() if v is not None}))
@@ -158,8 +176,12 @@ def _cfg_to_argv(cfg: RunConfig, args) -> List[str]:
                     ("checkpoint_dir", "--checkpoint-dir"), ("workdir", "--workdir")):
         if k in cfg.extra:
             a += [flag, cfg.extra[k]]
+    a += ["--lr", repr(cfg.lr), "--momentum", repr(cfg.momentum), "--wd", repr(cfg.weight_decay)]
+    for k, flag in (("lr_policy", "--lr_policy"), ("lr_warmup", "--lr_warmup")):
+        if k in cfg.extra:
+            a += [flag, cfg.extra[k]]
     for k, flag in (("straight", "--straight"), ("no_input_pipelining", "--no-input-pipelining"),
-                    ("macrobatch", "--macrobatch")):
+                    ("macrobatch", "--macrobatch"), ("forward_only", "--forward_only")):
         if cfg.extra.get(k) == "1":
             a.append(flag)
     return a

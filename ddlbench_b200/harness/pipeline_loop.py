@@ -258,7 +258,11 @@ def run_pipedream(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
             rt.backward_stats.reset_stats()
             rt.forward_stats.spans, rt.backward_stats.spans = [], []
             rt.forward_stats.keep_spans = rt.backward_stats.keep_spans = True
-        rt.run_epoch(loader() if topo.is_first else None, n, on_forward=on_fwd)
+        if cfg.extra.get("forward_only") == "1":
+            # --forward_only (main_with_runtime.py:87-88): the timed region is a forward-only pass
+            rt.run_eval(loader() if topo.is_first else None, n)
+        else:
+            rt.run_epoch(loader() if topo.is_first else None, n, on_forward=on_fwd)
         ms = timer.stop()
         if trace_dir:
             # one Chrome-trace file per rank: load them together to see the 1F1B interleaving

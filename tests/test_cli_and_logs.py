@@ -113,3 +113,18 @@ def test_run_sh_pipedream_plans_and_runs_on_cpu(tmp_path):
     assert any(n == "graph.txt" for n in produced) and any(n.endswith("_conf.json") for n in produced)
     outs = list((tmp_path / "out").glob("*/slurm.out"))
     assert outs and "pipedream - mnist - resnet18" in outs[0].read_text()
+
+
+def test_script_level_hyperparameter_flags():
+    (c,) = _expand(["-b", "imagenet", "-f", "pipedream", "-g", "4", "-m", "vgg16", "--lr", "0.02",
+                    "--momentum", "0.8", "--wd", "1e-5", "--lr_policy", "polynomial", "--lr_warmup", "2",
+                    "--forward_only", "--recompute", "--fp16", "--loss_scale", "128"])
+    assert (c.lr, c.momentum, c.weight_decay) == (0.02, 0.8, 1e-5)
+    assert c.extra["lr_policy"] == "polynomial" and c.extra["lr_warmup"] == "2" and c.extra["forward_only"] == "1"
+    back = cli._cfg_to_argv(c, cli.build_parser().parse_args(["-f", "pipedream"]))
+    again = cli.expand(cli.build_parser().parse_args(back))[0]
+    assert (again.lr, again.momentum, again.weight_decay) == (0.02, 0.8, 1e-5)
+    assert again.extra["lr_policy"] == "polynomial" and again.extra["forward_only"] == "1"
+    # defaults still come from the reference's per-script table when the flags are absent
+    (d,) = _expand(["-b", "mnist", "-f", "pytorch", "-m", "resnet18"])
+    assert (d.lr, d.momentum, d.weight_decay) == (0.01, 0.5, 0.0)
