@@ -56,7 +56,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--stages", default=None, help="pipedream: '<stages>x<replicas>' e.g. 4x2")
     p.add_argument("--straight", action="store_true", help="pipedream: no replication")
-    p.add_argument("--no-input-pipelining", action="store_true")
+    p.add_argument("--no-input-pipelining", "--no_input_pipelining", action="store_true",
+                   dest="no_input_pipelining")
     p.add_argument("--macrobatch", action="store_true")
     # accepted for command-line parity with main_with_runtime.py; see the notes printed at start
     # hyper-parameters of the reference scripts (argparse flags of benchmark/*/*.py and
@@ -75,8 +76,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--fp16", action="store_true",
                    help="reference: apex fp16 + loss scale; here compute is bf16 with fp32 master weights already")
     p.add_argument("--loss_scale", "--loss-scale", type=float, default=1.0, dest="loss_scale")
-    p.add_argument("--config-path", default=None, help="pipedream: explicit *_conf.json")
-    p.add_argument("--checkpoint-dir", default=None)
+    p.add_argument("--config-path", "--config_path", dest="config_path", default=None, help="pipedream: explicit *_conf.json")
+    p.add_argument("--checkpoint-dir", "--checkpoint_dir", dest="checkpoint_dir", default=None)
     p.add_argument("--workdir", default=None)
     p.add_argument("--out", default="out")
     p.add_argument("--master-port", type=int, default=29400)
