@@ -112,6 +112,9 @@ class RunConfig:
             cores_gpu=_env_int("CORES_GPU", 4),
             microbatches=_env_int("MICROBATCHES", None),
             datadir=os.environ.get("DATADIR", ""),
+            # extensions (not in the reference): cap the iterations of an epoch / of validation
+            steps_per_epoch=_env_int("STEPS", None),
+            eval_steps=_env_int("EVAL_STEPS", None),
         )
         kw.update(overrides)
         return cls(**kw)

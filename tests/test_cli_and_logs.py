@@ -128,3 +128,28 @@ def test_script_level_hyperparameter_flags():
     # defaults still come from the reference's per-script table when the flags are absent
     (d,) = _expand(["-b", "mnist", "-f", "pytorch", "-m", "resnet18"])
     assert (d.lr, d.momentum, d.weight_decay) == (0.01, 0.5, 0.0)
+
+
+def test_reference_named_script_entry_points(tmp_path, monkeypatch):
+    """benchmark/<ds>/<ds>_<framework>.py keep the reference scripts' command line (-a, -s, --lr ...)
+    and environment contract."""
+    import os
+    import subprocess
+    import sys
+    from ddlbench_b200 import scripts
+    monkeypatch.setenv("BATCH_SIZE", "16")
+    monkeypatch.setenv("EPOCHS", "2")
+    a = scripts.parse("imagenet", ["-a", "vgg16", "-s", "-1", "--lr", "0.05"])
+    cfg = scripts.config_from_args("imagenet", "horovod", a)
+    assert (cfg.benchmark, cfg.arch, cfg.lr, cfg.batch_size, cfg.epochs) == ("highres", "vgg16", 0.05, 16, 2)
+    assert not scripts.config_from_args("cifar10", "pytorch", scripts.parse("cifar10", ["-s", "1"])).synthetic
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for ds in ("mnist", "cifar10", "imagenet"):
+        for fw in ("pytorch", "horovod", "gpipe"):
+            assert os.path.isfile(os.path.join(root, "benchmark", ds, "%s_%s.py" % (ds, fw)))
+    env = dict(os.environ, BATCH_SIZE="8", EPOCHS="1", STEPS="2", EVAL_STEPS="1", LOGINTER="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "benchmark", "mnist", "mnist_pytorch.py"),
+                        "-a", "resnet18", "-s", "0", "--device", "cpu"], env=env, capture_output=True,
+                       text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert "=> creating model 'resnet18'" in r.stdout and "valid accuracy:" in r.stdout
