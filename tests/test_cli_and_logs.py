@@ -1,5 +1,6 @@
 """run.sh flag parsing / expansion, environment contract, and golden log lines (the formats the
 reference's post-processing greps for — SURVEY.md §5.5)."""
+import os
 import re
 
 import torch
@@ -97,6 +98,7 @@ def test_hvd_allreduce_equals_serial_sum_single_process():
 def test_run_sh_pipedream_plans_and_runs_on_cpu(tmp_path):
     """run.sh front end -> profile -> partition -> generate -> 2-rank PipeDream run (Gloo)."""
     import os
+    import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = ["bash", os.path.join(root, "run", "run", "run.sh"), "-b", "mnist", "-f", "pipedream", "-g", "2",
@@ -153,3 +155,40 @@ def test_reference_named_script_entry_points(tmp_path, monkeypatch):
                        text=True, timeout=600, cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr[-1500:]
     assert "=> creating model 'resnet18'" in r.stdout and "valid accuracy:" in r.stdout
+
+
+def test_pipedream_fork_path_shims(tmp_path):
+    """The reference's tool paths (pipedream-fork/{profiler,optimizer,runtime}/...) exist here with
+    its flags: profile -> partition -> generate -> run two gloo ranks from the generated conf."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fork = os.path.join(root, "pipedream-fork")
+    env = dict(os.environ, STEPS="2", EVAL_STEPS="1")
+
+    def run(*cmd):
+        r = subprocess.run([sys.executable, *cmd], cwd=tmp_path, env=env, capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return r.stdout
+
+    run(os.path.join(fork, "profiler/image_classification/main.py"), "-a", "cifar10_resnet18", "-b", "4",
+        "--profile_directory", "pp/", "-s", "1")
+    out = run(os.path.join(fork, "optimizer/optimizer_graph_hierarchical.py"), "-f",
+              "pp/cifar10_resnet18/graph.txt", "-n", "2", "-b", "1e10", "-s", "16e9",
+              "--use_memory_constraint", "-o", "pp/part")
+    assert "Time taken by single-stage pipeline" in out
+    run(os.path.join(fork, "optimizer/convert_graph_to_model.py"), "-f", "pp/part/gpus=2.txt", "-n", "resnet18",
+        "-a", "resnet18", "-o", "pp/models/resnet18/gpus=2", "--stage_to_num_ranks_map", "0:1,1:1")
+    conf = tmp_path / "pp/models/resnet18/gpus=2/mp_conf.json"
+    assert conf.exists()
+    port = str(29700 + os.getpid() % 200)
+    procs = [subprocess.Popen([sys.executable, os.path.join(fork, "runtime/image_classification/main_with_runtime.py"),
+                               "--module", "models.cifar10_resnet18.gpus=2", "-b", "8", "--config_path", str(conf),
+                               "--rank", str(r), "--local_rank", str(r), "--master_addr", "127.0.0.1",
+                               "--master_port", port, "--distributed_backend", "gloo", "--epochs", "1"],
+                              cwd=tmp_path, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "Loss:" in outs[1] and "Prec@1" in outs[1]
