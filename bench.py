@@ -27,7 +27,6 @@ import os
 import statistics
 import subprocess
 import sys
-import tempfile
 import threading
 import time
 

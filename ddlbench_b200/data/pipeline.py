@@ -9,11 +9,10 @@ captured graph's static input.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 
-from .. import ops
 from .synthetic import SyntheticImages
 
 

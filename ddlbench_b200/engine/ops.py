@@ -13,7 +13,7 @@ Parameter gradients are written straight into views of the flat gradient buffer
 from __future__ import annotations
 
 import os as _os
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence
 
 import torch
 import torch.nn as nn

@@ -15,11 +15,11 @@ consumer and does not cross the slice boundary.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Set, Tuple
+from typing import Dict, List, Optional, Set, Tuple
 
 import torch.nn as nn
 
-from ..models.graph import Add, Flatten, INPUT, LayerGraphModel, LayerNode
+from ..models.graph import Add, Flatten, INPUT, LayerGraphModel
 from ..ops import ACT_NONE, ACT_RELU, ACT_RELU6
 from . import ops as E
 

@@ -13,8 +13,7 @@ from __future__ import annotations
 
 import os
 
-import time
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional
 
 import torch
 import torch.distributed as dist

@@ -19,7 +19,7 @@ from __future__ import annotations
 import argparse
 import os
 import time
-from typing import Dict, List, Optional
+from typing import Dict
 
 import torch
 import torch.distributed as dist

@@ -8,8 +8,6 @@ hypotheses and a single device->host read at the end.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
-
 import torch
 
 from ..models.gnmt import BOS, EOS, GNMT, PAD

@@ -7,7 +7,7 @@ and the fused engine for free; channel joins are explicit ``Concat`` nodes.
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import Tuple
 
 import torch
 import torch.nn as nn

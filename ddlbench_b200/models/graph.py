@@ -19,10 +19,9 @@ reference keeps as three separate hand-written copies of every network:
 from __future__ import annotations
 
 from collections import OrderedDict
-from dataclasses import dataclass, field
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Dict, List, Sequence, Tuple
 
-import torch
 import torch.nn as nn
 
 INPUT = "input0"

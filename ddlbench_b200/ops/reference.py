@@ -6,7 +6,7 @@ task's rule: a kernel test compares against a plain PyTorch fp32 reference of th
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 import torch.nn.functional as F

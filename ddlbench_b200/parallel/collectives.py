@@ -5,10 +5,7 @@ GPUs, by the PipeDream replica groups, and by the micro-benchmarks in ``bench/``
 (reference: ``pipedream-fork/runtime/tests/communication/all_to_all.py``)."""
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
-import torch.distributed as dist
 
 from .. import ops
 from ..dist.symm import SymmContext, SymmetricBuffer

@@ -21,13 +21,12 @@ reference's single-process layout, or a single device for tests).
 """
 from __future__ import annotations
 
-import time
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 
-from ..dist.transport import DistP2P, PairGroups, TensorSpec
+from ..dist.transport import DistP2P, PairGroups
 from ..engine import FwdContext, StageExecutor
 from ..engine import ops as E
 from ..models.graph import LayerGraphModel

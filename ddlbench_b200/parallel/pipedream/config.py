@@ -18,7 +18,7 @@ replicas, the replica lists of the neighbouring stages, and the number of warm-u
 from __future__ import annotations
 
 import json
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from math import gcd
 from typing import Dict, List, Optional, Sequence
 

@@ -16,12 +16,11 @@ from __future__ import annotations
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
-import torch.distributed as dist
 import torch.nn as nn
 
 from ...dist.transport import DistP2P, PairGroups, TensorSpec
 from .optimizer import OptimizerWithWeightStashing
-from .schedule import B as OP_B, F as OP_F, one_f_one_b
+from .schedule import F as OP_F, one_f_one_b
 
 
 def infer_specs(stages: Sequence[nn.Module], sample_inputs: Sequence[torch.Tensor],

@@ -17,7 +17,7 @@ user-written ``nn.Module`` stages and for API parity.
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 import torch
 import torch.nn as nn

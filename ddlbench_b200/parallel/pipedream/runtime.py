@@ -20,8 +20,6 @@ checkpoints.  What is different by design:
 """
 from __future__ import annotations
 
-import os
-import time
 from typing import Dict, Iterator, List, Optional, Sequence, Tuple
 
 import torch
@@ -31,7 +29,7 @@ from ...dist.transport import DistP2P, PairGroups, TensorSpec
 from ...engine import FwdContext, StageExecutor
 from ...models.graph import INPUT, LayerGraphModel
 from .config import PipelineConfig, RankTopology
-from .schedule import B, F, Routing, one_f_one_b
+from .schedule import F, Routing, one_f_one_b
 
 
 def infer_boundary_specs(model: LayerGraphModel, cuts: Sequence[int], batch: int,

@@ -18,7 +18,7 @@ Routing rules reproduced (replica index arithmetic, not code):
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, Iterator, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 from .config import PipelineConfig, RankTopology
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 import argparse
 import csv
 import math
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Tuple
 
 from .graph import Graph, Node
 

@@ -12,11 +12,11 @@ import argparse
 import json
 import os
 import time
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Sequence, Tuple
 
 import torch
 
-from ..models.gnmt import GNMT, PAD, LabelSmoothing
+from ..models.gnmt import GNMT
 from . import optimizer as part_opt
 
 

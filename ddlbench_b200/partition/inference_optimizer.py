@@ -11,7 +11,7 @@ out; ``B[i][m]`` = (time per input, latency) of the best way to run the states u
 from __future__ import annotations
 
 import argparse
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Tuple
 
 from .graph import Graph
 

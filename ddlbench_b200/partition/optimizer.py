@@ -23,9 +23,8 @@ from __future__ import annotations
 import argparse
 import math
 import os
-import sys
 from collections import OrderedDict
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 from .graph import Graph
 

@@ -16,7 +16,7 @@ import argparse
 import json
 from typing import Dict, List, Optional, Sequence, Tuple
 
-from ..parallel.pipedream.schedule import B as OP_B, F as OP_F, fill_drain, one_f_one_b
+from ..parallel.pipedream.schedule import F as OP_F, fill_drain, one_f_one_b
 
 
 def simulate_1f1b(fwd: Sequence[float], bwd: Sequence[float], replicas: Optional[Sequence[int]] = None,

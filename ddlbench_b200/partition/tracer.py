@@ -16,7 +16,7 @@ user-supplied modules.  ``to_layer_graph`` additionally converts a traced module
 from __future__ import annotations
 
 import operator
-from typing import Dict, List, Optional
+from typing import Dict
 
 import torch
 import torch.fx as fx

@@ -104,7 +104,6 @@ def profile_layers(model: LayerGraphModel, sample: torch.Tensor, device=None,
                     (bwd if ident % 2 else fwd)[i] += ms * wi / tot / trials
     ex.profiler = None
     # shapes / sizes from a meta dry run of the plain graph
-    from ..parallel.pipedream.runtime import infer_boundary_specs  # shape walker
     prof = LayerProfile()
     live_shapes = _node_output_shapes(model, sample.shape[0])
     for i, n in enumerate(model.nodes):

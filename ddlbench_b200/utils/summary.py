@@ -4,11 +4,11 @@
 (no forward hooks, no real compute)."""
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import Tuple
 
 import torch
 
-from ..models import ARCHS, build_model
+from ..models import build_model
 from ..models.graph import LayerGraphModel
 from .layer_profiler import _node_output_shapes
 
