@@ -126,8 +126,10 @@ class DistP2P:
         return _Pending(works, bufs)
 
     # ---------------------------------------------------------------- send
-    def send(self, dst: int, tensors: Sequence[torch.Tensor], channel: str) -> None:
-        """Asynchronous send; the tensors are kept alive until the transfer completes."""
+    def send(self, dst: int, tensors: Sequence[torch.Tensor], channel: str):
+        """Asynchronous send; the tensors are kept alive until the transfer completes.  On GPUs
+        returns an event (communication stream) that fires once the transfers have been issued
+        and read their sources — callers that overwrite ``tensors`` in place wait on it."""
         g = self._group(self.rank, dst)
         self._reap()
         if self.gpu:
@@ -139,11 +141,15 @@ class DistP2P:
                     t = t if t.is_contiguous() or t.is_contiguous(
                         memory_format=torch.channels_last) else t.contiguous()
                     self._inflight_sends.append((dist.isend(t, dst=dst, group=g), t))
+                done = torch.cuda.Event()
+                done.record(self.comm_stream)
         else:
+            done = None
             for t in tensors:
                 t = t.contiguous()
                 self._inflight_sends.append((dist.isend(t, dst=dst, group=g), t))
         self.bytes_sent += sum(t.numel() * t.element_size() for t in tensors)
+        return done
 
     def _reap(self) -> None:
         self._inflight_sends = [(w, t) for (w, t) in self._inflight_sends if not w.is_completed()]

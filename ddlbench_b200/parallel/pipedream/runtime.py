@@ -16,10 +16,14 @@ checkpoints.  What is different by design:
   into rings on a communication stream, no helper threads, no per-message allocation;
 * replica gradient reduction uses the fused all-reduce+SGD kernel over the stage's replica
   group on GPUs (Gloo/NCCL ``all_reduce`` + fused SGD otherwise);
-* evaluation needs no ack tokens: back-pressure comes from the bounded receive rings.
+* evaluation needs no ack tokens: back-pressure comes from the bounded receive rings;
+* (opt-in, ``DDLB_PIPE_GRAPHS=1``) the forward and the backward of a stage replay as CUDA graphs,
+  one pair per weight-version slot: an eager pipeline is bound by launch cost (~2.1 ms per
+  minibatch and stage for ResNet-50), not by the GPU.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Iterator, List, Optional, Sequence, Tuple
 
 import torch
@@ -75,6 +79,34 @@ def reorder_by_stage(model: LayerGraphModel, stage_of_node: Sequence[int]) -> Tu
     return m, cuts
 
 
+class _EagerGraph:
+    """Stand-in for ``torch.cuda.CUDAGraph`` where graphs do not exist (CPU tests of the slot
+    logic): "capture" runs the body once, "replay" runs it again."""
+
+    def __init__(self, body):
+        self.body = body
+
+    def replay(self) -> None:
+        self.body()
+
+
+class _GraphSlot:
+    """Static tensors and the two captured graphs (forward, backward) of ONE weight-version
+    slot.  A minibatch whose forward ran on weight slot v keeps the slot ``busy`` until its
+    backward has replayed: the saved activations live in the graph's private memory pool, so
+    a second in-flight minibatch on the same weight slot (only during the warm-up forwards,
+    which all see version 0) takes the eager path instead."""
+    __slots__ = ("version", "x", "target", "outs", "stats", "dl", "ctx", "g", "gin", "fwd", "bwd",
+                 "pool", "busy", "sent")
+
+    def __init__(self, version: int):
+        self.version = version
+        self.x = self.target = self.outs = self.stats = self.dl = self.ctx = None
+        self.g = self.gin = self.fwd = self.bwd = self.pool = None
+        self.busy = False
+        self.sent = []          # events of the transfers that still read this slot's tensors
+
+
 class StageRuntime:
     def __init__(self, model: LayerGraphModel, cuts: Sequence[int], cfg: PipelineConfig,
                  batch_size: int, device="cpu", dtype: torch.dtype = torch.float32,
@@ -82,7 +114,8 @@ class StageRuntime:
                  rank: Optional[int] = None, num_versions: Optional[int] = None,
                  no_input_pipelining: bool = False, macrobatch: bool = False,
                  tcgen05: bool = False, fused_replica_allreduce: bool = True,
-                 groups: Optional[PairGroups] = None, verbose: bool = False):
+                 groups: Optional[PairGroups] = None, verbose: bool = False,
+                 graphs: Optional[bool] = None):
         self.cfg = cfg
         self.rank = dist.get_rank() if rank is None else rank
         self.topo = RankTopology.of(cfg, self.rank)
@@ -167,6 +200,133 @@ class StageRuntime:
         self.training = True
         self.verbose = verbose
         self._accum = 0
+        # graph replay of the stage's forward / backward (see _GraphSlot)
+        self.graphs = (os.environ.get("DDLB_PIPE_GRAPHS", "0") == "1") if graphs is None else bool(graphs)
+        if self.graphs and (self.fdp is not None or self.update_interval != 1):
+            if verbose:
+                print("stage graphs off: fused replica all-reduce / macrobatching keep host-side "
+                      "state per minibatch", flush=True)
+            self.graphs = False
+        self._slots: Dict[int, _GraphSlot] = {}
+        self._seen_fwd = 0
+        # lazy initialisation (cuDNN autotune, workspaces, handles) must be over before a capture
+        self._graph_after = int(os.environ.get("DDLB_PIPE_GRAPH_AFTER", 2 * versions + 2))
+        self.graph_replays = 0
+
+    # ------------------------------------------------------------------ graphed stage passes
+    def _capture(self, slot: _GraphSlot, body):
+        """Run ``body`` under stream capture into the slot's private pool (GPU) or once, eagerly
+        (CPU stand-in); returns an object with ``replay()``, or None if the capture failed (the
+        caller then runs the pass eagerly and graphs are switched off for the rest of the run).
+        The raw capture_begin/end API is used instead of ``torch.cuda.graph``: its device-wide
+        synchronize would wait for the pre-posted receives of the NEXT messages."""
+        if self.device.type != "cuda":
+            body()
+            return _EagerGraph(body)
+        if slot.pool is None:
+            slot.pool = torch.cuda.graph_pool_handle()
+        if getattr(self, "_capture_stream", None) is None:
+            self._capture_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        side = self._capture_stream
+        side.wait_stream(cur)
+        g = torch.cuda.CUDAGraph()
+        ok = True
+        with torch.cuda.stream(side):
+            # thread_local: the NCCL watchdog and the loader threads keep making CUDA calls
+            g.capture_begin(pool=slot.pool, capture_error_mode="thread_local")
+            try:
+                body()
+            except Exception as e:  # noqa: BLE001
+                ok = False
+                print("[pipeline] stage graph capture failed (%s); continuing eagerly"
+                      % str(e).splitlines()[0][:160], flush=True)
+            try:
+                g.capture_end()
+            except Exception as e:  # noqa: BLE001
+                if ok:
+                    print("[pipeline] stage graph capture failed (%s); continuing eagerly"
+                          % str(e).splitlines()[0][:160], flush=True)
+                ok = False
+        cur.wait_stream(side)
+        if not ok:
+            self.graphs = False
+            return None
+        return g
+
+    def _slot_for(self, version: int) -> Optional[_GraphSlot]:
+        if not (self.graphs and self.training) or self._seen_fwd < self._graph_after:
+            return None
+        slot = self._slots.get(version)
+        if slot is None:
+            slot = self._slots[version] = _GraphSlot(version)
+        return None if slot.busy else slot
+
+    def _wait_sent(self, slot: _GraphSlot) -> None:
+        """The transfers that read the slot's static outputs must be over before a replay
+        overwrites them (always true w+1 minibatches later; this makes it explicit)."""
+        if slot.sent and self.device.type == "cuda":
+            cur = torch.cuda.current_stream(self.device)
+            for ev in slot.sent:
+                cur.wait_event(ev)
+        slot.sent = []
+
+    def _graphed_forward(self, slot: _GraphSlot, xs: List[torch.Tensor], target: torch.Tensor):
+        ex, last = self.ex, self.topo.is_last
+        if slot.x is None:
+            slot.x = [torch.empty_like(x) for x in xs]
+            slot.target = torch.empty_like(target)
+        for d, s_ in zip(slot.x, xs):
+            d.copy_(s_)
+        slot.target.copy_(target)
+        self._wait_sent(slot)
+        if slot.fwd is None:
+            def body():
+                slot.outs, slot.ctx = ex.forward(slot.x, training=True, version=slot.version)
+                if last:
+                    slot.stats, slot.dl = ex.loss(slot.outs[0], slot.target, want_grad=True,
+                                                  grad_scale=1.0 / self.update_interval)
+            slot.fwd = self._capture(slot, body)
+            if slot.fwd is None:
+                return None
+            if self.device.type != "cuda":          # the stand-in's "capture" already computed
+                slot.busy = True
+                return slot.outs, (slot.stats.clone() if last else None)
+        slot.fwd.replay()
+        self.graph_replays += 1
+        slot.busy = True
+        return slot.outs, (slot.stats.clone() if last else None)
+
+    def _graphed_backward(self, slot: _GraphSlot, grads: Optional[List[torch.Tensor]]):
+        ex = self.ex
+        if grads is not None:                        # last stage: slot.dl is already in place
+            if slot.g is None:
+                slot.g = [torch.empty_like(g) for g in grads]
+            for d, s_ in zip(slot.g, grads):
+                d.copy_(s_)
+        self._wait_sent(slot)
+        if slot.bwd is None:
+            def body():
+                # backward() empties the context as it goes: hand it a copy of the list so a
+                # failed capture leaves slot.ctx usable for the eager fallback below
+                view = FwdContext(0, slot.ctx.version)
+                view.saved = [dict(d) for d in slot.ctx.saved]
+                view.outputs, view.need_input_grad = slot.ctx.outputs, slot.ctx.need_input_grad
+                slot.gin = ex.backward(view, slot.g if grads is not None else [slot.dl],
+                                       accumulate=False, final=True)
+            slot.bwd = self._capture(slot, body)
+            if slot.bwd is None:
+                # the forward replay filled slot.ctx's tensors, so the plain backward works on them
+                slot.busy = False
+                return ex.backward(slot.ctx, slot.g if grads is not None else [slot.dl],
+                                   accumulate=False, final=True)
+            if self.device.type != "cuda":
+                slot.busy = False
+                return slot.gin
+        slot.bwd.replay()
+        self.graph_replays += 1
+        slot.busy = False
+        return slot.gin
 
     # ------------------------------------------------------------------ epoch control
     def train(self, num_iterations: int) -> None:
@@ -178,6 +338,8 @@ class StageRuntime:
         self._next_fwd = self._next_bwd = None
         self._posted_fwd = self._posted_bwd = 0
         self._accum = 0
+        for slot in self._slots.values():
+            slot.busy = False
         self._prepost_fwd()
 
     def eval(self, num_iterations: int) -> None:
@@ -219,20 +381,31 @@ class StageRuntime:
             self.forward_stats.received(bufs)
             self._prepost_fwd()               # overlap the next transfer with this compute
         version = ex.store.latest
+        slot = self._slot_for(version)
         tok = self.forward_stats.begin_compute(self.device)
-        outs, ctx = ex.forward(xs, training=self.training, version=version)
-        self.forward_stats.end_compute(tok)
         stats = None
         dl = None
+        res = self._graphed_forward(slot, xs, target) if slot is not None else None
+        if res is not None:
+            outs, stats = res
+            ctx = slot
+        else:
+            slot = None
+            outs, ctx = ex.forward(xs, training=self.training, version=version)
+            if t.is_last:
+                stats, dl = ex.loss(outs[0], target, want_grad=self.training,
+                                    grad_scale=1.0 / self.update_interval)
+        self.forward_stats.end_compute(tok)
         if t.is_last:
-            stats, dl = ex.loss(outs[0], target, want_grad=self.training,
-                                grad_scale=1.0 / self.update_interval)
             self.loss_stats = stats
         else:
-            self.p2p.send(self.routing.fwd_send_peer(self.fwd_id), list(outs) + [target], "fwd")
+            ev = self.p2p.send(self.routing.fwd_send_peer(self.fwd_id), list(outs) + [target], "fwd")
+            if slot is not None and ev is not None:
+                slot.sent.append(ev)
             self.forward_stats.sent(list(outs) + [target])
         if self.training:
             self._ctxs.append((ctx, dl, None))
+            self._seen_fwd += 1
         self.fwd_id += 1
         return stats
 
@@ -254,10 +427,16 @@ class StageRuntime:
         accumulate = self._accum > 0
         final = (self._accum + 1) == self.update_interval
         tok = self.backward_stats.begin_compute(self.device)
-        gin = ex.backward(ctx, grads, accumulate=accumulate, final=final)
+        slot = ctx if isinstance(ctx, _GraphSlot) else None
+        if slot is not None:
+            gin = self._graphed_backward(slot, None if t.is_last else grads)
+        else:
+            gin = ex.backward(ctx, grads, accumulate=accumulate, final=final)
         self.backward_stats.end_compute(tok)
         if not t.is_first:
-            self.p2p.send(self.routing.next_bwd_send_peer(), [g for g in gin], "bwd")
+            ev = self.p2p.send(self.routing.next_bwd_send_peer(), [g for g in gin], "bwd")
+            if slot is not None and ev is not None:
+                slot.sent.append(ev)
             self.backward_stats.sent(gin)
         self._accum += 1
         if final:

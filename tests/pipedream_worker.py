@@ -50,7 +50,8 @@ def main():
     sd = rt.ex.state_dict()
     torch.save({"rank": rank, "stage": topo.stage, "losses": losses, "state": sd,
                 "warmup": rt.warmup, "versions": rt.ex.store.versions,
-                "bytes_sent": rt.p2p.bytes_sent}, os.path.join(out, f"rank{rank}.pt"))
+                "bytes_sent": rt.p2p.bytes_sent, "graph_replays": rt.graph_replays,
+                "graph_slots": len(rt._slots)}, os.path.join(out, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 

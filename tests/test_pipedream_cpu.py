@@ -157,3 +157,20 @@ def test_macrobatch_mode(tmp_path):
     res = _launch([1, 1], tmp_path, {"PD_MACRO": "1"}, iters=6)
     s0 = [r for r in res if r["stage"] == 0][0]
     assert s0["versions"] <= 2
+
+
+def test_stage_graph_slots_match_eager(tmp_path):
+    """DDLB_PIPE_GRAPHS: the per-version-slot replay logic (static inputs, busy slots during the
+    warm-up forwards, static gradient buffers) must reproduce the eager 1F1B run exactly.  On the
+    CPU the graph object is a stand-in that re-runs the captured body."""
+    a = tmp_path / "eager"
+    b = tmp_path / "graphs"
+    a.mkdir(), b.mkdir()
+    eager = _launch([1, 1, 1], a, iters=10)
+    graphed = _launch([1, 1, 1], b, {"DDLB_PIPE_GRAPHS": "1", "DDLB_PIPE_GRAPH_AFTER": "2"}, iters=10)
+    for e, g in zip(eager, graphed):
+        assert e["stage"] == g["stage"] and e["graph_replays"] == 0
+        assert g["graph_replays"] > 0 and g["graph_slots"] == g["versions"]
+        assert e["losses"] == g["losses"]
+        for k, v in e["state"].items():
+            assert torch.equal(v, g["state"][k]), k
