@@ -10,8 +10,8 @@ O=gpurun_out/optin
 step() { echo "=== $*" | tee -a $O.log; }
 
 step "numerics: tcgen05 conv3x3 / stem im2col / wgrad (descriptor variant 0)"
-DDLB_TEST_CONV_TCGEN05=1 timeout 400 python -m pytest tests/test_kernels_gpu.py -q -k "im2col or dwconv3x3" 2>&1 | tail -3 | tee -a $O.log
-BENCH=0 CHECK_WGRAD=0 CHECK_BNFOLD=0 timeout 300 python tests/conv_check.py 2>&1 | tail -14 | tee -a $O.log
+DDLB_TEST_CONV_TCGEN05=1 timeout 400 python -m pytest tests/test_kernels_gpu.py -q -k "im2col or dwconv3x3 or conv3x3" < /dev/null 2>&1 | tail -3 | tee -a $O.log
+BENCH=0 CHECK_WGRAD=0 CHECK_BNFOLD=0 timeout 300 python tests/conv_check.py < /dev/null 2>&1 | tail -14 | tee -a $O.log
 for v in 0 1; do
   step "wgrad GEMM, DDLB_WGRAD_DESC_VARIANT=$v"
   DDLB_WGRAD_DESC_VARIANT=$v timeout 200 python - <<'PY' 2>&1 | tail -9 | tee -a $O.log
@@ -31,12 +31,12 @@ ok = all(c.check_bnfold(*a) for a in [(32, 64, 256, 56, 1, False), (32, 256, 64,
 print("bnfold", "OK" if ok else "FAIL")
 PY
 step "timing vs cuDNN"
-CHECK_WGRAD=0 CHECK_BNFOLD=0 timeout 300 python tests/conv_check.py 2>&1 | grep "^{" | tee -a $O.log
+CHECK_WGRAD=0 CHECK_BNFOLD=0 timeout 300 python tests/conv_check.py < /dev/null 2>&1 | grep "^{" | tee -a $O.log
 
 bench() {  # name, env...
   local name=$1; shift
   step "bench $name"
-  env "$@" timeout 240 python bench.py --steps 40 --warmup 5 2>&1 | tail -1 > gpurun_out/bench_optin_$name.json
+  env "$@" timeout 240 python bench.py --steps 40 --warmup 5 < /dev/null 2>&1 | tail -1 > gpurun_out/bench_optin_$name.json
   python - "$name" <<'PY' | tee -a $O.log
 import json, sys
 try:
