@@ -7,6 +7,13 @@ consumes), gradient accumulation across micro-batches, forward/backward on a cho
 VERSION (weight stashing), and fires ``on_bucket_ready(i)`` during backward the moment the
 last gradient of flat-buffer bucket ``i`` has been written — the hook the data-parallel layer
 uses to launch the fused all-reduce+SGD kernel for that bucket on the communication stream.
+
+Reference counterpart: ``torch.autograd`` running the stage's ``nn.Module`` (forward in
+``pipedream-fork/runtime/runtime.py::_run_forward``, ``torch.autograd.backward`` in
+``::_run_backward``; the benchmark scripts' ``loss.backward()``), Horovod's per-parameter
+gradient hooks (``imagenet_horovod.py:135-139``) and the patched backward pre-hook
+(``pre_hook.patch``) the upstream profiler needs — all replaced by explicit per-op backward
+functions and the two hook points above.
 """
 from __future__ import annotations
 

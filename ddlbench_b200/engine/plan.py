@@ -12,6 +12,11 @@ Pattern matching over the single model definition (``models/graph.py``):
 
 A node is only absorbed into its producer when the intermediate value has no other
 consumer and does not cross the slice boundary.
+
+Reference counterpart: none at run time (eager ``nn.Module`` calls, one library kernel per layer);
+the closest artefact is the code generator's stage modules
+(``pipedream-fork/optimizer/convert_graph_to_model.py``), which this plan replaces for execution —
+a stage here is a slice ``[start, stop)`` of the same layer graph, compiled, not generated source.
 """
 from __future__ import annotations
 
