@@ -420,8 +420,11 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   }
 }
 
-// dx = coef0 * (dz - coef1 - xhat * coef2); dz is read from dz_in, or rebuilt from dy & y
-__global__ void __launch_bounds__(kBnThreads, 4)
+// dx = coef0 * (dz - coef1 - xhat * coef2); dz is read from dz_in, or rebuilt from dy & y.
+// kMinBlocks = 4 (default, validated): 64 registers, 52 B of spills; kMinBlocks = 3
+// (DDLB_BN_BWD_APPLY_BLOCKS=3, for A/B): 85 registers, no spills, 25 % fewer resident warps.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kBnThreads, kMinBlocks)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz_in, const __nv_bfloat16* __restrict__ dy,
                     const __nv_bfloat16* __restrict__ dy2, const __nv_bfloat16* __restrict__ y,
                     const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dx,
@@ -649,9 +652,18 @@ extern "C" int ddl_bn_bwd_apply(const void* dz_in, const void* dy, const void* d
                                 int64_t M, int C, int act, int sms, cudaStream_t st) {
   if (C % 8) return -1;
   BnDims d = bn_dims(M, C, sms, 8, 2);
-  launch_pdl(bn_bwd_apply_kernel, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st, 
-      (const bf16*)dz_in, (const bf16*)dy, (const bf16*)dy2, (const bf16*)y, (const bf16*)x,
-      (bf16*)dx, stat, coef, M, C, d.rows_per_block, act);
+  static const int min_blocks = [] {
+    const char* e = std::getenv("DDLB_BN_BWD_APPLY_BLOCKS");
+    return (e && e[0] == '3') ? 3 : 4;
+  }();
+  if (min_blocks == 3)
+    launch_pdl(bn_bwd_apply_kernel<3>, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st,
+        (const bf16*)dz_in, (const bf16*)dy, (const bf16*)dy2, (const bf16*)y, (const bf16*)x,
+        (bf16*)dx, stat, coef, M, C, d.rows_per_block, act);
+  else
+    launch_pdl(bn_bwd_apply_kernel<4>, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st,
+        (const bf16*)dz_in, (const bf16*)dy, (const bf16*)dy2, (const bf16*)y, (const bf16*)x,
+        (bf16*)dx, stat, coef, M, C, d.rows_per_block, act);
   return (int)cudaGetLastError();
 }
 
