@@ -184,6 +184,29 @@ class _ConvMixin:
                              self.groups)
         return y, False
 
+    def _wgrad_tc(self, dy, x, w, patch=None):
+        """Weight gradient on the tcgen05 kernels (opt-in paths), or None: the caller then uses the
+        library.  Returned in [Cout, Cin, KH, KW] logical shape, fp32."""
+        if not (dy.is_cuda and dy.is_contiguous(memory_format=torch.channels_last)):
+            return None
+        if patch is not None:
+            # stem: dW[Cout, kh*kw*Cin (padded)] = dY^T @ patch matrix, then drop the padding
+            co, ci, kh, kw = self.wshape
+            n, _, oh, ow = dy.shape
+            dwm = ops.gemm_nt_mn(dy.permute(0, 2, 3, 1).reshape(n * oh * ow, co), patch)
+            return dwm[:, :kh * kw * ci].reshape(co, kh, kw, ci).permute(0, 3, 1, 2)
+        if not WGRAD_TCGEN05:
+            return None
+        if self._is_conv_tc(x, w):
+            # 3x3 / strided convolutions: shifted-window MN-major kernel (may decline -> None)
+            return ops.conv_wgrad(dy, x, self.wshape, self.stride[0], self.padding)
+        if self._is_gemm(x):
+            n, ci, h, wd = x.shape
+            co = self.wshape[0]
+            return ops.gemm_nt_mn(dy.permute(0, 2, 3, 1).reshape(n * h * wd, co),
+                                  x.permute(0, 2, 3, 1).reshape(n * h * wd, ci)).view(co, ci, 1, 1)
+        return None
+
     def _conv_bwd(self, dy, x, w, need_dx: bool, gw: torch.Tensor, accumulate: bool, patch=None):
         """Data gradient (returned) and weight gradient (written into ``gw``).  With a side
         stream configured (``WGRAD_OVERLAP``) the weight-gradient kernel — which nothing
@@ -207,7 +230,11 @@ class _ConvMixin:
             dx_tc = ops.conv_tn(dy, wt)
         lib_dx = need_dx and dx_tc is None
         if side is None:
-            dx, dw, _ = aten.convolution_backward(dy, x, w, *args, [lib_dx, True, False])
+            dw = self._wgrad_tc(dy, x, w, patch)
+            if dw is None:
+                dx, dw, _ = aten.convolution_backward(dy, x, w, *args, [lib_dx, True, False])
+            else:
+                dx = aten.convolution_backward(dy, x, w, *args, [True, False, False])[0] if lib_dx else None
             _write(gw, dw, accumulate)
             return dx_tc if dx_tc is not None else dx
         main = torch.cuda.current_stream(dy.device)
@@ -217,22 +244,8 @@ class _ConvMixin:
             aten.convolution_backward(dy, x, w, *args, [True, False, False])[0] if lib_dx else None)
         with torch.cuda.stream(side):
             side.wait_event(ev)
-            if patch is not None and dy.is_contiguous(memory_format=torch.channels_last):
-                # stem: dW[Cout, kh*kw*Cin (padded)] = dY^T @ patch matrix, then drop the padding
-                co, ci, kh, kw = self.wshape
-                n, _, oh, ow = dy.shape
-                dwm = ops.gemm_nt_mn(dy.permute(0, 2, 3, 1).reshape(n * oh * ow, co), patch)
-                dw = dwm[:, :kh * kw * ci].reshape(co, kh, kw, ci).permute(0, 3, 1, 2)
-            elif WGRAD_TCGEN05 and self._is_conv_tc(x, w) and \
-                    dy.is_contiguous(memory_format=torch.channels_last) and \
-                    (dw := ops.conv_wgrad(dy, x, self.wshape, self.stride[0], self.padding)) is not None:
-                pass        # 3x3 / strided convolutions: shifted-window MN-major kernel
-            elif WGRAD_TCGEN05 and self._is_gemm(x) and dy.is_contiguous(memory_format=torch.channels_last):
-                n, ci, h, wd = x.shape
-                co = self.wshape[0]
-                dw = ops.gemm_nt_mn(dy.permute(0, 2, 3, 1).reshape(n * h * wd, co),
-                                    x.permute(0, 2, 3, 1).reshape(n * h * wd, ci)).view(co, ci, 1, 1)
-            else:
+            dw = self._wgrad_tc(dy, x, w, patch)
+            if dw is None:
                 dw = aten.convolution_backward(dy, x, w, *args, [False, True, False])[1]
             _write(gw, dw, accumulate)
         # keep the operands alive until the streams are joined (executor.backward)

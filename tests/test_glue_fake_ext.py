@@ -1,0 +1,152 @@
+"""The device branches of the Python glue, executed on the CPU: tensors that claim ``is_cuda`` and
+a PyTorch stand-in for the extension with the bindings' signatures and argument checks
+(``tests/fake_ext.py``).  Catches wrong argument order / views / layouts in the paths that only
+run on a GPU (most of them opt-in and still waiting for their first hardware run)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from fake_ext import FakeExt, fake_cuda  # noqa: E402
+
+from ddlbench_b200 import ops  # noqa: E402
+from ddlbench_b200.engine import ops as E  # noqa: E402
+
+BF16 = torch.bfloat16
+CL = torch.channels_last
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    fe = FakeExt()
+    monkeypatch.setattr(ops, "ext", lambda: fe)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    # what the glue allocates lives "on the device" as well
+    for name in ("empty", "zeros", "empty_like", "zeros_like"):
+        real = getattr(torch, name)
+        monkeypatch.setattr(torch, name, (lambda real: lambda *a, **k: fake_cuda(real(*a, **k)))(real))
+    monkeypatch.setitem(E.TCGEN05, "conv1x1", True)
+    for name in ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "DWCONV"):
+        monkeypatch.setattr(E, name, True)
+    return fe
+
+
+def _t(*shape, cl=True):
+    t = torch.randn(*shape).to(BF16)
+    if cl and t.dim() == 4:
+        t = t.contiguous(memory_format=CL)
+    return fake_cuda(t)
+
+
+def _conv_op(ci, co, k, s, p, groups=1):
+    conv = nn.Conv2d(ci, co, k, s, p, groups=groups, bias=False)
+    return E.ConvBnAct("op", ["x"], "y", conv, nn.BatchNorm2d(co), E.ACT_RELU, False, "conv", "bn")
+
+
+def _reference(x, w, dy, s, p, groups=1):
+    xf = x.float().as_subclass(torch.Tensor).contiguous().requires_grad_(True)
+    wf = w.float().as_subclass(torch.Tensor).contiguous().requires_grad_(True)
+    y = F.conv2d(xf, wf, None, s, p, groups=groups)
+    y.backward(dy.float().as_subclass(torch.Tensor).contiguous())
+    return y.detach(), xf.grad, wf.grad
+
+
+def _close(a, b, tol=2e-2):
+    a = a.as_subclass(torch.Tensor).float()
+    b = b.as_subclass(torch.Tensor).float()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    assert err <= tol * max(1.0, b.abs().max().item()), err
+
+
+@pytest.mark.parametrize("ci,co,k,s,p,expect", [
+    (64, 64, 3, 1, 1, ["conv_bf16_nhwc", "conv_bf16_nhwc", "conv_wgrad_bf16_nhwc"]),     # fwd, dgrad, wgrad
+    (64, 128, 3, 2, 1, ["conv_bf16_nhwc", "conv_wgrad_bf16_nhwc"]),                     # strided: library dgrad
+    (64, 128, 1, 2, 0, ["conv_bf16_nhwc", "conv_wgrad_bf16_nhwc"]),                     # downsample
+    (64, 128, 1, 1, 0, ["gemm_bf16_tn", "gemm_bf16_nt_mn"]),                            # plain GEMM pair
+])
+def test_conv_paths(fake, ci, co, k, s, p, expect):
+    torch.manual_seed(0)
+    op = _conv_op(ci, co, k, s, p)
+    x, w = _t(2, ci, 9, 9), _t(co, ci, k, k)
+    sums = torch.zeros(8 * 2 * co)
+    y, fused = op._conv_fwd(x, w, col_sums=sums, ctx={})
+    dy = _t(*y.shape)
+    gw = torch.zeros(co, ci, k, k)
+    dx = op._conv_bwd(dy, x, w, True, gw, False)
+    y_ref, dx_ref, dw_ref = _reference(x, w, dy, s, p)
+    assert fused and fake.calls == expect
+    _close(y, y_ref)
+    _close(sums[:co], y.as_subclass(torch.Tensor).float().sum((0, 2, 3)), 1e-3)
+    _close(dx, dx_ref)
+    _close(gw, dw_ref)
+    assert y.is_contiguous(memory_format=CL)
+
+
+def test_stem_im2col_paths(fake):
+    torch.manual_seed(1)
+    op = _conv_op(3, 64, 7, 2, 3)
+    x, w = _t(2, 3, 32, 32), _t(64, 3, 7, 7)
+    ctx = {}
+    y, fused = op._conv_fwd(x, w, col_sums=torch.zeros(8 * 2 * 64), ctx=ctx)
+    assert fake.calls == ["im2col_rows", "gemm_bf16_tn"] and "patch" in ctx and ctx["patch"].shape[1] == 152
+    dy = _t(*y.shape)
+    gw = torch.zeros(64, 3, 7, 7)
+    dx = op._conv_bwd(dy, x, w, False, gw, False, patch=ctx["patch"])
+    y_ref, _, dw_ref = _reference(x, w, dy, 2, 3)
+    assert dx is None and fake.calls[-1] == "gemm_bf16_nt_mn"
+    _close(y, y_ref)
+    _close(gw, dw_ref)
+
+
+@pytest.mark.parametrize("s", [1, 2])
+def test_depthwise_paths(fake, s):
+    torch.manual_seed(2)
+    op = _conv_op(16, 16, 3, s, 1, groups=16)
+    x, w = _t(2, 16, 10, 10), _t(16, 1, 3, 3)
+    y, fused = op._conv_fwd(x, w)
+    dy = _t(*y.shape)
+    gw = torch.zeros(16, 1, 3, 3)
+    dx = op._conv_bwd(dy, x, w, True, gw, False)
+    y_ref, dx_ref, dw_ref = _reference(x, w, dy, s, 1, groups=16)
+    assert not fused and fake.calls == ["dwconv3x3:0", "dwconv3x3:1", "dwconv3x3:2"]
+    _close(y, y_ref)
+    _close(dx, dx_ref)
+    _close(gw, dw_ref)
+
+
+@pytest.mark.parametrize("has_res", [False, True])
+def test_bnfold_glue_writes_y_and_mask_in_place(fake, has_res):
+    """The consumer GEMM must write y / mask through VIEWS of the tensors the producer allocated
+    (a reshape that silently copies would leave them unwritten)."""
+    torch.manual_seed(3)
+    n, k, h, w_, co = 2, 64, 6, 6, 128
+    c = _t(n, k, h, w_)
+    res = _t(n, k, h, w_) if has_res else None
+    mean, var = torch.randn(k) * 0.1, torch.rand(k) + 0.5
+    stat = torch.stack([mean, (var + 1e-5).rsqrt()])
+    gamma, beta = torch.rand(k) + 0.5, torch.randn(k) * 0.1
+    y = torch.full_like(c, float("nan"))
+    mask = torch.zeros(c.numel() // 8, dtype=torch.uint8)
+    fold = ops.BnFold(c, res, stat, gamma, beta, 1, y, mask)
+    b = _t(co, k)
+    d = ops.gemm_tn_bnfold(fold, b)
+    assert fake.calls == ["gemm_bf16_tn_bnfold"]
+    cf = c.float().as_subclass(torch.Tensor)
+    y_ref = (cf - mean.view(1, -1, 1, 1)) * stat[1].view(1, -1, 1, 1) * gamma.view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)
+    if has_res:
+        y_ref = y_ref + res.float().as_subclass(torch.Tensor)
+    y_ref = y_ref.relu()
+    yp = y.as_subclass(torch.Tensor).float()
+    assert not torch.isnan(yp).any()
+    _close(yp, y_ref)
+    d_ref = yp.permute(0, 2, 3, 1).reshape(-1, k) @ b.float().as_subclass(torch.Tensor).t()
+    _close(d, d_ref)
+    # bit j of byte [pixel][channel // 8] <-> y[pixel, channel] > 0 (the layout bn_backward reads)
+    bits = (yp.permute(0, 2, 3, 1).reshape(-1, k // 8, 8) > 0).to(torch.int32)
+    packed = (bits << torch.arange(8, dtype=torch.int32)).sum(-1).to(torch.uint8)
+    assert torch.equal(mask.view(-1, k // 8), packed)
