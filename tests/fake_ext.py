@@ -188,3 +188,206 @@ class FakeExt:
                 [pad, pad], [1, 1], False, [0, 0], C, [False, True, False])[1]
             op += dw.reshape(C, 9).t()
         return True
+
+
+R = 8            # DDL_BN_REPLICAS
+ACT_BITMASK = 0x100
+
+
+def _unpack_mask(mask, M, C):
+    m = _plain(mask).view(-1)[:M * C // 8].view(M, C // 8, 1).to(torch.int32)
+    return ((m >> torch.arange(8, dtype=torch.int32)) & 1).view(M, C).bool()
+
+
+def _rows(t, M, C):
+    """[N, C, H, W] channels-last (or [M, C]) -> [M, C] fp32 copy."""
+    t = _plain(t)
+    if t.dim() == 4:
+        assert t.is_contiguous(memory_format=CL), "kernel expects NHWC memory"
+        t = t.permute(0, 2, 3, 1)
+    return t.reshape(M, C).float()
+
+
+def _store_rows(dst, rows):
+    d = _plain(dst)
+    if d.dim() == 4:
+        assert d.is_contiguous(memory_format=CL)
+        d.permute(0, 2, 3, 1).copy_(rows.view(d.shape[0], d.shape[2], d.shape[3], d.shape[1]).to(d.dtype))
+    else:
+        d.copy_(rows.view(d.shape).to(d.dtype))
+
+
+class FullFakeExt(FakeExt):
+    """+ the kernels of the default path (BatchNorm, pooling, loss, optimizer), so that a whole
+    model can run through the device branches of the engine on the CPU."""
+
+    def __init__(self):
+        super().__init__()
+        self._pool_idx = {}
+
+    def set_pdl(self, on):
+        return False
+
+    def bn_replicas(self):
+        return R
+
+    # -------------------------------------------------------------------------- optimizer / loss
+    def sgd_flat(self, master, mom, grad, w_out, w_out2, hyper):
+        self.calls.append("sgd_flat")
+        master, mom, grad, w_out, w_out2, hyper = map(_plain, (master, mom, grad, w_out, w_out2, hyper))
+        assert master.dtype == torch.float32 and mom.dtype == torch.float32 and hyper.numel() >= 4
+        n = master.numel()
+        assert mom.numel() == n and grad.numel() == n and w_out.numel() == n
+        lr, mu, wd, gs = [float(v) for v in hyper.tolist()[:4]]
+        g = grad.float() * gs + wd * master
+        mom.mul_(mu).add_(g)
+        master.add_(mom, alpha=-lr)
+        w_out.copy_(master.to(w_out.dtype))
+        if w_out2 is not None:
+            w_out2.copy_(master.to(w_out2.dtype))
+
+    def xent(self, logits, target, dlogits, row_stats, ticket, smoothing, grad_scale):
+        self.calls.append("xent")
+        logits, target = _plain(logits), _plain(target)
+        assert logits.dim() == 2 and logits.is_contiguous() and target.dtype == torch.int64
+        assert target.numel() == logits.shape[0] and _plain(row_stats).numel() >= logits.shape[0] * 3
+        x = logits.float()
+        n, c = x.shape
+        logp = F.log_softmax(x, dim=1)
+        nll = -logp.gather(1, target.view(-1, 1)).squeeze(1)
+        loss = ((1.0 - smoothing) * nll + smoothing * (-logp.mean(dim=1))).mean()
+        if dlogits is not None:
+            onehot = torch.zeros_like(logp).scatter_(1, target.view(-1, 1), 1.0)
+            _plain(dlogits).copy_(((logp.exp() - (1.0 - smoothing) * onehot - smoothing / c) * grad_scale).to(logits.dtype))
+        greater = (x > x.gather(1, target.view(-1, 1))).sum(dim=1)
+        return fake_cuda(torch.stack([loss, (greater == 0).sum().float(), (greater < 5).sum().float()]))
+
+    # -------------------------------------------------------------------------- BatchNorm
+    def _finalize(self, s, q, stat, rmean, rvar, M, C, eps, mom):
+        mean = s / M
+        var = (q / M - mean * mean).clamp_min(0)
+        st = _plain(stat).view(-1)
+        st[:C] = mean
+        st[C:2 * C] = torch.rsqrt(var + eps)
+        if rmean is not None:
+            _plain(rmean).add_(mom * (mean - _plain(rmean)))
+            _plain(rvar).add_(mom * (var * (M / max(M - 1, 1)) - _plain(rvar)))
+
+    def bn_stats(self, x, sums, counter, stat, rmean, rvar, M, C, eps, mom):
+        self.calls.append("bn_stats")
+        assert _plain(sums).numel() >= R * 2 * C and float(_plain(sums).abs().sum()) == 0.0, "workspace not zero"
+        xr = _rows(x, M, C)
+        self._finalize(xr.sum(0), (xr * xr).sum(0), stat, rmean, rvar, M, C, eps, mom)
+
+    def bn_finalize(self, sums, stat, rmean, rvar, M, C, eps, mom):
+        self.calls.append("bn_finalize")
+        sp = _plain(sums)
+        v = sp[:R * 2 * C].view(R, 2, C).sum(0)
+        self._finalize(v[0], v[1], stat, rmean, rvar, M, C, eps, mom)
+        sp.zero_()                                     # the kernel leaves its workspace zeroed
+
+    def bn_apply(self, x, res, y, stat, gamma, beta, mask_out, M, C, act):
+        self.calls.append("bn_apply")
+        st = _plain(stat).view(-1)
+        assert st.is_contiguous() and (mask_out is None or _plain(mask_out).numel() * 8 >= M * C)
+        sc = _plain(gamma).float() * st[C:2 * C]
+        v = _rows(x, M, C) * sc + (_plain(beta).float() - st[:C] * sc)
+        if res is not None:
+            v = v + _rows(res, M, C)
+        if act == 1:
+            v = v.relu()
+        elif act == 2:
+            v = v.clamp(0, 6)
+        vb = v.to(BF16)
+        _store_rows(y, vb)
+        if mask_out is not None:
+            bits = _act_mask(vb.float(), act).view(M, C // 8, 8).to(torch.int32)
+            _plain(mask_out).view(-1)[:M * C // 8].copy_(
+                (bits << torch.arange(8, dtype=torch.int32)).sum(-1).to(torch.uint8).view(-1))
+
+    def _dz(self, dy, dy2, y, M, C, act_flags):
+        d = _rows(dy, M, C)
+        if dy2 is not None:
+            d = d + _rows(dy2, M, C)
+        act = act_flags & 0xff
+        if act:
+            if act_flags & ACT_BITMASK:
+                d = d * _unpack_mask(y, M, C)
+            else:
+                d = d * _act_mask(_rows(y, M, C), act)
+        return d
+
+    def bn_bwd_reduce(self, dy, dy2, y, x, dz_out, stat, sums, counter, gamma, coef, dgamma, dbeta,
+                      accumulate, M, C, act):
+        self.calls.append("bn_bwd_reduce")
+        st = _plain(stat).view(-1)
+        d = self._dz(dy, dy2, y, M, C, act)
+        if dz_out is not None:
+            _store_rows(dz_out, d.to(BF16))
+            d = d.to(BF16).float()                     # the kernel sums what it stored
+        xhat = (_rows(x, M, C) - st[:C]) * st[C:2 * C]
+        s1, s2 = d.sum(0), (d * xhat).sum(0)
+        cf = _plain(coef)
+        cf[:C] = _plain(gamma).float() * st[C:2 * C]
+        cf[C:2 * C] = s1 / M
+        cf[2 * C:3 * C] = s2 / M
+        for out, val in ((dgamma, s2), (dbeta, s1)):
+            o = _plain(out)
+            o.copy_((o.float() + val if accumulate else val).to(o.dtype))
+
+    def bn_bwd_apply(self, dz_in, dy, dy2, y, x, dx, stat, coef, M, C, act):
+        self.calls.append("bn_bwd_apply")
+        st, cf = _plain(stat).view(-1), _plain(coef)
+        d = _rows(dz_in, M, C) if dz_in is not None else self._dz(dy, dy2, y, M, C, act)
+        xhat = (_rows(x, M, C) - st[:C]) * st[C:2 * C]
+        _store_rows(dx, cf[:C] * (d - cf[C:2 * C] - xhat * cf[2 * C:3 * C]))
+
+    def act_bwd(self, dy, dy2, y, dz, act):
+        self.calls.append("act_bwd")
+        d = _plain(dy).float()
+        if dy2 is not None:
+            d = d + _plain(dy2).float()
+        if act:
+            d = d * _act_mask(_plain(y).float(), act)
+        _plain(dz).copy_(d.to(BF16))
+
+    def bias_act(self, x, bias, y, M, C, act):
+        self.calls.append("bias_act")
+        v = _rows(x, M, C)
+        if bias is not None:
+            v = v + _plain(bias).float()
+        _store_rows(y, v.relu() if act == 1 else (v.clamp(0, 6) if act == 2 else v))
+
+    def colsum(self, x, sums, counter, out, accumulate, M, C):
+        self.calls.append("colsum")
+        o = _plain(out)
+        s = _rows(x, M, C).sum(0)
+        o.copy_((o.float() + s if accumulate else s).to(o.dtype))
+
+    # -------------------------------------------------------------------------- pooling
+    def gap_fwd(self, x, y, N, HW, C):
+        self.calls.append("gap_fwd")
+        _plain(y).copy_(_rows(x, N * HW, C).view(N, HW, C).mean(1).to(BF16))
+
+    def gap_bwd(self, dy, dx, N, HW, C):
+        self.calls.append("gap_bwd")
+        d = (_plain(dy).float().view(N, 1, C) / HW).expand(N, HW, C).reshape(N * HW, C)
+        _store_rows(dx, d)
+
+    def maxpool_fwd(self, x, y, idx, k, s, p):
+        self.calls.append("maxpool_fwd")
+        xp = _plain(x)
+        assert xp.is_contiguous(memory_format=CL) and _plain(y).is_contiguous(memory_format=CL)
+        v, i = F.max_pool2d(xp.float(), k, s, p, return_indices=True)
+        _plain(y).copy_(v.to(BF16))
+        if idx is not None:
+            self._pool_idx[_plain(idx).data_ptr()] = i
+
+    def maxpool_bwd(self, dy, idx, dx, k, s, p):
+        self.calls.append("maxpool_bwd")
+        i = self._pool_idx[_plain(idx).data_ptr()]
+        dxp = _plain(dx)
+        assert dxp.is_contiguous(memory_format=CL) and _plain(dy).is_contiguous(memory_format=CL)
+        n, c, h, w = dxp.shape
+        g = torch.zeros(n, c, h * w).scatter_add_(2, i.view(n, c, -1), _plain(dy).float().reshape(n, c, -1))
+        dxp.copy_(g.view(n, c, h, w).to(BF16))

@@ -150,3 +150,116 @@ def test_bnfold_glue_writes_y_and_mask_in_place(fake, has_res):
     bits = (yp.permute(0, 2, 3, 1).reshape(-1, k // 8, 8) > 0).to(torch.int32)
     packed = (bits << torch.arange(8, dtype=torch.int32)).sum(-1).to(torch.uint8)
     assert torch.equal(mask.view(-1, k // 8), packed)
+
+
+def test_resnet50_through_device_branches_with_every_optin_switch(monkeypatch):
+    """Whole ResNet-50 steps (forward, loss, backward, SGD) through the DEVICE branches of the
+    engine.  (1) BN folding into the 1x1 consumers + tcgen05 1x1 weight gradients must reproduce
+    the default device path (same rounding points: equal up to the last bit); (2) with every opt-in
+    switch on — tcgen05 stem / 3x3 / strided convolutions, conv dgrad and wgrad — every kernel is
+    reached, nothing stays pending, and the loss tracks the plain CPU engine.  (Gradients of this
+    tiny-batch random network are chaotic — a 2e-3 input perturbation decorrelates them — so the
+    per-op tests above carry the numerics; this one carries the plumbing.)"""
+    from fake_ext import FullFakeExt
+    from ddlbench_b200.engine import StageExecutor
+    from ddlbench_b200.engine.plan import compile_plan
+    from ddlbench_b200.models import build_model
+
+    def run(fake_device: bool, steps: int = 2):
+        torch.manual_seed(0)
+        model = build_model("resnet50", "imagenet")
+        plan = compile_plan(model)
+        ex = StageExecutor(plan, device="cpu", dtype=BF16, channels_last=True, lr=0.002, momentum=0.9,
+                           weight_decay=1e-4, tcgen05=fake_device)
+        if fake_device:
+            for op in plan.ops:                     # what to_device() does on a CUDA device
+                if getattr(op, "ws", "absent") is None and hasattr(op, "channels"):
+                    op.ws = ops.BnWorkspace(op.channels, "cpu")
+        g = torch.Generator().manual_seed(5)
+        losses = []
+        for _ in range(steps):
+            x = torch.randn(4, 3, 64, 64, generator=g)
+            t = torch.randint(0, 1000, (4,), generator=g)
+            if fake_device:
+                x, t = fake_cuda(x), fake_cuda(t)
+            outs, ctx = ex.forward([ex.prepare_input(x)])
+            assert not E.PENDING_FOLD
+            stats, d = ex.loss(outs[0], t)
+            ex.backward(ctx, [d])
+            ex.store.sgd_step()
+            losses.append(float(stats[0]))
+        return losses, ex.store.master.as_subclass(torch.Tensor).clone()
+
+    ref_losses, _ = run(False)
+    results = {}
+    for label, switches in (("default", ()), ("fold+wgrad1x1", ("BN_FOLD", "WGRAD_TCGEN05")),
+                            ("all", ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "BN_FOLD"))):
+        with monkeypatch.context() as mp:
+            fe = FullFakeExt()
+            mp.setattr(ops, "ext", lambda: fe)
+            mp.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+            for name in ("empty", "zeros", "empty_like", "zeros_like"):
+                real = getattr(torch, name)
+                mp.setattr(torch, name, (lambda real: lambda *a, **k: fake_cuda(real(*a, **k)))(real))
+            for name in switches:
+                mp.setattr(E, name, True)
+            results[label] = run(True, 2 if label == "all" else 1) + (set(fe.calls),)
+    (l_d, w_d, used_d), (l_f, w_f, used_f), (l_a, w_a, used_a) = (results[k] for k in ("default", "fold+wgrad1x1", "all"))
+    assert "gemm_bf16_tn_bnfold" not in used_d and {"gemm_bf16_tn_bnfold", "gemm_bf16_nt_mn"} <= used_f
+    assert l_f == pytest.approx(l_d, rel=5e-3) and ((w_f - w_d).norm() / w_d.norm()).item() < 1e-3
+    for k in ("im2col_rows", "conv_bf16_nhwc", "conv_wgrad_bf16_nhwc", "gemm_bf16_tn_bnfold", "gemm_bf16_nt_mn",
+              "gemm_bf16_tn", "bn_finalize", "bn_apply", "bn_bwd_reduce", "bn_bwd_apply",
+              "maxpool_fwd", "maxpool_bwd", "gap_fwd", "gap_bwd", "xent", "sgd_flat"):
+        assert k in used_a, k
+    assert "bn_stats" not in used_a            # every convolution delivered its statistics fused
+    assert l_a == pytest.approx(ref_losses, rel=3e-2) and l_d == pytest.approx(ref_losses[:1], rel=3e-2)
+    assert torch.isfinite(w_a).all()
+
+
+@pytest.mark.parametrize("arch,ds,shape,expect", [
+    ("mobilenetv2", "cifar10", (4, 3, 32, 32), {"dwconv3x3:0", "dwconv3x3:1", "dwconv3x3:2", "gemm_bf16_tn_bnfold",
+                                                "gemm_bf16_nt_mn", "im2col_rows"}),
+    ("vgg16", "cifar10", (4, 3, 32, 32), {"conv_bf16_nhwc", "conv_wgrad_bf16_nhwc", "im2col_rows", "bias_act", "colsum"}),
+    ("resnet18", "mnist", (4, 1, 28, 28), {"conv_bf16_nhwc", "conv_wgrad_bf16_nhwc", "im2col_rows", "gemm_bf16_nt_mn"}),
+])
+def test_other_families_device_branches_optin_equals_default(monkeypatch, arch, ds, shape, expect):
+    """MobileNetV2 (depthwise kernels, ReLU6 folds), VGG (bias + ReLU fused into the convolution) and
+    the MNIST ResNet (1-channel stem): one step through the device branches with every opt-in
+    switch on must give the update of the default device path (well-conditioned small networks)."""
+    from fake_ext import FullFakeExt
+    from ddlbench_b200.engine import StageExecutor
+    from ddlbench_b200.engine.plan import compile_plan
+    from ddlbench_b200.models import build_model
+
+    def run():
+        torch.manual_seed(0)
+        plan = compile_plan(build_model(arch, ds))
+        ex = StageExecutor(plan, device="cpu", dtype=BF16, channels_last=True, lr=0.002, momentum=0.9,
+                           weight_decay=1e-4, tcgen05=True)
+        for op in plan.ops:
+            if getattr(op, "ws", "absent") is None and hasattr(op, "channels"):
+                op.ws = ops.BnWorkspace(op.channels, "cpu")
+        g = torch.Generator().manual_seed(5)
+        x, t = fake_cuda(torch.randn(*shape, generator=g)), fake_cuda(torch.randint(0, 10, (shape[0],), generator=g))
+        outs, ctx = ex.forward([ex.prepare_input(x)])
+        assert not E.PENDING_FOLD
+        stats, d = ex.loss(outs[0], t)
+        ex.backward(ctx, [d])
+        ex.store.sgd_step()
+        return float(stats[0]), ex.store.master.as_subclass(torch.Tensor).clone()
+
+    out = []
+    for switches in ((), ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "BN_FOLD", "DWCONV")):
+        with monkeypatch.context() as mp:
+            fe = FullFakeExt()
+            mp.setattr(ops, "ext", lambda: fe)
+            mp.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+            for name in ("empty", "zeros", "empty_like", "zeros_like"):
+                real = getattr(torch, name)
+                mp.setattr(torch, name, (lambda real: lambda *a, **k: fake_cuda(real(*a, **k)))(real))
+            for name in switches:
+                mp.setattr(E, name, True)
+            out.append(run() + (set(fe.calls),))
+    (l0, w0, _), (l1, w1, used) = out
+    assert expect <= used, expect - used
+    assert l1 == pytest.approx(l0, rel=1e-2) and ((w1 - w0).norm() / w0.norm()).item() < 2e-3
