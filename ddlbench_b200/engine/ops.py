@@ -51,6 +51,10 @@ DWCONV = _os.environ.get("DDLB_DWCONV", "0") == "1"
 WGRAD_TCGEN05 = _os.environ.get("DDLB_WGRAD_TCGEN05", "0") == "1"
 # data gradient of those 3x3 convolutions through the same kernel (flipped, transposed filter)
 CONV3X3_DGRAD = CONV3X3_TCGEN05 and _os.environ.get("DDLB_CONV3X3_DGRAD", "0") == "1"
+# data gradient of the 1x1 convolutions on the (validated) tcgen05 TN GEMM: dx = dy @ W needs W^T
+# as the K-major B operand, i.e. one small transpose per layer and step; opt-in until measured
+# against the library's dgrad
+DGRAD1X1_TCGEN05 = _os.environ.get("DDLB_DGRAD1X1_TCGEN05", "0") == "1"
 # weight-gradient kernels on a side stream during backward
 OVERLAP_WGRAD_DEFAULT = _os.environ.get("DDLB_WGRAD_OVERLAP", "1") == "1"
 
@@ -228,6 +232,14 @@ class _ConvMixin:
             # spatially flipped, channel-transposed filter: reuse the tcgen05 kernel
             wt = w.flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=torch.channels_last)
             dx_tc = ops.conv_tn(dy, wt)
+        elif need_dx and DGRAD1X1_TCGEN05 and self._is_gemm(x) and \
+                dy.is_contiguous(memory_format=torch.channels_last):
+            n, ci, h, wd = x.shape
+            co = self.wshape[0]
+            wt = w.reshape(co, ci).t().contiguous()                    # [Cin, Cout]: N x K, K-major
+            a = dy.permute(0, 2, 3, 1).reshape(n * h * wd, co)
+            if ops.gemm_tn_supported(a, wt):
+                dx_tc = ops.gemm_tn(a, wt).view(n, h, wd, ci).permute(0, 3, 1, 2)
         lib_dx = need_dx and dx_tc is None
         if side is None:
             dw = self._wgrad_tc(dy, x, w, patch)

@@ -30,7 +30,7 @@ def fake(monkeypatch):
         real = getattr(torch, name)
         monkeypatch.setattr(torch, name, (lambda real: lambda *a, **k: fake_cuda(real(*a, **k)))(real))
     monkeypatch.setitem(E.TCGEN05, "conv1x1", True)
-    for name in ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "DWCONV"):
+    for name in ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "DWCONV", "DGRAD1X1_TCGEN05"):
         monkeypatch.setattr(E, name, True)
     return fe
 
@@ -67,7 +67,7 @@ def _close(a, b, tol=2e-2):
     (64, 64, 3, 1, 1, ["conv_bf16_nhwc", "conv_bf16_nhwc", "conv_wgrad_bf16_nhwc"]),     # fwd, dgrad, wgrad
     (64, 128, 3, 2, 1, ["conv_bf16_nhwc", "conv_wgrad_bf16_nhwc"]),                     # strided: library dgrad
     (64, 128, 1, 2, 0, ["conv_bf16_nhwc", "conv_wgrad_bf16_nhwc"]),                     # downsample
-    (64, 128, 1, 1, 0, ["gemm_bf16_tn", "gemm_bf16_nt_mn"]),                            # plain GEMM pair
+    (64, 128, 1, 1, 0, ["gemm_bf16_tn", "gemm_bf16_tn", "gemm_bf16_nt_mn"]),            # fwd, dgrad (W^T), wgrad
 ])
 def test_conv_paths(fake, ci, co, k, s, p, expect):
     torch.manual_seed(0)
@@ -193,7 +193,8 @@ def test_resnet50_through_device_branches_with_every_optin_switch(monkeypatch):
     ref_losses, _ = run(False)
     results = {}
     for label, switches in (("default", ()), ("fold+wgrad1x1", ("BN_FOLD", "WGRAD_TCGEN05")),
-                            ("all", ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "BN_FOLD"))):
+                            ("all", ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "BN_FOLD",
+                                     "DGRAD1X1_TCGEN05"))):
         with monkeypatch.context() as mp:
             fe = FullFakeExt()
             mp.setattr(ops, "ext", lambda: fe)
@@ -249,7 +250,8 @@ def test_other_families_device_branches_optin_equals_default(monkeypatch, arch, 
         return float(stats[0]), ex.store.master.as_subclass(torch.Tensor).clone()
 
     out = []
-    for switches in ((), ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "BN_FOLD", "DWCONV")):
+    for switches in ((), ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "BN_FOLD", "DWCONV",
+                          "DGRAD1X1_TCGEN05")):
         with monkeypatch.context() as mp:
             fe = FullFakeExt()
             mp.setattr(ops, "ext", lambda: fe)

@@ -55,6 +55,7 @@ bench sgd_overlap DDLB_SGD_OVERLAP=1
 bench bn_fold DDLB_BN_FOLD=1
 bench bn_cluster DDLB_BN_CLUSTER=1
 bench bwd_apply_3blocks DDLB_BN_BWD_APPLY_BLOCKS=3
+bench dgrad1x1 DDLB_DGRAD1X1_TCGEN05=1
 bench all_validated DDLB_STEM_IM2COL=1 DDLB_CONV3X3_TCGEN05=1 DDLB_SGD_OVERLAP=1
 bench all_tcgen05 DDLB_STEM_IM2COL=1 DDLB_CONV3X3_TCGEN05=1 DDLB_CONV3X3_DGRAD=1 DDLB_WGRAD_TCGEN05=1
 bench default_again DDLB_NONE=1
