@@ -51,6 +51,9 @@ DWCONV = _os.environ.get("DDLB_DWCONV", "0") == "1"
 WGRAD_TCGEN05 = _os.environ.get("DDLB_WGRAD_TCGEN05", "0") == "1"
 # data gradient of those 3x3 convolutions through the same kernel (flipped, transposed filter)
 CONV3X3_DGRAD = CONV3X3_TCGEN05 and _os.environ.get("DDLB_CONV3X3_DGRAD", "0") == "1"
+# element-wise half of the BatchNorm backward folded into the 1x1 data-gradient GEMM's operand
+# load (csrc/gemm_bnbwd_tcgen05.cu, ops.bn_backward_dgrad_fold): opt-in until validated
+BN_BWD_FOLD = _os.environ.get("DDLB_BN_BWD_FOLD", "0") == "1"
 # data gradient of the 1x1 convolutions on the (validated) tcgen05 TN GEMM: dx = dy @ W needs W^T
 # as the K-major B operand, i.e. one small transpose per layer and step; opt-in until measured
 # against the library's dgrad
@@ -341,10 +344,23 @@ class ConvBnAct(Op, _ConvMixin):
         if len(dys) > 2:
             dys = [_sum_grads(dys[:-1]), dys[-1]]
             dy2 = dys[1]
+        x_in = ctx["x"]
+        if BN_BWD_FOLD and need[0] and self._is_gemm(x_in):
+            co, ci = self.wshape[:2]
+            wt = P[self.k_w].reshape(co, ci).t().contiguous()          # [Cin, Cout]: N x K, K-major
+            if ops.bn_bwd_fold_supported(ctx["c"], dys[0], dy2, self.act, ctx.get("mask"), wt):
+                dc, dz, dx2d = ops.bn_backward_dgrad_fold(
+                    dys[0], dy2, ctx["c"], ctx["stat"], P[self.k_g], self.act,
+                    self.has_res and need[1], G[self.k_g], G[self.k_b], accumulate, self.ws,
+                    ctx.get("mask"), wt)
+                n, _, h, wd = x_in.shape
+                dx = dx2d.view(n, h, wd, ci).permute(0, 3, 1, 2)
+                self._conv_bwd(dc, x_in, P[self.k_w], False, G[self.k_w], accumulate)   # weight gradient
+                return [dx, dz] if self.has_res else [dx]
         dc, dz = ops.bn_backward(dys[0], dy2, ctx["y"], ctx["c"], ctx["stat"], P[self.k_g],
                                  self.act, self.has_res and need[1], G[self.k_g], G[self.k_b],
                                  accumulate, self.ws, mask=ctx.get("mask"))
-        dx = self._conv_bwd(dc, ctx["x"], P[self.k_w], need[0], G[self.k_w], accumulate,
+        dx = self._conv_bwd(dc, x_in, P[self.k_w], need[0], G[self.k_w], accumulate,
                             patch=ctx.get("patch"))
         return [dx, dz] if self.has_res else [dx]
 

@@ -313,6 +313,57 @@ def bn_backward(dy, dy2, y, x, stat, gamma, act: int, want_dz: bool, dgamma_out,
     return dx, dz
 
 
+def bn_bwd_fold_supported(c, dy, dy2, act: int, mask, wt) -> bool:
+    """Can the BatchNorm backward of ``c`` be folded into the 1x1 data-gradient GEMM
+    (csrc/gemm_bnbwd_tcgen05.cu)?  Mirrors the kernel's own shape checks so that it never
+    declines after ``bn_bwd_reduce`` has already written dgamma / dbeta."""
+    if not (_nhwc_ok(c) and c.dim() == 4 and not BN_CLUSTER_FUSED):
+        return False
+    M, K = _mc(c)
+    cl = torch.channels_last
+    return (K % 64 == 0 and K <= 2048 and wt.dim() == 2 and wt.shape[1] == K and wt.shape[0] % 8 == 0 and
+            wt.is_contiguous() and wt.dtype == torch.bfloat16 and
+            dy.shape == c.shape and dy.dtype == c.dtype and dy.is_contiguous(memory_format=cl) and
+            (dy2 is None or (dy2.shape == c.shape and dy2.dtype == c.dtype and
+                             dy2.is_contiguous(memory_format=cl))) and
+            (act == ACT_NONE or mask is not None) and hasattr(ext(), "gemm_bf16_tn_bnbwd"))
+
+
+def bn_backward_dgrad_fold(dy, dy2, c, stat, gamma, act: int, want_dz: bool, dgamma_out, dbeta_out,
+                           accumulate: bool, ws: Optional[BnWorkspace], mask, wt):
+    """BatchNorm backward + the data gradient of the 1x1 convolution that produced ``c``, with the
+    element-wise half of the BatchNorm backward folded into the GEMM's operand load:
+    ``bn_bwd_reduce`` (sums, dgamma, dbeta, coefficients), then ONE kernel that rebuilds
+    dz = (dy [+ dy2]) * act' and dc = BN'(dz, c) tile by tile in shared memory, multiplies by
+    ``wt`` = W^T [Cin, Cout] and stores dc (for the weight gradient) and dz (residual gradient,
+    if ``want_dz``) on the way.  Call only when ``bn_bwd_fold_supported``.
+    Returns (dc [N, C, H, W], dz or None, dx2d [N*H*W, Cin])."""
+    M, C = _mc(c)
+    e = ext()
+    if ws is None:
+        ws = BnWorkspace(C, c.device)
+    stat_f = stat.reshape(-1)
+    yy, flags = (mask, act | ACT_BITMASK) if act != ACT_NONE else (None, act)
+    e.bn_bwd_reduce(dy, dy2, yy, c, None, stat_f, ws.sums, ws.counter, gamma, ws.coef,
+                    dgamma_out, dbeta_out, accumulate, M, C, flags)
+    dc = torch.empty_like(c)
+    dz = torch.empty_like(c) if want_dz else None
+    dx2d = torch.empty((M, wt.shape[0]), dtype=c.dtype, device=c.device)
+
+    def rows(t):
+        if t is None:
+            return None
+        v = t.permute(0, 2, 3, 1).reshape(M, C)
+        assert v.data_ptr() == t.data_ptr(), "NHWC operand expected (reshape must not copy)"
+        return v
+
+    ok = e.gemm_bf16_tn_bnbwd(rows(dy), rows(dy2), rows(c), yy, wt, dx2d, rows(dc), rows(dz), stat_f,
+                              ws.coef, act)
+    assert ok, "gemm_bf16_tn_bnbwd declined a shape bn_bwd_fold_supported accepted"
+    _count(2)
+    return dc, dz, dx2d
+
+
 def bias_act(x, bias, act: int):
     if _nhwc_ok(x):
         M, C = _mc(x)

@@ -123,6 +123,10 @@ int ddl_gemm_bf16_tn_bnfold(const void* C, const void* R, const void* B, void* D
                             int M, int N, int K, int ld, int ldb, int ldd, const float* stat,
                             const void* gamma, const void* beta, int param_is_bf16, int act,
                             float* col_sums, const void* bias, int relu, int sms, cudaStream_t st);
+int ddl_gemm_bf16_tn_bnbwd(const void* dy, const void* dy2, const void* c, const void* mask,
+                           const void* bt, void* dx, void* dc, void* dz, int M, int N, int K, int ld,
+                           int ldb, int ldd, const float* stat, const float* coef, int act, int sms,
+                           cudaStream_t st);
 int ddl_gemm_selftest_info(char* buf, int len);
 int ddl_set_pdl(int on);
 

@@ -366,6 +366,37 @@ bool gemm_bf16_tn_bnfold(at::Tensor C, c10::optional<at::Tensor> R, at::Tensor B
   check(rc, "gemm_bf16_tn_bnfold");
   return true;
 }
+// dx = dc @ Bt^T with dc = BN-backward(dy [+ dy2], mask, c) built while loading the operand; dc (and
+// dz, the residual gradient) are written as side effects.  All [M, K] operands are views with the
+// same leading dimension; returns false if the kernel declines the shape.
+bool gemm_bf16_tn_bnbwd(at::Tensor dy, c10::optional<at::Tensor> dy2, at::Tensor c,
+                        c10::optional<at::Tensor> mask, at::Tensor bt, at::Tensor dx, at::Tensor dc,
+                        c10::optional<at::Tensor> dz, at::Tensor stat, at::Tensor coef, int64_t act) {
+  TORCH_CHECK(dy.dim() == 2 && c.dim() == 2 && bt.dim() == 2 && dx.dim() == 2 && dc.dim() == 2);
+  TORCH_CHECK(is_bf16(dy) && is_bf16(c) && is_bf16(bt) && is_bf16(dx) && is_bf16(dc));
+  TORCH_CHECK(dy.stride(1) == 1 && c.stride(1) == 1 && bt.stride(1) == 1 && dx.stride(1) == 1 &&
+              dc.stride(1) == 1);
+  const int M = (int)c.size(0), K = (int)c.size(1), N = (int)bt.size(0);
+  TORCH_CHECK(bt.size(1) == K && dy.size(0) == M && dy.size(1) == K && dc.size(0) == M &&
+              dc.size(1) == K && dx.size(0) == M && dx.size(1) == N, "bnbwd: shapes");
+  const int64_t ld = c.stride(0);
+  TORCH_CHECK(dy.stride(0) == ld && dc.stride(0) == ld, "bnbwd: dy, c, dc must share the leading dimension");
+  for (const auto* o : {&dy2, &dz})
+    if (o->has_value() && (*o)->defined())
+      TORCH_CHECK((*o)->dim() == 2 && (*o)->size(0) == M && (*o)->size(1) == K &&
+                  (*o)->stride(0) == ld && (*o)->stride(1) == 1 && is_bf16(**o), "bnbwd: dy2 / dz layout");
+  TORCH_CHECK(stat.numel() >= 2 * K && coef.numel() >= 3 * K && stat.scalar_type() == at::kFloat &&
+              coef.scalar_type() == at::kFloat && stat.is_contiguous() && coef.is_contiguous());
+  TORCH_CHECK(!mask.has_value() || mask->numel() * 8 >= (int64_t)M * K, "bnbwd: mask too small");
+  c10::cuda::CUDAGuard g(c.device());
+  const int rc = ddl_gemm_bf16_tn_bnbwd(dy.data_ptr(), optr(dy2), c.data_ptr(), optr(mask), bt.data_ptr(),
+                                        dx.data_ptr(), dc.data_ptr(), optr(dz), M, N, K, (int)ld,
+                                        (int)bt.stride(0), (int)dx.stride(0), stat.data_ptr<float>(),
+                                        coef.data_ptr<float>(), (int)act, sm_count(), cur_stream());
+  if (rc == -1) return false;
+  check(rc, "gemm_bf16_tn_bnbwd");
+  return true;
+}
 void gemm_bf16_nt_mn(at::Tensor A, at::Tensor B, at::Tensor D, int64_t splits,
                      c10::optional<at::Tensor> workspace) {
   // A: [K, M], B: [K, N], D: [M, N] fp32, accumulated into (D += A^T B)
@@ -676,6 +707,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16_tn", &gemm_bf16_tn);
   m.def("gemm_bf16_nt_mn", &gemm_bf16_nt_mn);
   m.def("gemm_bf16_tn_bnfold", &gemm_bf16_tn_bnfold);
+  m.def("gemm_bf16_tn_bnbwd", &gemm_bf16_tn_bnbwd);
   m.def("conv_bf16_nhwc", &conv_bf16_nhwc);
   m.def("conv_wgrad_bf16_nhwc", &conv_wgrad_bf16_nhwc);
   m.def("im2col_rows", &im2col_rows);

@@ -119,6 +119,48 @@ def check_bnfold(n, k, co, hw, act=1, res=False, seed=0):
     return ok
 
 
+def check_bnbwd(n, ci, co, hw, act=1, res=False, two=False, seed=0):
+    """BN backward folded into the 1x1 data-gradient GEMM (gemm_bnbwd_tcgen05.cu) vs the unfused
+    device path (bn_bwd_reduce + bn_bwd_apply, then dc @ W): dx, dc, dz, dgamma, dbeta."""
+    from ddlbench_b200.ops import reference as ref
+    torch.manual_seed(seed)
+    cl = torch.channels_last
+    rnd = lambda *s_: torch.randn(*s_, device="cuda")                                  # noqa: E731
+    c = (rnd(n, co, hw, hw) * 1.5 + 0.3).to(torch.bfloat16).contiguous(memory_format=cl)
+    gamma = (torch.rand(co, device="cuda") + 0.5)
+    beta = rnd(co) * 0.2
+    w = (rnd(co, ci) * (1.0 / co ** 0.5)).to(torch.bfloat16)
+    stat = ref.bn_stat(c, 1e-5).contiguous()
+    r = rnd(n, co, hw, hw).to(torch.bfloat16).contiguous(memory_format=cl) if res else None
+    ws = ops.BnWorkspace(co, "cuda")
+    mask = torch.zeros(c.numel() // 8, dtype=torch.uint8, device="cuda") if act else None
+    y, _ = ops.bn_forward(c, r, gamma, beta, None, None, 1e-5, 0.1, act, ws, mask_out=mask)
+    dy = rnd(n, co, hw, hw).to(torch.bfloat16).contiguous(memory_format=cl)
+    dy2 = rnd(n, co, hw, hw).to(torch.bfloat16).contiguous(memory_format=cl) if two else None
+    dg0, db0, dg1, db1 = (torch.zeros(co, device="cuda") for _ in range(4))
+    dc_ref, dz_ref = ops.bn_backward(dy, dy2, y, c, stat, gamma, act, res, dg0, db0, False, ws, mask=mask)
+    dx_ref = dc_ref.permute(0, 2, 3, 1).reshape(-1, co).float() @ w.float()
+    wt = w.t().contiguous()
+    if not ops.bn_bwd_fold_supported(c, dy, dy2, act, mask, wt):
+        print(f"bnbwd n={n} ci={ci} co={co} hw={hw}: shape not supported (skipped)", flush=True)
+        return True
+    before = ops.launches
+    dc, dz, dx = ops.bn_backward_dgrad_fold(dy, dy2, c, stat, gamma, act, res, dg1, db1, False, ws, mask, wt)
+    torch.cuda.synchronize()
+    fused = ops.launches - before == 2
+
+    def err(a, b):
+        return (a.float() - b.float()).abs().max().item() / max(1.0, b.float().abs().max().item())
+
+    e = {"dx": err(dx, dx_ref), "dc": err(dc, dc_ref), "dgamma": err(dg1, dg0), "dbeta": err(db1, db0)}
+    if res:
+        e["dz"] = err(dz, dz_ref)
+    ok = fused and all(v <= 0.03 for v in e.values())
+    print(f"bnbwd n={n} ci={ci} co={co} hw={hw} act={act} res={res} two={two}: fused={fused} "
+          + " ".join(f"{k}={v:.4f}" for k, v in e.items()) + (" OK" if ok else " FAIL"), flush=True)
+    return ok
+
+
 def bench(n, ci, co, hw, k=3, iters=20):
     x = torch.randn(n, ci, hw, hw, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     w = torch.randn(co, ci, k, k, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
@@ -156,6 +198,11 @@ def main():
         for args in [(32, 64, 256, 56, 1, False), (32, 256, 64, 56, 1, True), (32, 512, 2048, 7, 1, False),
                      (5, 128, 64, 9, 2, True), (3, 64, 136, 11, 0, False)]:
             ok &= check_bnfold(*args)
+    if os.environ.get("CHECK_BNBWD", "1") == "1":
+        for args in [(32, 64, 256, 56, 1, True, True), (32, 256, 64, 56, 1, False, False),
+                     (32, 2048, 512, 7, 1, False, False), (5, 64, 128, 9, 2, True, False),
+                     (3, 136, 64, 11, 0, False, True)]:
+            ok &= check_bnbwd(*args)
     if os.environ.get("CHECK_WGRAD", "1") == "1":
         for args in [(64, 128, 64), (128, 128, 128), (6272, 256, 1024), (100352, 64, 256), (1000, 72, 200),
                      (200, 136, 64)]:

@@ -335,6 +335,39 @@ class FullFakeExt(FakeExt):
             o = _plain(out)
             o.copy_((o.float() + val if accumulate else val).to(o.dtype))
 
+    # bool gemm_bf16_tn_bnbwd(dy, dy2?, c, mask?, bt, dx, dc, dz?, stat, coef, act)
+    def gemm_bf16_tn_bnbwd(self, dy, dy2, c, mask, bt, dx, dc, dz, stat, coef, act):
+        self.calls.append("gemm_bf16_tn_bnbwd")
+        dy, dy2, c, bt, dxp, dcp, dzp = map(_plain, (dy, dy2, c, bt, dx, dc, dz))
+        for t in (dy, c, bt, dxp, dcp):
+            assert t.dim() == 2 and t.dtype == BF16 and t.stride(1) == 1
+        M, K = c.shape
+        N = bt.shape[0]
+        assert bt.shape[1] == K and tuple(dy.shape) == (M, K) and tuple(dcp.shape) == (M, K) and tuple(dxp.shape) == (M, N)
+        ld = c.stride(0)
+        assert dy.stride(0) == ld and dcp.stride(0) == ld
+        for o in (dy2, dzp):
+            if o is not None:
+                assert tuple(o.shape) == (M, K) and o.stride(0) == ld and o.stride(1) == 1 and o.dtype == BF16
+        st, cf = _plain(stat).view(-1), _plain(coef).view(-1)
+        assert st.numel() >= 2 * K and cf.numel() >= 3 * K and st.is_contiguous() and cf.is_contiguous()
+        assert mask is None or _plain(mask).numel() * 8 >= M * K
+        if K % 64 or K > 2048 or N % 8 or (act != 0 and mask is None):
+            return False
+        d = dy.float()
+        if dy2 is not None:
+            d = d + dy2.float()
+        if act != 0:
+            d = d * _unpack_mask(mask, M, K)
+        if dzp is not None:
+            dzp.copy_(d.to(BF16))
+            d = dzp.float()
+        xhat = (c.float() - st[:K]) * st[K:2 * K]
+        dcv = (cf[:K] * (d - cf[K:2 * K] - xhat * cf[2 * K:3 * K])).to(BF16)
+        dcp.copy_(dcv)
+        dxp.copy_((dcv.float() @ bt.float().t()).to(BF16))
+        return True
+
     def bn_bwd_apply(self, dz_in, dy, dy2, y, x, dx, stat, coef, M, C, act):
         self.calls.append("bn_bwd_apply")
         st, cf = _plain(stat).view(-1), _plain(coef)

@@ -63,6 +63,14 @@ def _close(a, b, tol=2e-2):
     assert err <= tol * max(1.0, b.abs().max().item()), err
 
 
+def _close_fro(a, b, tol):
+    """Relative Frobenius error: robust against the few ReLU bits that flip under bf16 rounding."""
+    a = a.as_subclass(torch.Tensor).float()
+    b = b.as_subclass(torch.Tensor).float()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert ((a - b).norm() / b.norm()).item() <= tol, ((a - b).norm() / b.norm()).item()
+
+
 @pytest.mark.parametrize("ci,co,k,s,p,expect", [
     (64, 64, 3, 1, 1, ["conv_bf16_nhwc", "conv_bf16_nhwc", "conv_wgrad_bf16_nhwc"]),     # fwd, dgrad, wgrad
     (64, 128, 3, 2, 1, ["conv_bf16_nhwc", "conv_wgrad_bf16_nhwc"]),                     # strided: library dgrad
@@ -117,6 +125,66 @@ def test_depthwise_paths(fake, s):
     _close(y, y_ref)
     _close(dx, dx_ref)
     _close(gw, dw_ref)
+
+
+@pytest.mark.parametrize("has_res,two_grads", [(False, False), (True, False), (True, True)])
+def test_bn_backward_folded_into_dgrad_matches_unfused(monkeypatch, has_res, two_grads):
+    """conv1x1 + BN (+ residual) + ReLU: backward with the element-wise BN-backward half folded into
+    the data-gradient GEMM (DDLB_BN_BWD_FOLD) against the unfused device path, and both against
+    autograd."""
+    from fake_ext import FullFakeExt
+    torch.manual_seed(4)
+    n, ci, co, h = 2, 64, 128, 6
+    results = []
+    for fold in (False, True):
+        with monkeypatch.context() as mp:
+            fe = FullFakeExt()
+            mp.setattr(ops, "ext", lambda: fe)
+            mp.setitem(E.TCGEN05, "conv1x1", True)
+            mp.setattr(E, "BN_BWD_FOLD", fold)
+            for name in ("empty", "zeros", "empty_like", "zeros_like"):
+                real = getattr(torch, name)
+                mp.setattr(torch, name, (lambda real: lambda *a, **k: fake_cuda(real(*a, **k)))(real))
+            g = torch.Generator().manual_seed(9)
+            conv = nn.Conv2d(ci, co, 1, bias=False)
+            op = E.ConvBnAct("op", ["x", "r"] if has_res else ["x"], "y", conv, nn.BatchNorm2d(co), E.ACT_RELU,
+                             has_res, "conv", "bn")
+            op.ws = ops.BnWorkspace(co, "cpu")
+            rnd = lambda *s: fake_cuda(torch.randn(*s, generator=g).to(BF16))        # noqa: E731
+            x = rnd(n, ci, h, h).contiguous(memory_format=CL)
+            r = rnd(n, co, h, h).contiguous(memory_format=CL) if has_res else None
+            w = rnd(co, ci, 1, 1).contiguous(memory_format=CL)
+            gamma, beta = fake_cuda(torch.rand(co, generator=g) + 0.5), fake_cuda(torch.randn(co, generator=g) * 0.1)
+            P = {"conv.weight": w, "bn.weight": gamma, "bn.bias": beta}
+            B = {"bn.running_mean": fake_cuda(torch.zeros(co)), "bn.running_var": fake_cuda(torch.ones(co))}
+            G = {"conv.weight": fake_cuda(torch.zeros(co, ci, 1, 1)), "bn.weight": fake_cuda(torch.zeros(co)),
+                 "bn.bias": fake_cuda(torch.zeros(co))}
+            ctx = {}
+            y = op.forward(P, B, [x, r] if has_res else [x], ctx, True)
+            dys = [rnd(*y.shape).contiguous(memory_format=CL) for _ in range(2 if two_grads else 1)]
+            outs = op.backward(P, G, dys, ctx, False, [True, True] if has_res else [True])
+            assert ("gemm_bf16_tn_bnbwd" in fe.calls) == fold and ("bn_bwd_apply" in fe.calls) != fold
+            results.append((y, outs, G, (x, r, w, gamma, beta, dys)))
+    (y0, o0, G0, inp), (y1, o1, G1, _) = results
+    for a, b in zip(o0, o1):
+        _close(a, b, 1e-2)
+    for k in G0:
+        _close(G0[k], G1[k], 1e-2)
+    # and against autograd (fp32 on the bf16-rounded inputs; the device path rounds c, y and dc to bf16
+    # and ReLU bits of elements next to zero may flip, hence the loose bound)
+    x, r, w, gamma, beta, dys = [t if not isinstance(t, torch.Tensor) else t.as_subclass(torch.Tensor).float() for t in inp[:5]] + [inp[5]]
+    xr, wr = x.contiguous().requires_grad_(True), w.contiguous().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rr = r.contiguous().requires_grad_(True) if has_res else None
+    z = F.batch_norm(F.conv2d(xr, wr), None, None, gr, br, True, 0.1, 1e-5)
+    yr = torch.relu(z + rr if has_res else z)
+    yr.backward(sum(d.as_subclass(torch.Tensor).float() for d in dys))
+    _close_fro(o1[0], xr.grad, 6e-2)
+    if has_res:
+        _close_fro(o1[1], rr.grad, 6e-2)
+    _close_fro(G1["conv.weight"], wr.grad, 6e-2)
+    _close_fro(G1["bn.weight"], gr.grad, 6e-2)
+    _close_fro(G1["bn.bias"], br.grad, 6e-2)
 
 
 @pytest.mark.parametrize("has_res", [False, True])
@@ -192,9 +260,9 @@ def test_resnet50_through_device_branches_with_every_optin_switch(monkeypatch):
 
     ref_losses, _ = run(False)
     results = {}
-    for label, switches in (("default", ()), ("fold+wgrad1x1", ("BN_FOLD", "WGRAD_TCGEN05")),
+    for label, switches in (("default", ()), ("fold+wgrad1x1", ("BN_FOLD", "WGRAD_TCGEN05", "BN_BWD_FOLD")),
                             ("all", ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "BN_FOLD",
-                                     "DGRAD1X1_TCGEN05"))):
+                                     "DGRAD1X1_TCGEN05", "BN_BWD_FOLD"))):
         with monkeypatch.context() as mp:
             fe = FullFakeExt()
             mp.setattr(ops, "ext", lambda: fe)
@@ -206,7 +274,8 @@ def test_resnet50_through_device_branches_with_every_optin_switch(monkeypatch):
                 mp.setattr(E, name, True)
             results[label] = run(True, 2 if label == "all" else 1) + (set(fe.calls),)
     (l_d, w_d, used_d), (l_f, w_f, used_f), (l_a, w_a, used_a) = (results[k] for k in ("default", "fold+wgrad1x1", "all"))
-    assert "gemm_bf16_tn_bnfold" not in used_d and {"gemm_bf16_tn_bnfold", "gemm_bf16_nt_mn"} <= used_f
+    assert "gemm_bf16_tn_bnfold" not in used_d and {"gemm_bf16_tn_bnfold", "gemm_bf16_nt_mn",
+                                                    "gemm_bf16_tn_bnbwd"} <= used_f
     assert l_f == pytest.approx(l_d, rel=5e-3) and ((w_f - w_d).norm() / w_d.norm()).item() < 1e-3
     for k in ("im2col_rows", "conv_bf16_nhwc", "conv_wgrad_bf16_nhwc", "gemm_bf16_tn_bnfold", "gemm_bf16_nt_mn",
               "gemm_bf16_tn", "bn_finalize", "bn_apply", "bn_bwd_reduce", "bn_bwd_apply",
@@ -251,7 +320,7 @@ def test_other_families_device_branches_optin_equals_default(monkeypatch, arch, 
 
     out = []
     for switches in ((), ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "BN_FOLD", "DWCONV",
-                          "DGRAD1X1_TCGEN05")):
+                          "DGRAD1X1_TCGEN05", "BN_BWD_FOLD")):
         with monkeypatch.context() as mp:
             fe = FullFakeExt()
             mp.setattr(ops, "ext", lambda: fe)

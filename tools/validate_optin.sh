@@ -11,7 +11,7 @@ step() { echo "=== $*" | tee -a $O.log; }
 
 step "numerics: tcgen05 conv3x3 / stem im2col / wgrad (descriptor variant 0)"
 DDLB_TEST_CONV_TCGEN05=1 timeout 400 python -m pytest tests/test_kernels_gpu.py -q -k "im2col or dwconv3x3 or conv3x3" < /dev/null 2>&1 | tail -3 | tee -a $O.log
-BENCH=0 CHECK_WGRAD=0 CHECK_BNFOLD=0 timeout 300 python tests/conv_check.py < /dev/null 2>&1 | tail -14 | tee -a $O.log
+BENCH=0 CHECK_WGRAD=0 CHECK_BNFOLD=0 CHECK_BNBWD=0 timeout 300 python tests/conv_check.py < /dev/null 2>&1 | tail -14 | tee -a $O.log
 for v in 0 1; do
   step "wgrad GEMM, DDLB_WGRAD_DESC_VARIANT=$v"
   DDLB_WGRAD_DESC_VARIANT=$v timeout 200 python - <<'PY' 2>&1 | tail -9 | tee -a $O.log
@@ -30,8 +30,16 @@ import conv_check as c
 ok = all(c.check_bnfold(*a) for a in [(32, 64, 256, 56, 1, False), (32, 256, 64, 56, 1, True), (32, 512, 2048, 7, 1, False), (5, 128, 64, 9, 2, True)])
 print("bnfold", "OK" if ok else "FAIL")
 PY
+step "BN-backward-fold GEMM numerics"
+BENCH=0 timeout 300 python - <<'PY' 2>&1 | tail -8 | tee -a $O.log
+import sys
+sys.path.insert(0, "tests")
+import conv_check as c
+ok = all(c.check_bnbwd(*a) for a in [(32, 64, 256, 56, 1, True, True), (32, 256, 64, 56, 1, False, False), (32, 2048, 512, 7, 1, False, False), (5, 64, 128, 9, 2, True, False)])
+print("bnbwd", "OK" if ok else "FAIL")
+PY
 step "timing vs cuDNN"
-CHECK_WGRAD=0 CHECK_BNFOLD=0 timeout 300 python tests/conv_check.py < /dev/null 2>&1 | grep "^{" | tee -a $O.log
+CHECK_WGRAD=0 CHECK_BNFOLD=0 CHECK_BNBWD=0 timeout 300 python tests/conv_check.py < /dev/null 2>&1 | grep "^{" | tee -a $O.log
 
 bench() {  # name, env...
   local name=$1; shift
@@ -56,6 +64,8 @@ bench bn_fold DDLB_BN_FOLD=1
 bench bn_cluster DDLB_BN_CLUSTER=1
 bench bwd_apply_3blocks DDLB_BN_BWD_APPLY_BLOCKS=3
 bench dgrad1x1 DDLB_DGRAD1X1_TCGEN05=1
+bench bn_bwd_fold DDLB_BN_BWD_FOLD=1
+bench bn_both_folds DDLB_BN_FOLD=1 DDLB_BN_BWD_FOLD=1
 bench all_validated DDLB_STEM_IM2COL=1 DDLB_CONV3X3_TCGEN05=1 DDLB_SGD_OVERLAP=1
 bench all_tcgen05 DDLB_STEM_IM2COL=1 DDLB_CONV3X3_TCGEN05=1 DDLB_CONV3X3_DGRAD=1 DDLB_WGRAD_TCGEN05=1
 bench default_again DDLB_NONE=1
