@@ -20,9 +20,10 @@ def lr_for(cfg: RunConfig, epoch: int, batch_idx: int, steps_per_epoch: int, wor
     base = cfg.lr
     if cfg.framework == "horovod":
         if cfg.benchmark in ("imagenet", "highres"):
-            if epoch < 1:
+            warm = float(cfg.extra.get("warmup_epochs", 1.0))       # --warmup-epochs (imagenet_horovod.py:52)
+            if epoch < warm:
                 e = epoch + float(batch_idx + 1) / max(steps_per_epoch, 1)
-                adj = 1.0 / world * (e * (world - 1) / 1.0 + 1)
+                adj = 1.0 / world * (e * (world - 1) / warm + 1)
             elif epoch < 30:
                 adj = 1.0
             elif epoch < 60:

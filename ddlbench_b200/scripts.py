@@ -24,6 +24,8 @@ def parse(dataset: str, argv: Optional[Sequence[str]] = None):
     ap.add_argument("--momentum", type=float, default=None)
     ap.add_argument("--wd", "--weight-decay", type=float, default=None, dest="weight_decay")
     ap.add_argument("-s", "--synthetic_data", type=int, default=0)
+    ap.add_argument("--warmup-epochs", type=float, default=None,
+                    help="Horovod scripts: epochs of linear LR warm-up from lr to lr*world (default 1)")
     ap.add_argument("--device", default="auto")
     return ap.parse_args(argv)
 
@@ -35,6 +37,8 @@ def config_from_args(dataset: str, framework: str, a) -> RunConfig:
         benchmark, synthetic = "highres", True          # -1: synthetic HIGHRES directories
     kw = dict(benchmark=benchmark, framework=framework, arch=a.arch, synthetic=synthetic,
               device=a.device, lr=a.lr, momentum=a.momentum, weight_decay=a.weight_decay)
+    if a.warmup_epochs is not None:
+        kw["extra"] = {"warmup_epochs": str(a.warmup_epochs)}
     return RunConfig.from_env(**{k: v for k, v in kw.items() if v is not None})
 
 
