@@ -192,3 +192,24 @@ def test_pipedream_fork_path_shims(tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "Loss:" in outs[1] and "Prec@1" in outs[1]
+
+
+def test_translation_path_shims(tmp_path):
+    """pipedream-fork/runtime/translation/{main_with_runtime,compute_bleu_scores}.py with the
+    reference's flags: train a tiny GNMT for a few minibatches, write the stage checkpoint, score it."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "pipedream-fork", "runtime", "translation")
+    env = dict(os.environ, TMPDIR=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(d, "main_with_runtime.py"), "--module", "models.gnmt.gpus=1", "-b", "16",
+                        "--epochs", "1", "--num_minibatches", "4", "--hidden", "32", "--max-length-train", "24",
+                        "--checkpoint_dir", "ck", "--distributed_backend", "gloo", "-s", "--lr", "0.001"],
+                       cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "Epoch 0: BLEU" in r.stdout, r.stdout + r.stderr
+    assert (tmp_path / "ck" / "checkpoint.0.pth.tar").exists()
+    r = subprocess.run([sys.executable, os.path.join(d, "compute_bleu_scores.py"), "--checkpoint_path", "ck", "--num_layers", "4",
+                        "--num_stages", "1", "--hidden", "32", "--max-seq-len", "24", "--no-cuda", "--module",
+                        "models.gnmt.gpus=1", "-i", "in", "-o", "out"],
+                       cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "BLEU = " in r.stdout, r.stdout + r.stderr
