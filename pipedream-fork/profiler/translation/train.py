@@ -1,0 +1,9 @@
+"""GNMT profiler at the reference's path: writes the profile graph and partitions; see ddlbench_b200/partition/gnmt_tools.py."""
+import os
+import sys
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "..")))
+from ddlbench_b200.partition.gnmt_tools import cli  # noqa: E402
+
+if __name__ == "__main__":
+    raise SystemExit(cli())

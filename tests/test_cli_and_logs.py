@@ -3,6 +3,7 @@ reference's post-processing greps for — SURVEY.md §5.5)."""
 import os
 import re
 
+import pytest
 import torch
 import torch.distributed as dist
 
@@ -213,3 +214,14 @@ def test_translation_path_shims(tmp_path):
                         "models.gnmt.gpus=1", "-i", "in", "-o", "out"],
                        cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "BLEU = " in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("rel", ["optimizer/optimizer.py", "optimizer/inference_optimizer_graph.py", "runtime/driver.py",
+                                 "runtime/launch.py", "profiler/translation/train.py"])
+def test_reference_path_wrappers_start(rel):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "pipedream-fork", rel), "--help"], capture_output=True,
+                       text=True, timeout=300, cwd="/tmp")
+    assert r.returncode == 0 and "usage:" in r.stdout, r.stdout + r.stderr
