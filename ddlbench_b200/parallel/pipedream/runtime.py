@@ -23,13 +23,14 @@ checkpoints.  What is different by design:
 """
 from __future__ import annotations
 
+import math
 import os
 from typing import Dict, Iterator, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 
-from ...dist.transport import DistP2P, PairGroups, TensorSpec
+from ...dist.transport import DistP2P, PairGroups, SymmP2P, TensorSpec
 from ...engine import FwdContext, StageExecutor
 from ...models.graph import INPUT, LayerGraphModel
 from .config import PipelineConfig, RankTopology
@@ -187,8 +188,17 @@ class StageRuntime:
                     for b in cfg.stage_to_rank_map[s + 1]:
                         pairs.append((a, b))
             groups = PairGroups(pairs)
-        self.p2p = DistP2P(self.device, groups)
         self.ring = self.warmup + 3
+        if os.environ.get("DDLB_P2P", "nccl") == "symm" and on_gpu and groups is not None:
+            # peer-store transport: every rank derives the same slot size / ring depth
+            def msg_bytes(sp):
+                return sum((math.prod(s.shape) * torch.empty((), dtype=s.dtype).element_size() + 255) // 256 * 256
+                           for s in sp + [lab])
+            slot = max(msg_bytes(sp) for sp in specs) if specs else 256
+            depth = 3 + max(RankTopology.of(cfg, r).warmup for r in range(cfg.num_ranks))
+            self.p2p = SymmP2P.from_groups(self.device, groups, slot, depth)
+        else:
+            self.p2p = DistP2P(self.device, groups)
         self.routing = Routing(self.topo)
         self.fwd_id = self.bwd_id = 0
         self._ctxs: List[Tuple[FwdContext, Optional[torch.Tensor], Optional[int]]] = []
