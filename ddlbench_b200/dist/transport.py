@@ -339,8 +339,12 @@ class SymmP2P:
         return done
 
     def flush(self) -> None:
+        """End of an epoch: drain the communication stream and fail loudly if any flag wait gave
+        up (``p2p_wait`` stops spinning after ~10 s and records it instead of hanging the GPU)."""
         if self.gpu:
             self.comm_stream.synchronize()
+            torch.cuda.current_stream(self.device).synchronize()
+        self.check()
 
     def check(self) -> None:
         s = int(self.status.item())
