@@ -135,6 +135,45 @@ class JpegFolder:
                 a = a[:, ::-1]
         return np.ascontiguousarray(a)
 
+    def _transform_decoded(self, d: torch.Tensor, rng: np.random.RandomState) -> torch.Tensor:
+        """The transforms of ``_load_one`` on an already decoded [C, H, W] uint8 tensor (device
+        side of the nvJPEG path; the same random draws, bilinear resampling with antialiasing).
+        Returns [s, s, C] uint8."""
+        import torch.nn.functional as F
+        s = self.size
+        _, h, w = d.shape
+
+        def resize(t, oh, ow):
+            return F.interpolate(t[None].float(), size=(oh, ow), mode="bilinear", align_corners=False,
+                                 antialias=True)[0]
+
+        if self.dataset in ("imagenet", "highres"):
+            if self.augment and self.dataset == "imagenet":
+                area = w * h * rng.uniform(0.08, 1.0)
+                ar = np.exp(rng.uniform(np.log(3 / 4), np.log(4 / 3)))
+                cw = int(min(w, max(1, round(np.sqrt(area * ar)))))
+                ch = int(min(h, max(1, round(np.sqrt(area / ar)))))
+                x0, y0 = rng.randint(0, w - cw + 1), rng.randint(0, h - ch + 1)
+                d = resize(d[:, y0:y0 + ch, x0:x0 + cw], s, s)
+            elif (h, w) != (s, s):
+                r = (s * 256 // 224) / min(w, h)
+                nh, nw = max(s, round(h * r)), max(s, round(w * r))
+                d = resize(d, nh, nw)
+                d = d[:, (nh - s) // 2:(nh - s) // 2 + s, (nw - s) // 2:(nw - s) // 2 + s]
+        elif (h, w) != (s, s):
+            d = resize(d, s, s)
+        if d.is_floating_point():
+            d = d.round().clamp_(0, 255).to(torch.uint8)
+        if self.augment:
+            if self.dataset == "cifar10":
+                pad = torch.zeros((d.shape[0], s + 8, s + 8), dtype=torch.uint8, device=d.device)
+                pad[:, 4:4 + s, 4:4 + s] = d
+                y0, x0 = rng.randint(0, 9), rng.randint(0, 9)
+                d = pad[:, y0:y0 + s, x0:x0 + s]
+            if self.dataset != "mnist" and rng.rand() < 0.5:
+                d = d.flip(2)
+        return d.permute(1, 2, 0)
+
     def _make_batch(self, i: int, order: np.ndarray, epoch: int):
         sel = order[(i % self.length) * self.batch_size:(i % self.length + 1) * self.batch_size]
         labels = torch.tensor([self.samples[j][1] for j in sel], dtype=torch.int64)
@@ -143,7 +182,8 @@ class JpegFolder:
             raw = [read_file(self.samples[j][0]) for j in sel]
             mode = ImageReadMode.GRAY if self.channels == 1 else ImageReadMode.RGB
             dec = decode_jpeg(raw, device=self.device, mode=mode)
-            img = torch.stack([d.permute(1, 2, 0) for d in dec]).contiguous()
+            rngs = [np.random.RandomState((self.seed * 1000003 + epoch * 7919 + int(j)) & 0x7FFFFFFF) for j in sel]
+            img = torch.stack([self._transform_decoded(d, r) for d, r in zip(dec, rngs)]).contiguous()
             return img, labels.to(self.device, non_blocking=True)
         img = torch.empty(self.shape, dtype=torch.uint8)
         if self.pinned:

@@ -37,3 +37,34 @@ def test_run_with_real_data_mode(tmp_path, capsys):
     assert out["throughput"] > 0
     text = capsys.readouterr().out
     assert "train | 1/1 epoch" in text and "valid accuracy" in text
+
+
+def test_decoded_tensor_transforms_match_pil_path(tmp_path):
+    """The nvJPEG path applies the loader's transforms to decoded tensors: same random draws and
+    geometry as the PIL path (resampling filters differ slightly, hence a mean-error bound), also
+    for images that are NOT already of the training size."""
+    from PIL import Image
+    rs = np.random.RandomState(0)
+    yy, xx = np.mgrid[0:300, 0:400]
+    img = np.stack([(xx * 0.5 + yy * 0.2) % 256, (yy * 0.7) % 256, ((xx + yy) * 0.3) % 256], -1).astype(np.uint8)
+    img = (img.astype(np.int32) + rs.randint(0, 8, img.shape)).clip(0, 255).astype(np.uint8)
+    root = tmp_path / "IMAGENET" / "train" / "class_0"
+    root.mkdir(parents=True)
+    for i in range(4):
+        Image.fromarray(img).save(root / ("%d.png" % i))             # lossless: both paths see the same pixels
+    for split, augment in (("train", True), ("train", False)):
+        f = JpegFolder(str(tmp_path), "imagenet", 2, split=split, augment=augment, workers=1)
+        for seed in range(3):
+            ref = f._load_one(str(root / "0.png"), np.random.RandomState(seed))
+            d = torch.from_numpy(img).permute(2, 0, 1).contiguous()
+            out = f._transform_decoded(d, np.random.RandomState(seed))
+            assert tuple(out.shape) == (224, 224, 3) and out.dtype == torch.uint8
+            err = (out.float() - torch.from_numpy(ref).float()).abs().mean().item()
+            assert err < 3.0, (augment, seed, err)
+    generate_jpeg_tree(str(tmp_path / "c"), "cifar10", train=8, val=0, workers=1, verbose=False)
+    f = JpegFolder(str(tmp_path / "c"), "cifar10", 2, workers=1)
+    path = f.samples[0][0]
+    d = torch.from_numpy(np.asarray(Image.open(path).convert("RGB"))).permute(2, 0, 1).contiguous()
+    for seed in range(3):
+        ref = f._load_one(path, np.random.RandomState(seed))
+        assert torch.equal(f._transform_decoded(d, np.random.RandomState(seed)), torch.from_numpy(ref))
