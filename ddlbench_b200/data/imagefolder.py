@@ -181,9 +181,15 @@ class JpegFolder:
             from torchvision.io import ImageReadMode, decode_jpeg, read_file
             raw = [read_file(self.samples[j][0]) for j in sel]
             mode = ImageReadMode.GRAY if self.channels == 1 else ImageReadMode.RGB
-            dec = decode_jpeg(raw, device=self.device, mode=mode)
             rngs = [np.random.RandomState((self.seed * 1000003 + epoch * 7919 + int(j)) & 0x7FFFFFFF) for j in sel]
-            img = torch.stack([self._transform_decoded(d, r) for d, r in zip(dec, rngs)]).contiguous()
+            try:
+                dec = decode_jpeg(raw, device=self.device, mode=mode)
+                img = torch.stack([self._transform_decoded(d, r) for d, r in zip(dec, rngs)]).contiguous()
+            except RuntimeError:
+                # a file nvJPEG does not take (CMYK, progressive corner cases, not a JPEG): decode
+                # this batch on the host, as the default path does
+                img = torch.stack([torch.from_numpy(self._load_one(self.samples[j][0], r))
+                                   for j, r in zip(sel, rngs)]).to(self.device, non_blocking=True)
             return img, labels.to(self.device, non_blocking=True)
         img = torch.empty(self.shape, dtype=torch.uint8)
         if self.pinned:
