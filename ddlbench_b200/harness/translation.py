@@ -61,9 +61,24 @@ def parse(argv=None):
     return ap.parse_args(argv)
 
 
+# file names of the reference's WMT16 en-de directory (seq2seq/data/config.py:14-24)
+WMT16 = {"vocab": "vocab.bpe.32000",
+         "train": ("train.tok.clean.bpe.32000.en", "train.tok.clean.bpe.32000.de"),
+         "val": ("newstest_dev.tok.clean.bpe.32000.en", "newstest_dev.tok.clean.bpe.32000.de")}
+PLAIN = {"vocab": "vocab.txt", "train": ("train.src", "train.tgt"), "val": ("val.src", "val.tgt")}
+
+
 def prepare_data(a, rank: int = 0):
+    """Tokenizer + train / validation sets from ``--data-dir``: the reference's WMT16 layout
+    (``vocab.bpe.32000``, ``train.tok.clean.bpe.32000.{en,de}``, ``newstest_dev...``) or the plain
+    ``{train,val}.{src,tgt}`` + ``vocab.txt`` layout; a missing / empty directory gets a synthetic
+    corpus (there is no network here).  A directory with other content is never written to."""
     d = a.data_dir or os.path.join(os.environ.get("TMPDIR", "/tmp"), "ddlb_gnmt_data")
-    if not os.path.exists(os.path.join(d, "train.src")):
+    names = WMT16 if os.path.exists(os.path.join(d, WMT16["vocab"])) else PLAIN
+    if not os.path.exists(os.path.join(d, names["train"][0])):
+        if os.path.isdir(d) and os.listdir(d) and not os.path.exists(os.path.join(d, PLAIN["vocab"])):
+            raise FileNotFoundError("%s has neither the WMT16 files (%s, %s, ...) nor train.src/train.tgt/vocab.txt"
+                                    % (d, WMT16["vocab"], WMT16["train"][0]))
         if rank == 0:
             text.generate_synthetic_corpus(d, a.synthetic_sentences, a.synthetic_vocab, 3,
                                            min(30, a.max_len - 2), seed=0, name="train")
@@ -72,10 +87,10 @@ def prepare_data(a, rank: int = 0):
                                            name="val")
         if dist.is_initialized():
             dist.barrier()
-    tok = text.Tokenizer(os.path.join(d, "vocab.txt"))
-    train = text.ParallelDataset(os.path.join(d, "train.src"), os.path.join(d, "train.tgt"), tok,
+    tok = text.Tokenizer(os.path.join(d, names["vocab"]))
+    train = text.ParallelDataset(os.path.join(d, names["train"][0]), os.path.join(d, names["train"][1]), tok,
                                  max_len=a.max_len)
-    val = text.ParallelDataset(os.path.join(d, "val.src"), os.path.join(d, "val.tgt"), tok,
+    val = text.ParallelDataset(os.path.join(d, names["val"][0]), os.path.join(d, names["val"][1]), tok,
                                max_len=a.max_len, sort=True)
     return tok, train, val
 

@@ -1,4 +1,7 @@
 """GNMT model, stage splitting, text pipeline, BLEU, beam search (CPU)."""
+import os
+
+import pytest
 import torch
 
 from ddlbench_b200.data.text import (BucketingSampler, ParallelDataset, TextLoader, Tokenizer,
@@ -167,3 +170,29 @@ def test_translation_harness_bf16_master_weights_and_lr_schedule(tmp_path):
                             "--synthetic-vocab", "40", "--beam-size", "1", "--eval-sentences", "4",
                             "--dtype", "bf16", "--warmup-steps", "4"])
     assert res["train_loss"] == res["train_loss"] and res["train_loss"] > 0
+
+
+def test_translation_reads_the_reference_wmt16_layout(tmp_path):
+    """--data_dir pointing at the reference's WMT16 directory (vocab.bpe.32000, train.tok.clean.bpe...)
+    is read as is; a directory with unrelated content is refused, not filled with synthetic data."""
+    import types
+    from ddlbench_b200.data import text
+    from ddlbench_b200.harness import translation as tr
+    src = tmp_path / "plain"
+    paths = text.generate_synthetic_corpus(str(src), 60, 40, 3, 10, seed=0, name="train")
+    text.generate_synthetic_corpus(str(src), 20, 40, 3, 10, seed=1, name="val")
+    wmt = tmp_path / "wmt16_de_en"
+    wmt.mkdir()
+    (wmt / tr.WMT16["vocab"]).write_text(open(paths["vocab"]).read())
+    for split, plain in (("train", ("train.src", "train.tgt")), ("val", ("val.src", "val.tgt"))):
+        for dst, name in zip(tr.WMT16[split], plain):
+            (wmt / dst).write_text((src / name).read_text())
+    a = types.SimpleNamespace(data_dir=str(wmt), max_len=20, synthetic_sentences=10, synthetic_vocab=10)
+    tok, train, val = tr.prepare_data(a)
+    assert len(train) == 60 and len(val) == 20 and tok.vocab_size % 8 == 0
+    assert sorted(os.listdir(wmt)) == sorted([tr.WMT16["vocab"], *tr.WMT16["train"], *tr.WMT16["val"]])
+    other = tmp_path / "other"
+    other.mkdir()
+    (other / "README").write_text("x")
+    with pytest.raises(FileNotFoundError):
+        tr.prepare_data(types.SimpleNamespace(data_dir=str(other), max_len=20, synthetic_sentences=10, synthetic_vocab=10))
