@@ -7,9 +7,14 @@ def make_source(cfg, batch_size, device, rank=0, world=1, split="train", num_bat
     import os
     from .synthetic import SyntheticImages
     if not cfg.synthetic or cfg.data_mode == "jpeg":
-        from .imagefolder import JpegFolder
+        from .imagefolder import ArrayFolder, JpegFolder, has_native_format
         if not cfg.datadir or not os.path.isdir(cfg.datadir):
             raise FileNotFoundError("real-data mode needs DATADIR (got %r)" % cfg.datadir)
+        if has_native_format(cfg.datadir, cfg.benchmark):
+            # the real MNIST / CIFAR-10 files as torchvision's dataset classes read them
+            return ArrayFolder(cfg.datadir, cfg.benchmark, batch_size, split=split,
+                               shuffle=(split == "train"), seed=cfg.seed, rank=rank, world=world,
+                               workers=cfg.cores_gpu or None, pinned=True)
         return JpegFolder(cfg.datadir, cfg.benchmark, batch_size, split=split,
                           shuffle=(split == "train"), seed=cfg.seed, rank=rank, world=world,
                           workers=cfg.cores_gpu or None, pinned=True,

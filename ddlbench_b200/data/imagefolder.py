@@ -55,7 +55,10 @@ class JpegFolder:
         name = {"highres": "HIGHRES", "imagenet": "IMAGENET", "cifar10": "CIFAR10",
                 "mnist": "MNIST"}[dataset]
         self.root = os.path.join(datadir, name, split)
-        self.samples, self.classes = scan_tree(self.root)
+        if getattr(self, "_scan_override", None) is not None:
+            self.samples, self.classes = self._scan_override, [str(k) for k in range(ncls)]
+        else:
+            self.samples, self.classes = scan_tree(self.root)
         self.dataset, self.batch_size, self.split = dataset, batch_size, split
         self.channels, self.size, self.num_classes = c, hw, ncls
         self.shape = (batch_size, hw, hw, c)
@@ -123,6 +126,11 @@ class JpegFolder:
             elif im.size != (s, s):
                 im = im.resize((s, s), Image.BILINEAR)
             a = np.asarray(im, dtype=np.uint8)
+        return self._augment(a, rng)
+
+    def _augment(self, a: np.ndarray, rng: np.random.RandomState) -> np.ndarray:
+        """[H, W(, C)] uint8 of the training size -> augmented [s, s, C] (CIFAR pad-crop, flip)."""
+        s = self.size
         if a.ndim == 2:
             a = a[:, :, None]
         if self.augment:
@@ -222,3 +230,76 @@ class JpegFolder:
 
     def close(self) -> None:
         self.pool.shutdown(wait=False, cancel_futures=True)
+
+
+# ------------------------------------------------------------------------------------------
+# MNIST / CIFAR-10 in the formats torchvision's dataset classes read (what the reference's
+# scripts use in real-data mode: ``datasets.MNIST(datadir)``, ``datasets.CIFAR10(datadir)``,
+# ``cifar10_pytorch.py:163-181``, ``mnist_pytorch.py:175-190``)
+# ------------------------------------------------------------------------------------------
+def _open_maybe_gz(path: str):
+    import gzip
+    if os.path.exists(path):
+        return open(path, "rb")
+    if os.path.exists(path + ".gz"):
+        return gzip.open(path + ".gz", "rb")
+    raise FileNotFoundError(path)
+
+
+def load_mnist_idx(root: str, train: bool) -> Tuple[np.ndarray, np.ndarray]:
+    """``<root>/MNIST/raw/{train,t10k}-{images-idx3,labels-idx1}-ubyte[.gz]`` -> ([N, 28, 28] uint8, [N])."""
+    import struct
+    stem = "train" if train else "t10k"
+    for base in (os.path.join(root, "MNIST", "raw"), os.path.join(root, "raw"), root):
+        if os.path.exists(os.path.join(base, stem + "-images-idx3-ubyte")) or \
+                os.path.exists(os.path.join(base, stem + "-images-idx3-ubyte.gz")):
+            break
+    else:
+        raise FileNotFoundError("no MNIST idx files under %s" % root)
+    with _open_maybe_gz(os.path.join(base, stem + "-images-idx3-ubyte")) as f:
+        magic, n, h, w = struct.unpack(">IIII", f.read(16))
+        assert magic == 2051, "not an idx3 image file"
+        x = np.frombuffer(f.read(n * h * w), dtype=np.uint8).reshape(n, h, w)
+    with _open_maybe_gz(os.path.join(base, stem + "-labels-idx1-ubyte")) as f:
+        magic, n2 = struct.unpack(">II", f.read(8))
+        assert magic == 2049 and n2 == n, "label file does not match"
+        y = np.frombuffer(f.read(n), dtype=np.uint8).astype(np.int64)
+    return x, y
+
+
+def load_cifar10_batches(root: str, train: bool) -> Tuple[np.ndarray, np.ndarray]:
+    """``<root>/cifar-10-batches-py/{data_batch_1..5,test_batch}`` -> ([N, 32, 32, 3] uint8, [N])."""
+    import pickle
+    d = os.path.join(root, "cifar-10-batches-py")
+    xs, ys = [], []
+    for name in (["data_batch_%d" % i for i in range(1, 6)] if train else ["test_batch"]):
+        with open(os.path.join(d, name), "rb") as f:
+            e = pickle.load(f, encoding="latin1")
+        xs.append(np.asarray(e["data"], dtype=np.uint8))
+        ys += list(e["labels"] if "labels" in e else e["fine_labels"])
+    x = np.vstack(xs).reshape(-1, 3, 32, 32).transpose(0, 2, 3, 1)
+    return np.ascontiguousarray(x), np.asarray(ys, dtype=np.int64)
+
+
+def has_native_format(datadir: str, dataset: str) -> bool:
+    if dataset == "cifar10":
+        return os.path.isdir(os.path.join(datadir, "cifar-10-batches-py"))
+    if dataset == "mnist":
+        return any(os.path.exists(os.path.join(b, "train-images-idx3-ubyte" + ext))
+                   for b in (os.path.join(datadir, "MNIST", "raw"), os.path.join(datadir, "raw"), datadir)
+                   for ext in ("", ".gz"))
+    return False
+
+
+class ArrayFolder(JpegFolder):
+    """The real MNIST / CIFAR-10 files held in memory; same sharding, augmentation, prefetch and
+    batch interface as ``JpegFolder`` (a "sample" is an index into the array)."""
+
+    def __init__(self, datadir: str, dataset: str, batch_size: int, split: str = "train", **kw):
+        self._arrays = (load_cifar10_batches if dataset == "cifar10" else load_mnist_idx)(datadir, split == "train")
+        kw.pop("gpu_decode", None)
+        self._scan_override = [(i, int(l)) for i, l in enumerate(self._arrays[1])]
+        super().__init__(datadir, dataset, batch_size, split=split, gpu_decode=False, **kw)
+
+    def _load_one(self, index, rng: np.random.RandomState) -> np.ndarray:
+        return self._augment(self._arrays[0][index], rng)

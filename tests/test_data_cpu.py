@@ -68,3 +68,49 @@ def test_decoded_tensor_transforms_match_pil_path(tmp_path):
     for seed in range(3):
         ref = f._load_one(path, np.random.RandomState(seed))
         assert torch.equal(f._transform_decoded(d, np.random.RandomState(seed)), torch.from_numpy(ref))
+
+
+def test_native_mnist_and_cifar_files(tmp_path):
+    """Real-data mode reads MNIST idx files and CIFAR-10 python batches (what the reference's
+    ``datasets.MNIST`` / ``datasets.CIFAR10`` calls read) when they are what DATADIR holds."""
+    import gzip
+    import pickle
+    import struct
+    from ddlbench_b200.data import make_source
+    from ddlbench_b200.data.imagefolder import ArrayFolder, has_native_format
+    rs = np.random.RandomState(0)
+    raw = tmp_path / "MNIST" / "raw"
+    raw.mkdir(parents=True)
+    for stem, n in (("train", 64), ("t10k", 16)):
+        x = rs.randint(0, 256, (n, 28, 28), dtype=np.uint8)
+        y = (np.arange(n) % 10).astype(np.uint8)
+        with gzip.open(raw / (stem + "-images-idx3-ubyte.gz"), "wb") as f:       # gz, as downloaded
+            f.write(struct.pack(">IIII", 2051, n, 28, 28) + x.tobytes())
+        with open(raw / (stem + "-labels-idx1-ubyte"), "wb") as f:               # and unpacked
+            f.write(struct.pack(">II", 2049, n) + y.tobytes())
+        if stem == "train":
+            mnist_x = x
+    cdir = tmp_path / "cifar-10-batches-py"
+    cdir.mkdir()
+    cx = rs.randint(0, 256, (50, 3072), dtype=np.uint8)
+    for i in range(1, 6):
+        with open(cdir / ("data_batch_%d" % i), "wb") as f:
+            pickle.dump({"data": cx[(i - 1) * 10:i * 10], "labels": list(range(10))}, f)
+    with open(cdir / "test_batch", "wb") as f:
+        pickle.dump({"data": cx[:10], "labels": list(range(10))}, f)
+    assert has_native_format(str(tmp_path), "mnist") and has_native_format(str(tmp_path), "cifar10")
+    assert not has_native_format(str(tmp_path), "imagenet")
+    m = ArrayFolder(str(tmp_path), "mnist", 8, shuffle=False, workers=1)
+    x, t = m.batch(0)
+    assert x.shape == (8, 28, 28, 1) and t.tolist() == list(range(8))
+    assert np.array_equal(x[..., 0].numpy(), mnist_x[:8])                       # no augmentation for MNIST
+    assert len(ArrayFolder(str(tmp_path), "mnist", 8, split="val", workers=1)) == 2
+    c = ArrayFolder(str(tmp_path), "cifar10", 10, shuffle=False, augment=False, workers=1)
+    x, t = c.batch(0)
+    assert x.shape == (10, 32, 32, 3) and np.array_equal(x.numpy(), cx[:10].reshape(10, 3, 32, 32).transpose(0, 2, 3, 1))
+    a = ArrayFolder(str(tmp_path), "cifar10", 10, rank=0, world=2, workers=1)
+    b = ArrayFolder(str(tmp_path), "cifar10", 10, rank=1, world=2, workers=1)
+    assert len(a) == len(b) == 2 and not set(a._order.tolist()) & set(b._order.tolist())
+    cfg = RunConfig.from_env(benchmark="cifar10", framework="pytorch", arch="resnet18", synthetic=False,
+                             datadir=str(tmp_path), batch_size=10, device="cpu")
+    assert isinstance(make_source(cfg, 10, "cpu"), ArrayFolder)
