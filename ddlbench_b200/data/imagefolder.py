@@ -246,11 +246,19 @@ def _open_maybe_gz(path: str):
     raise FileNotFoundError(path)
 
 
+def _mnist_bases(root: str):
+    """Where the idx files may sit below DATADIR: ``datasets.MNIST(root)`` puts them in
+    ``root/MNIST/raw``; the PipeDream runtime passes ``data_dir + '/MNIST'`` as that root
+    (``main_with_runtime.py:275``), the benchmark scripts pass DATADIR itself (``mnist_pytorch.py:175``)."""
+    return (os.path.join(root, "MNIST", "raw"), os.path.join(root, "MNIST", "MNIST", "raw"),
+            os.path.join(root, "raw"), root)
+
+
 def load_mnist_idx(root: str, train: bool) -> Tuple[np.ndarray, np.ndarray]:
     """``<root>/MNIST/raw/{train,t10k}-{images-idx3,labels-idx1}-ubyte[.gz]`` -> ([N, 28, 28] uint8, [N])."""
     import struct
     stem = "train" if train else "t10k"
-    for base in (os.path.join(root, "MNIST", "raw"), os.path.join(root, "raw"), root):
+    for base in _mnist_bases(root):
         if os.path.exists(os.path.join(base, stem + "-images-idx3-ubyte")) or \
                 os.path.exists(os.path.join(base, stem + "-images-idx3-ubyte.gz")):
             break
@@ -286,8 +294,7 @@ def has_native_format(datadir: str, dataset: str) -> bool:
         return os.path.isdir(os.path.join(datadir, "cifar-10-batches-py"))
     if dataset == "mnist":
         return any(os.path.exists(os.path.join(b, "train-images-idx3-ubyte" + ext))
-                   for b in (os.path.join(datadir, "MNIST", "raw"), os.path.join(datadir, "raw"), datadir)
-                   for ext in ("", ".gz"))
+                   for b in _mnist_bases(datadir) for ext in ("", ".gz"))
     return False
 
 

@@ -39,7 +39,10 @@ def main(argv=None) -> int:
     ap.add_argument("--highres", type=int, default=0)
     ap.add_argument("--dataset", default=os.environ.get("BENCHMARK", "imagenet"),
                     help="extension: mnist | cifar10 | imagenet | highres (the reference encodes it in --module)")
-    for flag in ("--data_dir", "-j", "--workers", "-s", "--synthetic_data", "--num_ranks_in_server",
+    ap.add_argument("--data_dir", default=None,
+                    help="image trees (<SET>/{train,val}/<class>/*) or the MNIST / CIFAR-10 dataset files; "
+                         "without it batches are generated in memory")
+    for flag in ("-j", "--workers", "-s", "--synthetic_data", "--num_ranks_in_server",
                  "--eval-batch-size", "-v", "--verbose_frequency", "--loss_scale", "--resume", "--start-epoch"):
         ap.add_argument(flag, default=None)
     ap.add_argument("--fp16", action="store_true")
@@ -71,7 +74,10 @@ def main(argv=None) -> int:
         extra["lr_warmup"] = "5"
     if a.checkpoint_dir:
         extra["checkpoint_dir"] = a.checkpoint_dir
-    kw = dict(benchmark=dataset, framework="pipedream", arch=arch, gpus=world, batch_size=a.batch_size,
+    data = {}
+    if a.data_dir and os.path.isdir(a.data_dir):
+        data = dict(datadir=a.data_dir, synthetic=False)
+    kw = dict(benchmark=dataset, framework="pipedream", arch=arch, gpus=world, batch_size=a.batch_size, **data,
               epochs=a.epochs, lr=a.lr, momentum=a.momentum, weight_decay=a.wd, log_interval=a.print_freq,
               steps_per_epoch=a.num_minibatches, extra=extra,
               device=("cpu" if a.distributed_backend == "gloo" else "auto"))
