@@ -126,10 +126,16 @@ class _ConvMixin:
                 x.dtype == torch.bfloat16 and ci % 8 == 0 and co % 8 == 0 and
                 x.is_contiguous(memory_format=torch.channels_last))
 
+    def _is_ig(self, x: torch.Tensor, stats: bool = False) -> bool:
+        """Persistent tcgen05 implicit-GEMM family (default path of every dense convolution)."""
+        return TCGEN05["conv1x1"] and ops.igemm_conv_supported(
+            x, self.wshape, self.stride, self.padding, self.dilation, self.groups,
+            self.wshape[0] if stats else 0)
+
     def _is_stem_gemm(self, x: torch.Tensor) -> bool:
         """Few-channel first convolution (7x7/s2 on RGB, 3x3 on RGB/grey) as patch matrix + GEMM."""
         co, ci, kh, kw = self.wshape
-        return (STEM_IM2COL and TCGEN05["conv1x1"] and ci <= 4 and kh * kw > 1 and
+        return ((STEM_IM2COL or ops.IGEMM) and TCGEN05["conv1x1"] and ci <= 4 and kh * kw > 1 and
                 self.groups == 1 and self.dilation == [1, 1] and self.stride[0] == self.stride[1] and
                 self.padding[0] == self.padding[1] and kh == kw and co % 8 == 0 and x.is_cuda and
                 x.dtype == torch.bfloat16 and x.dim() == 4 and
@@ -161,6 +167,12 @@ class _ConvMixin:
             return d.view(n, h, wd, co).permute(0, 3, 1, 2), col_sums is not None
         if fold is not None:
             fold.materialize()              # consumer cannot fold after all: plain application
+        if self._is_ig(x, col_sums is not None):
+            y = ops.conv_fprop(x, w, self.stride[0], self.padding, col_sums=col_sums, bias=bias,
+                               relu=relu, bn_finalize=bn_finalize)
+            if y is not None:
+                return y, col_sums is not None
+            assert bn_finalize is None, "igemm declined a shape igemm_conv_supported accepted"
         if self._is_gemm(x):
             n, ci, h, wd = x.shape
             co = self.wshape[0]
@@ -172,12 +184,15 @@ class _ConvMixin:
             n, ci, h, wd = x.shape
             co, _, kh, kw = self.wshape
             a = ops.im2col_rows(x, kh, kw, self.stride[0], self.padding[0])
-            if ctx is not None and WGRAD_TCGEN05:
+            if ctx is not None and (WGRAD_TCGEN05 or ops.IGEMM):
                 ctx["patch"] = a
             oh = (h + 2 * self.padding[0] - kh) // self.stride[0] + 1
             ow = (wd + 2 * self.padding[1] - kw) // self.stride[1] + 1
-            d = ops.gemm_tn(a, self._stem_weight_matrix(w, a.shape[1]), col_sums=col_sums, bias=bias,
-                            relu=relu, bn_finalize=bn_finalize)
+            wm = self._stem_weight_matrix(w, a.shape[1])
+            d = ops.gemm_ig(a, wm, col_sums=col_sums, bias=bias, relu=relu,
+                            bn_finalize=bn_finalize) if ops.igemm_ok2d(a, co) else None
+            if d is None:
+                d = ops.gemm_tn(a, wm, col_sums=col_sums, bias=bias, relu=relu, bn_finalize=bn_finalize)
             return d.view(n, oh, ow, co).permute(0, 3, 1, 2), col_sums is not None
         if DWCONV and ops.dwconv_supported(x, self.wshape, self.stride, self.padding, self.dilation,
                                            self.groups) and bias is None and not relu:
@@ -200,7 +215,10 @@ class _ConvMixin:
             # stem: dW[Cout, kh*kw*Cin (padded)] = dY^T @ patch matrix, then drop the padding
             co, ci, kh, kw = self.wshape
             n, _, oh, ow = dy.shape
-            dwm = ops.gemm_nt_mn(dy.permute(0, 2, 3, 1).reshape(n * oh * ow, co), patch)
+            dy2 = dy.permute(0, 2, 3, 1).reshape(n * oh * ow, co)
+            dwm = torch.empty((co, patch.shape[1]), dtype=torch.float32, device=dy.device)
+            if not ops.wgrad_gemm_into(dy2, patch, dwm, False):
+                dwm = ops.gemm_nt_mn(dy2, patch)
             return dwm[:, :kh * kw * ci].reshape(co, kh, kw, ci).permute(0, 3, 1, 2)
         if not WGRAD_TCGEN05:
             return None
@@ -214,6 +232,33 @@ class _ConvMixin:
                                   x.permute(0, 2, 3, 1).reshape(n * h * wd, ci)).view(co, ci, 1, 1)
         return None
 
+    def _conv_bwd_ig(self, dy, x, w, need_dx, gw, accumulate, side):
+        """Data + weight gradient on the tcgen05 kernels: dgrad reads the forward filter as an
+        MN-major operand (no flip / transpose), the weight gradient lands in the flat gradient
+        buffer in one launch (on the side stream when one is configured)."""
+        args = (None, self.stride, self.padding, self.dilation, False, [0, 0], self.groups)
+        dx = None
+        if need_dx:
+            dx = ops.conv_dgrad(dy, w, x.shape, self.stride[0], self.padding)
+            if dx is None:
+                dx = aten.convolution_backward(dy, x, w, *args, [True, False, False])[0]
+
+        def wgrad():
+            if not ops.conv_wgrad_into(dy, x, gw, self.stride[0], self.padding, accumulate):
+                _write(gw, aten.convolution_backward(dy, x, w, *args, [False, True, False])[1], accumulate)
+
+        if side is None:
+            wgrad()
+            return dx
+        main = torch.cuda.current_stream(dy.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            wgrad()
+        WGRAD_OVERLAP["keep"].append((dy, x))
+        return dx
+
     def _conv_bwd(self, dy, x, w, need_dx: bool, gw: torch.Tensor, accumulate: bool, patch=None):
         """Data gradient (returned) and weight gradient (written into ``gw``).  With a side
         stream configured (``WGRAD_OVERLAP``) the weight-gradient kernel — which nothing
@@ -225,6 +270,9 @@ class _ConvMixin:
             _write(gw, dw, accumulate)
             return dx
         side = WGRAD_OVERLAP["stream"] if dy.is_cuda else None
+        if patch is None and self._is_ig(x) and dy.is_cuda and dy.dtype == torch.bfloat16 and \
+                dy.is_contiguous(memory_format=torch.channels_last):
+            return self._conv_bwd_ig(dy, x, w, need_dx, gw, accumulate, side)
         args = (None, self.stride, self.padding, self.dilation, False, [0, 0], self.groups)
         dx_tc = None
         if need_dx and CONV3X3_DGRAD and self._is_conv_tc(x, w) and self.stride == [1, 1] and \
@@ -304,11 +352,12 @@ class ConvBnAct(Op, _ConvMixin):
     def forward(self, P, B, xs, ctx, training):
         x = xs[0]
         res = xs[1] if self.has_res else None
+        ig = self._is_ig(x, True) or (ops.IGEMM and self._is_stem_gemm(x) and self.channels <= 2048)
         fuse_stats = training and self.ws is not None and \
-            (self._is_gemm(x) or self._is_stem_gemm(x) or self._is_conv_tc(x, P[self.k_w]))
+            (ig or self._is_gemm(x) or self._is_stem_gemm(x) or self._is_conv_tc(x, P[self.k_w]))
         mom = self.momentum * BN_MOMENTUM_SCALE[0]
         stat_ready = None
-        if fuse_stats and FUSE_BN_FINALIZE:
+        if fuse_stats and (FUSE_BN_FINALIZE or ig) and not getattr(self, "defer_apply", False):
             # statistics AND their finalize ride in the GEMM epilogue (last CTA).  Measured
             # slower than a separate 4 us finalize launch (the last CTA gathers R*2*N values
             # with 128 threads and every CTA pays a fence + ticket), so this is off by default.
@@ -445,7 +494,13 @@ class LinearAct(Op):
         x = xs[0]
         w = P[self.k_w]
         b = P[self.k_b] if self.has_bias else None
+        y = None
         if (TCGEN05["linear"] and self.act in (ACT_NONE, ACT_RELU) and x.dim() == 2 and
+                ops.igemm_ok2d(x, self.out_f) and w.dtype == torch.bfloat16):
+            y = ops.gemm_ig(x, w, bias=b, relu=self.act == ACT_RELU)
+        if y is not None:
+            pass
+        elif (TCGEN05["linear"] and self.act in (ACT_NONE, ACT_RELU) and x.dim() == 2 and
                 ops.gemm_tn_supported(x, w) and self.out_f % 8 == 0):
             y = ops.gemm_tn(x, w, bias=b, relu=self.act == ACT_RELU)
         else:
@@ -462,10 +517,24 @@ class LinearAct(Op):
         if self.act != ACT_NONE:
             dy = ops.act_bwd(dy, None, ctx["y"], self.act)
         x = ctx["x"]
-        _write(G[self.k_w], dy.t() @ x, accumulate)
+        w = P[self.k_w]
+        native = (TCGEN05["linear"] and dy.dim() == 2 and x.dim() == 2 and dy.is_contiguous() and
+                  ops.igemm_ok2d(dy, self.in_f) and ops.igemm_ok2d(x, self.out_f) and
+                  w.dtype == torch.bfloat16)
+        # dW[out, in] = dy^T x: both operands MN-major, written straight into the gradient buffer
+        if not (native and ops.wgrad_gemm_into(dy, x, G[self.k_w], accumulate)):
+            _write(G[self.k_w], dy.t() @ x, accumulate)
         if self.has_bias:
-            _write(G[self.k_b], dy.float().sum(0).to(dy.dtype), accumulate)
-        return [dy @ P[self.k_w] if need[0] else None]
+            if native:
+                if getattr(self, "_bias_ws", None) is None or self._bias_ws.sums.device != dy.device:
+                    self._bias_ws = ops.BnWorkspace(self.out_f, dy.device)
+                ops.bias_grad_(dy, G[self.k_b], accumulate, self._bias_ws)
+            else:
+                _write(G[self.k_b], dy.float().sum(0).to(dy.dtype), accumulate)
+        if not need[0]:
+            return [None]
+        dx = ops.gemm_ig(dy, w, b_mn=True) if native else None     # dx = dy @ W: W is the MN-major B
+        return [dx if dx is not None else dy @ w]
 
 
 class MaxPool(Op):

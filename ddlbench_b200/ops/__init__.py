@@ -553,6 +553,135 @@ def gemm_nt_mn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = N
     return out
 
 
+
+# ------------------------------------------------------------------------------- implicit GEMM
+# Persistent tcgen05 implicit-GEMM family (csrc/igemm_tcgen05.cu) + one-launch weight gradients
+# (csrc/gemm_wgrad_tcgen05.cu): every dense convolution forward / data gradient / weight gradient
+# and the FC layers.  DDLB_IGEMM=0 routes back to the library (A/B and bring-up only).
+IGEMM = os.environ.get("DDLB_IGEMM", "1") == "1"
+_WG_WS: dict = {}
+_WG_TICKETS = 16384
+
+
+def _wgrad_ws(device, numel: int):
+    """Zero fp32 scratch shared by the weight-gradient kernels that run back to back on one stream
+    (they leave it zero) + the ticket array."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0)
+    ent = _WG_WS.get(key)
+    if ent is None or ent[0].numel() < numel:
+        cap = max(numel, 1 << 22)
+        ent = (torch.zeros(cap, dtype=torch.float32, device=device),
+               torch.zeros(_WG_TICKETS, dtype=torch.int32, device=device) if ent is None else ent[1])
+        _WG_WS[key] = ent
+    return ent
+
+
+def igemm_conv_supported(x: torch.Tensor, wshape, stride, padding, dilation, groups,
+                         stats_channels: int = 0) -> bool:
+    """Shapes the persistent implicit-GEMM kernels take: bf16 NHWC, groups 1, dilation 1, square
+    stride 1 or 2, channel counts that are multiples of 8 (TMA 16-byte rows)."""
+    if not (IGEMM and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
+        return False
+    co, ci, kh, kw = wshape
+    st = list(stride)
+    return (st[0] == st[1] and st[0] in (1, 2) and list(dilation) == [1, 1] and groups == 1 and
+            kh * kw <= 49 and kh <= 7 and kw <= 7 and ci % 8 == 0 and co % 8 == 0 and
+            stats_channels <= 2048 and padding[0] < kh + st[0] and padding[1] < kw + st[0] and
+            x.is_contiguous(memory_format=torch.channels_last))
+
+
+def _fin_args(bn_finalize):
+    if bn_finalize is None:
+        return (None, None, None, None, 0.0, 0.0)
+    tk, st, rm, rv, eps, mom = bn_finalize
+    return (tk, st, rm, rv, float(eps), float(mom))
+
+
+def conv_fprop(x: torch.Tensor, w: torch.Tensor, stride: int, padding: Sequence[int],
+               col_sums: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+               relu: bool = False, bn_finalize=None) -> Optional[torch.Tensor]:
+    """y = conv2d(x, w, stride, padding) [+bias, ReLU] with the BatchNorm sum / sum-of-squares (and,
+    with ``bn_finalize``, mean / invstd / running statistics) produced by the same kernel."""
+    co, ci, kh, kw = w.shape
+    ph, pw = int(padding[0]), int(padding[1])
+    oh = (x.shape[2] + 2 * ph - kh) // stride + 1
+    ow = (x.shape[3] + 2 * pw - kw) // stride + 1
+    if not w.is_contiguous(memory_format=torch.channels_last):
+        w = w.contiguous(memory_format=torch.channels_last)
+    y = torch.empty((x.shape[0], co, oh, ow), dtype=x.dtype, device=x.device,
+                    memory_format=torch.channels_last)
+    if ext().igemm_conv_fprop(x, w, y, ph, pw, stride, col_sums, bias, relu, *_fin_args(bn_finalize)):
+        _count()
+        return y
+    return None
+
+
+def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int,
+               padding: Sequence[int]) -> Optional[torch.Tensor]:
+    """Data gradient of conv2d(x, w): reads the FORWARD filter (MN-major B operand), no transposes."""
+    if not w.is_contiguous(memory_format=torch.channels_last):
+        w = w.contiguous(memory_format=torch.channels_last)
+    dx = torch.empty(tuple(x_shape), dtype=dy.dtype, device=dy.device,
+                     memory_format=torch.channels_last)
+    if ext().igemm_conv_dgrad(dy, w, dx, int(padding[0]), int(padding[1]), stride):
+        _count()
+        return dx
+    return None
+
+
+def conv_wgrad_into(dy: torch.Tensor, x: torch.Tensor, gw: torch.Tensor, stride: int,
+                    padding: Sequence[int], accumulate: bool) -> bool:
+    """gw (+)= weight gradient of conv2d(x, w); ``gw`` is the [Cout, Cin, KH, KW] KRSC view of the
+    flat gradient buffer, written in ONE launch (split-K partials meet in a self-cleaning fp32
+    workspace, the last split converts)."""
+    co, ci, kh, kw = gw.shape
+    if not (gw.is_cuda and gw.is_contiguous(memory_format=torch.channels_last) and
+            gw.dtype in (torch.bfloat16, torch.float32) and gw.data_ptr() % 16 == 0):
+        return False
+    ws, tickets = _wgrad_ws(gw.device, gw.numel())
+    if kh == 1 and kw == 1 and stride == 1 and padding[0] == 0 and padding[1] == 0:
+        n, _, h, wd = x.shape
+        a = dy.permute(0, 2, 3, 1).reshape(n * h * wd, co)
+        b = x.permute(0, 2, 3, 1).reshape(n * h * wd, ci)
+        ok = ext().wgrad_gemm(a, b, ws, tickets, gw.permute(0, 2, 3, 1).reshape(co, ci), accumulate)
+    else:
+        ok = ext().wgrad_conv(dy, x, ws, tickets, gw, accumulate, int(padding[0]), int(padding[1]),
+                              stride)
+    if ok:
+        _count()
+    return bool(ok)
+
+
+def igemm_ok2d(a: torch.Tensor, n: int) -> bool:
+    return (IGEMM and a.is_cuda and a.dtype == torch.bfloat16 and a.dim() == 2 and a.stride(1) == 1 and
+            a.shape[1] % 8 == 0 and a.stride(0) % 8 == 0 and n % 8 == 0 and a.data_ptr() % 16 == 0)
+
+
+def gemm_ig(a: torch.Tensor, b: torch.Tensor, b_mn: bool = False,
+            col_sums: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+            relu: bool = False, bn_finalize=None) -> Optional[torch.Tensor]:
+    """D[M, N] = a[M, K] @ (b[N, K]^T if not b_mn else b[K, N]) on the persistent kernel."""
+    n = b.shape[1] if b_mn else b.shape[0]
+    out = torch.empty((a.shape[0], n), dtype=torch.bfloat16, device=a.device)
+    if ext().igemm_gemm(a, b, out, b_mn, col_sums, bias, relu, *_fin_args(bn_finalize)):
+        _count()
+        return out
+    return None
+
+
+def wgrad_gemm_into(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, accumulate: bool) -> bool:
+    """out[M, N] (+)= a[K, M]^T @ b[K, N] in one launch (see ``conv_wgrad_into``)."""
+    if not (IGEMM and gemm_nt_mn_supported(a, b) and out.is_cuda and out.dim() == 2 and
+            out.stride(1) == 1 and out.stride(0) % 8 == 0 and out.data_ptr() % 16 == 0 and
+            out.dtype in (torch.bfloat16, torch.float32)):
+        return False
+    # one k-block (K <= 64 rows: FC layers at small batch) is written directly, no workspace needed
+    ws, tickets = _wgrad_ws(out.device, out.shape[0] * out.stride(0) if a.shape[0] > 64 else 1)
+    if ext().wgrad_gemm(a, b, ws, tickets, out, accumulate):
+        _count()
+        return True
+    return False
+
 def im2col_rows(x: torch.Tensor, kh: int, kw: int, stride: int, pad: int) -> torch.Tensor:
     """[N, C, H, W] -> patch matrix [N*OH*OW, roundup(kh*kw*C, 8)] with K ordered (kh, kw, c) — the
     A operand that turns a few-channel first convolution into a tensor-core GEMM

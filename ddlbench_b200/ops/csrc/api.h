@@ -127,6 +127,26 @@ int ddl_gemm_bf16_tn_bnbwd(const void* dy, const void* dy2, const void* c, const
                            const void* bt, void* dx, void* dc, void* dz, int M, int N, int K, int ld,
                            int ldb, int ldd, const float* stat, const float* coef, int act, int sms,
                            cudaStream_t st);
+
+// ---- igemm_tcgen05.cu  (persistent implicit-GEMM: every dense conv fprop / dgrad and the FC layers)
+int ddl_igemm_gemm(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb,
+                   int ldd, int b_mn_major, float* col_sums, const void* bias, int relu,
+                   const DdlBnFinalize* fin, int sms, cudaStream_t st);
+int ddl_igemm_conv_fprop(const void* x, const void* w, void* y, int NB, int H, int W, int Cin,
+                         int Cout, int KH, int KW, int pad_h, int pad_w, int stride, float* col_sums,
+                         const void* bias, int relu, const DdlBnFinalize* fin, int sms,
+                         cudaStream_t st);
+int ddl_igemm_conv_dgrad(const void* dy, const void* w, void* dx, int NB, int H, int W, int Cin,
+                         int Cout, int KH, int KW, int pad_h, int pad_w, int stride, int sms,
+                         cudaStream_t st);
+// ---- gemm_wgrad_tcgen05.cu, one-launch weight gradients (self-cleaning fp32 workspace)
+int ddl_wgrad_gemm(const void* A, const void* B, float* ws, unsigned int* tickets, void* out,
+                   int out_bf16, int accumulate, int M, int N, int K, int lda, int ldb, int ldd,
+                   int max_tickets, int sms, cudaStream_t st);
+int ddl_wgrad_conv(const void* dy, const void* x, float* ws, unsigned int* tickets, void* out,
+                   int out_bf16, int accumulate, int NB, int H, int W, int Cin, int Cout, int KH,
+                   int KW, int pad_h, int pad_w, int stride, int max_tickets, int sms,
+                   cudaStream_t st);
 int ddl_gemm_selftest_info(char* buf, int len);
 int ddl_set_pdl(int on);
 

@@ -411,6 +411,123 @@ void gemm_bf16_nt_mn(at::Tensor A, at::Tensor B, at::Tensor D, int64_t splits,
                             (float*)optr(workspace), sm_count(), cur_stream()),
         "gemm_bf16_nt_mn");
 }
+
+// ---- persistent implicit-GEMM family (igemm_tcgen05.cu)
+static inline DdlBnFinalize make_fin(const c10::optional<at::Tensor>& ticket,
+                                     const c10::optional<at::Tensor>& stat_out,
+                                     const c10::optional<at::Tensor>& rmean,
+                                     const c10::optional<at::Tensor>& rvar, double eps, double momentum) {
+  return DdlBnFinalize{(unsigned int*)optr(ticket), (float*)optr(stat_out), (float*)optr(rmean),
+                       (float*)optr(rvar), (float)eps, (float)momentum};
+}
+// D[M,N] = A[M,K] op(B): b_mn = false -> B is [N,K]; true -> B is [K,N].  Returns false if declined.
+bool igemm_gemm(at::Tensor A, at::Tensor B, at::Tensor D, bool b_mn, c10::optional<at::Tensor> col_sums,
+                c10::optional<at::Tensor> bias, bool relu, c10::optional<at::Tensor> ticket,
+                c10::optional<at::Tensor> stat_out, c10::optional<at::Tensor> rmean,
+                c10::optional<at::Tensor> rvar, double eps, double momentum) {
+  TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && D.dim() == 2 && is_bf16(A) && is_bf16(B) && is_bf16(D));
+  TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1 && D.stride(1) == 1);
+  const int M = (int)A.size(0), K = (int)A.size(1), N = (int)D.size(1);
+  TORCH_CHECK(D.size(0) == M && (b_mn ? (B.size(0) == K && B.size(1) == N)
+                                      : (B.size(0) == N && B.size(1) == K)), "igemm_gemm: shapes");
+  c10::cuda::CUDAGuard g(A.device());
+  DdlBnFinalize fin = make_fin(ticket, stat_out, rmean, rvar, eps, momentum);
+  const bool use_fin = fin.ticket != nullptr && fin.stat_out != nullptr;
+  const int rc = ddl_igemm_gemm(A.data_ptr(), B.data_ptr(), D.data_ptr(), M, N, K, (int)A.stride(0),
+                                (int)B.stride(0), (int)D.stride(0), b_mn ? 1 : 0,
+                                (float*)optr(col_sums), optr(bias), relu, use_fin ? &fin : nullptr,
+                                sm_count(), cur_stream());
+  if (rc == -1) return false;
+  check(rc, "igemm_gemm");
+  return true;
+}
+bool igemm_conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int64_t pad_h, int64_t pad_w,
+                      int64_t stride, c10::optional<at::Tensor> col_sums,
+                      c10::optional<at::Tensor> bias, bool relu, c10::optional<at::Tensor> ticket,
+                      c10::optional<at::Tensor> stat_out, c10::optional<at::Tensor> rmean,
+                      c10::optional<at::Tensor> rvar, double eps, double momentum) {
+  TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && y.dim() == 4 && is_bf16(x) && is_bf16(w) && is_bf16(y));
+  TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast) &&
+              w.is_contiguous(at::MemoryFormat::ChannelsLast) &&
+              y.is_contiguous(at::MemoryFormat::ChannelsLast), "igemm_conv_fprop: channels_last operands");
+  const int NB = (int)x.size(0), Cin = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
+  const int Cout = (int)w.size(0), KH = (int)w.size(2), KW = (int)w.size(3);
+  const int OH = (H + 2 * (int)pad_h - KH) / (int)stride + 1;
+  const int OW = (W + 2 * (int)pad_w - KW) / (int)stride + 1;
+  TORCH_CHECK(w.size(1) == Cin && y.size(0) == NB && y.size(1) == Cout && y.size(2) == OH &&
+              y.size(3) == OW, "igemm_conv_fprop: output shape");
+  c10::cuda::CUDAGuard g(x.device());
+  DdlBnFinalize fin = make_fin(ticket, stat_out, rmean, rvar, eps, momentum);
+  const bool use_fin = fin.ticket != nullptr && fin.stat_out != nullptr;
+  const int rc = ddl_igemm_conv_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), NB, H, W, Cin, Cout,
+                                      KH, KW, (int)pad_h, (int)pad_w, (int)stride,
+                                      (float*)optr(col_sums), optr(bias), relu,
+                                      use_fin ? &fin : nullptr, sm_count(), cur_stream());
+  if (rc == -1) return false;
+  check(rc, "igemm_conv_fprop");
+  return true;
+}
+// dx [N, Cin, H, W] = data gradient of conv2d(x, w) given dy [N, Cout, OH, OW]; w is the FORWARD filter
+bool igemm_conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int64_t pad_h, int64_t pad_w,
+                      int64_t stride) {
+  TORCH_CHECK(dy.dim() == 4 && w.dim() == 4 && dx.dim() == 4 && is_bf16(dy) && is_bf16(w) && is_bf16(dx));
+  TORCH_CHECK(dy.is_contiguous(at::MemoryFormat::ChannelsLast) &&
+              w.is_contiguous(at::MemoryFormat::ChannelsLast) &&
+              dx.is_contiguous(at::MemoryFormat::ChannelsLast), "igemm_conv_dgrad: channels_last operands");
+  const int NB = (int)dx.size(0), Cin = (int)dx.size(1), H = (int)dx.size(2), W = (int)dx.size(3);
+  const int Cout = (int)w.size(0), KH = (int)w.size(2), KW = (int)w.size(3);
+  const int OH = (H + 2 * (int)pad_h - KH) / (int)stride + 1;
+  const int OW = (W + 2 * (int)pad_w - KW) / (int)stride + 1;
+  TORCH_CHECK(w.size(1) == Cin && dy.size(0) == NB && dy.size(1) == Cout && dy.size(2) == OH &&
+              dy.size(3) == OW, "igemm_conv_dgrad: shapes");
+  c10::cuda::CUDAGuard g(dy.device());
+  const int rc = ddl_igemm_conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), NB, H, W, Cin, Cout,
+                                      KH, KW, (int)pad_h, (int)pad_w, (int)stride, sm_count(),
+                                      cur_stream());
+  if (rc == -1) return false;
+  check(rc, "igemm_conv_dgrad");
+  return true;
+}
+// out[M,N] (bf16 or fp32; += if accumulate) = A[K,M]^T B[K,N] through the zero fp32 workspace `ws`
+bool wgrad_gemm(at::Tensor A, at::Tensor B, at::Tensor ws, at::Tensor tickets, at::Tensor out,
+                bool accumulate) {
+  TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && out.dim() == 2 && is_bf16(A) && is_bf16(B));
+  TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1 && out.stride(1) == 1);
+  TORCH_CHECK(ws.scalar_type() == at::kFloat && tickets.scalar_type() == at::kInt);
+  const int K = (int)A.size(0), M = (int)A.size(1), N = (int)B.size(1);
+  TORCH_CHECK(B.size(0) == K && out.size(0) == M && out.size(1) == N);
+  const int ldd = (int)out.stride(0);
+  TORCH_CHECK(K <= 64 || ws.numel() >= (int64_t)M * ldd, "wgrad_gemm: workspace too small");
+  c10::cuda::CUDAGuard g(A.device());
+  const int rc = ddl_wgrad_gemm(A.data_ptr(), B.data_ptr(), ws.data_ptr<float>(),
+                                (unsigned int*)tickets.data_ptr(), out.data_ptr(), is_bf16(out),
+                                accumulate, M, N, K, (int)A.stride(0), (int)B.stride(0), ldd,
+                                (int)tickets.numel(), sm_count(), cur_stream());
+  if (rc == -1) return false;
+  check(rc, "wgrad_gemm");
+  return true;
+}
+// out: [Cout, Cin, KH, KW] logical with KRSC memory (channels_last), bf16 or fp32
+bool wgrad_conv(at::Tensor dy, at::Tensor x, at::Tensor ws, at::Tensor tickets, at::Tensor out,
+                bool accumulate, int64_t pad_h, int64_t pad_w, int64_t stride) {
+  TORCH_CHECK(dy.dim() == 4 && x.dim() == 4 && out.dim() == 4 && is_bf16(dy) && is_bf16(x));
+  TORCH_CHECK(dy.is_contiguous(at::MemoryFormat::ChannelsLast) &&
+              x.is_contiguous(at::MemoryFormat::ChannelsLast) &&
+              out.is_contiguous(at::MemoryFormat::ChannelsLast), "wgrad_conv: channels_last operands");
+  TORCH_CHECK(ws.scalar_type() == at::kFloat && tickets.scalar_type() == at::kInt);
+  const int NB = (int)x.size(0), Cin = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
+  const int Cout = (int)out.size(0), KH = (int)out.size(2), KW = (int)out.size(3);
+  TORCH_CHECK(out.size(1) == Cin && dy.size(0) == NB && dy.size(1) == Cout);
+  TORCH_CHECK(ws.numel() >= out.numel(), "wgrad_conv: workspace too small");
+  c10::cuda::CUDAGuard g(x.device());
+  const int rc = ddl_wgrad_conv(dy.data_ptr(), x.data_ptr(), ws.data_ptr<float>(),
+                                (unsigned int*)tickets.data_ptr(), out.data_ptr(), is_bf16(out),
+                                accumulate, NB, H, W, Cin, Cout, KH, KW, (int)pad_h, (int)pad_w,
+                                (int)stride, (int)tickets.numel(), sm_count(), cur_stream());
+  if (rc == -1) return false;
+  check(rc, "wgrad_conv");
+  return true;
+}
 std::string gemm_info() {
   char buf[512];
   ddl_gemm_selftest_info(buf, sizeof(buf));
@@ -708,6 +825,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16_nt_mn", &gemm_bf16_nt_mn);
   m.def("gemm_bf16_tn_bnfold", &gemm_bf16_tn_bnfold);
   m.def("gemm_bf16_tn_bnbwd", &gemm_bf16_tn_bnbwd);
+  m.def("igemm_gemm", &igemm_gemm);
+  m.def("igemm_conv_fprop", &igemm_conv_fprop);
+  m.def("igemm_conv_dgrad", &igemm_conv_dgrad);
+  m.def("wgrad_gemm", &wgrad_gemm);
+  m.def("wgrad_conv", &wgrad_conv);
   m.def("conv_bf16_nhwc", &conv_bf16_nhwc);
   m.def("conv_wgrad_bf16_nhwc", &conv_wgrad_bf16_nhwc);
   m.def("im2col_rows", &im2col_rows);

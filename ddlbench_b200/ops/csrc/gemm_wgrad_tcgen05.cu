@@ -47,11 +47,143 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
   return d;
 }
 
+
+// Where the finished gradient goes.  With `tickets` set, D is a ZERO fp32 workspace shared by the
+// k-splits of a tile: every split adds its partial tile with vector atomics, takes a ticket, and
+// the LAST one converts the sum into `out` (bf16 or fp32, same indexing as D; `accumulate` adds to
+// what is there — micro-batches after the first) and re-zeroes the workspace.  One launch per
+// weight gradient: no memset, no fp32->bf16 copy kernel.
+struct WgradOut {
+  unsigned int* tickets;   // one per (tile, tap), zero on entry, self-resetting; null: plain atomics into D
+  void* out;
+  int out_bf16;
+  int accumulate;
+};
+
+__device__ __forceinline__ void wgrad_store32(const WgradOut& o, size_t idx, const float* v) {
+  if (o.out_bf16) {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(o.out) + idx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = v[8 * j + i];
+      if (o.accumulate) {
+        float g[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dst + 8 * j), g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += g[i];
+      }
+      *reinterpret_cast<bf16x8*>(dst + 8 * j) = pack8(f);
+    }
+  } else {
+    float* dst = reinterpret_cast<float*>(o.out) + idx;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 t = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      if (o.accumulate) {
+        const float4 g = *reinterpret_cast<const float4*>(dst + 4 * j);
+        t.x += g.x; t.y += g.y; t.z += g.z; t.w += g.w;
+      }
+      *reinterpret_cast<float4*>(dst + 4 * j) = t;
+    }
+  }
+}
+
+// Epilogue of both weight-gradient kernels (128 threads, thread = one row of the 128 x BLOCK_N
+// tile).  `row` / `col0`: global coordinates of the tile inside D; `ncols`: valid columns from col0.
+template <int BLOCK_N>
+__device__ __forceinline__ void wgrad_epilogue(uint32_t tmem_base, int warp, int lane, float* D,
+                                               int ldd, int row, int nrows, int col0, int ncols,
+                                               const WgradOut& o, int ticket_idx, int splits) {
+  const int quad = warp & 3;
+  const int et = threadIdx.x - 64;
+  const bool vec_ok = (ldd & 7) == 0 && (col0 & 7) == 0;
+  const bool direct = o.tickets != nullptr && splits == 1;
+#pragma unroll
+  for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * 32), r);
+    const int c0 = cb * 32;
+    if (row < nrows && c0 < ncols) {
+      const size_t idx = (size_t)row * ldd + col0 + c0;
+      if (direct && vec_ok && c0 + 32 <= ncols) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        wgrad_store32(o, idx, v);
+      } else if (direct) {
+        for (int j = 0; j < 32 && c0 + j < ncols; ++j) {
+          float v = __uint_as_float(r[j]);
+          if (o.out_bf16) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(o.out) + idx + j;
+            if (o.accumulate) v += __bfloat162float(*dst);
+            *dst = __float2bfloat16_rn(v);
+          } else {
+            float* dst = reinterpret_cast<float*>(o.out) + idx + j;
+            *dst = o.accumulate ? *dst + v : v;
+          }
+        }
+      } else if (vec_ok && c0 + 32 <= ncols) {
+        float* dst = D + idx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          atomicAdd(reinterpret_cast<float4*>(dst + 4 * j),
+                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+      } else {
+        for (int j = 0; j < 32 && c0 + j < ncols; ++j) atomicAdd(D + idx + j, __uint_as_float(r[j]));
+      }
+    }
+  }
+  if (o.tickets == nullptr || direct) return;
+  __shared__ bool is_last;
+  __threadfence();
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (et == 0) {
+    const unsigned int t = atomicAdd(&o.tickets[ticket_idx], 1u);
+    is_last = (t == (unsigned int)splits - 1);
+    if (is_last) o.tickets[ticket_idx] = 0u;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (!is_last) return;
+  __threadfence();
+  if (row >= nrows) return;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_N && c0 < ncols; c0 += 32) {
+    const size_t idx = (size_t)row * ldd + col0 + c0;
+    if (vec_ok && c0 + 32 <= ncols) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(D + idx + 4 * j));
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        *reinterpret_cast<float4*>(D + idx + 4 * j) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      wgrad_store32(o, idx, v);
+    } else {
+      for (int j = 0; j < 32 && c0 + j < ncols; ++j) {
+        float v = __ldcg(D + idx + j);
+        D[idx + j] = 0.f;
+        if (o.out_bf16) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(o.out) + idx + j;
+          if (o.accumulate) v += __bfloat162float(*dst);
+          *dst = __float2bfloat16_rn(v);
+        } else {
+          float* dst = reinterpret_cast<float*>(o.out) + idx + j;
+          *dst = o.accumulate ? *dst + v : v;
+        }
+      }
+    }
+  }
+}
+
 struct WgradParams {
   float* D;          // [M, N] fp32, accumulated into
   int M, N, K, ldd;
   int kb_per_split;  // k-blocks (of 64 rows) per CTA
   int desc_variant;  // 0: (LBO = MN atom stride, SBO = K group stride); 1: swapped
+  WgradOut o;
 };
 
 template <int BLOCK_N, int kStages>
@@ -157,29 +289,12 @@ gemm_bf16_mn_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else {
     // ------------------------------------------------------------------ epilogue (128 thr)
-    const int quad = warp & 3;
-    const int row = tile_m * BLOCK_M + quad * 32 + lane;
+    const int row = tile_m * BLOCK_M + (warp & 3) * 32 + lane;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-#pragma unroll
-    for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * 32), r);
-      const int col0 = tile_n * BLOCK_N + cb * 32;
-      if (row < wp.M) {
-        float* dst = wp.D + (size_t)row * wp.ldd + col0;
-        if (col0 + 32 <= wp.N && (wp.ldd & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            atomicAdd(reinterpret_cast<float4*>(dst + 4 * j),
-                      make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < wp.N) atomicAdd(dst + j, __uint_as_float(r[j]));
-        }
-      }
-    }
+    const int col0 = tile_n * BLOCK_N;
+    wgrad_epilogue<BLOCK_N>(tmem_base, warp, lane, wp.D, wp.ldd, row, wp.M, col0, wp.N - col0, wp.o,
+                            (int)blockIdx.x, (int)gridDim.y);
   }
   tc_fence_before();
   __syncthreads();
@@ -191,7 +306,7 @@ gemm_bf16_mn_kernel(const __grid_constant__ CUtensorMap map_a,
 
 template <int BLOCK_N, int kStages>
 static int launch_mn(const void* A, const void* B, float* D, int M, int N, int K, int lda, int ldb,
-                     int ldd, int splits, int variant, cudaStream_t st) {
+                     int ldd, int splits, int variant, cudaStream_t st, WgradOut o = WgradOut{}) {
   using L = WgradSmem<BLOCK_N, kStages>;
   CUtensorMap ma, mb;
   int rc;
@@ -210,7 +325,7 @@ static int launch_mn(const void* A, const void* B, float* D, int M, int N, int K
   if (splits > total_kb) splits = total_kb;
   int per = (total_kb + splits - 1) / splits;
   splits = (total_kb + per - 1) / per;            // no empty CTAs
-  WgradParams wp{D, M, N, K, ldd, per, variant};
+  WgradParams wp{D, M, N, K, ldd, per, variant, o};
   const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
   cudaError_t err = launch_pdl((gemm_bf16_mn_kernel<BLOCK_N, kStages>), dim3(tiles, splits),
                                dim3(kThreads), (size_t)L::kDynamic, st, ma, mb, wp);
@@ -264,6 +379,7 @@ struct ConvWgradParams {
   int KW, pad_h, pad_w, stride;
   int TW, TH, TN, tiles_w, tiles_h, total_tiles;
   int tiles_per_split;
+  WgradOut o;
 };
 
 template <int BLOCK_N, int kStages>
@@ -354,24 +470,13 @@ conv_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy,
       __syncwarp();
     }
   } else {
-    const int quad = warp & 3;
-    const int row = tile_m * BLOCK_M + quad * 32 + lane;          // output channel
+    const int row = tile_m * BLOCK_M + (warp & 3) * 32 + lane;    // output channel
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-#pragma unroll
-    for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * 32), r);
-      const int ci0 = tile_n * BLOCK_N + cb * 32;
-      if (row < wp.Cout && ci0 + 32 <= wp.Cin) {
-        float* dst = wp.D + (size_t)row * wp.ldd + (size_t)tap * wp.Cin + ci0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          atomicAdd(reinterpret_cast<float4*>(dst + 4 * j),
-                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
-      }
-    }
+    const int ci0 = tile_n * BLOCK_N;
+    wgrad_epilogue<BLOCK_N>(tmem_base, warp, lane, wp.D, wp.ldd, row, wp.Cout, tap * wp.Cin + ci0,
+                            wp.Cin - ci0, wp.o, (int)(blockIdx.x + gridDim.x * blockIdx.z),
+                            (int)gridDim.y);
   }
   tc_fence_before();
   __syncthreads();
@@ -384,9 +489,10 @@ conv_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy,
 template <int BLOCK_N, int kStages>
 static int launch_conv_wgrad(const void* dy, const void* x, float* D, int NB, int H, int W, int OH,
                              int OW, int Cin, int Cout, int KH, int KW, int pad_h, int pad_w,
-                             int stride, int sms, cudaStream_t st) {
+                             int stride, int sms, cudaStream_t st, WgradOut o = WgradOut{}) {
   using L = WgradSmem<BLOCK_N, kStages>;
   ConvWgradParams wp{};
+  wp.o = o;
   wp.D = D; wp.Cout = Cout; wp.Cin = Cin; wp.ldd = KH * KW * Cin;
   wp.KW = KW; wp.pad_h = pad_h; wp.pad_w = pad_w; wp.stride = stride;
   choose_pixel_box(kMnBox, NB, OH, OW, &wp.TW, &wp.TH, &wp.TN);
@@ -435,4 +541,50 @@ extern "C" int ddl_conv_wgrad_bf16_nhwc(const void* dy, const void* x, float* D,
   if (Cin <= 64)
     return launch_conv_wgrad<64, 4>(dy, x, D, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w, stride, sms, st);
   return launch_conv_wgrad<128, 4>(dy, x, D, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w, stride, sms, st);
+}
+
+// ---- one-launch weight gradients: partial tiles meet in the zero fp32 workspace `ws` (same
+// indexing as the output, at least M*ldd floats), the last k-split of every tile writes the
+// finished gradient to `out` (bf16 or fp32; `accumulate`: add to it) and re-zeroes `ws`.
+// `tickets`: zero-initialised, >= tiles*taps entries, self-resetting.
+extern "C" int ddl_wgrad_gemm(const void* A, const void* B, float* ws, unsigned int* tickets,
+                              void* out, int out_bf16, int accumulate, int M, int N, int K, int lda,
+                              int ldb, int ldd, int max_tickets, int sms, cudaStream_t st) {
+  using namespace ddl::gemm;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda % 8) || (ldb % 8) || (M % 8) || (N % 8)) return -1;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
+       reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return -1;
+  const int bn = N <= 64 ? 64 : 128;
+  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
+  if (tiles > max_tickets) return -1;
+  const int splits = (2 * sms + tiles - 1) / tiles;
+  WgradOut o{tickets, out, out_bf16, accumulate};
+  if (bn == 64) return launch_mn<64, 4>(A, B, ws, M, N, K, lda, ldb, ldd, splits, 0, st, o);
+  return launch_mn<128, 4>(A, B, ws, M, N, K, lda, ldb, ldd, splits, 0, st, o);
+}
+
+extern "C" int ddl_wgrad_conv(const void* dy, const void* x, float* ws, unsigned int* tickets,
+                              void* out, int out_bf16, int accumulate, int NB, int H, int W, int Cin,
+                              int Cout, int KH, int KW, int pad_h, int pad_w, int stride,
+                              int max_tickets, int sms, cudaStream_t st) {
+  using namespace ddl::gemm;
+  if (NB <= 0 || H <= 0 || W <= 0) return 0;
+  if (Cin % 8 || Cout % 8 || KH < 1 || KW < 1 || KH > 7 || KW > 7) return -1;
+  if (stride != 1 && stride != 2) return -1;
+  const int OH = (H + 2 * pad_h - KH) / stride + 1, OW = (W + 2 * pad_w - KW) / stride + 1;
+  if (OH <= 0 || OW <= 0) return -1;
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) |
+       reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return -1;
+  const int bn = Cin <= 64 ? 64 : 128;
+  const int tiles = ((Cout + BLOCK_M - 1) / BLOCK_M) * ((Cin + bn - 1) / bn);
+  if (tiles * KH * KW > max_tickets) return -1;
+  WgradOut o{tickets, out, out_bf16, accumulate};
+  if (bn == 64)
+    return launch_conv_wgrad<64, 4>(dy, x, ws, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w,
+                                    stride, sms, st, o);
+  return launch_conv_wgrad<128, 4>(dy, x, ws, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w,
+                                   stride, sms, st, o);
 }

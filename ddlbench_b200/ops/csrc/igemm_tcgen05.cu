@@ -1,0 +1,634 @@
+// Persistent, warp-specialised implicit-GEMM on the tcgen05 tensor cores — ONE kernel family for
+// every dense convolution forward AND data gradient of the model zoo (and the FC layers):
+//
+//   fprop :  Y[n,oh,ow,:]  = sum_{tap}  X[n, s*oh+kh-ph, s*ow+kw-pw, :] * W[:, kh, kw, :]^T
+//   dgrad :  dX[n,h,w,:]   = sum_{tap} dY[n, (h+ph-kh)/s, (w+pw-kw)/s, :] * W[:, kh, kw, :]
+//   GEMM  :  D[M,N] = A[M,K] B^T   (1x1 convolutions / linear layers: the 1-tap, flat-pixel case)
+//
+// (reference: these run as cuDNN / cuBLAS library kernels picked by PyTorch — e.g.
+//  benchmark/imagenet/gpipemodels/resnet/block.py:66-74 — with BatchNorm statistics as a
+//  separate pass)
+//
+// What is Blackwell-specific here
+//   * A tiles (128 output pixels x 64 reduction channels) are 4-D TMA boxes of the NHWC
+//     activation SHIFTED by the tap offset: the padding halo is zero-filled by the TMA unit, a
+//     strided convolution is the tensor map's element stride, and no im2col buffer exists.
+//   * B (the KRSC filter matrix [Cout][KH*KW*Cin], never transposed or flipped in memory) is
+//     consumed K-major for fprop and MN-MAJOR for dgrad (instruction-descriptor b_major bit +
+//     the canonical SWIZZLE_128B MN-major shared-memory descriptor), so the data gradient reads
+//     the very same weight buffer as the forward pass.
+//   * A stride-2 data gradient is decomposed into its 4 output-parity classes; each class is a
+//     stride-1 problem over the taps of matching parity whose result is TMA-stored through a
+//     strided tensor-map VIEW of dX (no scatter, no zero-insertion).
+//   * Persistent CTAs (one per SM) loop over output tiles with a DOUBLE-BUFFERED TMEM
+//     accumulator: the 4 epilogue warps drain tile i (tcgen05.ld -> bias/ReLU -> bf16 -> swizzled
+//     staging -> TMA store) while the MMA warp already accumulates tile i+1 and the TMA warp
+//     runs ahead through the shared-memory ring across tile boundaries.
+//   * BatchNorm statistics are accumulated per CTA in shared memory over all of its tiles and
+//     flushed once; the last CTA to finish turns them into (mean, invstd), updates the running
+//     statistics and re-zeroes the workspace — the BatchNorm after a convolution needs no
+//     statistics or finalize launch at all.
+//
+// Every spin loop is bounded (mbar_wait traps after ~2 s): a protocol bug cannot hang the GPU.
+#include <cuda.h>
+#include <cstdio>
+#include <cstring>
+
+#include "api.h"
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace ddl {
+namespace gemm {
+
+constexpr int kIgMaxTaps = 49;
+constexpr int kIgStatCap = 2048;     // channels whose statistics fit the per-CTA accumulator
+
+struct IgemmParams {
+  int OW, OH, NB;                 // output pixel space (tiles iterate here)
+  int Nout;                       // GEMM N = output channels
+  int kc_blocks;                  // 64-channel blocks of the reduction per tap
+  int a_step;                     // A coordinate = tile origin * a_step + tap offset
+  int ntaps;
+  int TW, TH, TN, tiles_w, tiles_h, tiles_n, total_tiles;
+  float* col_sums;                // [R][2][Nout] replicated workspace, or null
+  const __nv_bfloat16* bias;      // [Nout] or null
+  int relu;
+  unsigned int* ticket;           // fused BatchNorm finalize (null: sums only)
+  float* stat_out;
+  float* running_mean;
+  float* running_var;
+  float eps, momentum;
+  long long stat_count;           // rows behind the statistics (NB*OH*OW)
+  short tap_dw[kIgMaxTaps], tap_dh[kIgMaxTaps];
+  int tap_bcol[kIgMaxTaps];       // column of the tap's block inside the filter matrix
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// MN-major SWIZZLE_128B descriptor (same encoding as gemm_wgrad_tcgen05.cu, validated there):
+// 64 contiguous N elements per 128-byte row, 8-row K groups 1024 B apart (SBO), 64-element N
+// atoms `lbo` bytes apart.
+__device__ __forceinline__ uint64_t make_mn_sw128_desc(uint32_t smem_addr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BLOCK_N, int kStages, bool kStats>
+struct IgSmem {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;            // 16 KB
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;            // 8 / 16 / 32 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  static constexpr int kOutBytes = BLOCK_M * BLOCK_N * 2;          // one staged bf16 output tile
+  static constexpr int kOutOffset = kRingBytes;
+  static constexpr int kStatOffset = kOutOffset + 2 * kOutBytes;
+  static constexpr int kStatBytes = kStats ? 2 * kIgStatCap * 4 : 0;
+  static constexpr int kBiasOffset = kStatOffset + kStatBytes;
+  static constexpr int kBarOffset = kBiasOffset + BLOCK_N * 4;     // full[], empty[], tfull[2], tempty[2]
+  static constexpr int kTmemPtrOffset = kBarOffset + (2 * kStages + 4) * 8;
+  static constexpr int kTouchedOffset = kTmemPtrOffset + 8;        // 2 x uint32 touched n-tiles
+  static constexpr int kTotal = kTouchedOffset + 16;
+  static constexpr int kDynamic = kTotal + 1024;
+  static_assert(kDynamic <= 232448, "shared memory budget");
+};
+
+template <int BLOCK_N, int kStages, bool kBMn, bool kStats>
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
+                  const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_d,
+                  const __grid_constant__ IgemmParams p) {
+  using L = IgSmem<BLOCK_N, kStages, kStats>;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;          // two accumulators (power of two >= 128)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;           // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOffset);
+  uint32_t* touched = reinterpret_cast<uint32_t*>(smem + L::kTouchedOffset);
+  float* bias_s = reinterpret_cast<float*>(smem + L::kBiasOffset);
+  float* stat_s = reinterpret_cast<float*>(smem + L::kStatOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_k_blocks = p.ntaps * p.kc_blocks;
+
+  pdl_trigger();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_d);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tfull_bar[0], 1);
+    mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 4);
+    mbar_init(&tempty_bar[1], 4);
+    touched[0] = touched[1] = 0u;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  if (kStats && warp >= 2) {
+    for (int i = threadIdx.x - 64; i < 2 * kIgStatCap; i += 128) stat_s[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();      // everything above overlapped the previous grid; from here we read its output
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int tile_n = tile % p.tiles_n;
+        const int tp = tile / p.tiles_n;
+        const int w0 = (tp % p.tiles_w) * p.TW;
+        const int h0 = ((tp / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (tp / (p.tiles_w * p.tiles_h)) * p.TN;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int aw = w0 * p.a_step + p.tap_dw[t];
+          const int ah = h0 * p.a_step + p.tap_dh[t];
+          const int bcol = p.tap_bcol[t];
+          for (int cb = 0; cb < p.kc_blocks; ++cb, ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* a_dst = smem + s * L::kStageBytes;
+            uint8_t* b_dst = a_dst + L::kABytes;
+            mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
+            tma_load_4d(a_dst, &map_a, &full_bar[s], cb * BLOCK_K, aw, ah, n0);
+            if (kBMn) {
+#pragma unroll
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_2d(b_dst + j * 8192, &map_b, &full_bar[s],
+                            bcol + tile_n * BLOCK_N + j * 64, cb * BLOCK_K);
+            } else {
+              tma_load_2d(b_dst, &map_b, &full_bar[s], bcol + cb * BLOCK_K, tile_n * BLOCK_N);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, kBMn ? 1 : 0);
+    uint32_t it = 0, iter = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+      const uint32_t acc = iter & 1, acc_ph = (iter >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_ph ^ 1);          // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABytes;
+          const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // A: +32 B along K inside the swizzle atom; B K-major: same; B MN-major: 16 K rows
+            // = 2048 B further down every 8 KB box
+            const uint64_t bdesc = kBMn ? make_mn_sw128_desc(b_addr + k * (UMMA_K * 128), 8192)
+                                        : make_kmajor_sw128_desc(b_addr) + (uint64_t)(k * 2);
+            umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (kb == num_k_blocks - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (128 threads)
+    const int et = threadIdx.x - 64;
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;           // output pixel of the tile held by this thread
+    const int lw = row % p.TW, lh = (row / p.TW) % p.TH, ln = row / (p.TW * p.TH);
+    uint32_t iter = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+      const uint32_t acc = iter & 1, acc_ph = (iter >> 1) & 1;
+      const int tile_n = tile % p.tiles_n;
+      const int tp = tile / p.tiles_n;
+      const int w0 = (tp % p.tiles_w) * p.TW;
+      const int h0 = ((tp / p.tiles_w) % p.tiles_h) * p.TH;
+      const int n0 = (tp / (p.tiles_w * p.tiles_h)) * p.TN;
+      const bool valid = (w0 + lw < p.OW) && (h0 + lh < p.OH) && (n0 + ln < p.NB);
+      if (p.bias) {
+        for (int i = et; i < BLOCK_N; i += 128) {
+          const int col = tile_n * BLOCK_N + i;
+          bias_s[i] = col < p.Nout ? __bfloat162float(p.bias[col]) : 0.f;
+        }
+      }
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      // staging buffer `acc` was last read by the TMA store of tile iter-2
+      if (et == 0 && iter >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint8_t* stage = smem + L::kOutOffset + acc * L::kOutBytes;
+#pragma unroll
+      for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N + (uint32_t)(cb * 32), r);
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(r[i]);
+          if (p.bias) v += bias_s[cb * 32 + i];
+          if (p.relu) v = fmaxf(v, 0.f);
+          f[i] = valid ? v : 0.f;              // rows outside the image contribute nothing
+        }
+        uint8_t* region = stage + (cb / 2) * (BLOCK_M * 128);
+        const int chunk0 = (cb & 1) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          bf16x8 pk = pack8(f + j * 8);
+          const int chunk = (chunk0 + j) ^ (row & 7);
+          *reinterpret_cast<bf16x8*>(region + row * 128 + chunk * 16) = pk;
+        }
+      }
+      // accumulator drained: hand it back to the MMA warp (one arrival per epilogue warp)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+#pragma unroll
+        for (int h = 0; h < BLOCK_N / 64; ++h)
+          if (tile_n * BLOCK_N + h * 64 < p.Nout)
+            tma_store_4d(&map_d, stage + h * (BLOCK_M * 128), tile_n * BLOCK_N + h * 64, w0, h0, n0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (kStats && p.col_sums) {
+        // per-channel sum / sum-of-squares of the (bf16-rounded) tile into the CTA accumulator
+        constexpr int kPairs = BLOCK_N / 2;
+        constexpr int kGroups = 128 / kPairs;
+        constexpr int kRowsPer = BLOCK_M / kGroups;
+        const int pair = et % kPairs, grp = et / kPairs;
+        const int c = pair * 2;
+        const uint8_t* region = stage + (c / 64) * (BLOCK_M * 128);
+        const int cc = c % 64;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < kRowsPer; ++rr) {
+          const int r_ = grp * kRowsPer + rr;
+          const int chunk = (cc >> 3) ^ (r_ & 7);
+          const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(
+              region + r_ * 128 + chunk * 16 + (cc & 7) * 2);
+          const float2 fv = __bfloat1622float2(v);
+          s0 += fv.x; s1 += fv.y;
+          q0 = fmaf(fv.x, fv.x, q0); q1 = fmaf(fv.y, fv.y, q1);
+        }
+        const int col = tile_n * BLOCK_N + c;
+        if (col + 1 < kIgStatCap) {
+          atomicAdd(&stat_s[col], s0);
+          atomicAdd(&stat_s[col + 1], s1);
+          atomicAdd(&stat_s[kIgStatCap + col], q0);
+          atomicAdd(&stat_s[kIgStatCap + col + 1], q1);
+        }
+        if (et == 0) touched[tile_n >> 5] |= 1u << (tile_n & 31);
+      }
+    }
+    if (kStats && p.col_sums) {
+      // flush this CTA's partial sums (one vector of atomics per touched n-tile), then let the
+      // last CTA of the grid finalize the statistics
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* cs = p.col_sums + (size_t)(blockIdx.x % DDL_BN_REPLICAS) * 2 * p.Nout;
+      for (int nt = 0; nt < p.tiles_n; ++nt) {
+        if (!((touched[nt >> 5] >> (nt & 31)) & 1u)) continue;
+        for (int i = et; i < BLOCK_N; i += 128) {
+          const int col = nt * BLOCK_N + i;
+          if (col < p.Nout) {
+            atomicAdd(&cs[col], stat_s[col]);
+            atomicAdd(&cs[p.Nout + col], stat_s[kIgStatCap + col]);
+          }
+        }
+      }
+      if (p.ticket) {
+        __shared__ bool is_last;
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const unsigned int t = atomicAdd(p.ticket, 1u);
+          is_last = (t == gridDim.x - 1);
+          if (is_last) *p.ticket = 0u;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (is_last) {
+          __threadfence();
+          const float inv_m = 1.f / (float)p.stat_count;
+          for (int c = et; c < p.Nout; c += 128) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int r = 0; r < DDL_BN_REPLICAS; ++r) {
+              float* pp = p.col_sums + (size_t)r * 2 * p.Nout;
+              s += __ldcg(pp + c);
+              q += __ldcg(pp + p.Nout + c);
+              pp[c] = 0.f;
+              pp[p.Nout + c] = 0.f;
+            }
+            const float mean = s * inv_m;
+            const float var = fmaxf(fmaf(-mean, mean, q * inv_m), 0.f);
+            p.stat_out[c] = mean;
+            p.stat_out[p.Nout + c] = rsqrtf(var + p.eps);
+            if (p.running_mean) {
+              const float unbiased =
+                  p.stat_count > 1 ? var * ((float)p.stat_count / (float)(p.stat_count - 1)) : var;
+              p.running_mean[c] = fmaf(p.momentum, mean - p.running_mean[c], p.running_mean[c]);
+              p.running_var[c] = fmaf(p.momentum, unbiased - p.running_var[c], p.running_var[c]);
+            }
+          }
+        }
+      }
+    }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+// Generic 4-D bf16 tensor map: dims {C, W, H, N} (elements), strides of W / H / N in ELEMENTS,
+// box {bc, bw, bh, bn} elements loaded, `step` = element stride on W and H.
+static inline int make_map_4d(CUtensorMap* map, const void* ptr, int64_t C, int64_t W, int64_t H,
+                              int64_t N, int64_t sW, int64_t sH, int64_t sN, int bc, int bw, int bh,
+                              int bn, int step) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -2;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)(bw * step), (cuuint32_t)(bh * step),
+                       (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)step, (cuuint32_t)step, 1};
+  if (box[1] > 256 || box[2] > 256 || box[3] > 256) return -1;
+  if ((strides[0] % 16) || (strides[1] % 16) || (strides[2] % 16)) return -1;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -3;
+}
+
+struct IgTensor {       // NHWC view: extents and element strides (C is contiguous)
+  const void* ptr;
+  int64_t C, W, H, N, sW, sH, sN;
+};
+
+struct IgProblem {
+  IgTensor a, d;        // activation operand, output (tiles iterate over d's W x H x N)
+  int a_step;
+  const void* b;        // filter matrix [b_rows][b_cols], leading dimension ldb
+  int64_t b_rows, b_cols, ldb;
+  int b_mn;             // 0: B[n][k] (K-major, fprop); 1: B[k][n] (MN-major, dgrad)
+  int kc;               // reduction channels per tap
+  int ntaps;
+  short tap_dw[kIgMaxTaps], tap_dh[kIgMaxTaps];
+  int tap_bcol[kIgMaxTaps];
+  float* col_sums;
+  const void* bias;
+  int relu;
+  const DdlBnFinalize* fin;
+};
+
+template <int BLOCK_N, int kStages, bool kBMn, bool kStats>
+static int launch_ig(const IgProblem& q, IgemmParams& p, int sms, cudaStream_t st) {
+  using L = IgSmem<BLOCK_N, kStages, kStats>;
+  CUtensorMap ma, mb, md;
+  int rc;
+  if ((rc = make_map_4d(&ma, q.a.ptr, q.a.C, q.a.W, q.a.H, q.a.N, q.a.sW, q.a.sH, q.a.sN, BLOCK_K,
+                        p.TW, p.TH, p.TN, q.a_step)))
+    return rc;
+  if (kBMn) {
+    if ((rc = make_map_2d(&mb, q.b, q.b_rows, q.b_cols, q.ldb, 64, 64))) return rc;
+  } else {
+    if ((rc = make_map_2d(&mb, q.b, q.b_rows, q.b_cols, q.ldb, BLOCK_K, BLOCK_N))) return rc;
+  }
+  if ((rc = make_map_4d(&md, q.d.ptr, q.d.C, q.d.W, q.d.H, q.d.N, q.d.sW, q.d.sH, q.d.sN, 64, p.TW,
+                        p.TH, p.TN, 1)))
+    return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  p.tiles_n = (int)((q.d.C + BLOCK_N - 1) / BLOCK_N);
+  p.total_tiles = p.tiles_w * p.tiles_h * (int)((q.d.N + p.TN - 1) / p.TN) * p.tiles_n;
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  cudaError_t err = launch_pdl((igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats>), dim3(grid),
+                               dim3(kThreads), (size_t)L::kDynamic, st, ma, mb, md, p);
+  return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
+}
+
+static int run_ig(const IgProblem& q, int sms, cudaStream_t st) {
+  if (q.ntaps < 1 || q.ntaps > kIgMaxTaps) return -1;
+  if ((q.a.C % 8) || (q.d.C % 8) || (q.ldb % 8)) return -1;
+  if ((reinterpret_cast<uintptr_t>(q.a.ptr) | reinterpret_cast<uintptr_t>(q.b) |
+       reinterpret_cast<uintptr_t>(q.d.ptr)) & 15)
+    return -1;
+  IgemmParams p{};
+  p.OW = (int)q.d.W; p.OH = (int)q.d.H; p.NB = (int)q.d.N;
+  p.Nout = (int)q.d.C;
+  p.kc_blocks = (q.kc + BLOCK_K - 1) / BLOCK_K;
+  p.a_step = q.a_step;
+  p.ntaps = q.ntaps;
+  memcpy(p.tap_dw, q.tap_dw, sizeof(p.tap_dw));
+  memcpy(p.tap_dh, q.tap_dh, sizeof(p.tap_dh));
+  memcpy(p.tap_bcol, q.tap_bcol, sizeof(p.tap_bcol));
+  if (q.d.H == 1 && q.d.N == 1) {           // flat GEMM rows: no edge waste
+    p.TW = 128; p.TH = 1; p.TN = 1;
+  } else {
+    choose_pixel_box(128, (int)q.d.N, (int)q.d.H, (int)q.d.W, &p.TW, &p.TH, &p.TN);
+  }
+  if (p.TW * q.a_step > 256 || p.TH * q.a_step > 256) return -1;
+  p.tiles_w = (int)((q.d.W + p.TW - 1) / p.TW);
+  p.tiles_h = (int)((q.d.H + p.TH - 1) / p.TH);
+  const bool stats = q.col_sums != nullptr;
+  if (stats && q.d.C > kIgStatCap) return -1;
+  p.col_sums = q.col_sums;
+  p.bias = (const __nv_bfloat16*)q.bias;
+  p.relu = q.relu;
+  p.stat_count = (long long)q.d.W * q.d.H * q.d.N;
+  if (q.fin && stats) {
+    p.ticket = q.fin->ticket;
+    p.stat_out = q.fin->stat_out;
+    p.running_mean = q.fin->running_mean;
+    p.running_var = q.fin->running_var;
+    p.eps = q.fin->eps;
+    p.momentum = q.fin->momentum;
+  }
+  const bool narrow = q.d.C <= 64;
+  if (q.b_mn) {
+    if (stats) return -1;
+    return narrow ? launch_ig<64, 6, true, false>(q, p, sms, st)
+                  : launch_ig<128, 4, true, false>(q, p, sms, st);
+  }
+  if (stats)
+    return narrow ? launch_ig<64, 6, false, true>(q, p, sms, st)
+                  : launch_ig<128, 4, false, true>(q, p, sms, st);
+  return narrow ? launch_ig<64, 6, false, false>(q, p, sms, st)
+                : launch_ig<128, 4, false, false>(q, p, sms, st);
+}
+
+static inline IgTensor dense_nhwc(const void* ptr, int64_t N, int64_t H, int64_t W, int64_t C) {
+  return IgTensor{ptr, C, W, H, N, C, W * C, H * W * C};
+}
+
+}  // namespace gemm
+}  // namespace ddl
+
+using ddl::gemm::IgProblem;
+using ddl::gemm::IgTensor;
+
+// D[M, N] = A[M, K] op(B) with optional bias/ReLU/BatchNorm statistics (+finalize).
+// b_mn_major = 0: B is [N, K] (K contiguous);  1: B is [K, N] (N contiguous).
+extern "C" int ddl_igemm_gemm(const void* A, const void* B, void* D, int M, int N, int K, int lda,
+                              int ldb, int ldd, int b_mn_major, float* col_sums, const void* bias,
+                              int relu, const DdlBnFinalize* fin, int sms, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda % 8) || (ldd % 8) || (K % 8) || (N % 8)) return -1;
+  IgProblem q{};
+  q.a = IgTensor{A, K, M, 1, 1, lda, (int64_t)lda * M, (int64_t)lda * M};
+  q.d = IgTensor{D, N, M, 1, 1, ldd, (int64_t)ldd * M, (int64_t)ldd * M};
+  q.a_step = 1;
+  q.b = B;
+  q.b_mn = b_mn_major;
+  q.b_rows = b_mn_major ? K : N;
+  q.b_cols = b_mn_major ? N : K;
+  q.ldb = ldb;
+  q.kc = K;
+  q.ntaps = 1;
+  q.col_sums = col_sums; q.bias = bias; q.relu = relu; q.fin = fin;
+  return ddl::gemm::run_ig(q, sms, st);
+}
+
+// y = conv2d(x, w) (+bias, ReLU, BatchNorm statistics).  x: [NB,H,W,Cin], w: [Cout,KH,KW,Cin] (KRSC),
+// y: [NB,OH,OW,Cout], all bf16.  stride 1 or 2, dilation 1, groups 1.  -1: unsupported shape.
+extern "C" int ddl_igemm_conv_fprop(const void* x, const void* w, void* y, int NB, int H, int W,
+                                    int Cin, int Cout, int KH, int KW, int pad_h, int pad_w,
+                                    int stride, float* col_sums, const void* bias, int relu,
+                                    const DdlBnFinalize* fin, int sms, cudaStream_t st) {
+  if (NB <= 0 || H <= 0 || W <= 0) return 0;
+  if ((Cin % 8) || (Cout % 8) || KH < 1 || KW < 1 || KH * KW > ddl::gemm::kIgMaxTaps) return -1;
+  if (stride != 1 && stride != 2) return -1;
+  const int OH = (H + 2 * pad_h - KH) / stride + 1, OW = (W + 2 * pad_w - KW) / stride + 1;
+  if (OH <= 0 || OW <= 0) return -1;
+  IgProblem q{};
+  const int64_t kdim = (int64_t)KH * KW * Cin;
+  if (KH == 1 && KW == 1 && stride == 1 && pad_h == 0 && pad_w == 0) {
+    const int64_t M = (int64_t)NB * H * W;
+    q.a = IgTensor{x, Cin, M, 1, 1, Cin, M * Cin, M * Cin};
+    q.d = IgTensor{y, Cout, M, 1, 1, Cout, M * Cout, M * Cout};
+  } else {
+    q.a = ddl::gemm::dense_nhwc(x, NB, H, W, Cin);
+    q.d = ddl::gemm::dense_nhwc(y, NB, OH, OW, Cout);
+  }
+  q.a_step = stride;
+  q.b = w; q.b_mn = 0; q.b_rows = Cout; q.b_cols = kdim; q.ldb = kdim;
+  q.kc = Cin;
+  q.ntaps = KH * KW;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) {
+      const int t = kh * KW + kw;
+      q.tap_dw[t] = (short)(kw - pad_w);
+      q.tap_dh[t] = (short)(kh - pad_h);
+      q.tap_bcol[t] = t * Cin;
+    }
+  q.col_sums = col_sums; q.bias = bias; q.relu = relu; q.fin = fin;
+  return ddl::gemm::run_ig(q, sms, st);
+}
+
+// dx = conv2d_backward_data(dy, w).  dy: [NB,OH,OW,Cout], w: [Cout,KH,KW,Cin] (the forward filter,
+// untouched), dx: [NB,H,W,Cin] — fully written.  stride 1 or 2.
+extern "C" int ddl_igemm_conv_dgrad(const void* dy, const void* w, void* dx, int NB, int H, int W,
+                                    int Cin, int Cout, int KH, int KW, int pad_h, int pad_w,
+                                    int stride, int sms, cudaStream_t st) {
+  if (NB <= 0 || H <= 0 || W <= 0) return 0;
+  if ((Cin % 8) || (Cout % 8) || KH < 1 || KW < 1 || KH * KW > ddl::gemm::kIgMaxTaps) return -1;
+  if (stride != 1 && stride != 2) return -1;
+  const int OH = (H + 2 * pad_h - KH) / stride + 1, OW = (W + 2 * pad_w - KW) / stride + 1;
+  if (OH <= 0 || OW <= 0) return -1;
+  const int64_t kdim = (int64_t)KH * KW * Cin;
+  IgProblem q{};
+  q.b = w; q.b_mn = 1; q.b_rows = Cout; q.b_cols = kdim; q.ldb = kdim;
+  q.kc = Cout;
+  q.a_step = 1;
+  if (stride == 1) {
+    if (KH == 1 && KW == 1 && pad_h == 0 && pad_w == 0) {
+      const int64_t M = (int64_t)NB * H * W;
+      q.a = IgTensor{dy, Cout, M, 1, 1, Cout, M * Cout, M * Cout};
+      q.d = IgTensor{dx, Cin, M, 1, 1, Cin, M * Cin, M * Cin};
+    } else {
+      q.a = ddl::gemm::dense_nhwc(dy, NB, OH, OW, Cout);
+      q.d = ddl::gemm::dense_nhwc(dx, NB, H, W, Cin);
+    }
+    q.ntaps = KH * KW;
+    for (int kh = 0; kh < KH; ++kh)
+      for (int kw = 0; kw < KW; ++kw) {
+        const int t = kh * KW + kw;
+        q.tap_dw[t] = (short)(pad_w - kw);
+        q.tap_dh[t] = (short)(pad_h - kh);
+        q.tap_bcol[t] = t * Cin;
+      }
+    return ddl::gemm::run_ig(q, sms, st);
+  }
+  // stride 2: one stride-1 problem per output parity class (a, b), stored through a strided view
+  bool need_zero = false;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      int n = 0;
+      for (int kh = 0; kh < KH; ++kh)
+        for (int kw = 0; kw < KW; ++kw)
+          if (((a + pad_h - kh) % 2 == 0) && ((b + pad_w - kw) % 2 == 0)) ++n;
+      if (n == 0 && (H - a + 1) / 2 > 0 && (W - b + 1) / 2 > 0) need_zero = true;
+    }
+  if (need_zero) {
+    cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)NB * H * W * Cin * 2, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  q.a = ddl::gemm::dense_nhwc(dy, NB, OH, OW, Cout);
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const int Ha = (H - a + 1) / 2, Wb = (W - b + 1) / 2;
+      if (Ha <= 0 || Wb <= 0) continue;
+      q.ntaps = 0;
+      for (int kh = 0; kh < KH; ++kh)
+        for (int kw = 0; kw < KW; ++kw) {
+          const int nh = a + pad_h - kh, nw = b + pad_w - kw;
+          if ((nh % 2) || (nw % 2)) continue;
+          q.tap_dh[q.ntaps] = (short)(nh / 2);
+          q.tap_dw[q.ntaps] = (short)(nw / 2);
+          q.tap_bcol[q.ntaps] = (kh * KW + kw) * Cin;
+          ++q.ntaps;
+        }
+      if (q.ntaps == 0) continue;
+      const __nv_bfloat16* base = (const __nv_bfloat16*)dx + ((int64_t)a * W + b) * Cin;
+      q.d = IgTensor{base, Cin, Wb, Ha, NB, 2 * (int64_t)Cin, 2 * (int64_t)W * Cin,
+                     (int64_t)H * W * Cin};
+      const int rc = ddl::gemm::run_ig(q, sms, st);
+      if (rc) return rc;
+    }
+  return 0;
+}

@@ -132,6 +132,131 @@ class FakeExt:
             cs[Cout:2 * Cout] += (df * df).sum((0, 2, 3))
         return True
 
+    # ---- persistent implicit-GEMM family (igemm_tcgen05.cu) + one-launch weight gradients
+    def _fin(self, cs, N, M, ticket, stat, rm, rv, eps, mom):
+        if ticket is None or stat is None:
+            return
+        v = cs[:R * 2 * N].view(R, 2, N).sum(0)
+        mean = v[0] / M
+        var = (v[1] / M - mean * mean).clamp_min(0)
+        st = _plain(stat).view(-1)
+        st[:N] = mean
+        st[N:2 * N] = torch.rsqrt(var + eps)
+        if rm is not None:
+            _plain(rm).add_(mom * (mean - _plain(rm)))
+            _plain(rv).add_(mom * (var * (M / max(M - 1, 1)) - _plain(rv)))
+        cs.zero_()
+
+    # bool igemm_gemm(A, B, D, b_mn, col_sums?, bias?, relu, ticket?, stat?, rm?, rv?, eps, mom)
+    def igemm_gemm(self, A, B, D, b_mn, col_sums, bias, relu, ticket, stat, rm, rv, eps, mom):
+        self.calls.append("igemm_gemm")
+        A, B, Dp = _plain(A), _plain(B), _plain(D)
+        assert A.dim() == 2 and B.dim() == 2 and Dp.dim() == 2 and A.dtype == BF16 and B.dtype == BF16 and Dp.dtype == BF16
+        assert A.stride(1) == 1 and B.stride(1) == 1 and Dp.stride(1) == 1
+        M, K = A.shape
+        N = Dp.shape[1]
+        assert Dp.shape[0] == M and tuple(B.shape) == ((K, N) if b_mn else (N, K))
+        if K % 8 or N % 8:
+            return False
+        d = A.float() @ (B.float() if b_mn else B.float().t())
+        if bias is not None:
+            d = d + _plain(bias).float()
+        if relu:
+            d = d.relu()
+        Dp.copy_(d.to(BF16))
+        if col_sums is not None:
+            assert not b_mn and N <= 2048
+            cs = _plain(col_sums).view(-1)
+            df = Dp.float()
+            cs[:N] += df.sum(0)
+            cs[N:2 * N] += (df * df).sum(0)
+            self._fin(cs, N, M, ticket, stat, rm, rv, eps, mom)
+        return True
+
+    # bool igemm_conv_fprop(x, w, y, pad_h, pad_w, stride, col_sums?, bias?, relu, ticket?, stat?, rm?, rv?, eps, mom)
+    def igemm_conv_fprop(self, x, w, y, pad_h, pad_w, stride, col_sums, bias, relu, ticket, stat, rm, rv, eps, mom):
+        self.calls.append("igemm_conv_fprop")
+        x, w, yp = _plain(x), _plain(w), _plain(y)
+        assert x.dim() == 4 and w.dim() == 4 and yp.dim() == 4 and x.dtype == BF16 and w.dtype == BF16 and yp.dtype == BF16
+        assert x.is_contiguous(memory_format=CL) and w.is_contiguous(memory_format=CL) and yp.is_contiguous(memory_format=CL)
+        NB, Cin, H, W = x.shape
+        Cout, _, KH, KW = w.shape
+        OH, OW = (H + 2 * pad_h - KH) // stride + 1, (W + 2 * pad_w - KW) // stride + 1
+        assert w.shape[1] == Cin and tuple(yp.shape) == (NB, Cout, OH, OW)
+        if Cin % 8 or Cout % 8 or stride not in (1, 2) or KH * KW > 49:
+            return False
+        d = F.conv2d(x.float(), w.float(), None, stride, (pad_h, pad_w))
+        if bias is not None:
+            d = d + _plain(bias).float().view(1, -1, 1, 1)
+        if relu:
+            d = d.relu()
+        yp.copy_(d.to(BF16))
+        if col_sums is not None:
+            assert Cout <= 2048
+            cs = _plain(col_sums).view(-1)
+            df = yp.float()
+            cs[:Cout] += df.sum((0, 2, 3))
+            cs[Cout:2 * Cout] += (df * df).sum((0, 2, 3))
+            self._fin(cs, Cout, NB * OH * OW, ticket, stat, rm, rv, eps, mom)
+        return True
+
+    # bool igemm_conv_dgrad(dy, w, dx, pad_h, pad_w, stride)
+    def igemm_conv_dgrad(self, dy, w, dx, pad_h, pad_w, stride):
+        self.calls.append("igemm_conv_dgrad")
+        dy, w, dxp = _plain(dy), _plain(w), _plain(dx)
+        assert dy.dtype == BF16 and w.dtype == BF16 and dxp.dtype == BF16
+        assert dy.is_contiguous(memory_format=CL) and w.is_contiguous(memory_format=CL) and dxp.is_contiguous(memory_format=CL)
+        NB, Cin, H, W = dxp.shape
+        Cout, _, KH, KW = w.shape
+        OH, OW = (H + 2 * pad_h - KH) // stride + 1, (W + 2 * pad_w - KW) // stride + 1
+        assert w.shape[1] == Cin and tuple(dy.shape) == (NB, Cout, OH, OW)
+        if Cin % 8 or Cout % 8 or stride not in (1, 2):
+            return False
+        g = torch.ops.aten.convolution_backward(
+            dy.float().contiguous(), torch.zeros(NB, Cin, H, W), w.float().contiguous(), None, [stride, stride],
+            [pad_h, pad_w], [1, 1], False, [0, 0], 1, [True, False, False])[0]
+        dxp.copy_(g.to(BF16))
+        return True
+
+    def _wg_check(self, ws, tickets, need):
+        ws, tickets = _plain(ws), _plain(tickets)
+        assert ws.dtype == torch.float32 and tickets.dtype == torch.int32 and ws.numel() >= need
+        assert float(ws.abs().sum()) == 0.0 and int(tickets.abs().sum()) == 0, "wgrad workspace must be zero"
+
+    # bool wgrad_gemm(A[K, M], B[K, N], ws, tickets, out[M, N], accumulate)
+    def wgrad_gemm(self, A, B, ws, tickets, out, accumulate):
+        self.calls.append("wgrad_gemm")
+        A, B, op = _plain(A), _plain(B), _plain(out)
+        assert A.dim() == 2 and B.dim() == 2 and op.dim() == 2 and A.dtype == BF16 and B.dtype == BF16
+        assert A.stride(1) == 1 and B.stride(1) == 1 and op.stride(1) == 1
+        K, M = A.shape
+        N = B.shape[1]
+        assert B.shape[0] == K and tuple(op.shape) == (M, N)
+        self._wg_check(ws, tickets, M * op.stride(0))
+        if M % 8 or N % 8:
+            return False
+        g = A.float().t() @ B.float()
+        op.copy_((op.float() + g if accumulate else g).to(op.dtype))
+        return True
+
+    # bool wgrad_conv(dy, x, ws, tickets, out [Cout, Cin, KH, KW] KRSC memory, accumulate, pad_h, pad_w, stride)
+    def wgrad_conv(self, dy, x, ws, tickets, out, accumulate, pad_h, pad_w, stride):
+        self.calls.append("wgrad_conv")
+        dy, x, op = _plain(dy), _plain(x), _plain(out)
+        assert dy.dtype == BF16 and x.dtype == BF16 and op.dim() == 4
+        assert dy.is_contiguous(memory_format=CL) and x.is_contiguous(memory_format=CL) and op.is_contiguous(memory_format=CL)
+        NB, Cin, H, W = x.shape
+        Cout, _, KH, KW = op.shape
+        assert op.shape[1] == Cin and dy.shape[0] == NB and dy.shape[1] == Cout
+        self._wg_check(ws, tickets, op.numel())
+        if Cin % 8 or Cout % 8 or stride not in (1, 2):
+            return False
+        g = torch.ops.aten.convolution_backward(
+            dy.float().contiguous(), x.float().contiguous(), torch.zeros(Cout, Cin, KH, KW), None, [stride, stride],
+            [pad_h, pad_w], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+        op.copy_((op.float() + g if accumulate else g).to(op.dtype))
+        return True
+
     # bool im2col_rows(x, a, KH, KW, stride, pad)
     def im2col_rows(self, x, a, KH, KW, stride, pad):
         self.calls.append("im2col_rows")

@@ -30,9 +30,18 @@ def fake(monkeypatch):
         real = getattr(torch, name)
         monkeypatch.setattr(torch, name, (lambda real: lambda *a, **k: fake_cuda(real(*a, **k)))(real))
     monkeypatch.setitem(E.TCGEN05, "conv1x1", True)
+    monkeypatch.setattr(ops, "IGEMM", False)        # the legacy (round-1) kernels; igemm: fake_ig below
+    monkeypatch.setattr(ops, "_WG_WS", {})
     for name in ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "DWCONV", "DGRAD1X1_TCGEN05"):
         monkeypatch.setattr(E, name, True)
     return fe
+
+
+@pytest.fixture
+def fake_ig(fake, monkeypatch):
+    """Default configuration: the persistent implicit-GEMM family."""
+    monkeypatch.setattr(ops, "IGEMM", True)
+    return fake
 
 
 def _t(*shape, cl=True):
@@ -93,6 +102,67 @@ def test_conv_paths(fake, ci, co, k, s, p, expect):
     _close(dx, dx_ref)
     _close(gw, dw_ref)
     assert y.is_contiguous(memory_format=CL)
+
+
+@pytest.mark.parametrize("ci,co,k,s,p", [(64, 64, 3, 1, 1), (64, 128, 3, 2, 1), (64, 128, 1, 2, 0),
+                                          (64, 128, 1, 1, 0), (24, 40, 3, 1, 1), (16, 8, 5, 2, 2)])
+def test_igemm_conv_paths(fake_ig, ci, co, k, s, p):
+    """Default path: fprop + fused statistics/finalize, dgrad from the forward filter, one-launch
+    weight gradient straight into the (bf16, KRSC) gradient view — for every stride / kernel size."""
+    fake = fake_ig
+    torch.manual_seed(0)
+    op = _conv_op(ci, co, k, s, p)
+    x, w = _t(2, ci, 9, 9), _t(co, ci, k, k)
+    sums = torch.zeros(8 * 2 * co)
+    stat = torch.zeros(2 * co)
+    fin = (torch.zeros(1, dtype=torch.int32), stat, torch.zeros(co), torch.ones(co), 1e-5, 0.1)
+    y, fused = op._conv_fwd(x, w, col_sums=sums, bn_finalize=fin, ctx={})
+    dy = _t(*y.shape)
+    gw = fake_cuda(torch.zeros(co, k, k, ci).to(BF16)).permute(0, 3, 1, 2)     # KRSC view, as in the store
+    dx = op._conv_bwd(dy, x, w, True, gw, False)
+    y_ref, dx_ref, dw_ref = _reference(x, w, dy, s, p)
+    assert fused and fake.calls == ["igemm_conv_fprop", "igemm_conv_dgrad",
+                                    "wgrad_gemm" if (k == 1 and s == 1) else "wgrad_conv"]
+    _close(y, y_ref)
+    yf = y.as_subclass(torch.Tensor).float()
+    _close(stat[:co], yf.mean((0, 2, 3)), 1e-2)
+    assert float(sums.as_subclass(torch.Tensor).abs().sum()) == 0.0          # finalize re-zeroes the workspace
+    _close(dx, dx_ref)
+    _close(gw, dw_ref)
+    # accumulate (micro-batches after the first)
+    fake.calls.clear()
+    op._conv_bwd(dy, x, w, False, gw, True)
+    _close(gw, 2 * dw_ref, 4e-2)
+    assert y.is_contiguous(memory_format=CL) and dx.is_contiguous(memory_format=CL)
+
+
+def test_igemm_linear_paths(fake_ig, monkeypatch):
+    fake = fake_ig
+    monkeypatch.setitem(E.TCGEN05, "linear", True)
+    torch.manual_seed(3)
+    lin = nn.Linear(64, 24)
+    op = E.LinearAct("fc", ["x"], "y", lin, E.ACT_RELU, "fc")
+    P = {"fc.weight": fake_cuda(lin.weight.detach().to(BF16)), "fc.bias": fake_cuda(lin.bias.detach().to(BF16))}
+    G = {"fc.weight": fake_cuda(torch.zeros(24, 64).to(BF16)), "fc.bias": fake_cuda(torch.zeros(24).to(BF16))}
+    x = _t(16, 64)
+    ctx = {}
+    y = op.forward(P, {}, [x], ctx, True)
+    dy = _t(16, 24)
+    fe = fake
+    # bias gradient goes through the colsum kernel, which the conv-only fake does not model
+    monkeypatch.setattr(ops, "bias_grad_", lambda dz, out, acc, ws=None: out.copy_(
+        dz.as_subclass(torch.Tensor).float().sum(0).to(out.dtype)))
+    monkeypatch.setattr(ops, "act_bwd", lambda dy_, dy2, y_, act: fake_cuda(
+        (dy_.as_subclass(torch.Tensor).float() * (y_.as_subclass(torch.Tensor) > 0)).to(BF16)))
+    monkeypatch.setattr(ops, "BnWorkspace", lambda c, d: type("W", (), {"sums": torch.zeros(1)})())
+    dx, = op.backward(P, G, [dy], ctx, False, [True])
+    assert fe.calls == ["igemm_gemm", "wgrad_gemm", "igemm_gemm"]
+    xr, wr = x.as_subclass(torch.Tensor).float(), P["fc.weight"].as_subclass(torch.Tensor).float()
+    y_ref = (xr @ wr.t() + P["fc.bias"].as_subclass(torch.Tensor).float()).relu()
+    _close(y, y_ref)
+    dz = dy.as_subclass(torch.Tensor).float() * (y_ref > 0)
+    _close(dx, dz @ wr, 3e-2)
+    _close(G["fc.weight"], dz.t() @ xr, 3e-2)
 
 
 def test_stem_im2col_paths(fake):
@@ -260,20 +330,41 @@ def test_resnet50_through_device_branches_with_every_optin_switch(monkeypatch):
 
     ref_losses, _ = run(False)
     results = {}
-    for label, switches in (("default", ()), ("fold+wgrad1x1", ("BN_FOLD", "WGRAD_TCGEN05", "BN_BWD_FOLD")),
+    lib_convs = []
+
+    class AtenSpy:
+        """torch.ops.aten with the library convolutions recorded (the default path must not use them)."""
+        def __getattr__(self, name):
+            if name in ("convolution", "convolution_backward"):
+                lib_convs.append(name)
+            return getattr(torch.ops.aten, name)
+
+    for label, switches in (("igemm", ()), ("default", ()), ("fold+wgrad1x1", ("BN_FOLD", "WGRAD_TCGEN05", "BN_BWD_FOLD")),
                             ("all", ("CONV3X3_TCGEN05", "WGRAD_TCGEN05", "STEM_IM2COL", "CONV3X3_DGRAD", "BN_FOLD",
                                      "DGRAD1X1_TCGEN05", "BN_BWD_FOLD"))):
         with monkeypatch.context() as mp:
             fe = FullFakeExt()
             mp.setattr(ops, "ext", lambda: fe)
+            mp.setattr(ops, "IGEMM", label == "igemm")
+            mp.setattr(ops, "_WG_WS", {})
+            if label == "igemm":
+                mp.setattr(E, "aten", AtenSpy())
             mp.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
             for name in ("empty", "zeros", "empty_like", "zeros_like"):
                 real = getattr(torch, name)
                 mp.setattr(torch, name, (lambda real: lambda *a, **k: fake_cuda(real(*a, **k)))(real))
             for name in switches:
                 mp.setattr(E, name, True)
-            results[label] = run(True, 2 if label == "all" else 1) + (set(fe.calls),)
+            results[label] = run(True, 2 if label in ("all", "igemm") else 1) + (set(fe.calls),)
     (l_d, w_d, used_d), (l_f, w_f, used_f), (l_a, w_a, used_a) = (results[k] for k in ("default", "fold+wgrad1x1", "all"))
+    # the shipped configuration: every convolution / FC layer on the persistent implicit-GEMM family,
+    # statistics + finalize fused, no library convolution anywhere in the step
+    l_i, w_i, used_i = results["igemm"]
+    assert {"igemm_conv_fprop", "igemm_conv_dgrad", "wgrad_conv", "wgrad_gemm", "igemm_gemm", "im2col_rows",
+            "bn_apply", "bn_bwd_reduce", "bn_bwd_apply", "xent", "sgd_flat"} <= used_i, used_i
+    assert not ({"bn_stats", "bn_finalize", "gemm_bf16_tn", "conv_bf16_nhwc"} & used_i), used_i
+    assert lib_convs == [], lib_convs
+    assert l_i == pytest.approx(ref_losses, rel=3e-2) and torch.isfinite(w_i).all()
     assert "gemm_bf16_tn_bnfold" not in used_d and {"gemm_bf16_tn_bnfold", "gemm_bf16_nt_mn",
                                                     "gemm_bf16_tn_bnbwd"} <= used_f
     assert l_f == pytest.approx(l_d, rel=5e-3) and ((w_f - w_d).norm() / w_d.norm()).item() < 1e-3
@@ -324,6 +415,7 @@ def test_other_families_device_branches_optin_equals_default(monkeypatch, arch, 
         with monkeypatch.context() as mp:
             fe = FullFakeExt()
             mp.setattr(ops, "ext", lambda: fe)
+            mp.setattr(ops, "IGEMM", False)
             mp.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
             for name in ("empty", "zeros", "empty_like", "zeros_like"):
                 real = getattr(torch, name)
