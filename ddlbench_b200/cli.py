@@ -77,7 +77,11 @@ def build_parser() -> argparse.ArgumentParser:
                    help="reference: apex fp16 + loss scale; here compute is bf16 with fp32 master weights already")
     p.add_argument("--loss_scale", "--loss-scale", type=float, default=1.0, dest="loss_scale")
     p.add_argument("--config-path", "--config_path", dest="config_path", default=None, help="pipedream: explicit *_conf.json")
-    p.add_argument("--checkpoint-dir", "--checkpoint_dir", dest="checkpoint_dir", default=None)
+    p.add_argument("--checkpoint-dir", "--checkpoint_dir", dest="checkpoint_dir", default=None,
+                   help="pipedream: write checkpoint.<stage>.pth.tar here after every epoch")
+    p.add_argument("--resume", default=None,
+                   help="pipedream: directory with checkpoint.<stage>.pth.tar files to continue from "
+                        "(weights, fp32 master, momentum, BatchNorm buffers, epoch)")
     p.add_argument("--workdir", default=None)
     p.add_argument("--out", default="out")
     p.add_argument("--master-port", type=int, default=29400)
@@ -105,7 +109,7 @@ def expand(args) -> List[RunConfig]:
                 if fw == "pipedream" and m == "resnet152" and args.model in ("all", "exp2"):
                     continue   # the reference disables this pair; explicit -m resnet152 runs it here
                 extra = {}
-                for k in ("stages", "config_path", "checkpoint_dir", "workdir"):
+                for k in ("stages", "config_path", "checkpoint_dir", "workdir", "resume"):
                     v = getattr(args, k)
                     if v:
                         extra[k] = str(v)
@@ -174,7 +178,8 @@ def _cfg_to_argv(cfg: RunConfig, args) -> List[str]:
     if not cfg.synthetic:
         a.append("-s")
     for k, flag in (("stages", "--stages"), ("config_path", "--config-path"),
-                    ("checkpoint_dir", "--checkpoint-dir"), ("workdir", "--workdir")):
+                    ("checkpoint_dir", "--checkpoint-dir"), ("workdir", "--workdir"),
+                    ("resume", "--resume")):
         if k in cfg.extra:
             a += [flag, cfg.extra[k]]
     a += ["--lr", repr(cfg.lr), "--momentum", repr(cfg.momentum), "--wd", repr(cfg.weight_decay)]

@@ -69,7 +69,9 @@ def build_command(conf: Dict, resume: str = "", dataset: str = "imagenet", port:
     if conf.get("distributed_backend") == "gloo":
         cmd += ["--device", "cpu"]
     if resume:
-        cmd += ["--checkpoint-dir", resume]
+        # continue FROM the checkpoints and keep writing them to the same place (reference:
+        # main_with_runtime.py --resume <prefix> + --checkpoint_dir)
+        cmd += ["--resume", resume, "--checkpoint-dir", resume]
     return cmd
 
 
@@ -96,7 +98,7 @@ def worker_args(conf: Dict, resume: str = "", dataset: str = "imagenet") -> List
         if conf.get("data_dir") and conf["data_dir"] != "synthetic":
             args += ["--data-dir", str(conf["data_dir"])]
         if resume:
-            args += ["--checkpoint-dir", resume]
+            args += ["--resume", resume, "--checkpoint-dir", resume]
         return args
     return build_command(conf, resume, dataset)[build_command(conf, resume, dataset).index("ddlbench_b200.cli"):]
 

@@ -160,6 +160,36 @@ class ParamStore:
             off += sl
         return out
 
+    def gather_full_state(self, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Full (unsharded) fp32 master and momentum.  With a sharded optimizer every rank of the
+        replica group must call this (it all-gathers the per-bucket slices)."""
+        if not self.shard_optimizer:
+            return self.master, self.mom
+        import torch.distributed as dist
+        out = []
+        for src in (self.master, self.mom):
+            parts = [torch.empty_like(src) for _ in range(self.world)]
+            dist.all_gather(parts, src.contiguous(), group=group)
+            full = torch.zeros(self.layout.total, dtype=torch.float32, device=self.device)
+            for b, (mo, ln) in zip(self.layout.buckets, self.master_slices()):
+                for r in range(self.world):
+                    full[b.offset + r * ln: b.offset + (r + 1) * ln].copy_(parts[r][mo:mo + ln])
+            out.append(full)
+        return out[0], out[1]
+
+    def load_full_state(self, master: torch.Tensor, mom: torch.Tensor) -> None:
+        """Inverse of ``gather_full_state``: take this rank's slices of full master / momentum and
+        refresh every weight version from the master."""
+        master = master.to(self.device, torch.float32)
+        mom = mom.to(self.device, torch.float32)
+        assert master.numel() == self.layout.total == mom.numel(), "checkpoint / layout size mismatch"
+        self.load_full_master(master)
+        if self.shard_optimizer:
+            for b, (mo, ln) in zip(self.layout.buckets, self.master_slices()):
+                self.mom[mo:mo + ln].copy_(mom[b.offset + self.rank * ln: b.offset + (self.rank + 1) * ln])
+        else:
+            self.mom.copy_(mom)
+
     def weights(self, version: Optional[int] = None) -> Dict[str, torch.Tensor]:
         return self._w_views[self.latest if version is None else version]
 

@@ -77,12 +77,16 @@ def run_gpipe(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
     first, last = rank == 0, rank == parts - 1 or world == 1
     from ..data import make_source
     src = make_source(cfg, batch, device, 0, 1, "train", num_batches=2)
+    # real-data mode validates on the val split (the synthetic source has none)
+    val_src = src if not hasattr(src, "set_epoch") else make_source(cfg, batch, device, 0, 1, "val", num_batches=2)
     steps = len(src)
     if cfg.steps_per_epoch:
         steps = min(steps, cfg.steps_per_epoch)
     throughputs, elapsed, dev_tputs = [], [], []
     vacc = 0.0
     for epoch in range(cfg.epochs):
+        if hasattr(src, "set_epoch"):
+            src.set_epoch(epoch)
         timer = StepTimer(device)
         tick = time.time()
         timer.start()
@@ -106,7 +110,7 @@ def run_gpipe(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
         n, correct, vl = 0, 0.0, 0.0
         pipe.set_micro_batch(batch)
         for i in range(nval):
-            x, t = _float_batch(src, i, device, dtype)
+            x, t = _float_batch(val_src, i, device, dtype)
             st = pipe.eval_step(x if (first or world == 1) else None, t if last else None)
             if st is not None:
                 vl += float(st[0]) * batch
@@ -210,6 +214,17 @@ def run_pipedream(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
     from ..data import make_source
     src = make_source(cfg, cfg.batch_size, device, topo.rank_in_stage, pcfg.replicas(0), "train",
                       num_batches=2)
+    # validation reads the val split in real-data mode (the synthetic source has no splits)
+    val_src = src if not hasattr(src, "set_epoch") else \
+        make_source(cfg, cfg.batch_size, device, topo.rank_in_stage, pcfg.replicas(0), "val", num_batches=2)
+    start_epoch = 0
+    if cfg.extra.get("resume"):
+        from ..utils.checkpoint import load_stage_checkpoint
+        payload = load_stage_checkpoint(cfg.extra["resume"], topo.stage, rt)
+        if payload is None:
+            raise FileNotFoundError("--resume: no checkpoint.%d.pth.tar under %s" % (topo.stage, cfg.extra["resume"]))
+        start_epoch = int(payload.get("epoch", 0))
+        say("=> loaded checkpoint '%s' (epoch %d)" % (cfg.extra["resume"], start_epoch))
     loader_size = len(src) if hasattr(src, "set_epoch") else len(src) // pcfg.replicas(0)
     if cfg.steps_per_epoch:
         loader_size = min(loader_size, cfg.steps_per_epoch)
@@ -219,7 +234,10 @@ def run_pipedream(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
     say("Running training for %d minibatches" % n)
     epoch_times, dev_tputs = [], []
     meters = {"loss": 0.0, "top1": 0.0, "top5": 0.0, "count": 0}
-    for epoch in range(cfg.epochs):
+    for epoch in range(start_epoch, cfg.epochs):
+        if hasattr(src, "set_epoch"):
+            src.set_epoch(epoch)               # a new shuffle every epoch (DistributedSampler.set_epoch)
+
         def loader():
             for i in range(n):
                 yield _float_batch(src, i, device, dtype)
@@ -294,15 +312,17 @@ def run_pipedream(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
 
         def vloader():
             for i in range(nv):
-                yield _float_batch(src, i, device, dtype)
+                yield _float_batch(val_src, i, device, dtype)
 
         rt.run_eval(vloader() if topo.is_first else None, nv, on_forward=on_eval)
         if topo.is_last and acc["n"]:
             say(logfmt.pd_prec(acc["p1"] / acc["n"], acc["p5"] / acc["n"]))
         ckpt_dir = cfg.extra.get("checkpoint_dir")
-        if ckpt_dir and topo.rank_in_stage == 0:
+        if ckpt_dir:
             from ..utils.checkpoint import save_stage_checkpoint
-            save_stage_checkpoint(ckpt_dir, topo.stage, epoch + 1, cfg.arch, rt)
+            # collective over the stage's replicas (sharded optimizer state is gathered); replica 0 writes
+            save_stage_checkpoint(ckpt_dir, topo.stage, epoch + 1, cfg.arch, rt,
+                                  write=topo.rank_in_stage == 0)
     k = max(len(epoch_times), 1)
     images = n_first * pcfg.replicas(0) * cfg.batch_size
     return {"throughput": images / (sum(epoch_times) / k), "sec_per_epoch": sum(epoch_times) / k,

@@ -175,13 +175,24 @@ class Trainer:
         ex = self.ex
         self.static_x = ex.prepare_input(x).clone()
         self.static_t = target.to(self.device).clone()
-        # warm-up on a side stream: cuDNN autotune, workspace allocation, lazy inits
+        # warm-up on a side stream: workspace allocation, lazy inits.  The three warm-up steps are
+        # real steps (optimizer, momentum, BatchNorm running statistics, fused all-reduce): snapshot
+        # the training state and put it back afterwards, so the first counted step starts from the
+        # initial weights and the run is step-for-step identical to eager mode.
+        st = ex.store
+        snap = [t.clone() for t in [st.master, st.mom] + list(st.w_flat) + list(ex.buffers.values())]
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             for _ in range(3):
                 self._step_eager(self.static_x, self.static_t)
         torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        if self.distributed:
+            dist.barrier(self.group)          # nobody restores while a peer still reads its weights
+        for dst, src in zip([st.master, st.mom] + list(st.w_flat) + list(ex.buffers.values()), snap):
+            dst.copy_(src)
+        del snap
         torch.cuda.synchronize(self.device)
         if self.distributed:
             dist.barrier(self.group)

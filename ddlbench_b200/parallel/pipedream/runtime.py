@@ -171,6 +171,14 @@ class StageRuntime:
                 dist.broadcast(full, src=t.stage_ranks[0], group=self.replica_group)
                 self.ex.store.load_full_master(full)
                 self.ex.store.set_grad_scale(1.0 / t.num_ranks_in_stage)
+        if self.update_interval != 1:
+            # macrobatch: every stage averages the update_interval minibatch gradients it accumulates
+            # (its OWN interval: warm-up depth + 1), like the reference optimizer's
+            # ``p.grad /= update_interval`` (pipedream-fork/runtime/optimizer.py:140-142); the loss
+            # is not pre-scaled (the last stage has interval 1); the 1/replicas of the replica average
+            # rides in the same scale on both the fused and the NCCL reduction path.
+            reps = t.num_ranks_in_stage if self.replica_group is not None else 1
+            self.ex.store.set_grad_scale(1.0 / (reps * self.update_interval))
         if verbose and self.replica_group is not None:
             print("Replicating stage: ranks=%d, module_size=%d" % (
                 t.num_ranks_in_stage, self.ex.num_params() * 4), flush=True)
@@ -295,7 +303,7 @@ class StageRuntime:
                 slot.outs, slot.ctx = ex.forward(slot.x, training=True, version=slot.version)
                 if last:
                     slot.stats, slot.dl = ex.loss(slot.outs[0], slot.target, want_grad=True,
-                                                  grad_scale=1.0 / self.update_interval)
+                                                  grad_scale=1.0)
             slot.fwd = self._capture(slot, body)
             if slot.fwd is None:
                 return None
@@ -404,7 +412,7 @@ class StageRuntime:
             outs, ctx = ex.forward(xs, training=self.training, version=version)
             if t.is_last:
                 stats, dl = ex.loss(outs[0], target, want_grad=self.training,
-                                    grad_scale=1.0 / self.update_interval)
+                                    grad_scale=1.0)
         self.forward_stats.end_compute(tok)
         if t.is_last:
             self.loss_stats = stats
@@ -504,21 +512,20 @@ class StageRuntime:
     def state_dict(self) -> Dict[str, object]:
         """Per-stage checkpoint payload (reference ``checkpoint.<stage>.pth.tar``,
         ``main_with_runtime.py:392-403,580-584``).  Unlike the reference, the optimizer's
-        fp32 master + momentum are saved, so a resumed run continues bit-identically."""
+        fp32 master + momentum are saved, so a resumed run continues bit-identically.  COLLECTIVE
+        over the stage's replicas when the optimizer state is sharded (fused replica reduction):
+        the full master / momentum are gathered so that the file written by replica 0 is complete."""
         st = self.ex.store
+        master, mom = st.gather_full_state(self.replica_group)
         return {"stage": self.topo.stage, "state_dict": self.ex.state_dict(),
-                "master": st.master.detach().cpu().clone(), "momentum": st.mom.detach().cpu().clone(),
+                "master": master.detach().cpu().clone(), "momentum": mom.detach().cpu().clone(),
                 "hyper": st.hyper.detach().cpu().clone()}
 
     def load_state_dict(self, sd: Dict[str, object]) -> None:
         self.ex.load_state_dict(sd["state_dict"])
         st = self.ex.store
-        if "master" in sd and sd["master"].numel() == st.master.numel():
-            st.master.copy_(sd["master"].to(st.device))
-            st.mom.copy_(sd["momentum"].to(st.device))
-            for wf in st.w_flat:
-                if not st.shard_optimizer:
-                    wf.copy_(st.master.to(st.dtype))
+        if "master" in sd and sd["master"].numel() == st.layout.total:
+            st.load_full_state(sd["master"], sd["momentum"])     # re-sliced by rank when sharded
 
     def set_lr(self, lr: float) -> None:
         self.ex.store.set_lr(lr * self.cfg.lr_scale(self.topo.stage))

@@ -18,12 +18,17 @@ def checkpoint_path(directory: str, stage: int) -> str:
 
 
 def save_stage_checkpoint(directory: str, stage: int, epoch: int, arch: str, runtime,
-                          best_prec1: float = 0.0) -> str:
-    os.makedirs(directory, exist_ok=True)
+                          best_prec1: float = 0.0, write: bool = True) -> str:
+    """Every replica of the stage calls this (``runtime.state_dict()`` gathers sharded optimizer
+    state); only the one with ``write=True`` (replica 0) touches the file."""
     payload = runtime.state_dict()
-    payload.update({"epoch": epoch, "arch": arch, "best_prec1": best_prec1})
     path = checkpoint_path(directory, stage)
-    torch.save(payload, path)
+    if write:
+        os.makedirs(directory, exist_ok=True)
+        payload.update({"epoch": epoch, "arch": arch, "best_prec1": best_prec1})
+        tmp = path + ".tmp"
+        torch.save(payload, tmp)
+        os.replace(tmp, path)          # a crash mid-write never corrupts the previous checkpoint
     return path
 
 

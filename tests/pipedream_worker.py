@@ -51,7 +51,8 @@ def main():
     torch.save({"rank": rank, "stage": topo.stage, "losses": losses, "state": sd,
                 "warmup": rt.warmup, "versions": rt.ex.store.versions,
                 "bytes_sent": rt.p2p.bytes_sent, "graph_replays": rt.graph_replays,
-                "graph_slots": len(rt._slots)}, os.path.join(out, f"rank{rank}.pt"))
+                "graph_slots": len(rt._slots), "grad_scale": float(rt.ex.store.hyper[3]),
+                "update_interval": rt.update_interval}, os.path.join(out, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -154,9 +154,46 @@ def test_hybrid_replicated_first_stage(tmp_path):
 
 
 def test_macrobatch_mode(tmp_path):
-    res = _launch([1, 1], tmp_path, {"PD_MACRO": "1"}, iters=6)
-    s0 = [r for r in res if r["stage"] == 0][0]
-    assert s0["versions"] <= 2
+    """Macrobatch (2BW-like): <= 2 versions and EVERY stage averages the minibatch gradients of its
+    own update interval (reference optimizer.py:140-142 divides p.grad by update_interval in each
+    stage's optimizer), not just the last one through the loss."""
+    res = _launch([1, 1, 1], tmp_path, {"PD_MACRO": "1"}, iters=6)
+    by_stage = {r["stage"]: r for r in res}
+    assert by_stage[0]["versions"] <= 2
+    for s, r in by_stage.items():
+        assert r["update_interval"] == r["warmup"] + 1
+        assert r["grad_scale"] == pytest.approx(1.0 / r["update_interval"])
+    assert by_stage[0]["update_interval"] == 3 and by_stage[2]["update_interval"] == 1
+
+
+def test_accumulated_gradients_are_averaged_by_grad_scale():
+    """What the macrobatch scaling relies on: k accumulated minibatch gradients with
+    grad_scale = 1/k give the SGD step of their mean."""
+    torch.manual_seed(0)
+    m = build_model("vgg11", "mnist")
+    xs = [torch.randn(4, 1, 28, 28) for _ in range(3)]
+    ts = [torch.randint(0, 10, (4,)) for _ in range(3)]
+
+    def make():
+        return StageExecutor.from_model(m, device="cpu", dtype=torch.float32, lr=0.5, momentum=0.0)
+
+    a = make()
+    a.store.set_grad_scale(1.0 / 3)
+    for i, (x, t) in enumerate(zip(xs, ts)):
+        o, c = a.forward([x])
+        _, d = a.loss(o[0], t)
+        a.backward(c, [d], accumulate=i > 0, final=i == 2)
+    a.store.sgd_step()
+    b = make()
+    g = torch.zeros_like(b.store.g_flat)
+    for x, t in zip(xs, ts):
+        o, c = b.forward([x])
+        _, d = b.loss(o[0], t)
+        b.backward(c, [d])
+        g += b.store.g_flat
+    b.store.g_flat.copy_(g / 3)
+    b.store.sgd_step()
+    assert torch.allclose(a.store.master, b.store.master, atol=1e-6)
 
 
 def test_stage_graph_slots_match_eager(tmp_path):
@@ -174,3 +211,61 @@ def test_stage_graph_slots_match_eager(tmp_path):
         assert e["losses"] == g["losses"]
         for k, v in e["state"].items():
             assert torch.equal(v, g["state"][k]), k
+
+
+def _cli_pipedream(tmp_path, port, *extra):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), "-m", "ddlbench_b200.cli",
+           "-b", "mnist", "-f", "pipedream", "-g", "2", "-m", "resnet18", "--worker", "--device", "cpu",
+           "--steps", "3", "--eval-steps", "1", "--batch-size", "8", "--stages", "2x1", *extra]
+    env = dict(os.environ, OMP_NUM_THREADS="2", PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    return p.stdout
+
+
+def test_resume_continues_from_checkpoint(tmp_path):
+    """--resume loads weights + fp32 master + momentum + BatchNorm buffers + epoch
+    (main_with_runtime.py:240-262 --resume): one 2-epoch run == 1 epoch, stop, resume to epoch 2."""
+    a, b = tmp_path / "A", tmp_path / "B"
+    _cli_pipedream(tmp_path, 29811, "--epochs", "2", "--checkpoint-dir", str(a))
+    _cli_pipedream(tmp_path, 29812, "--epochs", "1", "--checkpoint-dir", str(b))
+    first = torch.load(b / "checkpoint.0.pth.tar")
+    assert first["epoch"] == 1
+    out = _cli_pipedream(tmp_path, 29813, "--epochs", "2", "--resume", str(b), "--checkpoint-dir", str(b))
+    assert "loaded checkpoint" in out and "Epoch 0:" not in out and "Epoch 1:" in out
+    for stage in (0, 1):
+        x = torch.load(a / ("checkpoint.%d.pth.tar" % stage))
+        y = torch.load(b / ("checkpoint.%d.pth.tar" % stage))
+        assert x["epoch"] == y["epoch"] == 2
+        assert torch.equal(x["master"], y["master"]) and torch.equal(x["momentum"], y["momentum"])
+        for k, v in x["state_dict"].items():
+            assert torch.equal(v, y["state_dict"][k]), k
+    # the weights moved between the epoch-1 and the epoch-2 checkpoint (the run really continued)
+    assert not torch.equal(first["master"], torch.load(b / "checkpoint.0.pth.tar")["master"])
+
+
+def test_sharded_optimizer_state_round_trip():
+    """gather_full_state / load_full_state: what a checkpoint of a fused-replica (sharded) stage
+    goes through — slices of every bucket from every rank and back."""
+    from ddlbench_b200.engine.store import ParamSpec, ParamStore
+    specs = [ParamSpec("a", (5, 7), torch.randn(5, 7), False, 0), ParamSpec("b", (33,), torch.randn(33), False, 1),
+             ParamSpec("c", (4, 3, 3, 3), torch.randn(4, 3, 3, 3), True, 2)]
+    full = ParamStore(specs, "cpu", torch.float32, bucket_elems=40)
+    full.mom.copy_(torch.randn_like(full.mom))
+    world = 2
+    shards = [ParamStore(specs, "cpu", torch.float32, bucket_elems=40, world=world, rank=r, shard_optimizer=True)
+              for r in range(world)]
+    layout_total = shards[0].layout.total
+    m = torch.randn(layout_total)
+    v = torch.randn(layout_total)
+    for s in shards:
+        s.load_full_state(m, v)
+    # reassemble by hand what all_gather would deliver
+    rebuilt_m, rebuilt_v = torch.zeros(layout_total), torch.zeros(layout_total)
+    for bkt, (mo, ln) in zip(shards[0].layout.buckets, shards[0].master_slices()):
+        for r, s in enumerate(shards):
+            rebuilt_m[bkt.offset + r * ln: bkt.offset + (r + 1) * ln] = s.master[mo:mo + ln]
+            rebuilt_v[bkt.offset + r * ln: bkt.offset + (r + 1) * ln] = s.mom[mo:mo + ln]
+    assert torch.equal(rebuilt_m, m) and torch.equal(rebuilt_v, v)
+    assert torch.equal(shards[0].w_flat[0], m)          # every replica holds the full weights
