@@ -33,17 +33,17 @@ BATCH = 32
 
 
 def _gen_tree(datadir, n_train, n_val, classes=8):
-    from PIL import Image
-    import numpy as np
-    rng = np.random.RandomState(1)
-    for split, n in (("train", n_train), ("val", n_val)):
-        per = max(1, n // classes)
-        for c in range(classes):
-            d = os.path.join(datadir, "IMAGENET", split, "class_%d" % c)
-            os.makedirs(d, exist_ok=True)
-            for i in range(per):
-                arr = rng.randint(0, 256, (224, 224, 3), dtype=np.uint8)
-                Image.fromarray(arr, "RGB").save(os.path.join(d, "img_%d.JPEG" % i), quality=90)
+    from jpeg_tree import make_tree
+    make_tree(datadir, n_train, n_val, classes=classes)
+
+
+MIN_ITERS = 200      # iterations per epoch: long enough that DataLoader worker start-up is noise
+
+
+def _cores(gpus):
+    # the reference's run.sh gives 12 or 24 CPU cores per GPU depending on the partition
+    # (run/run/run.sh:65-69); use what this box has, capped at the larger of the two
+    return max(2, min(24, (os.cpu_count() or 8) // max(gpus, 1)))
 
 
 def _parse(out):
@@ -54,22 +54,31 @@ def _parse(out):
 
 
 def _result(metric, gpus, steps, value, per_epoch, script, cores, gen_s, launcher):
+    # the reference's own number IS end to end: host wall clock around DataLoader decode +
+    # augmentation + synchronous H2D of fp32 NCHW tensors + step + loss.item()
+    h2d = BATCH * 3 * 224 * 224 * 4 + BATCH * 8
     return {
         "metric": metric, "value": round(value, 2), "unit": "images/sec", "n_gpus": gpus,
         "steps": steps, "warmup": steps, "ms_per_step": round(BATCH * gpus / value * 1e3, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
-        "data": "synthetic JPEG ImageFolder tree (reference layout), decoded by the "
-                "reference's DataLoader",
+        "data": "synthetic JPEG ImageFolder tree (reference layout, baseline/jpeg_tree.py), decoded "
+                "by the reference's DataLoader",
         "impl": "reference",
         "config": {"model": "resnet50", "global_batch": BATCH * gpus, "per_gpu_batch": BATCH,
                    "parallelism": "single" if gpus == 1 else "dp%d (horovod API)" % gpus,
                    "script": os.path.relpath(script, HERE),
                    "timing": "the reference's own: host wall clock of the epoch's training "
-                             "loop (includes DataLoader JPEG decode + H2D), epoch 2 of 2",
+                             "loop (includes DataLoader JPEG decode + H2D), epoch 2 of 2; "
+                             "`steps` = iterations of that epoch, `warmup` = iterations of the "
+                             "discarded first epoch",
                    "cores_gpu": cores,
                    "horovod": None if gpus == 1 else
                    "baseline/hvd_shim (torch.distributed NCCL stand-in; Horovod is not "
                    "installable offline), launched with %s instead of horovodrun" % launcher},
+        "e2e": {"value": round(value, 2), "unit": "images/sec", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4,
+                "note": "identical to `value`: the reference's metric is its end-to-end loop"},
+        "gpu_launches": None,
         "epoch_throughputs": {str(k): v for k, v in sorted(per_epoch.items())},
         "datagen_seconds": round(gen_s, 1),
     }
@@ -93,7 +102,7 @@ def _run_inprocess(script, gpus, steps, metric):
         while not os.path.exists(ready):
             time.sleep(0.2)
     gen_s = time.time() - t0
-    cores = max(2, min(12, (os.cpu_count() or 8) // max(gpus, 1)))
+    cores = _cores(gpus)
     os.environ.update(DATADIR=tmp, EPOCHS="2", BATCH_SIZE=str(BATCH),
                       LOGINTER=str(max(steps // 2, 1)), CORES_GPU=str(cores))
     sys.path.insert(0, os.path.join(HERE, "hvd_shim"))
@@ -150,7 +159,8 @@ def main(gpus, steps, warmup, metric):
             return {"impl": "reference", "unavailable": "needs %d CUDA device(s)" % gpus}
     except Exception as e:  # noqa: BLE001
         return {"impl": "reference", "unavailable": "torch/torchvision import failed: %s" % e}
-    steps = max(steps, warmup)
+    steps = max(steps, warmup, MIN_ITERS)
+    sys.path.insert(0, HERE)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "RANK" in os.environ:
         try:
             return _run_inprocess(script, int(os.environ["WORLD_SIZE"]), steps, metric)
@@ -165,7 +175,7 @@ def main(gpus, steps, warmup, metric):
         t0 = time.time()
         _gen_tree(tmp, steps * BATCH * gpus, BATCH * gpus)
         gen_s = time.time() - t0
-        cores = max(2, min(12, (os.cpu_count() or 8) // max(gpus, 1)))
+        cores = _cores(gpus)
         env = dict(os.environ, DATADIR=tmp, EPOCHS="2", BATCH_SIZE=str(BATCH),
                    LOGINTER=str(max(steps // 2, 1)), CORES_GPU=str(cores))
         if gpus == 1:

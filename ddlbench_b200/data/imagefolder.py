@@ -68,8 +68,12 @@ class JpegFolder:
         self.pinned = pinned and torch.cuda.is_available()
         self.gpu_decode = gpu_decode and torch.cuda.is_available()
         self.device = torch.device(device)
-        self.pool = ThreadPoolExecutor(max_workers=workers or min(32, os.cpu_count() or 4))
+        nthreads = workers or min(32, os.cpu_count() or 4)
         self.prefetch = max(1, prefetch)
+        # two levels: `pool` assembles whole batches (`prefetch` of them in flight), `img_pool`
+        # decodes the images of a batch in parallel (PIL drops the GIL inside libjpeg / resize)
+        self.pool = ThreadPoolExecutor(max_workers=self.prefetch + 1)
+        self.img_pool = ThreadPoolExecutor(max_workers=nthreads)
         self.epoch = 0
         self._lock = threading.Lock()
         self._pending: Dict[int, object] = {}
@@ -203,9 +207,13 @@ class JpegFolder:
         if self.pinned:
             img, labels = img.pin_memory(), labels.pin_memory()
         out = img.numpy()
-        for k, j in enumerate(sel):
+
+        def one(kj):
+            k, j = kj
             rng = np.random.RandomState((self.seed * 1000003 + epoch * 7919 + int(j)) & 0x7FFFFFFF)
             out[k] = self._load_one(self.samples[j][0], rng)
+
+        list(self.img_pool.map(one, enumerate(sel)))
         return img, labels
 
     def _submit(self, i: int) -> None:
@@ -230,6 +238,7 @@ class JpegFolder:
 
     def close(self) -> None:
         self.pool.shutdown(wait=False, cancel_futures=True)
+        self.img_pool.shutdown(wait=False, cancel_futures=True)
 
 
 # ------------------------------------------------------------------------------------------

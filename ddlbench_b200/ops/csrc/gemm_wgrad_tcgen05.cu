@@ -199,7 +199,7 @@ struct WgradSmem {
 };
 
 template <int BLOCK_N, int kStages>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 gemm_bf16_mn_kernel(const __grid_constant__ CUtensorMap map_a,
                     const __grid_constant__ CUtensorMap map_b, WgradParams wp) {
   using L = WgradSmem<BLOCK_N, kStages>;
@@ -356,8 +356,8 @@ extern "C" int ddl_gemm_bf16_nt_mn(const void* A, const void* B, void* D, int M,
   const int bn = N <= 64 ? 64 : 128;
   const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
   if (splits <= 0) splits = (2 * sms + tiles - 1) / tiles;
-  if (bn == 64) return launch_mn<64, 4>(A, B, (float*)D, M, N, K, lda, ldb, ldd, splits, variant, st);
-  return launch_mn<128, 4>(A, B, (float*)D, M, N, K, lda, ldb, ldd, splits, variant, st);
+  if (bn == 64) return launch_mn<64, 3>(A, B, (float*)D, M, N, K, lda, ldb, ldd, splits, variant, st);
+  return launch_mn<128, 3>(A, B, (float*)D, M, N, K, lda, ldb, ldd, splits, variant, st);
 }
 
 // =====================================================================================
@@ -383,7 +383,7 @@ struct ConvWgradParams {
 };
 
 template <int BLOCK_N, int kStages>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 conv_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy,
                        const __grid_constant__ CUtensorMap map_x, ConvWgradParams wp) {
   using L = WgradSmem<BLOCK_N, kStages>;
@@ -539,8 +539,8 @@ extern "C" int ddl_conv_wgrad_bf16_nhwc(const void* dy, const void* x, float* D,
        reinterpret_cast<uintptr_t>(D)) & 15)
     return -1;
   if (Cin <= 64)
-    return launch_conv_wgrad<64, 4>(dy, x, D, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w, stride, sms, st);
-  return launch_conv_wgrad<128, 4>(dy, x, D, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w, stride, sms, st);
+    return launch_conv_wgrad<64, 3>(dy, x, D, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w, stride, sms, st);
+  return launch_conv_wgrad<128, 3>(dy, x, D, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w, stride, sms, st);
 }
 
 // ---- one-launch weight gradients: partial tiles meet in the zero fp32 workspace `ws` (same
@@ -561,8 +561,8 @@ extern "C" int ddl_wgrad_gemm(const void* A, const void* B, float* ws, unsigned 
   if (tiles > max_tickets) return -1;
   const int splits = (2 * sms + tiles - 1) / tiles;
   WgradOut o{tickets, out, out_bf16, accumulate};
-  if (bn == 64) return launch_mn<64, 4>(A, B, ws, M, N, K, lda, ldb, ldd, splits, 0, st, o);
-  return launch_mn<128, 4>(A, B, ws, M, N, K, lda, ldb, ldd, splits, 0, st, o);
+  if (bn == 64) return launch_mn<64, 3>(A, B, ws, M, N, K, lda, ldb, ldd, splits, 0, st, o);
+  return launch_mn<128, 3>(A, B, ws, M, N, K, lda, ldb, ldd, splits, 0, st, o);
 }
 
 extern "C" int ddl_wgrad_conv(const void* dy, const void* x, float* ws, unsigned int* tickets,
@@ -583,8 +583,8 @@ extern "C" int ddl_wgrad_conv(const void* dy, const void* x, float* ws, unsigned
   if (tiles * KH * KW > max_tickets) return -1;
   WgradOut o{tickets, out, out_bf16, accumulate};
   if (bn == 64)
-    return launch_conv_wgrad<64, 4>(dy, x, ws, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w,
+    return launch_conv_wgrad<64, 3>(dy, x, ws, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w,
                                     stride, sms, st, o);
-  return launch_conv_wgrad<128, 4>(dy, x, ws, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w,
+  return launch_conv_wgrad<128, 3>(dy, x, ws, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w,
                                    stride, sms, st, o);
 }

@@ -20,10 +20,17 @@
 //   * A stride-2 data gradient is decomposed into its 4 output-parity classes; each class is a
 //     stride-1 problem over the taps of matching parity whose result is TMA-stored through a
 //     strided tensor-map VIEW of dX (no scatter, no zero-insertion).
-//   * Persistent CTAs (one per SM) loop over output tiles with a DOUBLE-BUFFERED TMEM
-//     accumulator: the 4 epilogue warps drain tile i (tcgen05.ld -> bias/ReLU -> bf16 -> swizzled
-//     staging -> TMA store) while the MMA warp already accumulates tile i+1 and the TMA warp
-//     runs ahead through the shared-memory ring across tile boundaries.
+//   * Every CTA owns a CHUNK of consecutive pixel tiles of one output-channel tile and loops over
+//     them with a DOUBLE-BUFFERED TMEM accumulator: the 4 epilogue warps drain tile i
+//     (tcgen05.ld -> bias/ReLU -> bf16 -> swizzled staging -> TMA store) while the MMA warp already
+//     accumulates tile i+1 and the TMA warp runs ahead through the shared-memory ring across tile
+//     boundaries.  CTAs are ~100 KB of shared memory so TWO are co-resident per SM (8 epilogue
+//     warps per SM; any two tensor-core kernels of the step can share an SM, which keeps the
+//     weight-gradient kernels on the side stream overlapping with the main stream), and the chunks
+//     are handed out by the hardware block scheduler (more chunks than slots: no stragglers when a
+//     co-running kernel holds some SMs).  (v1 of this kernel was one 214 KB persistent CTA per SM:
+//     per layer it was faster, inside the training graph it serialised against the side stream —
+//     profiles/r2/.)
 //   * BatchNorm statistics are accumulated per CTA in shared memory over all of its tiles and
 //     flushed once; the last CTA to finish turns them into (mean, invstd), updates the running
 //     statistics and re-zeroes the workspace — the BatchNorm after a convolution needs no
@@ -42,7 +49,6 @@ namespace ddl {
 namespace gemm {
 
 constexpr int kIgMaxTaps = 49;
-constexpr int kIgStatCap = 2048;     // channels whose statistics fit the per-CTA accumulator
 
 struct IgemmParams {
   int OW, OH, NB;                 // output pixel space (tiles iterate here)
@@ -50,7 +56,7 @@ struct IgemmParams {
   int kc_blocks;                  // 64-channel blocks of the reduction per tap
   int a_step;                     // A coordinate = tile origin * a_step + tap offset
   int ntaps;
-  int TW, TH, TN, tiles_w, tiles_h, tiles_n, total_tiles;
+  int TW, TH, TN, tiles_w, tiles_h, tiles_n, pix_tiles, tiles_per_cta;
   float* col_sums;                // [R][2][Nout] replicated workspace, or null
   const __nv_bfloat16* bias;      // [Nout] or null
   int relu;
@@ -84,24 +90,23 @@ __device__ __forceinline__ uint64_t make_mn_sw128_desc(uint32_t smem_addr, uint3
 template <int BLOCK_N, int kStages, bool kStats>
 struct IgSmem {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;            // 16 KB
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;            // 8 / 16 / 32 KB
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;            // 8 / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRingBytes = kStages * kStageBytes;
-  static constexpr int kOutBytes = BLOCK_M * BLOCK_N * 2;          // one staged bf16 output tile
+  static constexpr int kOutBytes = BLOCK_M * BLOCK_N * 2;          // the staged bf16 output tile
   static constexpr int kOutOffset = kRingBytes;
-  static constexpr int kStatOffset = kOutOffset + 2 * kOutBytes;
-  static constexpr int kStatBytes = kStats ? 2 * kIgStatCap * 4 : 0;
+  static constexpr int kStatOffset = kOutOffset + kOutBytes;
+  static constexpr int kStatBytes = kStats ? 2 * BLOCK_N * 4 : 0;  // this CTA's n-tile only
   static constexpr int kBiasOffset = kStatOffset + kStatBytes;
   static constexpr int kBarOffset = kBiasOffset + BLOCK_N * 4;     // full[], empty[], tfull[2], tempty[2]
   static constexpr int kTmemPtrOffset = kBarOffset + (2 * kStages + 4) * 8;
-  static constexpr int kTouchedOffset = kTmemPtrOffset + 8;        // 2 x uint32 touched n-tiles
-  static constexpr int kTotal = kTouchedOffset + 16;
+  static constexpr int kTotal = kTmemPtrOffset + 16;
   static constexpr int kDynamic = kTotal + 1024;
-  static_assert(kDynamic <= 232448, "shared memory budget");
+  static_assert(kDynamic <= 113 * 1024, "two CTAs must fit in one SM's shared memory");
 };
 
 template <int BLOCK_N, int kStages, bool kBMn, bool kStats>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_d,
@@ -116,13 +121,17 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
   uint64_t* tfull_bar = empty_bar + kStages;           // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOffset);
-  uint32_t* touched = reinterpret_cast<uint32_t*>(smem + L::kTouchedOffset);
   float* bias_s = reinterpret_cast<float*>(smem + L::kBiasOffset);
   float* stat_s = reinterpret_cast<float*>(smem + L::kStatOffset);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_k_blocks = p.ntaps * p.kc_blocks;
+  // this CTA: n-tile blockIdx.x (fastest: CTAs sharing an A tile run together, L2 reuse), pixel
+  // tiles [tp0, tp1)
+  const int tile_n = blockIdx.x;
+  const int tp0 = blockIdx.y * p.tiles_per_cta;
+  const int tp1 = min(tp0 + p.tiles_per_cta, p.pix_tiles);
 
   pdl_trigger();
   if (warp == 0 && lane == 0) {
@@ -137,12 +146,11 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
     mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], 4);
     mbar_init(&tempty_bar[1], 4);
-    touched[0] = touched[1] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
   if (kStats && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < 2 * kIgStatCap; i += 128) stat_s[i] = 0.f;
+    for (int i = threadIdx.x - 64; i < 2 * BLOCK_N; i += 128) stat_s[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -154,9 +162,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int tile_n = tile % p.tiles_n;
-        const int tp = tile / p.tiles_n;
+      for (int tp = tp0; tp < tp1; ++tp) {
         const int w0 = (tp % p.tiles_w) * p.TW;
         const int h0 = ((tp / p.tiles_w) % p.tiles_h) * p.TH;
         const int n0 = (tp / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -188,7 +194,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, kBMn ? 1 : 0);
     uint32_t it = 0, iter = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+    for (int tp = tp0; tp < tp1; ++tp, ++iter) {
       const uint32_t acc = iter & 1, acc_ph = (iter >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_ph ^ 1);          // epilogue has drained this accumulator
       tc_fence_after();
@@ -223,26 +229,26 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
     const int row = quad * 32 + lane;           // output pixel of the tile held by this thread
     const int lw = row % p.TW, lh = (row / p.TW) % p.TH, ln = row / (p.TW * p.TH);
     uint32_t iter = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+    if (p.bias) {
+      for (int i = et; i < BLOCK_N; i += 128) {
+        const int col = tile_n * BLOCK_N + i;
+        bias_s[i] = col < p.Nout ? __bfloat162float(p.bias[col]) : 0.f;
+      }
+    }
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;     // this thread's share of the column sums
+    for (int tp = tp0; tp < tp1; ++tp, ++iter) {
       const uint32_t acc = iter & 1, acc_ph = (iter >> 1) & 1;
-      const int tile_n = tile % p.tiles_n;
-      const int tp = tile / p.tiles_n;
       const int w0 = (tp % p.tiles_w) * p.TW;
       const int h0 = ((tp / p.tiles_w) % p.tiles_h) * p.TH;
       const int n0 = (tp / (p.tiles_w * p.tiles_h)) * p.TN;
       const bool valid = (w0 + lw < p.OW) && (h0 + lh < p.OH) && (n0 + ln < p.NB);
-      if (p.bias) {
-        for (int i = et; i < BLOCK_N; i += 128) {
-          const int col = tile_n * BLOCK_N + i;
-          bias_s[i] = col < p.Nout ? __bfloat162float(p.bias[col]) : 0.f;
-        }
-      }
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
-      // staging buffer `acc` was last read by the TMA store of tile iter-2
-      if (et == 0 && iter >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      // the staging buffer was last read by the TMA store (and the statistics pass) of the
+      // previous tile
+      if (et == 0 && iter >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      uint8_t* stage = smem + L::kOutOffset + acc * L::kOutBytes;
+      uint8_t* stage = smem + L::kOutOffset;
 #pragma unroll
       for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
         uint32_t r[32];
@@ -278,7 +284,8 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (kStats && p.col_sums) {
-        // per-channel sum / sum-of-squares of the (bf16-rounded) tile into the CTA accumulator
+        // per-channel sum / sum-of-squares of the (bf16-rounded) tile: every thread owns a column
+        // pair and a group of rows, and keeps its partial sums in registers across the CTA's tiles
         constexpr int kPairs = BLOCK_N / 2;
         constexpr int kGroups = 128 / kPairs;
         constexpr int kRowsPer = BLOCK_M / kGroups;
@@ -286,8 +293,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
         const int c = pair * 2;
         const uint8_t* region = stage + (c / 64) * (BLOCK_M * 128);
         const int cc = c % 64;
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
+#pragma unroll 16
         for (int rr = 0; rr < kRowsPer; ++rr) {
           const int r_ = grp * kRowsPer + rr;
           const int chunk = (cc >> 3) ^ (r_ & 7);
@@ -297,29 +303,25 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
           s0 += fv.x; s1 += fv.y;
           q0 = fmaf(fv.x, fv.x, q0); q1 = fmaf(fv.y, fv.y, q1);
         }
-        const int col = tile_n * BLOCK_N + c;
-        if (col + 1 < kIgStatCap) {
-          atomicAdd(&stat_s[col], s0);
-          atomicAdd(&stat_s[col + 1], s1);
-          atomicAdd(&stat_s[kIgStatCap + col], q0);
-          atomicAdd(&stat_s[kIgStatCap + col + 1], q1);
-        }
-        if (et == 0) touched[tile_n >> 5] |= 1u << (tile_n & 31);
       }
     }
     if (kStats && p.col_sums) {
-      // flush this CTA's partial sums (one vector of atomics per touched n-tile), then let the
-      // last CTA of the grid finalize the statistics
+      // combine the row groups in shared memory, flush this CTA's sums with one vector of atomics,
+      // then let the last CTA of the grid finalize the statistics
+      {
+        const int c = (et % (BLOCK_N / 2)) * 2;
+        atomicAdd(&stat_s[c], s0);
+        atomicAdd(&stat_s[c + 1], s1);
+        atomicAdd(&stat_s[BLOCK_N + c], q0);
+        atomicAdd(&stat_s[BLOCK_N + c + 1], q1);
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      float* cs = p.col_sums + (size_t)(blockIdx.x % DDL_BN_REPLICAS) * 2 * p.Nout;
-      for (int nt = 0; nt < p.tiles_n; ++nt) {
-        if (!((touched[nt >> 5] >> (nt & 31)) & 1u)) continue;
-        for (int i = et; i < BLOCK_N; i += 128) {
-          const int col = nt * BLOCK_N + i;
-          if (col < p.Nout) {
-            atomicAdd(&cs[col], stat_s[col]);
-            atomicAdd(&cs[p.Nout + col], stat_s[kIgStatCap + col]);
-          }
+      float* cs = p.col_sums + (size_t)(blockIdx.y % DDL_BN_REPLICAS) * 2 * p.Nout;
+      for (int i = et; i < BLOCK_N; i += 128) {
+        const int col = tile_n * BLOCK_N + i;
+        if (col < p.Nout) {
+          atomicAdd(&cs[col], stat_s[i]);
+          atomicAdd(&cs[p.Nout + col], stat_s[BLOCK_N + i]);
         }
       }
       if (p.ticket) {
@@ -328,7 +330,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) {
           const unsigned int t = atomicAdd(p.ticket, 1u);
-          is_last = (t == gridDim.x - 1);
+          is_last = (t == gridDim.x * gridDim.y - 1);
           if (is_last) *p.ticket = 0u;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -435,10 +437,20 @@ static int launch_ig(const IgProblem& q, IgemmParams& p, int sms, cudaStream_t s
     attr_set = true;
   }
   p.tiles_n = (int)((q.d.C + BLOCK_N - 1) / BLOCK_N);
-  p.total_tiles = p.tiles_w * p.tiles_h * (int)((q.d.N + p.TN - 1) / p.TN) * p.tiles_n;
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  cudaError_t err = launch_pdl((igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats>), dim3(grid),
-                               dim3(kThreads), (size_t)L::kDynamic, st, ma, mb, md, p);
+  p.pix_tiles = p.tiles_w * p.tiles_h * (int)((q.d.N + p.TN - 1) / p.TN);
+  // chunks: enough CTAs for ~3 rounds of the 2-per-SM slots (the hardware scheduler balances
+  // them), at most 8 tiles each (amortises barrier / TMEM set-up, keeps the epilogue of tile i
+  // under the main loop of tile i+1)
+  const long long total = (long long)p.pix_tiles * p.tiles_n;
+  int per = (int)(total / (6LL * sms));
+  if (per < 1) per = 1;
+  if (per > 8) per = 8;
+  p.tiles_per_cta = per;
+  const int chunks = (p.pix_tiles + per - 1) / per;
+  if (chunks > 65535 || p.tiles_n > 65535) return -1;
+  cudaError_t err = launch_pdl((igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats>),
+                               dim3(p.tiles_n, chunks), dim3(kThreads), (size_t)L::kDynamic, st, ma,
+                               mb, md, p);
   return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
 }
 
@@ -466,7 +478,6 @@ static int run_ig(const IgProblem& q, int sms, cudaStream_t st) {
   p.tiles_w = (int)((q.d.W + p.TW - 1) / p.TW);
   p.tiles_h = (int)((q.d.H + p.TH - 1) / p.TH);
   const bool stats = q.col_sums != nullptr;
-  if (stats && q.d.C > kIgStatCap) return -1;
   p.col_sums = q.col_sums;
   p.bias = (const __nv_bfloat16*)q.bias;
   p.relu = q.relu;
@@ -482,14 +493,14 @@ static int run_ig(const IgProblem& q, int sms, cudaStream_t st) {
   const bool narrow = q.d.C <= 64;
   if (q.b_mn) {
     if (stats) return -1;
-    return narrow ? launch_ig<64, 6, true, false>(q, p, sms, st)
-                  : launch_ig<128, 4, true, false>(q, p, sms, st);
+    return narrow ? launch_ig<64, 3, true, false>(q, p, sms, st)
+                  : launch_ig<128, 2, true, false>(q, p, sms, st);
   }
   if (stats)
-    return narrow ? launch_ig<64, 6, false, true>(q, p, sms, st)
-                  : launch_ig<128, 4, false, true>(q, p, sms, st);
-  return narrow ? launch_ig<64, 6, false, false>(q, p, sms, st)
-                : launch_ig<128, 4, false, false>(q, p, sms, st);
+    return narrow ? launch_ig<64, 3, false, true>(q, p, sms, st)
+                  : launch_ig<128, 2, false, true>(q, p, sms, st);
+  return narrow ? launch_ig<64, 3, false, false>(q, p, sms, st)
+                : launch_ig<128, 2, false, false>(q, p, sms, st);
 }
 
 static inline IgTensor dense_nhwc(const void* ptr, int64_t N, int64_t H, int64_t W, int64_t C) {

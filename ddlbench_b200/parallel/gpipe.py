@@ -156,6 +156,35 @@ class GPipe:
             ex.store.set_lr(lr)
 
     # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _rng_get(device):
+        """RNG state a forward pass on ``device`` draws from (dropout masks)."""
+        device = torch.device(device)
+        if device.type == "cuda":
+            return (torch.get_rng_state(), torch.cuda.get_rng_state(device))
+        return (torch.get_rng_state(), None)
+
+    @staticmethod
+    def _rng_set(device, state) -> None:
+        device = torch.device(device)
+        torch.set_rng_state(state[0])
+        if state[1] is not None:
+            torch.cuda.set_rng_state(state[1], device)
+
+    def _recompute(self, ex, inp, rng):
+        """Re-run a checkpointed forward EXACTLY: same dropout masks (RNG state of the original
+        pass restored, as torchgpipe's checkpointing does), BatchNorm running statistics untouched;
+        the generator continues afterwards from where it was."""
+        now = self._rng_get(ex.device)
+        self._rng_set(ex.device, rng)
+        E.BN_MOMENTUM_SCALE[0] = 0.0
+        try:
+            _, ctx = ex.forward(inp, training=True)
+        finally:
+            E.BN_MOMENTUM_SCALE[0] = 1.0
+            self._rng_set(ex.device, now)
+        return ctx
+
     def _keep_ctx(self, mb: int) -> bool:
         if self.checkpoint == "never":
             return True
@@ -186,7 +215,7 @@ class GPipe:
         M, P = self.chunks, self.num_partitions
         xs = x.chunk(M)
         ts = target.chunk(M)
-        saved: List[List[Tuple[Optional[FwdContext], List[torch.Tensor]]]] = []
+        saved: list = []      # [mb][p] -> (ctx or None, inputs, rng state of the checkpointed pass)
         dls, stats_acc = [], None
         for mb in range(M):
             row = []
@@ -194,8 +223,10 @@ class GPipe:
             for p in range(P):
                 ex = self.execs[p]
                 cur = [c.to(ex.device, non_blocking=True) for c in cur]
+                keep = self._keep_ctx(mb)
+                rng = None if keep else self._rng_get(ex.device)
                 outs, ctx = ex.forward(cur, training=True)
-                row.append((ctx if self._keep_ctx(mb) else None, cur))
+                row.append((ctx if keep else None, cur, rng))
                 cur = outs
             st, dl = self.execs[P - 1].loss(cur[0], ts[mb].to(self.execs[P - 1].device),
                                             grad_scale=1.0 / M)
@@ -207,11 +238,9 @@ class GPipe:
             grads = [dls[mb]]
             for p in reversed(range(P)):
                 ex = self.execs[p]
-                ctx, inp = saved[mb][p]
+                ctx, inp, rng = saved[mb][p]
                 if ctx is None:
-                    E.BN_MOMENTUM_SCALE[0] = 0.0
-                    _, ctx = ex.forward(inp, training=True)
-                    E.BN_MOMENTUM_SCALE[0] = 1.0
+                    ctx = self._recompute(ex, inp, rng)
                 grads = [g.to(ex.device) if g is not None else None for g in grads]
                 grads = ex.backward(ctx, grads, accumulate=not first_bwd, final=(mb == 0))
             first_bwd = False
@@ -245,8 +274,10 @@ class GPipe:
             else:
                 cur = list(pending.wait())
                 pending = self.p2p.post_recv(r - 1, in_specs, "fwd", ring=ring) if mb + 1 < M else None
+            keep = self._keep_ctx(mb)
+            rng = None if keep else self._rng_get(ex.device)
             outs, ctx = ex.forward(cur, training=True)
-            saved.append((ctx if self._keep_ctx(mb) else None, cur))
+            saved.append((ctx if keep else None, cur, rng))
             if last:
                 st, dl = ex.loss(outs[0], ts[mb].to(ex.device), grad_scale=1.0 / M)
                 stats_acc = st.clone() if stats_acc is None else stats_acc + st
@@ -261,11 +292,9 @@ class GPipe:
             else:
                 grads = list(pending.wait())
                 pending = self.p2p.post_recv(r + 1, g_specs, "bwd", ring=3) if mb > 0 else None
-            ctx, inp = saved[mb]
+            ctx, inp, rng = saved[mb]
             if ctx is None:
-                E.BN_MOMENTUM_SCALE[0] = 0.0
-                _, ctx = ex.forward(inp, training=True)
-                E.BN_MOMENTUM_SCALE[0] = 1.0
+                ctx = self._recompute(ex, inp, rng)
             gin = ex.backward(ctx, grads, accumulate=not first_bwd, final=(mb == 0))
             first_bwd = False
             saved[mb] = None

@@ -103,3 +103,24 @@ def test_gpipe_multiprocess_matches_single_process(tmp_path):
     for r in res:
         for k, v in r["state"].items():
             assert torch.allclose(v, sd[k], atol=1e-3, rtol=1e-2), k
+
+
+def test_checkpoint_recompute_reuses_dropout_masks():
+    """torchgpipe restores the RNG state around a recompute; without it a checkpointed VGG (two
+    Dropout layers in the classifier) would back-propagate through different masks than its
+    forward.  checkpoint='always' must give the same update as checkpoint='never'."""
+    import torch
+    from ddlbench_b200.models import build_model
+    from ddlbench_b200.parallel.gpipe import GPipe, balance_by_size
+    torch.manual_seed(0)
+    m = build_model("vgg11", "cifar10")
+    x, t = torch.randn(8, 3, 32, 32), torch.randint(0, 10, (8,))
+    out = []
+    for mode in ("never", "always"):
+        torch.manual_seed(1)
+        pipe = GPipe(m, balance_by_size(2, m), chunks=2, checkpoint=mode, devices=["cpu"] * 2,
+                     dtype=torch.float32, lr=0.1, momentum=0.0)
+        torch.manual_seed(7)
+        pipe.train_step(x, t)
+        out.append(torch.cat([ex.store.master.clone() for ex in pipe.execs.values()]))
+    assert torch.allclose(out[0], out[1], atol=1e-6), (out[0] - out[1]).abs().max()
