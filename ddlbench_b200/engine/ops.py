@@ -362,7 +362,8 @@ class ConvBnAct(Op, _ConvMixin):
             # slower than a separate 4 us finalize launch (the last CTA gathers R*2*N values
             # with 128 threads and every CTA pays a fence + ticket), so this is off by default.
             stat_ready = torch.empty(2 * self.channels, dtype=torch.float32, device=x.device)
-            fin = (self.ws.counter[32:33], stat_ready, B[self.k_rm], B[self.k_rv], self.eps, mom)
+            fin = (self.ws.counter[64:] if ig else self.ws.counter[32:33], stat_ready, B[self.k_rm],
+                   B[self.k_rv], self.eps, mom)
             c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums, bn_finalize=fin, ctx=ctx)
         elif fuse_stats:
             c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums, ctx=ctx)

@@ -155,7 +155,9 @@ class BnWorkspace:
 
     def __init__(self, channels: int, device):
         self.sums = torch.zeros(BN_REPLICAS * 2 * channels, dtype=torch.float32, device=device)
-        self.counter = torch.zeros(64, dtype=torch.int32, device=device)
+        # [0:32) block counters of the BN kernels, [32:64) legacy GEMM ticket, [64:) one finalize
+        # ticket per 64-channel tile for the implicit-GEMM kernels
+        self.counter = torch.zeros(64 + (channels + 63) // 64 + 1, dtype=torch.int32, device=device)
         self.coef = torch.empty(3 * channels, dtype=torch.float32, device=device)
 
 
@@ -576,6 +578,22 @@ def _wgrad_ws(device, numel: int):
     return ent
 
 
+_IG_WS: dict = {}
+_IG_SPLIT_TILES = 148
+
+
+def _ig_ws(device):
+    """Zero fp32 scratch + tickets of the split-K implicit-GEMM launches of one stream (the kernels
+    leave both zero): up to 148 partial 128x128 tiles."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0)
+    ent = _IG_WS.get(key)
+    if ent is None:
+        ent = (torch.zeros(_IG_SPLIT_TILES * 16384, dtype=torch.float32, device=device),
+               torch.zeros(_IG_SPLIT_TILES, dtype=torch.int32, device=device))
+        _IG_WS[key] = ent
+    return ent
+
+
 def igemm_conv_supported(x: torch.Tensor, wshape, stride, padding, dilation, groups,
                          stats_channels: int = 0) -> bool:
     """Shapes the persistent implicit-GEMM kernels take: bf16 NHWC, groups 1, dilation 1, square
@@ -610,7 +628,8 @@ def conv_fprop(x: torch.Tensor, w: torch.Tensor, stride: int, padding: Sequence[
         w = w.contiguous(memory_format=torch.channels_last)
     y = torch.empty((x.shape[0], co, oh, ow), dtype=x.dtype, device=x.device,
                     memory_format=torch.channels_last)
-    if ext().igemm_conv_fprop(x, w, y, ph, pw, stride, col_sums, bias, relu, *_fin_args(bn_finalize)):
+    if ext().igemm_conv_fprop(x, w, y, ph, pw, stride, col_sums, bias, relu, *_fin_args(bn_finalize),
+                              *_ig_ws(x.device)):
         _count()
         return y
     return None
@@ -623,7 +642,7 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int,
         w = w.contiguous(memory_format=torch.channels_last)
     dx = torch.empty(tuple(x_shape), dtype=dy.dtype, device=dy.device,
                      memory_format=torch.channels_last)
-    if ext().igemm_conv_dgrad(dy, w, dx, int(padding[0]), int(padding[1]), stride):
+    if ext().igemm_conv_dgrad(dy, w, dx, int(padding[0]), int(padding[1]), stride, *_ig_ws(dy.device)):
         _count()
         return dx
     return None
@@ -663,7 +682,7 @@ def gemm_ig(a: torch.Tensor, b: torch.Tensor, b_mn: bool = False,
     """D[M, N] = a[M, K] @ (b[N, K]^T if not b_mn else b[K, N]) on the persistent kernel."""
     n = b.shape[1] if b_mn else b.shape[0]
     out = torch.empty((a.shape[0], n), dtype=torch.bfloat16, device=a.device)
-    if ext().igemm_gemm(a, b, out, b_mn, col_sums, bias, relu, *_fin_args(bn_finalize)):
+    if ext().igemm_gemm(a, b, out, b_mn, col_sums, bias, relu, *_fin_args(bn_finalize), *_ig_ws(a.device)):
         _count()
         return out
     return None

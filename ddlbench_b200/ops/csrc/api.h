@@ -129,15 +129,19 @@ int ddl_gemm_bf16_tn_bnbwd(const void* dy, const void* dy2, const void* c, const
                            cudaStream_t st);
 
 // ---- igemm_tcgen05.cu  (persistent implicit-GEMM: every dense conv fprop / dgrad and the FC layers)
+// `fin->ticket` here is an ARRAY with one counter per 128-wide output-channel tile; splitk_*: zero
+// fp32 scratch of `splitk_tiles` x 16384 floats + as many zero tickets (null / 0: never split K).
 int ddl_igemm_gemm(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb,
                    int ldd, int b_mn_major, float* col_sums, const void* bias, int relu,
-                   const DdlBnFinalize* fin, int sms, cudaStream_t st);
+                   const DdlBnFinalize* fin, float* splitk_ws, unsigned int* splitk_tickets,
+                   int splitk_tiles, int sms, cudaStream_t st);
 int ddl_igemm_conv_fprop(const void* x, const void* w, void* y, int NB, int H, int W, int Cin,
                          int Cout, int KH, int KW, int pad_h, int pad_w, int stride, float* col_sums,
-                         const void* bias, int relu, const DdlBnFinalize* fin, int sms,
-                         cudaStream_t st);
+                         const void* bias, int relu, const DdlBnFinalize* fin, float* splitk_ws,
+                         unsigned int* splitk_tickets, int splitk_tiles, int sms, cudaStream_t st);
 int ddl_igemm_conv_dgrad(const void* dy, const void* w, void* dx, int NB, int H, int W, int Cin,
-                         int Cout, int KH, int KW, int pad_h, int pad_w, int stride, int sms,
+                         int Cout, int KH, int KW, int pad_h, int pad_w, int stride,
+                         float* splitk_ws, unsigned int* splitk_tickets, int splitk_tiles, int sms,
                          cudaStream_t st);
 // ---- gemm_wgrad_tcgen05.cu, one-launch weight gradients (self-cleaning fp32 workspace)
 int ddl_wgrad_gemm(const void* A, const void* B, float* ws, unsigned int* tickets, void* out,

@@ -421,10 +421,31 @@ static inline DdlBnFinalize make_fin(const c10::optional<at::Tensor>& ticket,
                        (float*)optr(rvar), (float)eps, (float)momentum};
 }
 // D[M,N] = A[M,K] op(B): b_mn = false -> B is [N,K]; true -> B is [K,N].  Returns false if declined.
+struct SplitK {
+  float* ws = nullptr;
+  unsigned int* tickets = nullptr;
+  int tiles = 0;
+};
+static inline SplitK make_splitk(const c10::optional<at::Tensor>& ws, const c10::optional<at::Tensor>& tickets) {
+  SplitK s;
+  if (ws.has_value() && ws->defined() && tickets.has_value() && tickets->defined()) {
+    TORCH_CHECK(ws->scalar_type() == at::kFloat && tickets->scalar_type() == at::kInt);
+    s.ws = ws->data_ptr<float>();
+    s.tickets = (unsigned int*)tickets->data_ptr();
+    const int64_t a = ws->numel() / 16384, b = tickets->numel();
+    s.tiles = (int)(a < b ? a : b);
+  }
+  return s;
+}
+static inline void check_fin_tickets(const c10::optional<at::Tensor>& ticket, int64_t n_out) {
+  if (ticket.has_value() && ticket->defined())
+    TORCH_CHECK(ticket->numel() >= (n_out + 63) / 64, "igemm: one finalize ticket per n-tile needed");
+}
 bool igemm_gemm(at::Tensor A, at::Tensor B, at::Tensor D, bool b_mn, c10::optional<at::Tensor> col_sums,
                 c10::optional<at::Tensor> bias, bool relu, c10::optional<at::Tensor> ticket,
                 c10::optional<at::Tensor> stat_out, c10::optional<at::Tensor> rmean,
-                c10::optional<at::Tensor> rvar, double eps, double momentum) {
+                c10::optional<at::Tensor> rvar, double eps, double momentum,
+                c10::optional<at::Tensor> sk_ws, c10::optional<at::Tensor> sk_tickets) {
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && D.dim() == 2 && is_bf16(A) && is_bf16(B) && is_bf16(D));
   TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1 && D.stride(1) == 1);
   const int M = (int)A.size(0), K = (int)A.size(1), N = (int)D.size(1);
@@ -433,10 +454,12 @@ bool igemm_gemm(at::Tensor A, at::Tensor B, at::Tensor D, bool b_mn, c10::option
   c10::cuda::CUDAGuard g(A.device());
   DdlBnFinalize fin = make_fin(ticket, stat_out, rmean, rvar, eps, momentum);
   const bool use_fin = fin.ticket != nullptr && fin.stat_out != nullptr;
+  check_fin_tickets(ticket, N);
+  const SplitK sk = make_splitk(sk_ws, sk_tickets);
   const int rc = ddl_igemm_gemm(A.data_ptr(), B.data_ptr(), D.data_ptr(), M, N, K, (int)A.stride(0),
                                 (int)B.stride(0), (int)D.stride(0), b_mn ? 1 : 0,
                                 (float*)optr(col_sums), optr(bias), relu, use_fin ? &fin : nullptr,
-                                sm_count(), cur_stream());
+                                sk.ws, sk.tickets, sk.tiles, sm_count(), cur_stream());
   if (rc == -1) return false;
   check(rc, "igemm_gemm");
   return true;
@@ -445,7 +468,8 @@ bool igemm_conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int64_t pad_h, i
                       int64_t stride, c10::optional<at::Tensor> col_sums,
                       c10::optional<at::Tensor> bias, bool relu, c10::optional<at::Tensor> ticket,
                       c10::optional<at::Tensor> stat_out, c10::optional<at::Tensor> rmean,
-                      c10::optional<at::Tensor> rvar, double eps, double momentum) {
+                      c10::optional<at::Tensor> rvar, double eps, double momentum,
+                      c10::optional<at::Tensor> sk_ws, c10::optional<at::Tensor> sk_tickets) {
   TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && y.dim() == 4 && is_bf16(x) && is_bf16(w) && is_bf16(y));
   TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast) &&
               w.is_contiguous(at::MemoryFormat::ChannelsLast) &&
@@ -459,17 +483,20 @@ bool igemm_conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int64_t pad_h, i
   c10::cuda::CUDAGuard g(x.device());
   DdlBnFinalize fin = make_fin(ticket, stat_out, rmean, rvar, eps, momentum);
   const bool use_fin = fin.ticket != nullptr && fin.stat_out != nullptr;
+  check_fin_tickets(ticket, Cout);
+  const SplitK sk = make_splitk(sk_ws, sk_tickets);
   const int rc = ddl_igemm_conv_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), NB, H, W, Cin, Cout,
                                       KH, KW, (int)pad_h, (int)pad_w, (int)stride,
                                       (float*)optr(col_sums), optr(bias), relu,
-                                      use_fin ? &fin : nullptr, sm_count(), cur_stream());
+                                      use_fin ? &fin : nullptr, sk.ws, sk.tickets, sk.tiles,
+                                      sm_count(), cur_stream());
   if (rc == -1) return false;
   check(rc, "igemm_conv_fprop");
   return true;
 }
 // dx [N, Cin, H, W] = data gradient of conv2d(x, w) given dy [N, Cout, OH, OW]; w is the FORWARD filter
 bool igemm_conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int64_t pad_h, int64_t pad_w,
-                      int64_t stride) {
+                      int64_t stride, c10::optional<at::Tensor> sk_ws, c10::optional<at::Tensor> sk_tickets) {
   TORCH_CHECK(dy.dim() == 4 && w.dim() == 4 && dx.dim() == 4 && is_bf16(dy) && is_bf16(w) && is_bf16(dx));
   TORCH_CHECK(dy.is_contiguous(at::MemoryFormat::ChannelsLast) &&
               w.is_contiguous(at::MemoryFormat::ChannelsLast) &&
@@ -481,9 +508,10 @@ bool igemm_conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int64_t pad_h,
   TORCH_CHECK(w.size(1) == Cin && dy.size(0) == NB && dy.size(1) == Cout && dy.size(2) == OH &&
               dy.size(3) == OW, "igemm_conv_dgrad: shapes");
   c10::cuda::CUDAGuard g(dy.device());
+  const SplitK sk = make_splitk(sk_ws, sk_tickets);
   const int rc = ddl_igemm_conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), NB, H, W, Cin, Cout,
-                                      KH, KW, (int)pad_h, (int)pad_w, (int)stride, sm_count(),
-                                      cur_stream());
+                                      KH, KW, (int)pad_h, (int)pad_w, (int)stride, sk.ws, sk.tickets,
+                                      sk.tiles, sm_count(), cur_stream());
   if (rc == -1) return false;
   check(rc, "igemm_conv_dgrad");
   return true;

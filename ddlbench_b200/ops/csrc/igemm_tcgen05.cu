@@ -60,7 +60,10 @@ struct IgemmParams {
   float* col_sums;                // [R][2][Nout] replicated workspace, or null
   const __nv_bfloat16* bias;      // [Nout] or null
   int relu;
-  unsigned int* ticket;           // fused BatchNorm finalize (null: sums only)
+  int kb_per_split;               // k-blocks per split-K slice (gridDim.z slices)
+  float* splitk_ws;               // zero fp32 scratch [tiles][128 x BLOCK_N] (split-K only)
+  unsigned int* splitk_tickets;   // one per tile, zero on entry, self-resetting
+  unsigned int* ticket;           // fused BatchNorm finalize: one counter PER n-tile (null: sums only)
   float* stat_out;
   float* running_mean;
   float* running_var;
@@ -105,6 +108,24 @@ struct IgSmem {
   static_assert(kDynamic <= 113 * 1024, "two CTAs must fit in one SM's shared memory");
 };
 
+// 32 lanes x 32 fp32 columns -> registers, WITHOUT the wait (callers batch two loads per wait)
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 template <int BLOCK_N, int kStages, bool kBMn, bool kStats>
 __global__ void __launch_bounds__(kThreads, 2)
 igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -126,12 +147,15 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_k_blocks = p.ntaps * p.kc_blocks;
   // this CTA: n-tile blockIdx.x (fastest: CTAs sharing an A tile run together, L2 reuse), pixel
-  // tiles [tp0, tp1)
+  // tiles [tp0, tp1), k-blocks [kb0, kb1) of every tile (split-K over blockIdx.z)
   const int tile_n = blockIdx.x;
   const int tp0 = blockIdx.y * p.tiles_per_cta;
   const int tp1 = min(tp0 + p.tiles_per_cta, p.pix_tiles);
+  const int total_kb = p.ntaps * p.kc_blocks;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb1 = min(kb0 + p.kb_per_split, total_kb);
+  const bool split = gridDim.z > 1;
 
   pdl_trigger();
   if (warp == 0 && lane == 0) {
@@ -166,27 +190,26 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
         const int w0 = (tp % p.tiles_w) * p.TW;
         const int h0 = ((tp / p.tiles_w) % p.tiles_h) * p.TH;
         const int n0 = (tp / (p.tiles_w * p.tiles_h)) * p.TN;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const int aw = w0 * p.a_step + p.tap_dw[t];
-          const int ah = h0 * p.a_step + p.tap_dh[t];
-          const int bcol = p.tap_bcol[t];
-          for (int cb = 0; cb < p.kc_blocks; ++cb, ++it) {
-            const int s = it % kStages;
-            const uint32_t ph = (it / kStages) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* a_dst = smem + s * L::kStageBytes;
-            uint8_t* b_dst = a_dst + L::kABytes;
-            mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
-            tma_load_4d(a_dst, &map_a, &full_bar[s], cb * BLOCK_K, aw, ah, n0);
-            if (kBMn) {
+        int t = kb0 / p.kc_blocks, cb = kb0 % p.kc_blocks;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* a_dst = smem + s * L::kStageBytes;
+          uint8_t* b_dst = a_dst + L::kABytes;
+          mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
+          // input box shifted by the tap offset; the halo is zero-filled by the TMA unit
+          tma_load_4d(a_dst, &map_a, &full_bar[s], cb * BLOCK_K, w0 * p.a_step + p.tap_dw[t],
+                      h0 * p.a_step + p.tap_dh[t], n0);
+          if (kBMn) {
 #pragma unroll
-              for (int j = 0; j < BLOCK_N / 64; ++j)
-                tma_load_2d(b_dst + j * 8192, &map_b, &full_bar[s],
-                            bcol + tile_n * BLOCK_N + j * 64, cb * BLOCK_K);
-            } else {
-              tma_load_2d(b_dst, &map_b, &full_bar[s], bcol + cb * BLOCK_K, tile_n * BLOCK_N);
-            }
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(b_dst + j * 8192, &map_b, &full_bar[s],
+                          p.tap_bcol[t] + tile_n * BLOCK_N + j * 64, cb * BLOCK_K);
+          } else {
+            tma_load_2d(b_dst, &map_b, &full_bar[s], p.tap_bcol[t] + cb * BLOCK_K, tile_n * BLOCK_N);
           }
+          if (++cb == p.kc_blocks) { cb = 0; ++t; }
         }
       }
     }
@@ -199,7 +222,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
       mbar_wait(&tempty_bar[acc], acc_ph ^ 1);          // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-      for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&full_bar[s], ph);
@@ -214,10 +237,10 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
             // = 2048 B further down every 8 KB box
             const uint64_t bdesc = kBMn ? make_mn_sw128_desc(b_addr + k * (UMMA_K * 128), 8192)
                                         : make_kmajor_sw128_desc(b_addr) + (uint64_t)(k * 2);
-            umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc, idesc, (kb | k) ? 1u : 0u);
+            umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc, idesc, (kb > kb0 || k) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
-          if (kb == num_k_blocks - 1) umma_commit(&tfull_bar[acc]);
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
       }
@@ -228,7 +251,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
     const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;           // output pixel of the tile held by this thread
     const int lw = row % p.TW, lh = (row / p.TW) % p.TH, ln = row / (p.TW * p.TH);
-    uint32_t iter = 0;
+    __shared__ bool flag_last;
     if (p.bias) {
       for (int i = et; i < BLOCK_N; i += 128) {
         const int col = tile_n * BLOCK_N + i;
@@ -236,44 +259,95 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
       }
     }
     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;     // this thread's share of the column sums
+    int done_tiles = 0;
+    uint32_t iter = 0;
+    uint8_t* stage = smem + L::kOutOffset;
     for (int tp = tp0; tp < tp1; ++tp, ++iter) {
       const uint32_t acc = iter & 1, acc_ph = (iter >> 1) & 1;
       const int w0 = (tp % p.tiles_w) * p.TW;
       const int h0 = ((tp / p.tiles_w) % p.tiles_h) * p.TH;
       const int n0 = (tp / (p.tiles_w * p.tiles_h)) * p.TN;
       const bool valid = (w0 + lw < p.OW) && (h0 + lh < p.OH) && (n0 + ln < p.NB);
+      const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
+      // split-K partial sums of this tile: [(col/4)][row][4] fp32 — a warp's 16-byte accesses are
+      // 512 contiguous bytes
+      float* wst = split ? p.splitk_ws + (size_t)(tp * gridDim.x + tile_n) * (BLOCK_M * BLOCK_N) : nullptr;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
+      if (split) {
+        // ---- partial tile: vector reductions into the workspace, then a ticket; the LAST split
+        // to arrive turns the sum into the output tile (and re-zeroes the workspace)
+#pragma unroll
+        for (int cp = 0; cp < BLOCK_N / 64; ++cp) {
+          uint32_t r[64];
+          tmem_ld_32x32_nowait(tacc + cp * 64, r);
+          tmem_ld_32x32_nowait(tacc + cp * 64 + 32, r + 32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            atomicAdd(reinterpret_cast<float4*>(wst + ((size_t)(cp * 16 + j) * BLOCK_M + row) * 4),
+                      make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          unsigned int* tk = p.splitk_tickets + (tp * gridDim.x + tile_n);
+          const unsigned int t = atomicAdd(tk, 1u);
+          flag_last = (t == gridDim.z - 1);
+          if (flag_last) *tk = 0u;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (!flag_last) continue;
+        __threadfence();
+      }
       // the staging buffer was last read by the TMA store (and the statistics pass) of the
       // previous tile
       if (et == 0 && iter >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      uint8_t* stage = smem + L::kOutOffset;
 #pragma unroll
-      for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N + (uint32_t)(cb * 32), r);
-        float f[32];
+      for (int cp = 0; cp < BLOCK_N / 64; ++cp) {
+        float f[64];
+        if (!split) {
+          uint32_t r[64];
+          tmem_ld_32x32_nowait(tacc + cp * 64, r);            // two loads in flight per wait
+          tmem_ld_32x32_nowait(tacc + cp * 64 + 32, r + 32);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(r[i]);
-          if (p.bias) v += bias_s[cb * 32 + i];
+          for (int i = 0; i < 64; ++i) f[i] = __uint_as_float(r[i]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float4* src = reinterpret_cast<float4*>(wst + ((size_t)(cp * 16 + j) * BLOCK_M + row) * 4);
+            const float4 t = __ldcg(src);
+            *src = make_float4(0.f, 0.f, 0.f, 0.f);
+            f[4 * j] = t.x; f[4 * j + 1] = t.y; f[4 * j + 2] = t.z; f[4 * j + 3] = t.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          float v = f[i];
+          if (p.bias) v += bias_s[cp * 64 + i];
           if (p.relu) v = fmaxf(v, 0.f);
           f[i] = valid ? v : 0.f;              // rows outside the image contribute nothing
         }
-        uint8_t* region = stage + (cb / 2) * (BLOCK_M * 128);
-        const int chunk0 = (cb & 1) * 4;
+        uint8_t* region = stage + cp * (BLOCK_M * 128);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
           bf16x8 pk = pack8(f + j * 8);
-          const int chunk = (chunk0 + j) ^ (row & 7);
+          const int chunk = j ^ (row & 7);
           *reinterpret_cast<bf16x8*>(region + row * 128 + chunk * 16) = pk;
         }
       }
-      // accumulator drained: hand it back to the MMA warp (one arrival per epilogue warp)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (!split) {
+        // accumulator drained: hand it back to the MMA warp (one arrival per epilogue warp)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et == 0) {
@@ -283,6 +357,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
             tma_store_4d(&map_d, stage + h * (BLOCK_M * 128), tile_n * BLOCK_N + h * 64, w0, h0, n0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+      ++done_tiles;
       if (kStats && p.col_sums) {
         // per-channel sum / sum-of-squares of the (bf16-rounded) tile: every thread owns a column
         // pair and a group of rows, and keeps its partial sums in registers across the CTA's tiles
@@ -305,9 +380,10 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
         }
       }
     }
-    if (kStats && p.col_sums) {
-      // combine the row groups in shared memory, flush this CTA's sums with one vector of atomics,
-      // then let the last CTA of the grid finalize the statistics
+    if (kStats && p.col_sums && done_tiles > 0) {
+      // combine the row groups in shared memory, flush this CTA's sums with one vector of atomics;
+      // the CTA that completes the LAST pixel tile of this n-tile finalizes its BLOCK_N channels
+      // (one channel per thread: every n-tile is finalized in parallel by a different CTA)
       {
         const int c = (et % (BLOCK_N / 2)) * 2;
         atomicAdd(&stat_s[c], s0);
@@ -325,19 +401,20 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
         }
       }
       if (p.ticket) {
-        __shared__ bool is_last;
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) {
-          const unsigned int t = atomicAdd(p.ticket, 1u);
-          is_last = (t == gridDim.x * gridDim.y - 1);
-          if (is_last) *p.ticket = 0u;
+          const unsigned int t = atomicAdd(&p.ticket[tile_n], (unsigned int)done_tiles);
+          flag_last = (t + (unsigned int)done_tiles == (unsigned int)p.pix_tiles);
+          if (flag_last) p.ticket[tile_n] = 0u;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (is_last) {
+        if (flag_last) {
           __threadfence();
           const float inv_m = 1.f / (float)p.stat_count;
-          for (int c = et; c < p.Nout; c += 128) {
+          for (int i = et; i < BLOCK_N; i += 128) {
+            const int c = tile_n * BLOCK_N + i;
+            if (c >= p.Nout) continue;
             float s = 0.f, q = 0.f;
 #pragma unroll
             for (int r = 0; r < DDL_BN_REPLICAS; ++r) {
@@ -411,6 +488,9 @@ struct IgProblem {
   const void* bias;
   int relu;
   const DdlBnFinalize* fin;
+  float* splitk_ws;               // zero fp32 scratch for split-K (may be null: never split)
+  unsigned int* splitk_tickets;
+  int splitk_tiles;               // capacity of both, in 128x128 tiles
 };
 
 template <int BLOCK_N, int kStages, bool kBMn, bool kStats>
@@ -438,19 +518,31 @@ static int launch_ig(const IgProblem& q, IgemmParams& p, int sms, cudaStream_t s
   }
   p.tiles_n = (int)((q.d.C + BLOCK_N - 1) / BLOCK_N);
   p.pix_tiles = p.tiles_w * p.tiles_h * (int)((q.d.N + p.TN - 1) / p.TN);
-  // chunks: enough CTAs for ~3 rounds of the 2-per-SM slots (the hardware scheduler balances
-  // them), at most 8 tiles each (amortises barrier / TMEM set-up, keeps the epilogue of tile i
-  // under the main loop of tile i+1)
   const long long total = (long long)p.pix_tiles * p.tiles_n;
-  int per = (int)(total / (6LL * sms));
-  if (per < 1) per = 1;
-  if (per > 8) per = 8;
+  const int total_kb = p.ntaps * p.kc_blocks;
+  // Work decomposition.  Enough tiles: ONE wave of at most 2 CTAs per SM, every CTA a chunk of
+  // consecutive pixel tiles (set-up, statistics flush and ticket are paid once per chunk).  Too
+  // few tiles to fill the machine and a long reduction (the 14x14 / 7x7 layers): split-K over
+  // gridDim.z, partial tiles meet in the fp32 workspace, the last slice runs the epilogue.
+  int per = (int)((total + 2LL * sms - 1) / (2LL * sms));
+  if (per > 16) per = 16;
+  int splits = 1;
+  if (total < sms && total_kb >= 8 && q.splitk_ws && total <= q.splitk_tiles && BLOCK_N == 128) {
+    splits = (int)((3LL * sms / 2 + total - 1) / total);
+    if (splits > total_kb / 4) splits = total_kb / 4;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > 1) per = 1;
+  p.kb_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;      // no empty slices
+  p.splitk_ws = q.splitk_ws;
+  p.splitk_tickets = q.splitk_tickets;
   p.tiles_per_cta = per;
   const int chunks = (p.pix_tiles + per - 1) / per;
   if (chunks > 65535 || p.tiles_n > 65535) return -1;
   cudaError_t err = launch_pdl((igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats>),
-                               dim3(p.tiles_n, chunks), dim3(kThreads), (size_t)L::kDynamic, st, ma,
-                               mb, md, p);
+                               dim3(p.tiles_n, chunks, splits), dim3(kThreads), (size_t)L::kDynamic,
+                               st, ma, mb, md, p);
   return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
 }
 
@@ -517,7 +609,9 @@ using ddl::gemm::IgTensor;
 // b_mn_major = 0: B is [N, K] (K contiguous);  1: B is [K, N] (N contiguous).
 extern "C" int ddl_igemm_gemm(const void* A, const void* B, void* D, int M, int N, int K, int lda,
                               int ldb, int ldd, int b_mn_major, float* col_sums, const void* bias,
-                              int relu, const DdlBnFinalize* fin, int sms, cudaStream_t st) {
+                              int relu, const DdlBnFinalize* fin, float* splitk_ws,
+                              unsigned int* splitk_tickets, int splitk_tiles, int sms,
+                              cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldd % 8) || (K % 8) || (N % 8)) return -1;
   IgProblem q{};
@@ -532,6 +626,7 @@ extern "C" int ddl_igemm_gemm(const void* A, const void* B, void* D, int M, int 
   q.kc = K;
   q.ntaps = 1;
   q.col_sums = col_sums; q.bias = bias; q.relu = relu; q.fin = fin;
+  q.splitk_ws = splitk_ws; q.splitk_tickets = splitk_tickets; q.splitk_tiles = splitk_tiles;
   return ddl::gemm::run_ig(q, sms, st);
 }
 
@@ -540,7 +635,9 @@ extern "C" int ddl_igemm_gemm(const void* A, const void* B, void* D, int M, int 
 extern "C" int ddl_igemm_conv_fprop(const void* x, const void* w, void* y, int NB, int H, int W,
                                     int Cin, int Cout, int KH, int KW, int pad_h, int pad_w,
                                     int stride, float* col_sums, const void* bias, int relu,
-                                    const DdlBnFinalize* fin, int sms, cudaStream_t st) {
+                                    const DdlBnFinalize* fin, float* splitk_ws,
+                                    unsigned int* splitk_tickets, int splitk_tiles, int sms,
+                                    cudaStream_t st) {
   if (NB <= 0 || H <= 0 || W <= 0) return 0;
   if ((Cin % 8) || (Cout % 8) || KH < 1 || KW < 1 || KH * KW > ddl::gemm::kIgMaxTaps) return -1;
   if (stride != 1 && stride != 2) return -1;
@@ -568,6 +665,7 @@ extern "C" int ddl_igemm_conv_fprop(const void* x, const void* w, void* y, int N
       q.tap_bcol[t] = t * Cin;
     }
   q.col_sums = col_sums; q.bias = bias; q.relu = relu; q.fin = fin;
+  q.splitk_ws = splitk_ws; q.splitk_tickets = splitk_tickets; q.splitk_tiles = splitk_tiles;
   return ddl::gemm::run_ig(q, sms, st);
 }
 
@@ -575,7 +673,8 @@ extern "C" int ddl_igemm_conv_fprop(const void* x, const void* w, void* y, int N
 // untouched), dx: [NB,H,W,Cin] — fully written.  stride 1 or 2.
 extern "C" int ddl_igemm_conv_dgrad(const void* dy, const void* w, void* dx, int NB, int H, int W,
                                     int Cin, int Cout, int KH, int KW, int pad_h, int pad_w,
-                                    int stride, int sms, cudaStream_t st) {
+                                    int stride, float* splitk_ws, unsigned int* splitk_tickets,
+                                    int splitk_tiles, int sms, cudaStream_t st) {
   if (NB <= 0 || H <= 0 || W <= 0) return 0;
   if ((Cin % 8) || (Cout % 8) || KH < 1 || KW < 1 || KH * KW > ddl::gemm::kIgMaxTaps) return -1;
   if (stride != 1 && stride != 2) return -1;
@@ -583,6 +682,7 @@ extern "C" int ddl_igemm_conv_dgrad(const void* dy, const void* w, void* dx, int
   if (OH <= 0 || OW <= 0) return -1;
   const int64_t kdim = (int64_t)KH * KW * Cin;
   IgProblem q{};
+  q.splitk_ws = splitk_ws; q.splitk_tickets = splitk_tickets; q.splitk_tiles = splitk_tiles;
   q.b = w; q.b_mn = 1; q.b_rows = Cout; q.b_cols = kdim; q.ldb = kdim;
   q.kc = Cout;
   q.a_step = 1;

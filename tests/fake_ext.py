@@ -136,6 +136,7 @@ class FakeExt:
     def _fin(self, cs, N, M, ticket, stat, rm, rv, eps, mom):
         if ticket is None or stat is None:
             return
+        assert _plain(ticket).numel() >= (N + 63) // 64 and int(_plain(ticket).abs().sum()) == 0, "finalize tickets"
         v = cs[:R * 2 * N].view(R, 2, N).sum(0)
         mean = v[0] / M
         var = (v[1] / M - mean * mean).clamp_min(0)
@@ -148,7 +149,7 @@ class FakeExt:
         cs.zero_()
 
     # bool igemm_gemm(A, B, D, b_mn, col_sums?, bias?, relu, ticket?, stat?, rm?, rv?, eps, mom)
-    def igemm_gemm(self, A, B, D, b_mn, col_sums, bias, relu, ticket, stat, rm, rv, eps, mom):
+    def igemm_gemm(self, A, B, D, b_mn, col_sums, bias, relu, ticket, stat, rm, rv, eps, mom, sk_ws=None, sk_tickets=None):
         self.calls.append("igemm_gemm")
         A, B, Dp = _plain(A), _plain(B), _plain(D)
         assert A.dim() == 2 and B.dim() == 2 and Dp.dim() == 2 and A.dtype == BF16 and B.dtype == BF16 and Dp.dtype == BF16
@@ -174,7 +175,8 @@ class FakeExt:
         return True
 
     # bool igemm_conv_fprop(x, w, y, pad_h, pad_w, stride, col_sums?, bias?, relu, ticket?, stat?, rm?, rv?, eps, mom)
-    def igemm_conv_fprop(self, x, w, y, pad_h, pad_w, stride, col_sums, bias, relu, ticket, stat, rm, rv, eps, mom):
+    def igemm_conv_fprop(self, x, w, y, pad_h, pad_w, stride, col_sums, bias, relu, ticket, stat, rm, rv, eps, mom,
+                         sk_ws=None, sk_tickets=None):
         self.calls.append("igemm_conv_fprop")
         x, w, yp = _plain(x), _plain(w), _plain(y)
         assert x.dim() == 4 and w.dim() == 4 and yp.dim() == 4 and x.dtype == BF16 and w.dtype == BF16 and yp.dtype == BF16
@@ -201,7 +203,7 @@ class FakeExt:
         return True
 
     # bool igemm_conv_dgrad(dy, w, dx, pad_h, pad_w, stride)
-    def igemm_conv_dgrad(self, dy, w, dx, pad_h, pad_w, stride):
+    def igemm_conv_dgrad(self, dy, w, dx, pad_h, pad_w, stride, sk_ws=None, sk_tickets=None):
         self.calls.append("igemm_conv_dgrad")
         dy, w, dxp = _plain(dy), _plain(w), _plain(dx)
         assert dy.dtype == BF16 and w.dtype == BF16 and dxp.dtype == BF16

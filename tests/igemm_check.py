@@ -94,7 +94,7 @@ def check_conv(name, n, ci, co, hw, k, s, p, bias_relu=False, bench=False):
     sums = torch.zeros(ops.BN_REPLICAS * 2 * co, device=DEV)
     stat = torch.zeros(2 * co, device=DEV)
     rm, rv = torch.zeros(co, device=DEV), torch.ones(co, device=DEV)
-    ticket = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ticket = torch.zeros((co + 63) // 64, dtype=torch.int32, device=DEV)
     fin = None if bias_relu else (ticket, stat, rm, rv, 1e-5, 0.1)
     y = None
     for _ in range(2):        # twice: workspace + ticket must self-reset
@@ -114,7 +114,7 @@ def check_conv(name, n, ci, co, hw, k, s, p, bias_relu=False, bench=False):
         e1 = (stat[:co] - mean_ref).abs().max().item()
         e2 = (stat[co:] - torch.rsqrt(var_ref + 1e-5)).abs().max().item() / max(stat[co:].abs().max().item(), 1e-6)
         ok = ok and e1 < 2e-3 * max(1.0, mean_ref.abs().max().item()) and e2 < 5e-3
-        ok = ok and float(sums.abs().sum()) == 0.0 and int(ticket.item()) == 0
+        ok = ok and float(sums.abs().sum()) == 0.0 and int(ticket.abs().sum()) == 0
         # two calls with momentum 0.1 starting from 0: rm = (1 - 0.9^2) * mean
         e3 = (rm - 0.19 * mean_ref).abs().max().item()
         ok = ok and e3 < 2e-3 * max(1.0, mean_ref.abs().max().item())
@@ -143,6 +143,8 @@ def check_conv(name, n, ci, co, hw, k, s, p, bias_relu=False, bench=False):
     ok = ok and e <= 0.004 * max(m, 1.0)
     ws = ops._wgrad_ws(gw.device, 1)
     ok = ok and float(ws[0].abs().sum()) == 0.0 and int(ws[1].abs().sum()) == 0
+    sk = ops._ig_ws(gw.device)                      # split-K scratch of fprop / dgrad: left zero
+    ok = ok and float(sk[0].abs().sum()) == 0.0 and int(sk[1].abs().sum()) == 0
     print("%-18s n=%d %d->%d %dx%d k%d s%d: %s  %s" % (name, n, ci, co, hw, hw, k, s, "  ".join(msgs),
                                                      "OK" if ok else "FAIL"), flush=True)
     row = None
@@ -194,7 +196,7 @@ def check_gemm_stats(m, k, n):
     a, w = _rand((m, k)), _rand((n, k), k ** -0.5)
     sums = torch.zeros(ops.BN_REPLICAS * 2 * n, device=DEV)
     stat = torch.zeros(2 * n, device=DEV)
-    ticket = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ticket = torch.zeros((n + 63) // 64, dtype=torch.int32, device=DEV)
     y = ops.gemm_ig(a, w, col_sums=sums, bn_finalize=(ticket, stat, None, None, 1e-5, 0.1))
     yb = y.float()
     e, mx = _err(y, a.float() @ w.float().t())

@@ -115,7 +115,7 @@ def test_igemm_conv_paths(fake_ig, ci, co, k, s, p):
     x, w = _t(2, ci, 9, 9), _t(co, ci, k, k)
     sums = torch.zeros(8 * 2 * co)
     stat = torch.zeros(2 * co)
-    fin = (torch.zeros(1, dtype=torch.int32), stat, torch.zeros(co), torch.ones(co), 1e-5, 0.1)
+    fin = (torch.zeros((co + 63) // 64, dtype=torch.int32), stat, torch.zeros(co), torch.ones(co), 1e-5, 0.1)
     y, fused = op._conv_fwd(x, w, col_sums=sums, bn_finalize=fin, ctx={})
     dy = _t(*y.shape)
     gw = fake_cuda(torch.zeros(co, k, k, ci).to(BF16)).permute(0, 3, 1, 2)     # KRSC view, as in the store
