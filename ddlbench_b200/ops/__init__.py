@@ -562,33 +562,31 @@ def gemm_nt_mn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = N
 # and the FC layers.  DDLB_IGEMM=0 routes back to the library (A/B and bring-up only).
 IGEMM = os.environ.get("DDLB_IGEMM", "1") == "1"
 _WG_WS: dict = {}
-_WG_TICKETS = 16384
 
 
-def _wgrad_ws(device, numel: int):
-    """Zero fp32 scratch shared by the weight-gradient kernels that run back to back on one stream
-    (they leave it zero) + the ticket array."""
+def _wgrad_ws(device, numel: int = 0):
+    """fp32 scratch for the split-K planes of the weight-gradient kernels that run back to back on
+    one stream (48 MB: planes of the widest layers; a layer that needs more planes than fit simply
+    uses fewer k-splits).  Never needs zeroing."""
     key = (device, torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0)
     ent = _WG_WS.get(key)
-    if ent is None or ent[0].numel() < numel:
-        cap = max(numel, 1 << 22)
-        ent = (torch.zeros(cap, dtype=torch.float32, device=device),
-               torch.zeros(_WG_TICKETS, dtype=torch.int32, device=device) if ent is None else ent[1])
+    if ent is None:
+        ent = torch.empty(12 << 20, dtype=torch.float32, device=device)
         _WG_WS[key] = ent
     return ent
 
 
 _IG_WS: dict = {}
-_IG_SPLIT_TILES = 148
+_IG_SPLIT_TILES = 448        # slots (tile x k-slice) of 128x128 fp32: 28 MB
 
 
 def _ig_ws(device):
-    """Zero fp32 scratch + tickets of the split-K implicit-GEMM launches of one stream (the kernels
-    leave both zero): up to 148 partial 128x128 tiles."""
+    """fp32 scratch (partial tiles, never needs zeroing) + zero tickets (self-resetting) of the
+    split-K implicit-GEMM launches of one stream."""
     key = (device, torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0)
     ent = _IG_WS.get(key)
     if ent is None:
-        ent = (torch.zeros(_IG_SPLIT_TILES * 16384, dtype=torch.float32, device=device),
+        ent = (torch.empty(_IG_SPLIT_TILES * 16384, dtype=torch.float32, device=device),
                torch.zeros(_IG_SPLIT_TILES, dtype=torch.int32, device=device))
         _IG_WS[key] = ent
     return ent
@@ -651,20 +649,20 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int,
 def conv_wgrad_into(dy: torch.Tensor, x: torch.Tensor, gw: torch.Tensor, stride: int,
                     padding: Sequence[int], accumulate: bool) -> bool:
     """gw (+)= weight gradient of conv2d(x, w); ``gw`` is the [Cout, Cin, KH, KW] KRSC view of the
-    flat gradient buffer, written in ONE launch (split-K partials meet in a self-cleaning fp32
-    workspace, the last split converts)."""
+    flat gradient buffer (split-K partial tiles go to fp32 planes that a small reduce kernel sums;
+    no atomics, no zero-fill, no separate conversion pass)."""
     co, ci, kh, kw = gw.shape
     if not (gw.is_cuda and gw.is_contiguous(memory_format=torch.channels_last) and
             gw.dtype in (torch.bfloat16, torch.float32) and gw.data_ptr() % 16 == 0):
         return False
-    ws, tickets = _wgrad_ws(gw.device, gw.numel())
+    ws = _wgrad_ws(gw.device)
     if kh == 1 and kw == 1 and stride == 1 and padding[0] == 0 and padding[1] == 0:
         n, _, h, wd = x.shape
         a = dy.permute(0, 2, 3, 1).reshape(n * h * wd, co)
         b = x.permute(0, 2, 3, 1).reshape(n * h * wd, ci)
-        ok = ext().wgrad_gemm(a, b, ws, tickets, gw.permute(0, 2, 3, 1).reshape(co, ci), accumulate)
+        ok = ext().wgrad_gemm(a, b, ws, gw.permute(0, 2, 3, 1).reshape(co, ci), accumulate)
     else:
-        ok = ext().wgrad_conv(dy, x, ws, tickets, gw, accumulate, int(padding[0]), int(padding[1]),
+        ok = ext().wgrad_conv(dy, x, ws, gw, accumulate, int(padding[0]), int(padding[1]),
                               stride)
     if ok:
         _count()
@@ -694,9 +692,7 @@ def wgrad_gemm_into(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, accumul
             out.stride(1) == 1 and out.stride(0) % 8 == 0 and out.data_ptr() % 16 == 0 and
             out.dtype in (torch.bfloat16, torch.float32)):
         return False
-    # one k-block (K <= 64 rows: FC layers at small batch) is written directly, no workspace needed
-    ws, tickets = _wgrad_ws(out.device, out.shape[0] * out.stride(0) if a.shape[0] > 64 else 1)
-    if ext().wgrad_gemm(a, b, ws, tickets, out, accumulate):
+    if ext().wgrad_gemm(a, b, _wgrad_ws(out.device), out, accumulate):
         _count()
         return True
     return False

@@ -144,13 +144,12 @@ int ddl_igemm_conv_dgrad(const void* dy, const void* w, void* dx, int NB, int H,
                          float* splitk_ws, unsigned int* splitk_tickets, int splitk_tiles, int sms,
                          cudaStream_t st);
 // ---- gemm_wgrad_tcgen05.cu, one-launch weight gradients (self-cleaning fp32 workspace)
-int ddl_wgrad_gemm(const void* A, const void* B, float* ws, unsigned int* tickets, void* out,
+int ddl_wgrad_gemm(const void* A, const void* B, float* ws, long long ws_floats, void* out,
                    int out_bf16, int accumulate, int M, int N, int K, int lda, int ldb, int ldd,
-                   int max_tickets, int sms, cudaStream_t st);
-int ddl_wgrad_conv(const void* dy, const void* x, float* ws, unsigned int* tickets, void* out,
+                   int sms, cudaStream_t st);
+int ddl_wgrad_conv(const void* dy, const void* x, float* ws, long long ws_floats, void* out,
                    int out_bf16, int accumulate, int NB, int H, int W, int Cin, int Cout, int KH,
-                   int KW, int pad_h, int pad_w, int stride, int max_tickets, int sms,
-                   cudaStream_t st);
+                   int KW, int pad_h, int pad_w, int stride, int sms, cudaStream_t st);
 int ddl_gemm_selftest_info(char* buf, int len);
 int ddl_set_pdl(int on);
 

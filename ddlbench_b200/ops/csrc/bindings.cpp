@@ -516,42 +516,36 @@ bool igemm_conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int64_t pad_h,
   check(rc, "igemm_conv_dgrad");
   return true;
 }
-// out[M,N] (bf16 or fp32; += if accumulate) = A[K,M]^T B[K,N] through the zero fp32 workspace `ws`
-bool wgrad_gemm(at::Tensor A, at::Tensor B, at::Tensor ws, at::Tensor tickets, at::Tensor out,
-                bool accumulate) {
+// out[M,N] (bf16 or fp32; += if accumulate) = A[K,M]^T B[K,N]; `ws`: fp32 scratch for split-K planes
+bool wgrad_gemm(at::Tensor A, at::Tensor B, at::Tensor ws, at::Tensor out, bool accumulate) {
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && out.dim() == 2 && is_bf16(A) && is_bf16(B));
   TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1 && out.stride(1) == 1);
-  TORCH_CHECK(ws.scalar_type() == at::kFloat && tickets.scalar_type() == at::kInt);
+  TORCH_CHECK(ws.scalar_type() == at::kFloat);
   const int K = (int)A.size(0), M = (int)A.size(1), N = (int)B.size(1);
   TORCH_CHECK(B.size(0) == K && out.size(0) == M && out.size(1) == N);
-  const int ldd = (int)out.stride(0);
-  TORCH_CHECK(K <= 64 || ws.numel() >= (int64_t)M * ldd, "wgrad_gemm: workspace too small");
   c10::cuda::CUDAGuard g(A.device());
-  const int rc = ddl_wgrad_gemm(A.data_ptr(), B.data_ptr(), ws.data_ptr<float>(),
-                                (unsigned int*)tickets.data_ptr(), out.data_ptr(), is_bf16(out),
-                                accumulate, M, N, K, (int)A.stride(0), (int)B.stride(0), ldd,
-                                (int)tickets.numel(), sm_count(), cur_stream());
+  const int rc = ddl_wgrad_gemm(A.data_ptr(), B.data_ptr(), ws.data_ptr<float>(), (long long)ws.numel(),
+                                out.data_ptr(), is_bf16(out), accumulate, M, N, K, (int)A.stride(0),
+                                (int)B.stride(0), (int)out.stride(0), sm_count(), cur_stream());
   if (rc == -1) return false;
   check(rc, "wgrad_gemm");
   return true;
 }
 // out: [Cout, Cin, KH, KW] logical with KRSC memory (channels_last), bf16 or fp32
-bool wgrad_conv(at::Tensor dy, at::Tensor x, at::Tensor ws, at::Tensor tickets, at::Tensor out,
-                bool accumulate, int64_t pad_h, int64_t pad_w, int64_t stride) {
+bool wgrad_conv(at::Tensor dy, at::Tensor x, at::Tensor ws, at::Tensor out, bool accumulate,
+                int64_t pad_h, int64_t pad_w, int64_t stride) {
   TORCH_CHECK(dy.dim() == 4 && x.dim() == 4 && out.dim() == 4 && is_bf16(dy) && is_bf16(x));
   TORCH_CHECK(dy.is_contiguous(at::MemoryFormat::ChannelsLast) &&
               x.is_contiguous(at::MemoryFormat::ChannelsLast) &&
               out.is_contiguous(at::MemoryFormat::ChannelsLast), "wgrad_conv: channels_last operands");
-  TORCH_CHECK(ws.scalar_type() == at::kFloat && tickets.scalar_type() == at::kInt);
+  TORCH_CHECK(ws.scalar_type() == at::kFloat);
   const int NB = (int)x.size(0), Cin = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
   const int Cout = (int)out.size(0), KH = (int)out.size(2), KW = (int)out.size(3);
   TORCH_CHECK(out.size(1) == Cin && dy.size(0) == NB && dy.size(1) == Cout);
-  TORCH_CHECK(ws.numel() >= out.numel(), "wgrad_conv: workspace too small");
   c10::cuda::CUDAGuard g(x.device());
-  const int rc = ddl_wgrad_conv(dy.data_ptr(), x.data_ptr(), ws.data_ptr<float>(),
-                                (unsigned int*)tickets.data_ptr(), out.data_ptr(), is_bf16(out),
-                                accumulate, NB, H, W, Cin, Cout, KH, KW, (int)pad_h, (int)pad_w,
-                                (int)stride, (int)tickets.numel(), sm_count(), cur_stream());
+  const int rc = ddl_wgrad_conv(dy.data_ptr(), x.data_ptr(), ws.data_ptr<float>(), (long long)ws.numel(),
+                                out.data_ptr(), is_bf16(out), accumulate, NB, H, W, Cin, Cout, KH, KW,
+                                (int)pad_h, (int)pad_w, (int)stride, sm_count(), cur_stream());
   if (rc == -1) return false;
   check(rc, "wgrad_conv");
   return true;

@@ -48,16 +48,20 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
 }
 
 
-// Where the finished gradient goes.  With `tickets` set, D is a ZERO fp32 workspace shared by the
-// k-splits of a tile: every split adds its partial tile with vector atomics, takes a ticket, and
-// the LAST one converts the sum into `out` (bf16 or fp32, same indexing as D; `accumulate` adds to
-// what is there — micro-batches after the first) and re-zeroes the workspace.  One launch per
-// weight gradient: no memset, no fp32->bf16 copy kernel.
+// Where the finished gradient goes.
+//   out == null            : legacy mode, fp32 vector atomics into D (round-1 interface).
+//   out != null, 1 k-split : the tile is written straight to `out` (bf16 or fp32, same indexing
+//                            as D; `accumulate` adds to what is there — micro-batches after the first).
+//   out != null, S k-splits: split s writes its partial tile with PLAIN stores into plane s of the
+//                            fp32 workspace D (planes `plane_stride` floats apart, output indexing);
+//                            wgrad_reduce_kernel then sums the planes into `out`.  No atomics: fp32
+//                            vector atomics at this volume cost several times the GEMM itself
+//                            (profiles/r2/conv_vs_cudnn_v3_atomics_splitk.json).
 struct WgradOut {
-  unsigned int* tickets;   // one per (tile, tap), zero on entry, self-resetting; null: plain atomics into D
   void* out;
   int out_bf16;
   int accumulate;
+  long long plane_stride;
 };
 
 __device__ __forceinline__ void wgrad_store32(const WgradOut& o, size_t idx, const float* v) {
@@ -95,11 +99,11 @@ __device__ __forceinline__ void wgrad_store32(const WgradOut& o, size_t idx, con
 template <int BLOCK_N>
 __device__ __forceinline__ void wgrad_epilogue(uint32_t tmem_base, int warp, int lane, float* D,
                                                int ldd, int row, int nrows, int col0, int ncols,
-                                               const WgradOut& o, int ticket_idx, int splits) {
+                                               const WgradOut& o, int split, int splits) {
   const int quad = warp & 3;
-  const int et = threadIdx.x - 64;
   const bool vec_ok = (ldd & 7) == 0 && (col0 & 7) == 0;
-  const bool direct = o.tickets != nullptr && splits == 1;
+  const bool direct = o.out != nullptr && splits == 1;
+  float* plane = (o.out != nullptr) ? D + (size_t)split * o.plane_stride : D;
 #pragma unroll
   for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
     uint32_t r[32];
@@ -124,6 +128,18 @@ __device__ __forceinline__ void wgrad_epilogue(uint32_t tmem_base, int warp, int
             *dst = o.accumulate ? *dst + v : v;
           }
         }
+      } else if (o.out != nullptr) {
+        // partial tile -> this split's plane: 128 contiguous bytes per thread
+        float* dst = plane + idx;
+        if (vec_ok && c0 + 32 <= ncols) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            __stcg(reinterpret_cast<float4*>(dst + 4 * j),
+                   make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+        } else {
+          for (int j = 0; j < 32 && c0 + j < ncols; ++j) dst[j] = __uint_as_float(r[j]);
+        }
       } else if (vec_ok && c0 + 32 <= ncols) {
         float* dst = D + idx;
 #pragma unroll
@@ -136,46 +152,60 @@ __device__ __forceinline__ void wgrad_epilogue(uint32_t tmem_base, int warp, int
       }
     }
   }
-  if (o.tickets == nullptr || direct) return;
-  __shared__ bool is_last;
-  __threadfence();
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  if (et == 0) {
-    const unsigned int t = atomicAdd(&o.tickets[ticket_idx], 1u);
-    is_last = (t == (unsigned int)splits - 1);
-    if (is_last) o.tickets[ticket_idx] = 0u;
-  }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  if (!is_last) return;
-  __threadfence();
-  if (row >= nrows) return;
-#pragma unroll 1
-  for (int c0 = 0; c0 < BLOCK_N && c0 < ncols; c0 += 32) {
-    const size_t idx = (size_t)row * ldd + col0 + c0;
-    if (vec_ok && c0 + 32 <= ncols) {
-      float v[32];
+}
+
+// out[i] (+)= sum over `planes` of ws[p * stride + i]: the second half of a split-K weight gradient
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, int planes, long long stride, long long n,
+                    void* __restrict__ out, int out_bf16, int accumulate) {
+  pdl_enter();
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i0 >= n) return;
+  if (i0 + 8 <= n) {
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = 0; p < planes; ++p) {
+      const float4 u = __ldcg(reinterpret_cast<const float4*>(ws + (size_t)p * stride + i0));
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + (size_t)p * stride + i0 + 4));
+      a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
+      a[4] += v.x; a[5] += v.y; a[6] += v.z; a[7] += v.w;
+    }
+    if (out_bf16) {
+      bf16x8* dst = reinterpret_cast<bf16x8*>(reinterpret_cast<__nv_bfloat16*>(out) + i0);
+      if (accumulate) {
+        float g[8];
+        unpack8(*dst, g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 t = __ldcg(reinterpret_cast<const float4*>(D + idx + 4 * j));
-        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-        *reinterpret_cast<float4*>(D + idx + 4 * j) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 8; ++k) a[k] += g[k];
       }
-      wgrad_store32(o, idx, v);
+      *dst = pack8(a);
     } else {
-      for (int j = 0; j < 32 && c0 + j < ncols; ++j) {
-        float v = __ldcg(D + idx + j);
-        D[idx + j] = 0.f;
-        if (o.out_bf16) {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(o.out) + idx + j;
-          if (o.accumulate) v += __bfloat162float(*dst);
-          *dst = __float2bfloat16_rn(v);
-        } else {
-          float* dst = reinterpret_cast<float*>(o.out) + idx + j;
-          *dst = o.accumulate ? *dst + v : v;
-        }
+      float* dst = reinterpret_cast<float*>(out) + i0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[k] = accumulate ? dst[k] + a[k] : a[k];
+    }
+  } else {
+    for (long long i = i0; i < n; ++i) {
+      float a = 0.f;
+      for (int p = 0; p < planes; ++p) a += __ldcg(ws + (size_t)p * stride + i);
+      if (out_bf16) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out) + i;
+        if (accumulate) a += __bfloat162float(*dst);
+        *dst = __float2bfloat16_rn(a);
+      } else {
+        float* dst = reinterpret_cast<float*>(out) + i;
+        *dst = accumulate ? *dst + a : a;
       }
     }
   }
+}
+
+static inline int launch_wgrad_reduce(const float* ws, int planes, long long stride, long long n,
+                                      void* out, int out_bf16, int accumulate, cudaStream_t st) {
+  const long long threads = (n + 7) / 8;
+  const int blocks = (int)((threads + 255) / 256);
+  cudaError_t err = launch_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, ws, planes, stride, n,
+                               out, out_bf16, accumulate);
+  return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
 }
 
 struct WgradParams {
@@ -294,7 +324,7 @@ gemm_bf16_mn_kernel(const __grid_constant__ CUtensorMap map_a,
     tc_fence_after();
     const int col0 = tile_n * BLOCK_N;
     wgrad_epilogue<BLOCK_N>(tmem_base, warp, lane, wp.D, wp.ldd, row, wp.M, col0, wp.N - col0, wp.o,
-                            (int)blockIdx.x, (int)gridDim.y);
+                            (int)blockIdx.y, (int)gridDim.y);
   }
   tc_fence_before();
   __syncthreads();
@@ -306,7 +336,8 @@ gemm_bf16_mn_kernel(const __grid_constant__ CUtensorMap map_a,
 
 template <int BLOCK_N, int kStages>
 static int launch_mn(const void* A, const void* B, float* D, int M, int N, int K, int lda, int ldb,
-                     int ldd, int splits, int variant, cudaStream_t st, WgradOut o = WgradOut{}) {
+                     int ldd, int splits, int variant, cudaStream_t st, WgradOut o = WgradOut{},
+                     int* splits_used = nullptr) {
   using L = WgradSmem<BLOCK_N, kStages>;
   CUtensorMap ma, mb;
   int rc;
@@ -325,6 +356,7 @@ static int launch_mn(const void* A, const void* B, float* D, int M, int N, int K
   if (splits > total_kb) splits = total_kb;
   int per = (total_kb + splits - 1) / splits;
   splits = (total_kb + per - 1) / per;            // no empty CTAs
+  if (splits_used) *splits_used = splits;
   WgradParams wp{D, M, N, K, ldd, per, variant, o};
   const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
   cudaError_t err = launch_pdl((gemm_bf16_mn_kernel<BLOCK_N, kStages>), dim3(tiles, splits),
@@ -475,8 +507,7 @@ conv_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy,
     tc_fence_after();
     const int ci0 = tile_n * BLOCK_N;
     wgrad_epilogue<BLOCK_N>(tmem_base, warp, lane, wp.D, wp.ldd, row, wp.Cout, tap * wp.Cin + ci0,
-                            wp.Cin - ci0, wp.o, (int)(blockIdx.x + gridDim.x * blockIdx.z),
-                            (int)gridDim.y);
+                            wp.Cin - ci0, wp.o, (int)blockIdx.y, (int)gridDim.y);
   }
   tc_fence_before();
   __syncthreads();
@@ -489,7 +520,8 @@ conv_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy,
 template <int BLOCK_N, int kStages>
 static int launch_conv_wgrad(const void* dy, const void* x, float* D, int NB, int H, int W, int OH,
                              int OW, int Cin, int Cout, int KH, int KW, int pad_h, int pad_w,
-                             int stride, int sms, cudaStream_t st, WgradOut o = WgradOut{}) {
+                             int stride, int sms, cudaStream_t st, WgradOut o = WgradOut{},
+                             int max_planes = 1 << 30, int* splits_used = nullptr) {
   using L = WgradSmem<BLOCK_N, kStages>;
   ConvWgradParams wp{};
   wp.o = o;
@@ -515,8 +547,10 @@ static int launch_conv_wgrad(const void* dy, const void* x, float* D, int NB, in
   int splits = (2 * sms + tiles * taps - 1) / (tiles * taps);
   if (splits < 1) splits = 1;
   if (splits > wp.total_tiles) splits = wp.total_tiles;
+  if (splits > max_planes) splits = max_planes;
   wp.tiles_per_split = (wp.total_tiles + splits - 1) / splits;
   splits = (wp.total_tiles + wp.tiles_per_split - 1) / wp.tiles_per_split;
+  if (splits_used) *splits_used = splits;
   cudaError_t err = launch_pdl((conv_wgrad_bf16_kernel<BLOCK_N, kStages>), dim3(tiles, splits, taps),
                                dim3(kThreads), (size_t)L::kDynamic, st, mdy, mx, wp);
   return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
@@ -543,13 +577,13 @@ extern "C" int ddl_conv_wgrad_bf16_nhwc(const void* dy, const void* x, float* D,
   return launch_conv_wgrad<128, 3>(dy, x, D, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w, stride, sms, st);
 }
 
-// ---- one-launch weight gradients: partial tiles meet in the zero fp32 workspace `ws` (same
-// indexing as the output, at least M*ldd floats), the last k-split of every tile writes the
-// finished gradient to `out` (bf16 or fp32; `accumulate`: add to it) and re-zeroes `ws`.
-// `tickets`: zero-initialised, >= tiles*taps entries, self-resetting.
-extern "C" int ddl_wgrad_gemm(const void* A, const void* B, float* ws, unsigned int* tickets,
-                              void* out, int out_bf16, int accumulate, int M, int N, int K, int lda,
-                              int ldb, int ldd, int max_tickets, int sms, cudaStream_t st) {
+// ---- weight gradients straight into the gradient buffer: one launch when a single k-split fills
+// the machine, otherwise the splits write fp32 planes into `ws` (`ws_floats` available; plane =
+// M*ldd floats, output indexing) and a small reduce kernel sums them into `out` (bf16 or fp32;
+// `accumulate`: add to it).  No atomics, nothing to zero.
+extern "C" int ddl_wgrad_gemm(const void* A, const void* B, float* ws, long long ws_floats, void* out,
+                              int out_bf16, int accumulate, int M, int N, int K, int lda, int ldb,
+                              int ldd, int sms, cudaStream_t st) {
   using namespace ddl::gemm;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (M % 8) || (N % 8)) return -1;
@@ -558,17 +592,23 @@ extern "C" int ddl_wgrad_gemm(const void* A, const void* B, float* ws, unsigned 
     return -1;
   const int bn = N <= 64 ? 64 : 128;
   const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
-  if (tiles > max_tickets) return -1;
-  const int splits = (2 * sms + tiles - 1) / tiles;
-  WgradOut o{tickets, out, out_bf16, accumulate};
-  if (bn == 64) return launch_mn<64, 3>(A, B, ws, M, N, K, lda, ldb, ldd, splits, 0, st, o);
-  return launch_mn<128, 3>(A, B, ws, M, N, K, lda, ldb, ldd, splits, 0, st, o);
+  const long long plane = (long long)M * ldd;
+  int splits = (2 * sms + tiles - 1) / tiles;
+  const long long max_planes = ws ? ws_floats / plane : 0;
+  if (splits > max_planes) splits = (int)max_planes;
+  if (splits < 1) splits = 1;
+  WgradOut o{out, out_bf16, accumulate, plane};
+  int used = 1;
+  const int rc = bn == 64 ? launch_mn<64, 3>(A, B, ws, M, N, K, lda, ldb, ldd, splits, 0, st, o, &used)
+                          : launch_mn<128, 3>(A, B, ws, M, N, K, lda, ldb, ldd, splits, 0, st, o, &used);
+  if (rc || used == 1) return rc;
+  return launch_wgrad_reduce(ws, used, plane, plane, out, out_bf16, accumulate, st);
 }
 
-extern "C" int ddl_wgrad_conv(const void* dy, const void* x, float* ws, unsigned int* tickets,
-                              void* out, int out_bf16, int accumulate, int NB, int H, int W, int Cin,
-                              int Cout, int KH, int KW, int pad_h, int pad_w, int stride,
-                              int max_tickets, int sms, cudaStream_t st) {
+extern "C" int ddl_wgrad_conv(const void* dy, const void* x, float* ws, long long ws_floats, void* out,
+                              int out_bf16, int accumulate, int NB, int H, int W, int Cin, int Cout,
+                              int KH, int KW, int pad_h, int pad_w, int stride, int sms,
+                              cudaStream_t st) {
   using namespace ddl::gemm;
   if (NB <= 0 || H <= 0 || W <= 0) return 0;
   if (Cin % 8 || Cout % 8 || KH < 1 || KW < 1 || KH > 7 || KW > 7) return -1;
@@ -578,13 +618,15 @@ extern "C" int ddl_wgrad_conv(const void* dy, const void* x, float* ws, unsigned
   if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) |
        reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(out)) & 15)
     return -1;
-  const int bn = Cin <= 64 ? 64 : 128;
-  const int tiles = ((Cout + BLOCK_M - 1) / BLOCK_M) * ((Cin + bn - 1) / bn);
-  if (tiles * KH * KW > max_tickets) return -1;
-  WgradOut o{tickets, out, out_bf16, accumulate};
-  if (bn == 64)
-    return launch_conv_wgrad<64, 3>(dy, x, ws, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w,
-                                    stride, sms, st, o);
-  return launch_conv_wgrad<128, 3>(dy, x, ws, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w,
-                                   stride, sms, st, o);
+  const long long plane = (long long)Cout * KH * KW * Cin;
+  long long max_planes = ws ? ws_floats / plane : 0;
+  if (max_planes < 1) max_planes = 1;
+  WgradOut o{out, out_bf16, accumulate, plane};
+  int used = 1;
+  const int mp = (int)(max_planes > (1 << 20) ? (1 << 20) : max_planes);
+  const int rc = Cin <= 64
+      ? launch_conv_wgrad<64, 3>(dy, x, ws, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w, stride, sms, st, o, mp, &used)
+      : launch_conv_wgrad<128, 3>(dy, x, ws, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w, stride, sms, st, o, mp, &used);
+  if (rc || used == 1) return rc;
+  return launch_wgrad_reduce(ws, used, plane, plane, out, out_bf16, accumulate, st);
 }

@@ -61,7 +61,7 @@ struct IgemmParams {
   const __nv_bfloat16* bias;      // [Nout] or null
   int relu;
   int kb_per_split;               // k-blocks per split-K slice (gridDim.z slices)
-  float* splitk_ws;               // zero fp32 scratch [tiles][128 x BLOCK_N] (split-K only)
+  float* splitk_ws;               // fp32 scratch [tiles][slices][128 x BLOCK_N] (split-K only)
   unsigned int* splitk_tickets;   // one per tile, zero on entry, self-resetting
   unsigned int* ticket;           // fused BatchNorm finalize: one counter PER n-tile (null: sums only)
   float* stat_out;
@@ -269,14 +269,17 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
       const int n0 = (tp / (p.tiles_w * p.tiles_h)) * p.TN;
       const bool valid = (w0 + lw < p.OW) && (h0 + lh < p.OH) && (n0 + ln < p.NB);
       const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
-      // split-K partial sums of this tile: [(col/4)][row][4] fp32 — a warp's 16-byte accesses are
-      // 512 contiguous bytes
-      float* wst = split ? p.splitk_ws + (size_t)(tp * gridDim.x + tile_n) * (BLOCK_M * BLOCK_N) : nullptr;
+      // split-K: slice z of tile t parks its partial sums in slot [t][z] of the workspace, laid
+      // out [(col/4)][row][4] fp32 so that a warp's 16-byte accesses are 512 contiguous bytes.
+      // Plain stores, no atomics (fp32 vector atomics at this volume are several times slower
+      // than the GEMM itself); the LAST slice to arrive adds the other slots to its own
+      // accumulator and runs the epilogue.  Nothing needs zeroing.
+      const size_t slot_elems = (size_t)BLOCK_M * BLOCK_N;
+      float* wst = split ? p.splitk_ws + (size_t)(tp * gridDim.x + tile_n) * gridDim.z * slot_elems : nullptr;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       if (split) {
-        // ---- partial tile: vector reductions into the workspace, then a ticket; the LAST split
-        // to arrive turns the sum into the output tile (and re-zeroes the workspace)
+        float* mine = wst + (size_t)blockIdx.z * slot_elems;
 #pragma unroll
         for (int cp = 0; cp < BLOCK_N / 64; ++cp) {
           uint32_t r[64];
@@ -285,13 +288,10 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            atomicAdd(reinterpret_cast<float4*>(wst + ((size_t)(cp * 16 + j) * BLOCK_M + row) * 4),
-                      make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+            __stcg(reinterpret_cast<float4*>(mine + ((size_t)(cp * 16 + j) * BLOCK_M + row) * 4),
+                   make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) {
@@ -301,7 +301,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
           if (flag_last) *tk = 0u;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (!flag_last) continue;
+        if (!flag_last) continue;          // (one tile per CTA in split mode: the CTA is done)
         __threadfence();
       }
       // the staging buffer was last read by the TMA store (and the statistics pass) of the
@@ -311,20 +311,24 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
       for (int cp = 0; cp < BLOCK_N / 64; ++cp) {
         float f[64];
-        if (!split) {
+        {
           uint32_t r[64];
           tmem_ld_32x32_nowait(tacc + cp * 64, r);            // two loads in flight per wait
           tmem_ld_32x32_nowait(tacc + cp * 64 + 32, r + 32);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 64; ++i) f[i] = __uint_as_float(r[i]);
-        } else {
+        }
+        if (split) {
+          for (int z = 0; z < (int)gridDim.z; ++z) {
+            if (z == (int)blockIdx.z) continue;
+            const float* other = wst + (size_t)z * slot_elems;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float4* src = reinterpret_cast<float4*>(wst + ((size_t)(cp * 16 + j) * BLOCK_M + row) * 4);
-            const float4 t = __ldcg(src);
-            *src = make_float4(0.f, 0.f, 0.f, 0.f);
-            f[4 * j] = t.x; f[4 * j + 1] = t.y; f[4 * j + 2] = t.z; f[4 * j + 3] = t.w;
+            for (int j = 0; j < 16; ++j) {
+              const float4 t = __ldcg(reinterpret_cast<const float4*>(
+                  other + ((size_t)(cp * 16 + j) * BLOCK_M + row) * 4));
+              f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+            }
           }
         }
 #pragma unroll
@@ -342,12 +346,10 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
           *reinterpret_cast<bf16x8*>(region + row * 128 + chunk * 16) = pk;
         }
       }
-      if (!split) {
-        // accumulator drained: hand it back to the MMA warp (one arrival per epilogue warp)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      }
+      // accumulator drained: hand it back to the MMA warp (one arrival per epilogue warp)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et == 0) {
@@ -527,9 +529,11 @@ static int launch_ig(const IgProblem& q, IgemmParams& p, int sms, cudaStream_t s
   int per = (int)((total + 2LL * sms - 1) / (2LL * sms));
   if (per > 16) per = 16;
   int splits = 1;
-  if (total < sms && total_kb >= 8 && q.splitk_ws && total <= q.splitk_tiles && BLOCK_N == 128) {
+  if (total < sms && total_kb >= 8 && q.splitk_ws && BLOCK_N == 128) {
     splits = (int)((3LL * sms / 2 + total - 1) / total);
     if (splits > total_kb / 4) splits = total_kb / 4;
+    if (splits > 8) splits = 8;
+    while (splits > 1 && total * splits > q.splitk_tiles) --splits;   // slots available
     if (splits < 1) splits = 1;
   }
   if (splits > 1) per = 1;

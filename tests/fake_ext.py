@@ -220,13 +220,12 @@ class FakeExt:
         dxp.copy_(g.to(BF16))
         return True
 
-    def _wg_check(self, ws, tickets, need):
-        ws, tickets = _plain(ws), _plain(tickets)
-        assert ws.dtype == torch.float32 and tickets.dtype == torch.int32 and ws.numel() >= need
-        assert float(ws.abs().sum()) == 0.0 and int(tickets.abs().sum()) == 0, "wgrad workspace must be zero"
+    def _wg_check(self, ws, need):
+        ws = _plain(ws)
+        assert ws.dtype == torch.float32 and ws.numel() >= 1
 
     # bool wgrad_gemm(A[K, M], B[K, N], ws, tickets, out[M, N], accumulate)
-    def wgrad_gemm(self, A, B, ws, tickets, out, accumulate):
+    def wgrad_gemm(self, A, B, ws, out, accumulate):
         self.calls.append("wgrad_gemm")
         A, B, op = _plain(A), _plain(B), _plain(out)
         assert A.dim() == 2 and B.dim() == 2 and op.dim() == 2 and A.dtype == BF16 and B.dtype == BF16
@@ -234,7 +233,7 @@ class FakeExt:
         K, M = A.shape
         N = B.shape[1]
         assert B.shape[0] == K and tuple(op.shape) == (M, N)
-        self._wg_check(ws, tickets, M * op.stride(0))
+        self._wg_check(ws, M * op.stride(0))
         if M % 8 or N % 8:
             return False
         g = A.float().t() @ B.float()
@@ -242,7 +241,7 @@ class FakeExt:
         return True
 
     # bool wgrad_conv(dy, x, ws, tickets, out [Cout, Cin, KH, KW] KRSC memory, accumulate, pad_h, pad_w, stride)
-    def wgrad_conv(self, dy, x, ws, tickets, out, accumulate, pad_h, pad_w, stride):
+    def wgrad_conv(self, dy, x, ws, out, accumulate, pad_h, pad_w, stride):
         self.calls.append("wgrad_conv")
         dy, x, op = _plain(dy), _plain(x), _plain(out)
         assert dy.dtype == BF16 and x.dtype == BF16 and op.dim() == 4
@@ -250,7 +249,7 @@ class FakeExt:
         NB, Cin, H, W = x.shape
         Cout, _, KH, KW = op.shape
         assert op.shape[1] == Cin and dy.shape[0] == NB and dy.shape[1] == Cout
-        self._wg_check(ws, tickets, op.numel())
+        self._wg_check(ws, op.numel())
         if Cin % 8 or Cout % 8 or stride not in (1, 2):
             return False
         g = torch.ops.aten.convolution_backward(
