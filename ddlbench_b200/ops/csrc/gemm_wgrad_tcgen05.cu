@@ -154,55 +154,70 @@ __device__ __forceinline__ void wgrad_epilogue(uint32_t tmem_base, int warp, int
   }
 }
 
-// out[i] (+)= sum over `planes` of ws[p * stride + i]: the second half of a split-K weight gradient
+// out[i] (+)= sum over `planes` of ws[p * stride + i]: the second half of a split-K weight gradient.
+// Block = 32 element groups (float4) x 8 plane lanes: the planes of one element are summed by 8
+// threads in parallel (up to ~300 planes for the 64-channel layers) and combined in shared memory.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, int planes, long long stride, long long n,
                     void* __restrict__ out, int out_bf16, int accumulate) {
+  __shared__ float4 part[8][32];
   pdl_enter();
-  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (i0 >= n) return;
-  if (i0 + 8 <= n) {
-    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int p = 0; p < planes; ++p) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long i0 = ((long long)blockIdx.x * 32 + tx) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i0 + 4 <= n) {
+    int p = ty;
+#pragma unroll 4
+    for (; p < planes; p += 8) {
       const float4 u = __ldcg(reinterpret_cast<const float4*>(ws + (size_t)p * stride + i0));
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + (size_t)p * stride + i0 + 4));
-      a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
-      a[4] += v.x; a[5] += v.y; a[6] += v.z; a[7] += v.w;
+      a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
     }
-    if (out_bf16) {
-      bf16x8* dst = reinterpret_cast<bf16x8*>(reinterpret_cast<__nv_bfloat16*>(out) + i0);
+  } else if (i0 < n) {
+    for (int p = ty; p < planes; p += 8) {
+      const float* src = ws + (size_t)p * stride + i0;
+      a.x += __ldcg(src);
+      if (i0 + 1 < n) a.y += __ldcg(src + 1);
+      if (i0 + 2 < n) a.z += __ldcg(src + 2);
+    }
+  }
+  part[ty][tx] = a;
+  __syncthreads();
+  if (ty != 0 || i0 >= n) return;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) {
+    const float4 u = part[k][tx];
+    a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+  }
+  const float v[4] = {a.x, a.y, a.z, a.w};
+  const int cnt = (int)((n - i0) < 4 ? (n - i0) : 4);
+  if (out_bf16) {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out) + i0;
+    if (cnt == 4) {
+      float f[4] = {v[0], v[1], v[2], v[3]};
       if (accumulate) {
-        float g[8];
-        unpack8(*dst, g);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) a[k] += g[k];
+        const float2 g0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dst));
+        const float2 g1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dst + 2));
+        f[0] += g0.x; f[1] += g0.y; f[2] += g1.x; f[3] += g1.y;
       }
-      *dst = pack8(a);
+      *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(f[0], f[1]);
+      *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(f[2], f[3]);
     } else {
-      float* dst = reinterpret_cast<float*>(out) + i0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) dst[k] = accumulate ? dst[k] + a[k] : a[k];
+      for (int k = 0; k < cnt; ++k) {
+        float f = v[k];
+        if (accumulate) f += __bfloat162float(dst[k]);
+        dst[k] = __float2bfloat16_rn(f);
+      }
     }
   } else {
-    for (long long i = i0; i < n; ++i) {
-      float a = 0.f;
-      for (int p = 0; p < planes; ++p) a += __ldcg(ws + (size_t)p * stride + i);
-      if (out_bf16) {
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out) + i;
-        if (accumulate) a += __bfloat162float(*dst);
-        *dst = __float2bfloat16_rn(a);
-      } else {
-        float* dst = reinterpret_cast<float*>(out) + i;
-        *dst = accumulate ? *dst + a : a;
-      }
-    }
+    float* dst = reinterpret_cast<float*>(out) + i0;
+    for (int k = 0; k < cnt; ++k) dst[k] = accumulate ? dst[k] + v[k] : v[k];
   }
 }
 
 static inline int launch_wgrad_reduce(const float* ws, int planes, long long stride, long long n,
                                       void* out, int out_bf16, int accumulate, cudaStream_t st) {
-  const long long threads = (n + 7) / 8;
-  const int blocks = (int)((threads + 255) / 256);
+  const long long groups = (n + 3) / 4;
+  const int blocks = (int)((groups + 31) / 32);
   cudaError_t err = launch_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, ws, planes, stride, n,
                                out, out_bf16, accumulate);
   return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
@@ -544,9 +559,9 @@ static int launch_conv_wgrad(const void* dy, const void* x, float* D, int NB, in
   }
   const int tiles = ((Cout + BLOCK_M - 1) / BLOCK_M) * ((Cin + BLOCK_N - 1) / BLOCK_N);
   const int taps = KH * KW;
-  int splits = (2 * sms + tiles * taps - 1) / (tiles * taps);
+  int splits = (3 * sms / 2 + tiles * taps - 1) / (tiles * taps);
+  if (splits > wp.total_tiles / 8) splits = wp.total_tiles / 8;   // a split is worth >= 8 k-blocks
   if (splits < 1) splits = 1;
-  if (splits > wp.total_tiles) splits = wp.total_tiles;
   if (splits > max_planes) splits = max_planes;
   wp.tiles_per_split = (wp.total_tiles + splits - 1) / splits;
   splits = (wp.total_tiles + wp.tiles_per_split - 1) / wp.tiles_per_split;
@@ -593,7 +608,11 @@ extern "C" int ddl_wgrad_gemm(const void* A, const void* B, float* ws, long long
   const int bn = N <= 64 ? 64 : 128;
   const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
   const long long plane = (long long)M * ldd;
-  int splits = (2 * sms + tiles - 1) / tiles;
+  int splits = (3 * sms / 2 + tiles - 1) / tiles;
+  {
+    const int total_kb = (K + kMnBox - 1) / kMnBox;
+    if (splits > total_kb / 8) splits = total_kb / 8;      // a split is worth >= 8 k-blocks
+  }
   const long long max_planes = ws ? ws_floats / plane : 0;
   if (splits > max_planes) splits = (int)max_planes;
   if (splits < 1) splits = 1;
