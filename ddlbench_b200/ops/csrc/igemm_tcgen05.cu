@@ -40,6 +40,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "api.h"
 #include "common.cuh"
@@ -90,22 +91,30 @@ __device__ __forceinline__ uint64_t make_mn_sw128_desc(uint32_t smem_addr, uint3
   return d;
 }
 
-template <int BLOCK_N, int kStages, bool kStats>
+// kSmall: ONE tile per CTA — the staged output tile aliases the (by then idle) ring and there is a
+// single TMEM accumulator, so a CTA is 34-66 KB / <= 85 registers and 3-4 of them share an SM: the
+// short-K layers (1x1 convolutions of the first stages) are bound by the CUDA-core epilogue, and
+// 12-16 epilogue warps per SM hide its latency far better than the 8 of the chunked variant
+// (profiles/r2/timeline_igemm_v4.json vs timeline_cudnn_path.json).
+template <int BLOCK_N, int kStages, bool kStats, bool kSmall>
 struct IgSmem {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;            // 16 KB
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;            // 8 / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRingBytes = kStages * kStageBytes;
   static constexpr int kOutBytes = BLOCK_M * BLOCK_N * 2;          // the staged bf16 output tile
-  static constexpr int kOutOffset = kRingBytes;
-  static constexpr int kStatOffset = kOutOffset + kOutBytes;
+  static constexpr int kOutOffset = kSmall ? 0 : kRingBytes;
+  static constexpr int kDataBytes = kSmall ? (kRingBytes > kOutBytes ? kRingBytes : kOutBytes)
+                                           : kRingBytes + kOutBytes;
+  static constexpr int kStatOffset = kDataBytes;
   static constexpr int kStatBytes = kStats ? 2 * BLOCK_N * 4 : 0;  // this CTA's n-tile only
   static constexpr int kBiasOffset = kStatOffset + kStatBytes;
   static constexpr int kBarOffset = kBiasOffset + BLOCK_N * 4;     // full[], empty[], tfull[2], tempty[2]
   static constexpr int kTmemPtrOffset = kBarOffset + (2 * kStages + 4) * 8;
   static constexpr int kTotal = kTmemPtrOffset + 16;
   static constexpr int kDynamic = kTotal + 1024;
-  static_assert(kDynamic <= 113 * 1024, "two CTAs must fit in one SM's shared memory");
+  static constexpr int kMinCtas = kSmall ? (kStages == 1 ? 4 : 3) : 2;
+  static_assert(kDynamic * kMinCtas <= 227 * 1024, "CTAs per SM vs shared memory");
 };
 
 // 32 lanes x 32 fp32 columns -> registers, WITHOUT the wait (callers batch two loads per wait)
@@ -126,14 +135,15 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BLOCK_N, int kStages, bool kBMn, bool kStats>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int BLOCK_N, int kStages, bool kBMn, bool kStats, bool kSmall>
+__global__ void __launch_bounds__(kThreads, (IgSmem<BLOCK_N, kStages, kStats, kSmall>::kMinCtas))
 igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_d,
                   const __grid_constant__ IgemmParams p) {
-  using L = IgSmem<BLOCK_N, kStages, kStats>;
-  constexpr uint32_t kTmemCols = 2 * BLOCK_N;          // two accumulators (power of two >= 128)
+  using L = IgSmem<BLOCK_N, kStages, kStats, kSmall>;
+  constexpr uint32_t kTmemCols = kSmall ? BLOCK_N : 2 * BLOCK_N;   // one / two accumulators
+  constexpr int kStep = kSmall ? 32 : 64;              // columns drained per epilogue step
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -155,7 +165,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
   const int total_kb = p.ntaps * p.kc_blocks;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int kb1 = min(kb0 + p.kb_per_split, total_kb);
-  const bool split = gridDim.z > 1;
+  const bool split = !kSmall && gridDim.z > 1;      // the one-tile variant never splits K
 
   pdl_trigger();
   if (warp == 0 && lane == 0) {
@@ -281,14 +291,14 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
       if (split) {
         float* mine = wst + (size_t)blockIdx.z * slot_elems;
 #pragma unroll
-        for (int cp = 0; cp < BLOCK_N / 64; ++cp) {
-          uint32_t r[64];
-          tmem_ld_32x32_nowait(tacc + cp * 64, r);
-          tmem_ld_32x32_nowait(tacc + cp * 64 + 32, r + 32);
+        for (int cp = 0; cp < BLOCK_N / kStep; ++cp) {
+          uint32_t r[kStep];
+#pragma unroll
+          for (int h = 0; h < kStep / 32; ++h) tmem_ld_32x32_nowait(tacc + cp * kStep + h * 32, r + h * 32);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            __stcg(reinterpret_cast<float4*>(mine + ((size_t)(cp * 16 + j) * BLOCK_M + row) * 4),
+          for (int j = 0; j < kStep / 4; ++j)
+            __stcg(reinterpret_cast<float4*>(mine + ((size_t)(cp * (kStep / 4) + j) * BLOCK_M + row) * 4),
                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
         }
@@ -309,40 +319,42 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
       if (et == 0 && iter >= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-      for (int cp = 0; cp < BLOCK_N / 64; ++cp) {
-        float f[64];
+      for (int cp = 0; cp < BLOCK_N / kStep; ++cp) {
+        float f[kStep];
         {
-          uint32_t r[64];
-          tmem_ld_32x32_nowait(tacc + cp * 64, r);            // two loads in flight per wait
-          tmem_ld_32x32_nowait(tacc + cp * 64 + 32, r + 32);
+          uint32_t r[kStep];
+#pragma unroll
+          for (int h = 0; h < kStep / 32; ++h) tmem_ld_32x32_nowait(tacc + cp * kStep + h * 32, r + h * 32);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 64; ++i) f[i] = __uint_as_float(r[i]);
+          for (int i = 0; i < kStep; ++i) f[i] = __uint_as_float(r[i]);
         }
         if (split) {
           for (int z = 0; z < (int)gridDim.z; ++z) {
             if (z == (int)blockIdx.z) continue;
             const float* other = wst + (size_t)z * slot_elems;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < kStep / 4; ++j) {
               const float4 t = __ldcg(reinterpret_cast<const float4*>(
-                  other + ((size_t)(cp * 16 + j) * BLOCK_M + row) * 4));
+                  other + ((size_t)(cp * (kStep / 4) + j) * BLOCK_M + row) * 4));
               f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
             }
           }
         }
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
+        for (int i = 0; i < kStep; ++i) {
           float v = f[i];
-          if (p.bias) v += bias_s[cp * 64 + i];
+          if (p.bias) v += bias_s[cp * kStep + i];
           if (p.relu) v = fmaxf(v, 0.f);
           f[i] = valid ? v : 0.f;              // rows outside the image contribute nothing
         }
-        uint8_t* region = stage + cp * (BLOCK_M * 128);
+        const int c0 = cp * kStep;             // first column of this step inside the tile
+        uint8_t* region = stage + (c0 / 64) * (BLOCK_M * 128);
+        const int chunk0 = (c0 % 64) / 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < kStep / 8; ++j) {
           bf16x8 pk = pack8(f + j * 8);
-          const int chunk = j ^ (row & 7);
+          const int chunk = (chunk0 + j) ^ (row & 7);
           *reinterpret_cast<bf16x8*>(region + row * 128 + chunk * 16) = pk;
         }
       }
@@ -495,9 +507,9 @@ struct IgProblem {
   int splitk_tiles;               // capacity of both, in 128x128 tiles
 };
 
-template <int BLOCK_N, int kStages, bool kBMn, bool kStats>
+template <int BLOCK_N, int kStages, bool kBMn, bool kStats, bool kSmall>
 static int launch_ig(const IgProblem& q, IgemmParams& p, int sms, cudaStream_t st) {
-  using L = IgSmem<BLOCK_N, kStages, kStats>;
+  using L = IgSmem<BLOCK_N, kStages, kStats, kSmall>;
   CUtensorMap ma, mb, md;
   int rc;
   if ((rc = make_map_4d(&ma, q.a.ptr, q.a.C, q.a.W, q.a.H, q.a.N, q.a.sW, q.a.sH, q.a.sN, BLOCK_K,
@@ -513,7 +525,7 @@ static int launch_ig(const IgProblem& q, IgemmParams& p, int sms, cudaStream_t s
     return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats>,
+    cudaError_t e = cudaFuncSetAttribute(igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats, kSmall>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
@@ -528,8 +540,9 @@ static int launch_ig(const IgProblem& q, IgemmParams& p, int sms, cudaStream_t s
   // gridDim.z, partial tiles meet in the fp32 workspace, the last slice runs the epilogue.
   int per = (int)((total + 2LL * sms - 1) / (2LL * sms));
   if (per > 16) per = 16;
+  if (kSmall) per = 1;
   int splits = 1;
-  if (total < sms && total_kb >= 8 && q.splitk_ws && BLOCK_N == 128) {
+  if (!kSmall && total < sms && total_kb >= 8 && q.splitk_ws && BLOCK_N == 128) {
     splits = (int)((3LL * sms / 2 + total - 1) / total);
     if (splits > total_kb / 4) splits = total_kb / 4;
     if (splits > 8) splits = 8;
@@ -544,7 +557,7 @@ static int launch_ig(const IgProblem& q, IgemmParams& p, int sms, cudaStream_t s
   p.tiles_per_cta = per;
   const int chunks = (p.pix_tiles + per - 1) / per;
   if (chunks > 65535 || p.tiles_n > 65535) return -1;
-  cudaError_t err = launch_pdl((igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats>),
+  cudaError_t err = launch_pdl((igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats, kSmall>),
                                dim3(p.tiles_n, chunks, splits), dim3(kThreads), (size_t)L::kDynamic,
                                st, ma, mb, md, p);
   return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
@@ -587,16 +600,32 @@ static int run_ig(const IgProblem& q, int sms, cudaStream_t st) {
     p.momentum = q.fin->momentum;
   }
   const bool narrow = q.d.C <= 64;
+  // variant: short reductions (<= small_max_kb k-blocks of 64) -> one tile per CTA, 3-4 CTAs per SM;
+  // otherwise chunked + double-buffered accumulator (and split-K when the grid would be tiny)
+  static const int small_max_kb = [] {
+    const char* e = std::getenv("DDLB_IG_SMALL_MAXKB");
+    return e ? atoi(e) : 4;
+  }();
+  const int total_kb = q.ntaps * p.kc_blocks;
+  const int v = total_kb > small_max_kb ? 0 : (total_kb == 1 ? 1 : 2);   // 0 chunked, 1/2 small
+#define DDL_IG_DISPATCH(BMN, STATS)                                                          \
+  do {                                                                                       \
+    if (narrow) {                                                                            \
+      if (v == 0) return launch_ig<64, 3, BMN, STATS, false>(q, p, sms, st);                 \
+      if (v == 1) return launch_ig<64, 1, BMN, STATS, true>(q, p, sms, st);                  \
+      return launch_ig<64, 2, BMN, STATS, true>(q, p, sms, st);                              \
+    }                                                                                        \
+    if (v == 0) return launch_ig<128, 2, BMN, STATS, false>(q, p, sms, st);                  \
+    if (v == 1) return launch_ig<128, 1, BMN, STATS, true>(q, p, sms, st);                   \
+    return launch_ig<128, 2, BMN, STATS, true>(q, p, sms, st);                               \
+  } while (0)
   if (q.b_mn) {
     if (stats) return -1;
-    return narrow ? launch_ig<64, 3, true, false>(q, p, sms, st)
-                  : launch_ig<128, 2, true, false>(q, p, sms, st);
+    DDL_IG_DISPATCH(true, false);
   }
-  if (stats)
-    return narrow ? launch_ig<64, 3, false, true>(q, p, sms, st)
-                  : launch_ig<128, 2, false, true>(q, p, sms, st);
-  return narrow ? launch_ig<64, 3, false, false>(q, p, sms, st)
-                : launch_ig<128, 2, false, false>(q, p, sms, st);
+  if (stats) DDL_IG_DISPATCH(false, true);
+  DDL_IG_DISPATCH(false, false);
+#undef DDL_IG_DISPATCH
 }
 
 static inline IgTensor dense_nhwc(const void* ptr, int64_t N, int64_t H, int64_t W, int64_t C) {
