@@ -606,6 +606,14 @@ def igemm_conv_supported(x: torch.Tensor, wshape, stride, padding, dilation, gro
             x.is_contiguous(memory_format=torch.channels_last))
 
 
+def _finalize_after(col_sums, bn_finalize, rows: int, channels: int) -> None:
+    """The kernel delivered the sums only (its one-tile variant: ~1500 short CTAs, where a per-CTA
+    fence + ticket costs more than this 2 us launch): finalize them here, same outputs."""
+    _, st, rm, rv, eps, mom = bn_finalize
+    ext().bn_finalize(col_sums, st, rm, rv, rows, channels, float(eps), float(mom))
+    _count()
+
+
 def _fin_args(bn_finalize):
     if bn_finalize is None:
         return (None, None, None, None, 0.0, 0.0)
@@ -626,11 +634,14 @@ def conv_fprop(x: torch.Tensor, w: torch.Tensor, stride: int, padding: Sequence[
         w = w.contiguous(memory_format=torch.channels_last)
     y = torch.empty((x.shape[0], co, oh, ow), dtype=x.dtype, device=x.device,
                     memory_format=torch.channels_last)
-    if ext().igemm_conv_fprop(x, w, y, ph, pw, stride, col_sums, bias, relu, *_fin_args(bn_finalize),
-                              *_ig_ws(x.device)):
-        _count()
-        return y
-    return None
+    rc = ext().igemm_conv_fprop(x, w, y, ph, pw, stride, col_sums, bias, relu, *_fin_args(bn_finalize),
+                                *_ig_ws(x.device))
+    if rc < 0:
+        return None
+    _count()
+    if bn_finalize is not None and rc == 0:
+        _finalize_after(col_sums, bn_finalize, y.numel() // co, co)
+    return y
 
 
 def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int,
@@ -680,10 +691,13 @@ def gemm_ig(a: torch.Tensor, b: torch.Tensor, b_mn: bool = False,
     """D[M, N] = a[M, K] @ (b[N, K]^T if not b_mn else b[K, N]) on the persistent kernel."""
     n = b.shape[1] if b_mn else b.shape[0]
     out = torch.empty((a.shape[0], n), dtype=torch.bfloat16, device=a.device)
-    if ext().igemm_gemm(a, b, out, b_mn, col_sums, bias, relu, *_fin_args(bn_finalize), *_ig_ws(a.device)):
-        _count()
-        return out
-    return None
+    rc = ext().igemm_gemm(a, b, out, b_mn, col_sums, bias, relu, *_fin_args(bn_finalize), *_ig_ws(a.device))
+    if rc < 0:
+        return None
+    _count()
+    if bn_finalize is not None and rc == 0:
+        _finalize_after(col_sums, bn_finalize, a.shape[0], n)
+    return out
 
 
 def wgrad_gemm_into(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, accumulate: bool) -> bool:

@@ -129,6 +129,8 @@ int ddl_gemm_bf16_tn_bnbwd(const void* dy, const void* dy2, const void* c, const
                            cudaStream_t st);
 
 // ---- igemm_tcgen05.cu  (persistent implicit-GEMM: every dense conv fprop / dgrad and the FC layers)
+// Return: 0 ok (with col_sums: sums only, run ddl_bn_finalize), DDL_IGEMM_FINALIZED (-100) ok and the
+// statistics were finalized by the kernel, -1 unsupported shape, > 0 CUDA error.
 // `fin->ticket` here is an ARRAY with one counter per 128-wide output-channel tile; splitk_*: zero
 // fp32 scratch of `splitk_tiles` x 16384 floats + as many zero tickets (null / 0: never split K).
 int ddl_igemm_gemm(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb,

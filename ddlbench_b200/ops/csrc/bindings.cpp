@@ -441,7 +441,7 @@ static inline void check_fin_tickets(const c10::optional<at::Tensor>& ticket, in
   if (ticket.has_value() && ticket->defined())
     TORCH_CHECK(ticket->numel() >= (n_out + 63) / 64, "igemm: one finalize ticket per n-tile needed");
 }
-bool igemm_gemm(at::Tensor A, at::Tensor B, at::Tensor D, bool b_mn, c10::optional<at::Tensor> col_sums,
+int64_t igemm_gemm(at::Tensor A, at::Tensor B, at::Tensor D, bool b_mn, c10::optional<at::Tensor> col_sums,
                 c10::optional<at::Tensor> bias, bool relu, c10::optional<at::Tensor> ticket,
                 c10::optional<at::Tensor> stat_out, c10::optional<at::Tensor> rmean,
                 c10::optional<at::Tensor> rvar, double eps, double momentum,
@@ -460,11 +460,12 @@ bool igemm_gemm(at::Tensor A, at::Tensor B, at::Tensor D, bool b_mn, c10::option
                                 (int)B.stride(0), (int)D.stride(0), b_mn ? 1 : 0,
                                 (float*)optr(col_sums), optr(bias), relu, use_fin ? &fin : nullptr,
                                 sk.ws, sk.tickets, sk.tiles, sm_count(), cur_stream());
-  if (rc == -1) return false;
+  if (rc == -1) return -1;
+  if (rc == -100) return 1;
   check(rc, "igemm_gemm");
-  return true;
+  return 0;
 }
-bool igemm_conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int64_t pad_h, int64_t pad_w,
+int64_t igemm_conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int64_t pad_h, int64_t pad_w,
                       int64_t stride, c10::optional<at::Tensor> col_sums,
                       c10::optional<at::Tensor> bias, bool relu, c10::optional<at::Tensor> ticket,
                       c10::optional<at::Tensor> stat_out, c10::optional<at::Tensor> rmean,
@@ -490,9 +491,10 @@ bool igemm_conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int64_t pad_h, i
                                       (float*)optr(col_sums), optr(bias), relu,
                                       use_fin ? &fin : nullptr, sk.ws, sk.tickets, sk.tiles,
                                       sm_count(), cur_stream());
-  if (rc == -1) return false;
+  if (rc == -1) return -1;
+  if (rc == -100) return 1;
   check(rc, "igemm_conv_fprop");
-  return true;
+  return 0;
 }
 // dx [N, Cin, H, W] = data gradient of conv2d(x, w) given dy [N, Cout, OH, OW]; w is the FORWARD filter
 bool igemm_conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int64_t pad_h, int64_t pad_w,

@@ -559,7 +559,9 @@ static int launch_conv_wgrad(const void* dy, const void* x, float* D, int NB, in
   }
   const int tiles = ((Cout + BLOCK_M - 1) / BLOCK_M) * ((Cin + BLOCK_N - 1) / BLOCK_N);
   const int taps = KH * KW;
-  int splits = (3 * sms / 2 + tiles * taps - 1) / (tiles * taps);
+  // enough (tile, tap) units to cover 2/3 of the SMs: no split, the tile goes straight to the
+  // gradient buffer (no planes, no reduce launch); otherwise ~1.5 CTAs per SM
+  int splits = tiles * taps >= (2 * sms) / 3 ? 1 : (3 * sms / 2 + tiles * taps - 1) / (tiles * taps);
   if (splits > wp.total_tiles / 8) splits = wp.total_tiles / 8;   // a split is worth >= 8 k-blocks
   if (splits < 1) splits = 1;
   if (splits > max_planes) splits = max_planes;
@@ -608,7 +610,7 @@ extern "C" int ddl_wgrad_gemm(const void* A, const void* B, float* ws, long long
   const int bn = N <= 64 ? 64 : 128;
   const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
   const long long plane = (long long)M * ldd;
-  int splits = (3 * sms / 2 + tiles - 1) / tiles;
+  int splits = tiles >= (2 * sms) / 3 ? 1 : (3 * sms / 2 + tiles - 1) / tiles;
   {
     const int total_kb = (K + kMnBox - 1) / kMnBox;
     if (splits > total_kb / 8) splits = total_kb / 8;      // a split is worth >= 8 k-blocks

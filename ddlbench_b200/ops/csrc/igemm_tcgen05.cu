@@ -50,6 +50,8 @@ namespace ddl {
 namespace gemm {
 
 constexpr int kIgMaxTaps = 49;
+// return value of a launch whose LAST CTA also finalized the BatchNorm statistics (0: sums only)
+#define DDL_IGEMM_FINALIZED (-100)
 
 struct IgemmParams {
   int OW, OH, NB;                 // output pixel space (tiles iterate here)
@@ -414,7 +416,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
           atomicAdd(&cs[p.Nout + col], stat_s[BLOCK_N + i]);
         }
       }
-      if (p.ticket) {
+      if (!kSmall && p.ticket) {
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) {
@@ -560,7 +562,10 @@ static int launch_ig(const IgProblem& q, IgemmParams& p, int sms, cudaStream_t s
   cudaError_t err = launch_pdl((igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats, kSmall>),
                                dim3(p.tiles_n, chunks, splits), dim3(kThreads), (size_t)L::kDynamic,
                                st, ma, mb, md, p);
-  return err != cudaSuccess ? (int)err : (int)cudaGetLastError();
+  if (err != cudaSuccess) return (int)err;
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return (int)err;
+  return (kStats && p.col_sums && p.ticket) ? DDL_IGEMM_FINALIZED : 0;
 }
 
 static int run_ig(const IgProblem& q, int sms, cudaStream_t st) {
@@ -607,7 +612,9 @@ static int run_ig(const IgProblem& q, int sms, cudaStream_t st) {
     return e ? atoi(e) : 4;
   }();
   const int total_kb = q.ntaps * p.kc_blocks;
-  const int v = total_kb > small_max_kb ? 0 : (total_kb == 1 ? 1 : 2);   // 0 chunked, 1/2 small
+  // (the one-tile variant pays off only where the statistics make the epilogue the bottleneck)
+  const int v = (!stats || total_kb > small_max_kb) ? 0 : (total_kb == 1 ? 1 : 2);   // 0 chunked, 1/2 small
+  if (v != 0) p.ticket = nullptr;      // sums only: the caller runs the 2 us finalize kernel
 #define DDL_IG_DISPATCH(BMN, STATS)                                                          \
   do {                                                                                       \
     if (narrow) {                                                                            \

@@ -158,7 +158,7 @@ class FakeExt:
         N = Dp.shape[1]
         assert Dp.shape[0] == M and tuple(B.shape) == ((K, N) if b_mn else (N, K))
         if K % 8 or N % 8:
-            return False
+            return -1
         d = A.float() @ (B.float() if b_mn else B.float().t())
         if bias is not None:
             d = d + _plain(bias).float()
@@ -172,7 +172,7 @@ class FakeExt:
             cs[:N] += df.sum(0)
             cs[N:2 * N] += (df * df).sum(0)
             self._fin(cs, N, M, ticket, stat, rm, rv, eps, mom)
-        return True
+        return 1 if (col_sums is not None and ticket is not None and stat is not None) else 0
 
     # bool igemm_conv_fprop(x, w, y, pad_h, pad_w, stride, col_sums?, bias?, relu, ticket?, stat?, rm?, rv?, eps, mom)
     def igemm_conv_fprop(self, x, w, y, pad_h, pad_w, stride, col_sums, bias, relu, ticket, stat, rm, rv, eps, mom,
@@ -186,7 +186,7 @@ class FakeExt:
         OH, OW = (H + 2 * pad_h - KH) // stride + 1, (W + 2 * pad_w - KW) // stride + 1
         assert w.shape[1] == Cin and tuple(yp.shape) == (NB, Cout, OH, OW)
         if Cin % 8 or Cout % 8 or stride not in (1, 2) or KH * KW > 49:
-            return False
+            return -1
         d = F.conv2d(x.float(), w.float(), None, stride, (pad_h, pad_w))
         if bias is not None:
             d = d + _plain(bias).float().view(1, -1, 1, 1)
@@ -200,7 +200,7 @@ class FakeExt:
             cs[:Cout] += df.sum((0, 2, 3))
             cs[Cout:2 * Cout] += (df * df).sum((0, 2, 3))
             self._fin(cs, Cout, NB * OH * OW, ticket, stat, rm, rv, eps, mom)
-        return True
+        return 1 if (col_sums is not None and ticket is not None and stat is not None) else 0
 
     # bool igemm_conv_dgrad(dy, w, dx, pad_h, pad_w, stride)
     def igemm_conv_dgrad(self, dy, w, dx, pad_h, pad_w, stride, sk_ws=None, sk_tickets=None):
