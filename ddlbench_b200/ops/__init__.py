@@ -141,8 +141,10 @@ def _nhwc_ok(x: torch.Tensor) -> bool:
 # Single-pass cluster kernels (csrc/bn_cluster.cu).  Per kernel they beat the two-kernel path on
 # the 7x7/14x14 layers (ncu: 10-14 us vs 15-24 us) but inside the training graph the step time is
 # unchanged: 8/16-CTA clusters need whole-GPC slots and stop overlapping with the weight-gradient
-# kernels on the side stream.  Off by default; DDLB_BN_CLUSTER=1 enables them.
-BN_CLUSTER_FUSED = os.environ.get("DDLB_BN_CLUSTER", "0") == "1"
+# kernels on the side stream.  (Round 1: no gain inside the graph with the library's small wgrad
+# kernels on the side stream; round 2, with every convolution on the tcgen05 kernels: 5.52 -> 5.39
+# ms/step, profiles/r2/README.md.)  On by default; DDLB_BN_CLUSTER=0 disables them.
+BN_CLUSTER_FUSED = os.environ.get("DDLB_BN_CLUSTER", "1") == "1"
 # fused BN-fold GEMM kernel (csrc/gemm_bnfold_tcgen05.cu); without it a deferred BatchNorm is
 # applied by the ordinary kernel right before its consumer (same result, no saving)
 BNFOLD_KERNEL = os.environ.get("DDLB_BN_FOLD_KERNEL", "1") == "1"

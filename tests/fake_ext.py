@@ -354,6 +354,17 @@ class FullFakeExt(FakeExt):
     def set_pdl(self, on):
         return False
 
+    # single-pass cluster BatchNorm kernels (bn_cluster.cu): the stand-in always DECLINES (as the
+    # kernels do when a channel slab does not fit a cluster's shared memory), which exercises the
+    # two-kernel fall-through of the glue
+    def bn_fwd_fused(self, *a):
+        self.calls.append("bn_fwd_fused:declined")
+        return False
+
+    def bn_bwd_fused(self, *a):
+        self.calls.append("bn_bwd_fused:declined")
+        return False
+
     def bn_replicas(self):
         return R
 

@@ -212,6 +212,8 @@ def test_bn_backward_folded_into_dgrad_matches_unfused(monkeypatch, has_res, two
             mp.setattr(ops, "ext", lambda: fe)
             mp.setitem(E.TCGEN05, "conv1x1", True)
             mp.setattr(E, "BN_BWD_FOLD", fold)
+            mp.setattr(ops, "IGEMM", False)               # the legacy 1x1 GEMM path this fold belongs to
+            mp.setattr(ops, "BN_CLUSTER_FUSED", False)
             for name in ("empty", "zeros", "empty_like", "zeros_like"):
                 real = getattr(torch, name)
                 mp.setattr(torch, name, (lambda real: lambda *a, **k: fake_cuda(real(*a, **k)))(real))
@@ -346,6 +348,7 @@ def test_resnet50_through_device_branches_with_every_optin_switch(monkeypatch):
             fe = FullFakeExt()
             mp.setattr(ops, "ext", lambda: fe)
             mp.setattr(ops, "IGEMM", label == "igemm")
+            mp.setattr(ops, "BN_CLUSTER_FUSED", label == "igemm")     # the legacy folds exclude the cluster kernels
             mp.setattr(ops, "_WG_WS", {})
             if label == "igemm":
                 mp.setattr(E, "aten", AtenSpy())
@@ -416,6 +419,7 @@ def test_other_families_device_branches_optin_equals_default(monkeypatch, arch, 
             fe = FullFakeExt()
             mp.setattr(ops, "ext", lambda: fe)
             mp.setattr(ops, "IGEMM", False)
+            mp.setattr(ops, "BN_CLUSTER_FUSED", False)
             mp.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
             for name in ("empty", "zeros", "empty_like", "zeros_like"):
                 real = getattr(torch, name)
