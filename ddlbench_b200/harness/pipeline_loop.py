@@ -126,7 +126,8 @@ def run_gpipe(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
         elapsed.append(tock - tick)
     k = max(len(throughputs), 1)
     out = {"throughput": sum(throughputs) / k, "sec_per_epoch": sum(elapsed) / k,
-           "device_throughput": sum(dev_tputs) / k, "valid_accuracy": vacc,
+           "device_throughput": sum(dev_tputs) / k, "device_throughputs": list(dev_tputs),
+           "valid_accuracy": vacc,
            "peak_mem_gb": logfmt.memory_gb(device if device.type == "cuda" else None)[0]}
     say(logfmt.final_summary(vacc, out["throughput"], out["sec_per_epoch"]))
     return out
@@ -326,5 +327,5 @@ def run_pipedream(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
     k = max(len(epoch_times), 1)
     images = n_first * pcfg.replicas(0) * cfg.batch_size
     return {"throughput": images / (sum(epoch_times) / k), "sec_per_epoch": sum(epoch_times) / k,
-            "device_throughput": sum(dev_tputs) / k,
+            "device_throughput": sum(dev_tputs) / k, "device_throughputs": list(dev_tputs),
             "peak_mem_gb": logfmt.memory_gb(device if device.type == "cuda" else None)[0]}
