@@ -373,7 +373,7 @@ def _e2e_jpeg(args, trainer, dev, rank, n, dist, timed_loop, max_over_ranks, Dev
         while not os.path.exists(ready):
             time.sleep(0.1)
     gen_s = time.time() - t0
-    workers = max(2, min(32, (os.cpu_count() or 8) // n))
+    workers = max(2, min(int(os.environ.get("BENCH_DECODE_THREADS", "32")), (os.cpu_count() or 8) // n))
     try:
         src = JpegFolder(tmp, DATASET, PER_GPU_BATCH, split="train", shuffle=True, seed=3, rank=rank,
                          world=n, workers=workers, pinned=True, prefetch=6, gpu_decode=gpu_decode,

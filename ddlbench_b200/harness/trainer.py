@@ -217,7 +217,16 @@ class Trainer:
         g = torch.cuda.CUDAGraph()
         failed = 0
         try:
-            with torch.cuda.graph(g):
+            # DDLB_MAIN_PRIO=1: capture on a high-priority stream (the main-stream kernel nodes inherit
+            # it, the weight-gradient side stream keeps the default).  Measured SLOWER (5.87 vs 5.31
+            # ms/step, profiles/r2/README.md): the starved weight gradients end up on the critical
+            # path at the optimizer.  Off.
+            cap = None
+            if os.environ.get("DDLB_MAIN_PRIO", "0") == "1":
+                if getattr(self, "_cap_stream", None) is None:
+                    self._cap_stream = torch.cuda.Stream(device=self.device, priority=-1)
+                cap = self._cap_stream
+            with torch.cuda.graph(g, stream=cap):
                 self.static_stats = self._step_eager(self.static_x, self.static_t,
                                                      update=not self._nccl_outside_graph)
         except Exception as e:  # noqa: BLE001
