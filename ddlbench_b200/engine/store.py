@@ -138,6 +138,9 @@ class ParamStore:
             v = self.layout.view(full, s.name)
             v.copy_(s.init.to(self.device, torch.float32))
         self.load_full_master(full)
+        # kept until the first broadcast / step so that a sharded store can hand out the
+        # full-precision initial master (FusedDataParallel.broadcast_from)
+        self._init_full = full if self.shard_optimizer else None
 
     def load_full_master(self, full: torch.Tensor) -> None:
         """Set every weight version and the (possibly sharded) master from a full fp32 copy."""

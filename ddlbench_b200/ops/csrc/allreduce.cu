@@ -120,7 +120,14 @@ struct ArSgdArgs {
 };
 
 // MODE 0: peer-to-peer loads/stores.  MODE 1: NVLS multimem.
-template <int MODE>
+// U independent 16-byte vectors per thread per trip, KW = compile-time bound on the world size:
+// NVLink round trips are ~2-3 us, so the bytes in flight (CTAs x threads x U x 16 B x world for
+// peer loads) set the bandwidth.  With ONE peer (the 2-replica stages of a hybrid pipeline) U = 2
+// left 1 MB in flight and the kernel at 0.4x NCCL (profiles/allreduce_sweep_n2.json, round 1);
+// the generic kernel holds U x KW at 16 vectors per thread — (8, 2), (4, 4), (2, 8) —, the fused
+// one (which also carries the fp32 update of U vectors in registers) at (4, 2), (2, 4), (2, 8) and
+// makes up for it with more CTAs when there is a single peer.
+template <int MODE, int U, int KW>
 __global__ void __launch_bounds__(kArThreads, 1) ar_sgd_twoshot_kernel(ArSgdArgs a) {
   const uint32_t epoch = a.epoch[blockIdx.x] + 1;
   peer_barrier(a.flags, a.rank, a.world, 0, a.max_blocks, epoch, a.status);
@@ -129,9 +136,6 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_sgd_twoshot_kernel(ArSgdArgs
   const int64_t nvec = a.slice_len >> 3;
   const int64_t base = a.bucket_off + (int64_t)a.rank * a.slice_len;  // my slice, in elements
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  // U independent 16-byte vectors per thread per trip: NVLink round trips are ~2-3 us, so the
-  // bytes in flight (CTAs x threads x U x 16 B [x world for peer loads]) set the bandwidth.
-  constexpr int U = (MODE == 1) ? 4 : 2;
   for (int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * U) {
     float g[U][8];
     if (MODE == 1) {
@@ -144,13 +148,13 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_sgd_twoshot_kernel(ArSgdArgs
 #pragma unroll
       for (int u = 0; u < U; ++u) unpack8(*reinterpret_cast<bf16x8*>(&red[u]), g[u]);
     } else {
-      int4 raw[U][kMaxRanks];
+      int4 raw[U][KW];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t v = v0 + u * stride;
         if (v < nvec) {
 #pragma unroll
-          for (int r = 0; r < kMaxRanks; ++r)
+          for (int r = 0; r < KW; ++r)
             if (r < a.world)
               raw[u][r] = ld_peer16((const __nv_bfloat16*)a.grad.p[(a.rank + r) % a.world] + base + (v << 3));
         }
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_sgd_twoshot_kernel(ArSgdArgs
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[u][k] = 0.f;
 #pragma unroll
-        for (int r = 0; r < kMaxRanks; ++r)
+        for (int r = 0; r < KW; ++r)
           if (r < a.world) {
             float f[8];
             unpack8(*reinterpret_cast<bf16x8*>(&raw[u][r]), f);
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_sgd_twoshot_kernel(ArSgdArgs
         mc_st16((__nv_bfloat16*)a.weight_mc + e, wv);
       } else {
 #pragma unroll
-        for (int r = 0; r < kMaxRanks; ++r)
+        for (int r = 0; r < KW; ++r)
           if (r < a.world) st_peer16((__nv_bfloat16*)a.weight.p[(a.rank + r) % a.world] + e, wv);
       }
     }
@@ -220,7 +224,7 @@ struct ArArgs {
   int rank, world, max_blocks;
 };
 
-template <typename T, int MODE>
+template <typename T, int MODE, int U, int KW>
 __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(ArArgs a) {
   constexpr int EPV = 16 / sizeof(T);  // elements per 16-byte vector
   const uint32_t epoch = a.epoch[blockIdx.x] + 1;
@@ -228,59 +232,91 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(ArArgs a) {
   const int64_t nvec = a.slice_len / EPV;
   const int64_t base = a.off + (int64_t)a.rank * a.slice_len;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    const int64_t e = base + v * EPV;
-    int4 outv;
+  for (int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * U) {
+    int4 outv[U];
     if (MODE == 1) {
-      if (sizeof(T) == 2) {
-        int4 red = mc_ld_reduce_bf16x8((const T*)a.buf_mc + e);
-        float f[8];
-        unpack8(*reinterpret_cast<bf16x8*>(&red), f);
+      int4 red[U];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] *= a.scale;
-        bf16x8 o = pack8(f);
-        outv = *reinterpret_cast<int4*>(&o);
-      } else {
-        float4 red = mc_ld_reduce_f32x4((const T*)a.buf_mc + e);
-        red.x *= a.scale; red.y *= a.scale; red.z *= a.scale; red.w *= a.scale;
-        outv = *reinterpret_cast<int4*>(&red);
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = v0 + u * stride;
+        if (v < nvec) {
+          if (sizeof(T) == 2) red[u] = mc_ld_reduce_bf16x8((const T*)a.buf_mc + base + v * EPV);
+          else {
+            float4 f = mc_ld_reduce_f32x4((const T*)a.buf_mc + base + v * EPV);
+            red[u] = *reinterpret_cast<int4*>(&f);
+          }
+        }
       }
-      mc_st16((T*)a.buf_mc + e, outv);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (sizeof(T) == 2) {
+          float f[8];
+          unpack8(*reinterpret_cast<bf16x8*>(&red[u]), f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] *= a.scale;
+          bf16x8 o = pack8(f);
+          outv[u] = *reinterpret_cast<int4*>(&o);
+        } else {
+          float4 f = *reinterpret_cast<float4*>(&red[u]);
+          f.x *= a.scale; f.y *= a.scale; f.z *= a.scale; f.w *= a.scale;
+          outv[u] = *reinterpret_cast<int4*>(&f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = v0 + u * stride;
+        if (v < nvec) mc_st16((T*)a.buf_mc + base + v * EPV, outv[u]);
+      }
     } else {
-      int4 raw[kMaxRanks];
+      int4 raw[U][KW];
 #pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r)
-        if (r < a.world) raw[r] = ld_peer16((const T*)a.buf.p[(a.rank + r) % a.world] + e);
-      if (sizeof(T) == 2) {
-        float acc[8];
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = v0 + u * stride;
+        if (v < nvec) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-#pragma unroll
-        for (int r = 0; r < kMaxRanks; ++r)
-          if (r < a.world) {
-            float f[8];
-            unpack8(*reinterpret_cast<bf16x8*>(&raw[r]), f);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] += f[k];
-          }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] *= a.scale;
-        bf16x8 o = pack8(acc);
-        outv = *reinterpret_cast<int4*>(&o);
-      } else {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int r = 0; r < kMaxRanks; ++r)
-          if (r < a.world) {
-            float4 f = *reinterpret_cast<float4*>(&raw[r]);
-            acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
-          }
-        acc.x *= a.scale; acc.y *= a.scale; acc.z *= a.scale; acc.w *= a.scale;
-        outv = *reinterpret_cast<int4*>(&acc);
+          for (int r = 0; r < KW; ++r)
+            if (r < a.world) raw[u][r] = ld_peer16((const T*)a.buf.p[(a.rank + r) % a.world] + base + v * EPV);
+        }
       }
 #pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r)
-        if (r < a.world) st_peer16((T*)a.buf.p[(a.rank + r) % a.world] + e, outv);
+      for (int u = 0; u < U; ++u) {
+        if (sizeof(T) == 2) {
+          float acc[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+          for (int r = 0; r < KW; ++r)
+            if (r < a.world) {
+              float f[8];
+              unpack8(*reinterpret_cast<bf16x8*>(&raw[u][r]), f);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[k] += f[k];
+            }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] *= a.scale;
+          bf16x8 o = pack8(acc);
+          outv[u] = *reinterpret_cast<int4*>(&o);
+        } else {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int r = 0; r < KW; ++r)
+            if (r < a.world) {
+              float4 f = *reinterpret_cast<float4*>(&raw[u][r]);
+              acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+            }
+          acc.x *= a.scale; acc.y *= a.scale; acc.z *= a.scale; acc.w *= a.scale;
+          outv[u] = *reinterpret_cast<int4*>(&acc);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = v0 + u * stride;
+        if (v < nvec) {
+#pragma unroll
+          for (int r = 0; r < KW; ++r)
+            if (r < a.world) st_peer16((T*)a.buf.p[(a.rank + r) % a.world] + base + v * EPV, outv[u]);
+        }
+      }
     }
   }
   peer_barrier(a.flags, a.rank, a.world, 1, a.max_blocks, epoch, a.status);
@@ -410,9 +446,13 @@ extern "C" int ddl_ar_sgd_twoshot(void* const* grad_ptrs, void* const* weight_pt
   a.bucket_off = bucket_off; a.slice_len = slice_len;
   a.rank = rank; a.world = world; a.max_blocks = max_blocks;
   if (use_multimem && grad_mc && weight_mc)
-    ar_sgd_twoshot_kernel<1><<<blocks, kArThreads, 0, st>>>(a);
+    ar_sgd_twoshot_kernel<1, 4, 8><<<blocks, kArThreads, 0, st>>>(a);
+  else if (world <= 2)
+    ar_sgd_twoshot_kernel<0, 4, 2><<<blocks, kArThreads, 0, st>>>(a);
+  else if (world <= 4)
+    ar_sgd_twoshot_kernel<0, 2, 4><<<blocks, kArThreads, 0, st>>>(a);
   else
-    ar_sgd_twoshot_kernel<0><<<blocks, kArThreads, 0, st>>>(a);
+    ar_sgd_twoshot_kernel<0, 2, 8><<<blocks, kArThreads, 0, st>>>(a);
   return (int)cudaGetLastError();
 }
 
@@ -437,13 +477,16 @@ extern "C" int ddl_ar_twoshot(void* const* buf_ptrs, void* const* flag_ptrs, voi
     return -1;
   if (blocks > max_blocks || (slice_len * (is_bf16 ? 2 : 4)) % 16) return -1;
   const bool mm = use_multimem && buf_mc;
-  if (is_bf16) {
-    if (mm) ar_twoshot_kernel<__nv_bfloat16, 1><<<blocks, kArThreads, 0, st>>>(a);
-    else ar_twoshot_kernel<__nv_bfloat16, 0><<<blocks, kArThreads, 0, st>>>(a);
-  } else {
-    if (mm) ar_twoshot_kernel<float, 1><<<blocks, kArThreads, 0, st>>>(a);
-    else ar_twoshot_kernel<float, 0><<<blocks, kArThreads, 0, st>>>(a);
-  }
+#define DDL_AR2(T)                                                                             \
+  do {                                                                                         \
+    if (mm) ar_twoshot_kernel<T, 1, 4, 8><<<blocks, kArThreads, 0, st>>>(a);                   \
+    else if (world <= 2) ar_twoshot_kernel<T, 0, 8, 2><<<blocks, kArThreads, 0, st>>>(a);      \
+    else if (world <= 4) ar_twoshot_kernel<T, 0, 4, 4><<<blocks, kArThreads, 0, st>>>(a);      \
+    else ar_twoshot_kernel<T, 0, 2, 8><<<blocks, kArThreads, 0, st>>>(a);                      \
+  } while (0)
+  if (is_bf16) DDL_AR2(__nv_bfloat16);
+  else DDL_AR2(float);
+#undef DDL_AR2
   return (int)cudaGetLastError();
 }
 

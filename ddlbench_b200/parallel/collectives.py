@@ -16,7 +16,8 @@ ONE_SHOT_MAX_BYTES = 512 << 10
 class SymmAllreduce:
     def __init__(self, ctx: SymmContext, max_bytes: int = 64 << 20, blocks: int = 32):
         self.ctx = ctx
-        self.blocks = blocks
+        # a single peer needs more CTAs to keep the link full (see csrc/allreduce.cu)
+        self.blocks = min(blocks * 2, 64) if ctx.world <= 2 else blocks
         self.max_bytes = max_bytes
         # staging buffers per dtype share one allocation (viewed as bytes)
         self.stage: SymmetricBuffer = ctx.alloc(max_bytes // 4, torch.float32)

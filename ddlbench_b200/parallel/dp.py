@@ -210,7 +210,8 @@ class FusedDataParallel:
         self.ex = executor
         self.ctx = ctx
         self.ops = ops
-        self.blocks = min(blocks, 64)
+        # one peer (2-replica stages): twice the CTAs keep enough bytes in flight on the single link
+        self.blocks = min(blocks * 2 if ctx.world <= 2 else blocks, 64)
         st = executor.store
         assert st.shard_optimizer and st.world == ctx.world
         self.w_sym = executor._sym_w        # SymmetricBuffer list (per version)
@@ -238,7 +239,13 @@ class FusedDataParallel:
         st = self.ex.store
         bucket = st.layout.buckets[b]
         mo, ml = st.master_slices()[b]
-        out_v = st.latest
+        # weight stashing (PipeDream stages with V > 1 versions): the update reads the fp32 master
+        # (always the newest weights) and writes the NEXT slot of the ring, (latest + 1) % V — the
+        # slot of the minibatch whose backward is running, which no longer reads this bucket's
+        # weights (all of the bucket's gradients are final) — on every replica, after the kernel's
+        # barrier-in has established that all replicas are past this bucket.  finish_step() then
+        # advances the ring.
+        out_v = st.next_version() if st.versions > 1 else st.latest
         wsym = self.w_sym[out_v]
         use_mm = self.ctx.use_multimem and wsym.mc_ptr != 0 and self.g_sym.mc_ptr != 0
         main = torch.cuda.current_stream(st.device)
@@ -269,6 +276,8 @@ class FusedDataParallel:
             ev = torch.cuda.Event()
             ev.record(self.comm_stream)
             torch.cuda.current_stream(self.ex.store.device).wait_event(ev)
+        if self.ex.store.versions > 1:
+            self.ex.store.advance_version()
         if self._reduce_events:
             self.flush_reduce_log()
 
@@ -291,11 +300,17 @@ class FusedDataParallel:
         """Make every rank start from rank ``root``'s weights (hvd.broadcast_parameters) and
         rebuild the sharded fp32 master from them."""
         st = self.ex.store
-        w = st.w_flat[st.latest]
-        full = w.float()
+        # broadcast the fp32 MASTER (all-gather of the root's view is unnecessary: before the first
+        # step every rank still holds the full-precision initial values it was constructed with, so
+        # the root's full master is re-created from its init and sent as fp32 — the low bits survive)
+        full = getattr(st, "_init_full", None)
+        if full is None:
+            full = st.w_flat[st.latest].float()
+        full = full.clone()
         src = dist.get_global_rank(self.ctx.group, root) if self.ctx.group is not None else root
         dist.broadcast(full, src=src, group=self.ctx.group)
         st.load_full_master(full)
+        st._init_full = None
         for k in sorted(self.ex.buffers):
             dist.broadcast(self.ex.buffers[k], src=src, group=self.ctx.group)
         torch.cuda.synchronize(st.device)

@@ -152,7 +152,7 @@ class StageRuntime:
         kw = dict(device=self.device, dtype=dtype, versions=versions,
                   lr=lr * cfg.lr_scale(t.stage), momentum=momentum, weight_decay=weight_decay,
                   tcgen05=tcgen05, first_stage=t.is_first)
-        if self.replica_group is not None and on_gpu and fused_replica_allreduce and versions == 1:
+        if self.replica_group is not None and on_gpu and fused_replica_allreduce:
             from ...dist.symm import SymmContext
             from ..dp import FusedDataParallel
             self.symm = SymmContext(self.device, self.replica_group)
@@ -466,7 +466,9 @@ class StageRuntime:
         ex = self.ex
         st = ex.store
         if self.fdp is not None:
-            self.fdp.finish_step()             # fused all-reduce+SGD already ran per bucket
+            # fused all-reduce+SGD already ran per bucket (into the next weight slot when the stage
+            # stashes versions); this joins the communication stream and advances the ring
+            self.fdp.finish_step()
             return
         if self.replica_group is not None:
             dist.all_reduce(st.g_flat, group=self.replica_group)   # averaged via grad_scale

@@ -33,7 +33,8 @@ def main():
     cuts = even_cuts(model, len(reps))
     dev = f"cuda:{torch.cuda.current_device()}" if gpu else "cpu"
     kw = dict(no_input_pipelining=os.environ.get("PD_NOPIPE", "0") == "1",
-              macrobatch=os.environ.get("PD_MACRO", "0") == "1")
+              macrobatch=os.environ.get("PD_MACRO", "0") == "1",
+              fused_replica_allreduce=os.environ.get("PD_FUSED", "1") == "1")
     rt = StageRuntime(model, cuts, cfg, batch_size=8, device=dev,
                       dtype=torch.bfloat16 if gpu else torch.float32, lr=0.05, momentum=0.9,
                       weight_decay=1e-4, **kw)
@@ -51,7 +52,7 @@ def main():
     torch.save({"rank": rank, "stage": topo.stage, "losses": losses, "state": sd,
                 "warmup": rt.warmup, "versions": rt.ex.store.versions,
                 "bytes_sent": rt.p2p.bytes_sent, "graph_replays": rt.graph_replays,
-                "graph_slots": len(rt._slots), "grad_scale": float(rt.ex.store.hyper[3]),
+                "graph_slots": len(rt._slots), "fused_replicas": rt.fdp is not None, "grad_scale": float(rt.ex.store.hyper[3]),
                 "update_interval": rt.update_interval}, os.path.join(out, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()

@@ -1,0 +1,70 @@
+"""Multi-GPU numerics the driver can see (pytest -m gpu on a box with >= 2 GPUs; skipped on 1):
+the hand-written collectives against NCCL, the fused all-reduce+SGD against all_reduce-then-SGD,
+the data-parallel trainer (fused vs NCCL path, identical weights on every rank), and PipeDream
+stages that are BOTH replicated and weight-stashing on the fused replica reduction (K4)."""
+import glob
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_PORT = [29900]
+
+
+def _torchrun(n, script, env=None, timeout=900):
+    _PORT[0] += 1
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_PORT[0]), script]
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=timeout)
+    sys.stdout.write(p.stdout[-5000:])
+    sys.stderr.write(p.stderr[-3000:])
+    return p
+
+
+def test_collectives_and_fused_allreduce_sgd():
+    n = min(torch.cuda.device_count(), 8)
+    p = _torchrun(n, os.path.join(ROOT, "tests", "dist_check_gpu.py"), {"SWEEP": "0"})
+    assert p.returncode == 0, "dist_check_gpu failed"
+
+
+def _pd(tmp, reps, fused, iters=6):
+    d = os.path.join(str(tmp), "fused" if fused else "nccl")
+    os.makedirs(d, exist_ok=True)
+    p = _torchrun(sum(reps), os.path.join(ROOT, "tests", "pipedream_worker.py"),
+                  {"PD_REPS": ",".join(map(str, reps)), "PD_OUT": d, "PD_ITERS": str(iters),
+                   "PD_FUSED": "1" if fused else "0"})
+    assert p.returncode == 0
+    return [torch.load(f) for f in sorted(glob.glob(os.path.join(d, "rank*.pt")))]
+
+
+@pytest.mark.parametrize("reps", [[2, 1], [2, 2]])
+def test_pipedream_stashing_stage_on_fused_replica_reduction(tmp_path, reps):
+    """Stage 0 is replicated AND keeps >= 2 weight versions: its gradient reduction + SGD run in the
+    fused peer-memory kernel (writing the next slot of the version ring) and must reproduce the
+    NCCL all_reduce + separate SGD path."""
+    if torch.cuda.device_count() < sum(reps):
+        pytest.skip("needs %d GPUs" % sum(reps))
+    a = _pd(tmp_path, reps, True)
+    b = _pd(tmp_path, reps, False)
+    s0 = [r for r in a if r["stage"] == 0]
+    assert all(r["fused_replicas"] and r["versions"] >= 2 for r in s0)
+    assert not any(r["fused_replicas"] for r in b)
+    for x, y in zip(a, b):
+        assert x["stage"] == y["stage"]
+        for k, v in x["state"].items():
+            if not v.is_floating_point():
+                continue
+            ref = y["state"][k].float()
+            err = (v.float() - ref).abs().max().item()
+            assert err <= 3e-2 * max(1.0, ref.abs().max().item()), (k, err)
+        if x["losses"]:
+            assert x["losses"] == pytest.approx(y["losses"], rel=0.1, abs=0.05)
+    # replicas of a stage hold identical weights
+    for k, v in s0[0]["state"].items():
+        assert torch.equal(v, s0[1]["state"][k]), k
