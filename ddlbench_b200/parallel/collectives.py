@@ -11,6 +11,7 @@ from .. import ops
 from ..dist.symm import SymmContext, SymmetricBuffer
 
 ONE_SHOT_MAX_BYTES = 512 << 10
+ONE_SHOT_MAX_BYTES_PAIR = 2 << 20     # two ranks: one phase, same bytes per direction up to here
 
 
 class SymmAllreduce:
@@ -42,7 +43,8 @@ class SymmAllreduce:
             stage[:n].copy_(flat[off:off + n])
             if npad > n:
                 stage[n:npad].zero_()
-            use_one = algo == "oneshot" or (algo == "auto" and npad * item <= ONE_SHOT_MAX_BYTES)
+            one_max = ONE_SHOT_MAX_BYTES_PAIR if ctx.world <= 2 else ONE_SHOT_MAX_BYTES
+            use_one = algo == "oneshot" or (algo == "auto" and npad * item <= one_max)
             if use_one:
                 out = torch.empty(npad, dtype=t.dtype, device=t.device)
                 ops.ext().ar_oneshot(self.stage.ptrs, ctx.flags.ptrs, out, ctx.epoch, ctx.status, 0,
@@ -52,7 +54,9 @@ class SymmAllreduce:
                 ops.ext().ar_twoshot(self.stage.ptrs, ctx.flags.ptrs, self.stage.mc_ptr,
                                      t.dtype == torch.bfloat16, ctx.epoch, ctx.status, 0,
                                      npad // ctx.world, scale, ctx.rank, self.blocks,
-                                     ctx.use_multimem and algo != "p2p")
+                                     # NVLS pays off from 3 ranks on: with one peer the switch
+                                     # reduction only adds a hop (measured 285 vs 372 GB/s at 64 MiB)
+                                     ctx.use_multimem and algo != "p2p" and (ctx.world > 2 or algo == "nvls"))
                 flat[off:off + n].copy_(stage[:n])
             ops._count()
         return t

@@ -247,7 +247,8 @@ class FusedDataParallel:
         # advances the ring.
         out_v = st.next_version() if st.versions > 1 else st.latest
         wsym = self.w_sym[out_v]
-        use_mm = self.ctx.use_multimem and wsym.mc_ptr != 0 and self.g_sym.mc_ptr != 0
+        # NVLS from 3 ranks on; with a single peer plain P2P loads/stores are faster (profiles/allreduce_sweep_n2.json)
+        use_mm = self.ctx.use_multimem and self.ctx.world > 2 and wsym.mc_ptr != 0 and self.g_sym.mc_ptr != 0
         main = torch.cuda.current_stream(st.device)
         stream = self.comm_stream or main
         if self.comm_stream is not None:
