@@ -406,6 +406,9 @@ PIPE = {
     "gpipe_vgg16_c10_4": ("gpipe", "vgg16", "cifar10", 4, 64, {},
                           "images/sec (device-timed, max over ranks) VGG-16 CIFAR-10 GPipe 4-stage on 4 B200",
                           "gpipe 4 stages, micro-batch 64 x 32 chunks"),
+    "pd_r50_4": ("pipedream", "resnet50", "imagenet", 4, 128, {"stages": "4x1"},
+                 "images/sec (device-timed, max over ranks) ResNet-50 ImageNet PipeDream 1F1B 4-stage on 4 B200",
+                 "pipedream 1F1B, 4 stages, weight stashing"),
     "pd_r50_4x2": ("pipedream", "resnet50", "imagenet", 8, 128, {"stages": "4x2"},
                    "images/sec (device-timed, max over ranks) ResNet-50 ImageNet PipeDream 1F1B 4x2 on 8 B200",
                    "pipedream 1F1B, 4 stages x 2 replicas, weight stashing, fused replica reduction"),
