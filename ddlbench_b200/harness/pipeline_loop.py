@@ -189,8 +189,16 @@ def run_pipedream(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
         if cfg.extra.get("stages"):
             # explicit request: N equal-time stages x given replication ("4x2" = 4 stages, 2 replicas)
             ns, nr = (int(v) for v in str(cfg.extra["stages"]).split("x"))
-            from ..parallel.gpipe import balance_by_size
-            sizes = balance_by_size(ns, model)
+            from ..parallel.gpipe import balance_by_size, balance_by_time
+            # stages of equal TIME (profiled forward+backward of every layer on this device with a
+            # minibatch of the run's shape); parameter bytes only as the fallback — they put most of
+            # a ResNet's compute (the early, wide-activation layers) into the first stage
+            try:
+                sample = torch.randn((min(cfg.batch_size, 32),) + tuple(model.input_shape))
+                sizes = balance_by_time(ns, model, sample, device=device, dtype=dtype, trials=2)
+            except Exception as e:  # noqa: BLE001
+                say("balance_by_time failed (%s); falling back to balance_by_size" % e)
+                sizes = balance_by_size(ns, model)
             stage_ids = [s for s, n in enumerate(sizes) for _ in range(n)]
             reps = [nr] * ns
         else:
