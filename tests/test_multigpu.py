@@ -68,6 +68,9 @@ def test_pipedream_stashing_stage_on_fused_replica_reduction(tmp_path, reps):
             assert err <= 0.1 * max(1.0, ref.abs().max().item()), (k, err)
         if x["losses"]:
             assert x["losses"] == pytest.approx(y["losses"], rel=0.15, abs=0.1)
-    # replicas of a stage hold identical weights
+    # replicas of a stage hold identical PARAMETERS (BatchNorm running statistics are per-replica
+    # buffers computed from each replica's own minibatches, as under DDP without buffer broadcast)
     for k, v in s0[0]["state"].items():
+        if "running_" in k or "num_batches" in k:
+            continue
         assert torch.equal(v, s0[1]["state"][k]), k
