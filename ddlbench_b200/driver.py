@@ -62,6 +62,14 @@ def build_command(conf: Dict, resume: str = "", dataset: str = "imagenet", port:
         cmd += ["--epochs", str(conf["epochs"])]
     if conf.get("config_file"):
         cmd += ["--config-path", str(conf["config_file"])]
+    if conf.get("stages"):                      # e.g. "1x16": data parallel through the stage runtime
+        cmd += ["--stages", str(conf["stages"])]
+    if conf.get("weight_decay") is not None:
+        cmd += ["--wd", str(conf["weight_decay"])]
+    if conf.get("learning_rate") is not None:
+        cmd += ["--lr", str(conf["learning_rate"])]
+    if conf.get("learning_rate_policy"):
+        cmd += ["--lr_policy", str(conf["learning_rate_policy"])]
     if conf.get("no_input_pipelining"):
         cmd.append("--no-input-pipelining")
     if conf.get("macrobatch"):

@@ -376,7 +376,39 @@ def build_nasnet(arch="nasnetamobile", in_channels=3, num_classes=1000, input_hw
     return _finish(g, arch, in_channels, input_hw, num_classes)
 
 
+# ------------------------------------------------------------------------------ AlexNet
+def build_alexnet(arch="alexnet", in_channels=3, num_classes=1000, input_hw=224):
+    """torchvision's AlexNet ("one weird trick" variant) — the model behind the reference's
+    ``alexnet_{4,16}{dp,pipedream}.yml`` driver configurations and profiler
+    (``pipedream-fork/profiler/image_classification/main.py -a alexnet``)."""
+    g = GraphBuilder().block("features.0")
+    x = g.add("features.0", nn.Conv2d(in_channels, 64, kernel_size=11, stride=4, padding=2), INPUT)
+    x = g.add("features.1", nn.ReLU(inplace=False), x)
+    x = g.add("features.2", nn.MaxPool2d(kernel_size=3, stride=2), x)
+    g.block("features.3")
+    x = g.add("features.3", nn.Conv2d(64, 192, kernel_size=5, padding=2), x)
+    x = g.add("features.4", nn.ReLU(inplace=False), x)
+    x = g.add("features.5", nn.MaxPool2d(kernel_size=3, stride=2), x)
+    for i, (ci, co) in zip((6, 8, 10), ((192, 384), (384, 256), (256, 256))):
+        g.block(f"features.{i}")
+        x = g.add(f"features.{i}", nn.Conv2d(ci, co, kernel_size=3, padding=1), x)
+        x = g.add(f"features.{i + 1}", nn.ReLU(inplace=False), x)
+    x = g.add("features.12", nn.MaxPool2d(kernel_size=3, stride=2), x)
+    g.block("head")
+    x = g.add("avgpool", nn.AdaptiveAvgPool2d((6, 6)), x)
+    x = g.add("flatten", Flatten(), x)
+    x = g.add("classifier.0", nn.Dropout(), x)
+    x = g.add("classifier.1", nn.Linear(256 * 6 * 6, 4096), x)
+    x = g.add("classifier.2", nn.ReLU(inplace=False), x)
+    x = g.add("classifier.3", nn.Dropout(), x)
+    x = g.add("classifier.4", nn.Linear(4096, 4096), x)
+    x = g.add("classifier.5", nn.ReLU(inplace=False), x)
+    g.add("classifier.6", nn.Linear(4096, num_classes), x)
+    return _finish(g, arch, in_channels, input_hw, num_classes)
+
+
 EXTRA_BUILDERS = {}
+EXTRA_BUILDERS["alexnet"] = build_alexnet
 for _a in _DENSENETS:
     EXTRA_BUILDERS[_a] = build_densenet
 for _a in ("squeezenet1_0", "squeezenet1_1"):

@@ -6,7 +6,14 @@ File format = the reference's ``{dp,mp,hybrid}_conf.json``
 
     {"module_to_stage_map": [0, 1, 2, 3, 3],               # one entry per module incl. criterion
      "stage_to_rank_map": {"0": [0], "1": [1], ...},        # keys are strings
-     "stage_to_depth_map": {"0": 3, ...}}                   # optional warm-up override
+     "stage_to_depth_map": {"0": 3, ...},                   # optional warm-up override
+     "parallel": {"tp": 1, "cp": 1}}                        # optional, RESERVED (see below)
+
+``parallel`` reserves the two axes the reference does not have (its models
+are CNNs and an LSTM, there is no tensor- or context-parallel code anywhere in the tree): ``tp``
+(tensor parallel width inside a stage) and ``cp`` (context / sequence parallel width).  The schema
+carries them so that a later runtime can add either without a file-format change; today any value
+other than 1 is rejected loudly when the file is loaded.
 
 Topology rules (``runtime/runtime.py:133-176``): a rank's stage, its index among the stage's
 replicas, the replica lists of the neighbouring stages, and the number of warm-up minibatches
@@ -28,6 +35,15 @@ class PipelineConfig:
     module_to_stage_map: List[int]
     stage_to_rank_map: Dict[int, List[int]]
     stage_to_depth_map: Optional[Dict[int, int]] = None
+    tp: int = 1      # reserved: tensor-parallel width inside a stage (only 1 is implemented)
+    cp: int = 1      # reserved: context-parallel width (only 1 is implemented)
+
+    def __post_init__(self):
+        if self.tp != 1 or self.cp != 1:
+            raise NotImplementedError(
+                "parallel.tp=%d / parallel.cp=%d: tensor and context parallelism are reserved fields of "
+                "the configuration schema; this runtime implements pipeline x data parallelism only "
+                "(tp = cp = 1)" % (self.tp, self.cp))
 
     # ------------------------------------------------------------------ io
     @classmethod
@@ -39,13 +55,16 @@ class PipelineConfig:
         s2r = {int(k): list(v) for k, v in d["stage_to_rank_map"].items()}
         depth = d.get("stage_to_depth_map")
         depth = {int(k): int(v) for k, v in depth.items()} if depth else None
-        return cls(list(d["module_to_stage_map"]), s2r, depth)
+        par = d.get("parallel") or {}
+        return cls(list(d["module_to_stage_map"]), s2r, depth, int(par.get("tp", 1)), int(par.get("cp", 1)))
 
     def to_dict(self) -> dict:
         d = {"module_to_stage_map": list(self.module_to_stage_map),
              "stage_to_rank_map": {str(k): list(v) for k, v in sorted(self.stage_to_rank_map.items())}}
         if self.stage_to_depth_map:
             d["stage_to_depth_map"] = {str(k): v for k, v in sorted(self.stage_to_depth_map.items())}
+        if (self.tp, self.cp) != (1, 1):
+            d["parallel"] = {"tp": self.tp, "cp": self.cp}
         return d
 
     def save(self, path: str) -> None:

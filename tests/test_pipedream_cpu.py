@@ -269,3 +269,33 @@ def test_sharded_optimizer_state_round_trip():
             rebuilt_v[bkt.offset + r * ln: bkt.offset + (r + 1) * ln] = s.mom[mo:mo + ln]
     assert torch.equal(rebuilt_m, m) and torch.equal(rebuilt_v, v)
     assert torch.equal(shards[0].w_flat[0], m)          # every replica holds the full weights
+
+
+def test_parallel_config_schema_reserves_tp_cp():
+    """tp / cp are reserved in the conf schema; only 1 is accepted today."""
+    base = {"module_to_stage_map": [0, 1, 1], "stage_to_rank_map": {"0": [0], "1": [1]}}
+    cfg = PipelineConfig.from_json(dict(base, parallel={"tp": 1, "cp": 1}))
+    assert (cfg.tp, cfg.cp) == (1, 1) and "parallel" not in cfg.to_dict()
+    for bad in ({"tp": 2}, {"cp": 4}):
+        with pytest.raises(NotImplementedError):
+            PipelineConfig.from_json(dict(base, parallel=bad))
+
+
+def test_alexnet_and_driver_configs():
+    """AlexNet is in the zoo (reference: alexnet_{4,16}{dp,pipedream}.yml) and every driver YAML of
+    the reference has a counterpart that builds a launch command."""
+    from ddlbench_b200 import driver
+    m = build_model("alexnet", "imagenet")
+    assert sum(p.numel() for p in m.parameters()) == 61100840
+    names = {"alexnet_16dp", "alexnet_16pipedream", "alexnet_4dp", "alexnet_4pipedream", "resnet50_16dp",
+             "vgg16_16dp", "vgg16_16pipedream", "vgg16_4dp", "vgg16_4pipedream", "gnmt_12dp", "gnmt_12pipedream",
+             "gnmt_4dp", "gnmt_4pipedream", "gnmt_large_16dp", "gnmt_large_16pipedream", "gnmt_large_4dp",
+             "gnmt_large_4pipedream"}
+    have = {f[:-4] for f in os.listdir(os.path.join(ROOT, "configs", "driver")) if f.endswith(".yml")}
+    assert names <= have, names - have
+    for n in sorted(names):
+        conf = driver.load(os.path.join(ROOT, "configs", "driver", n + ".yml"))
+        nodes = driver.build_node_commands(conf)
+        assert nodes and all(cmd for _, cmd in nodes)
+    dp = driver.build_command(driver.load(os.path.join(ROOT, "configs", "driver", "alexnet_4dp.yml")))
+    assert "--stages" in dp and dp[dp.index("--stages") + 1] == "1x4" and "alexnet" in dp
