@@ -815,7 +815,10 @@ class ModuleOp(Op):
             with torch.no_grad():
                 return torch.func.functional_call(self.module, pb, tuple(xs))
         with torch.enable_grad():
-            ins = [x.detach().requires_grad_(x.is_floating_point()) for x in xs]
+            # CPU: dense inputs — oneDNN's backward of a strided 1x1 convolution corrupts the heap when
+            # handed a non-contiguous activation (hit by a torchgpipe-style Residual with a downsample)
+            ins = [(x.detach().contiguous() if not x.is_cuda else x.detach()).requires_grad_(x.is_floating_point())
+                   for x in xs]
             leafs = {n: P[f"{self.prefix}.{n}"].detach().requires_grad_(True) for n in self._pnames}
             call = dict(leafs)
             call.update({n: B[f"{self.prefix}.{n}"] for n in self._bnames})

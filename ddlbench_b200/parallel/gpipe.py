@@ -93,8 +93,17 @@ class GPipe:
                  checkpoint: str = "except_last", devices: Optional[Sequence] = None,
                  dtype: Optional[torch.dtype] = None, lr: float = 0.1, momentum: float = 0.9,
                  weight_decay: float = 0.0, batch_size: Optional[int] = None,
-                 tcgen05: bool = False, groups: Optional[PairGroups] = None):
+                 tcgen05: bool = False, groups: Optional[PairGroups] = None,
+                 sample_input: Optional[torch.Tensor] = None):
         assert checkpoint in ("always", "except_last", "never")
+        if isinstance(model, torch.nn.Sequential) and not isinstance(model, LayerGraphModel):
+            # torchgpipe-style model: an nn.Sequential, possibly with @skippable layers
+            # (stash / pop skip connections).  Needs one sample batch to resolve the skips.
+            from .skip import sequential_to_graph
+            if sample_input is None:
+                raise ValueError("GPipe(nn.Sequential, ...) needs sample_input=<one input batch> to "
+                                 "convert the model (and its stash/pop skips) into a layer graph")
+            model = sequential_to_graph(model, sample_input)
         self.model = model
         self.balance = list(balance)
         self.chunks = chunks
