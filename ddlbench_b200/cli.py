@@ -74,8 +74,10 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--recompute", action="store_true",
                    help="pipedream: plumbed but a no-op in the reference (runtime.py:72-78) and here")
     p.add_argument("--fp16", action="store_true",
-                   help="reference: apex fp16 + loss scale; here compute is bf16 with fp32 master weights already")
-    p.add_argument("--loss_scale", "--loss-scale", type=float, default=1.0, dest="loss_scale")
+                   help="reference: apex fp16 master-weight training; here the 16-bit compute type is bf16 "
+                        "(fp32 master weights + momentum), which --fp16 selects explicitly")
+    p.add_argument("--loss_scale", "--loss-scale", type=float, default=1.0, dest="loss_scale",
+                   help="pipedream: static loss scale S (loss gradient x S, every stage's optimizer / S)")
     p.add_argument("--config-path", "--config_path", dest="config_path", default=None, help="pipedream: explicit *_conf.json")
     p.add_argument("--checkpoint-dir", "--checkpoint_dir", dest="checkpoint_dir", default=None,
                    help="pipedream: write checkpoint.<stage>.pth.tar here after every epoch")
@@ -119,6 +121,11 @@ def expand(args) -> List[RunConfig]:
                     extra["no_input_pipelining"] = "1"
                 if args.macrobatch:
                     extra["macrobatch"] = "1"
+                if args.loss_scale != 1.0:
+                    if fw != "pipedream":
+                        raise SystemExit("--loss_scale is a pipedream runtime option (main_with_runtime.py); "
+                                         "the %s scripts of the reference have no loss scaling" % fw)
+                    extra["loss_scale"] = repr(args.loss_scale)
                 if args.lr_policy:
                     extra["lr_policy"] = args.lr_policy
                 if args.lr_warmup is not None:
@@ -183,7 +190,7 @@ def _cfg_to_argv(cfg: RunConfig, args) -> List[str]:
         if k in cfg.extra:
             a += [flag, cfg.extra[k]]
     a += ["--lr", repr(cfg.lr), "--momentum", repr(cfg.momentum), "--wd", repr(cfg.weight_decay)]
-    for k, flag in (("lr_policy", "--lr_policy"), ("lr_warmup", "--lr_warmup")):
+    for k, flag in (("lr_policy", "--lr_policy"), ("lr_warmup", "--lr_warmup"), ("loss_scale", "--loss_scale")):
         if k in cfg.extra:
             a += [flag, cfg.extra[k]]
     for k, flag in (("straight", "--straight"), ("no_input_pipelining", "--no-input-pipelining"),
@@ -202,10 +209,10 @@ def main(argv=None) -> int:
     if args.nodes > 1 and args.framework in ("pytorch", "gpipe"):
         print("\n\nOnly Horovod and Pipedream support multi-node execution. Continuing with 1 node.\n\n")
         args.nodes = 1
-    if (args.fp16 or args.loss_scale != 1.0 or args.recompute) and not args.worker:
-        print("note: --fp16/--loss_scale/--recompute are accepted for command-line parity; compute is "
-              "bf16 with fp32 master weights (no loss scaling needed) and --recompute is a no-op as in "
-              "the reference runtime")
+    if (args.fp16 or args.recompute) and not args.worker:
+        print("note: --fp16 selects 16-bit compute with fp32 master weights, which here is bf16 (the "
+              "tensor-core kernels are bf16; no fp16 kernels exist) — --loss_scale S is honoured exactly; "
+              "--recompute is a no-op as in the reference runtime (runtime.py:72-78)")
     cfgs = expand(args)
     if args.worker:
         assert len(cfgs) == 1

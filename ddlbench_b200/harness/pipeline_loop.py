@@ -194,6 +194,8 @@ def run_pipedream(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
             # minibatch of the run's shape); parameter bytes only as the fallback — they put most of
             # a ResNet's compute (the early, wide-activation layers) into the first stage
             try:
+                if os.environ.get("DDLB_STAGE_BALANCE", "time") == "size":
+                    raise RuntimeError("DDLB_STAGE_BALANCE=size")      # reproducible split (tests, resume)
                 sample = torch.randn((min(cfg.batch_size, 32),) + tuple(model.input_shape))
                 sizes = balance_by_time(ns, model, sample, device=device, dtype=dtype, trials=2)
             except Exception as e:  # noqa: BLE001
@@ -218,7 +220,7 @@ def run_pipedream(cfg: RunConfig, verbose: bool = True) -> Dict[str, float]:
                       momentum=cfg.momentum, weight_decay=cfg.weight_decay,
                       no_input_pipelining=cfg.extra.get("no_input_pipelining") == "1",
                       macrobatch=cfg.extra.get("macrobatch") == "1", tcgen05=cfg.fused,
-                      verbose=verbose)
+                      verbose=verbose, loss_scale=float(cfg.extra.get("loss_scale", 1.0)))
     topo = rt.topo
     from ..data import make_source
     src = make_source(cfg, cfg.batch_size, device, topo.rank_in_stage, pcfg.replicas(0), "train",

@@ -116,7 +116,7 @@ class StageRuntime:
                  no_input_pipelining: bool = False, macrobatch: bool = False,
                  tcgen05: bool = False, fused_replica_allreduce: bool = True,
                  groups: Optional[PairGroups] = None, verbose: bool = False,
-                 graphs: Optional[bool] = None):
+                 graphs: Optional[bool] = None, loss_scale: float = 1.0):
         self.cfg = cfg
         self.rank = dist.get_rank() if rank is None else rank
         self.topo = RankTopology.of(cfg, self.rank)
@@ -179,6 +179,13 @@ class StageRuntime:
             # rides in the same scale on both the fused and the NCCL reduction path.
             reps = t.num_ranks_in_stage if self.replica_group is not None else 1
             self.ex.store.set_grad_scale(1.0 / (reps * self.update_interval))
+        # static loss scaling (reference: --fp16 --loss_scale S, runtime.py:225-230,269-277 and
+        # optimizer.py:137-155): the loss gradient is multiplied by S on the last stage, so every
+        # gradient that flows back through the pipeline carries S, and every stage's optimizer divides
+        # it out again (folded into the gradient scale of the fused SGD / all-reduce kernels)
+        self.loss_scale = float(loss_scale)
+        if self.loss_scale != 1.0:
+            self.ex.store.set_grad_scale(float(self.ex.store.hyper[3]) / self.loss_scale)
         if verbose and self.replica_group is not None:
             print("Replicating stage: ranks=%d, module_size=%d" % (
                 t.num_ranks_in_stage, self.ex.num_params() * 4), flush=True)
@@ -303,7 +310,7 @@ class StageRuntime:
                 slot.outs, slot.ctx = ex.forward(slot.x, training=True, version=slot.version)
                 if last:
                     slot.stats, slot.dl = ex.loss(slot.outs[0], slot.target, want_grad=True,
-                                                  grad_scale=1.0)
+                                                  grad_scale=self.loss_scale)
             slot.fwd = self._capture(slot, body)
             if slot.fwd is None:
                 return None
@@ -412,7 +419,7 @@ class StageRuntime:
             outs, ctx = ex.forward(xs, training=self.training, version=version)
             if t.is_last:
                 stats, dl = ex.loss(outs[0], target, want_grad=self.training,
-                                    grad_scale=1.0)
+                                    grad_scale=self.loss_scale)
         self.forward_stats.end_compute(tok)
         if t.is_last:
             self.loss_stats = stats

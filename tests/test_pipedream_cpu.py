@@ -218,7 +218,8 @@ def _cli_pipedream(tmp_path, port, *extra):
            "--master-addr", "127.0.0.1", "--master-port", str(port), "-m", "ddlbench_b200.cli",
            "-b", "mnist", "-f", "pipedream", "-g", "2", "-m", "resnet18", "--worker", "--device", "cpu",
            "--steps", "3", "--eval-steps", "1", "--batch-size", "8", "--stages", "2x1", *extra]
-    env = dict(os.environ, OMP_NUM_THREADS="2", PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    env = dict(os.environ, OMP_NUM_THREADS="2", DDLB_STAGE_BALANCE="size",
+               PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     return p.stdout
@@ -299,3 +300,16 @@ def test_alexnet_and_driver_configs():
         assert nodes and all(cmd for _, cmd in nodes)
     dp = driver.build_command(driver.load(os.path.join(ROOT, "configs", "driver", "alexnet_4dp.yml")))
     assert "--stages" in dp and dp[dp.index("--stages") + 1] == "1x4" and "alexnet" in dp
+
+
+def test_loss_scale_is_transparent(tmp_path):
+    """--loss_scale S: gradients carry S through the whole pipeline and every stage's optimizer
+    divides it out — the update equals the unscaled run (fp32 on the CPU: up to rounding)."""
+    a, b = tmp_path / "A", tmp_path / "B"
+    _cli_pipedream(tmp_path, 29821, "--epochs", "1", "--checkpoint-dir", str(a))
+    _cli_pipedream(tmp_path, 29822, "--epochs", "1", "--checkpoint-dir", str(b), "--loss_scale", "128")
+    for stage in (0, 1):
+        x = torch.load(a / ("checkpoint.%d.pth.tar" % stage))
+        y = torch.load(b / ("checkpoint.%d.pth.tar" % stage))
+        assert float(y["hyper"][3]) == pytest.approx(float(x["hyper"][3]) / 128.0)
+        assert torch.allclose(x["master"], y["master"], rtol=1e-4, atol=1e-6)
