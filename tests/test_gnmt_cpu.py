@@ -196,3 +196,30 @@ def test_translation_reads_the_reference_wmt16_layout(tmp_path):
     (other / "README").write_text("x")
     with pytest.raises(FileNotFoundError):
         tr.prepare_data(types.SimpleNamespace(data_dir=str(other), max_len=20, synthetic_sentences=10, synthetic_vocab=10))
+
+
+def test_translation_trainer_profiler_and_translate_cli(tmp_path):
+    """profiler/translation/{train,translate}.py counterparts: train a tiny GNMT, write the layer
+    profile graph, then translate a file with the saved checkpoint (reference flags)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TMPDIR=str(tmp_path), OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, os.path.join(root, "pipedream-fork/profiler/translation/train.py"),
+                        "--num-layers", "1", "--hidden-size", "32", "--batch-size", "8", "--steps", "4", "--epochs", "1",
+                        "--max-length-train", "16", "--device", "cpu", "--save", "ck", "--profile-directory", "prof",
+                        "--eval-sentences", "8", "--beam-size", "2", "--warmup-steps", "2"],
+                       cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "Total forward" in r.stdout and (tmp_path / "prof/gnmt/graph.txt").exists()
+    assert (tmp_path / "ck/checkpoint.0.pth.tar").exists()
+    data = tmp_path / "ddlb_gnmt_data"
+    (tmp_path / "in.txt").write_text("".join(open(data / "val.src").readlines()[:3]))
+    (tmp_path / "ref.txt").write_text("".join(open(data / "val.tgt").readlines()[:3]))
+    r = subprocess.run([sys.executable, os.path.join(root, "pipedream-fork/profiler/translation/translate.py"),
+                        "--dataset-dir", str(data), "-i", "in.txt", "-o", "out/out.txt", "-r", "ref.txt", "-m", "ck",
+                        "--beam-size", "2", "--max-seq-len", "20", "--no-cuda", "--math", "fp16"],
+                       cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "BLEU on test dataset" in r.stdout
+    assert len((tmp_path / "out/out.txt").read_text().strip().splitlines()) == 3
