@@ -137,7 +137,52 @@ def write_confs(out_dir: str, arch: str, model: GNMT, cuts: Sequence[int], reps:
     json.dump({"module_to_stage_map": [0] * (len(layers) + 1),
                "stage_to_rank_map": {"0": list(range(n))}, "cuts": [len(layers)], "layers": layers,
                "arch": arch}, open(os.path.join(d, "dp_conf.json"), "w"), indent=1)
+    write_stage_package(d, arch, model, list(cuts), even)
     return d
+
+
+_PKG = '''"""GENERATED by ddlbench_b200.partition.gnmt_tools — the stage modules of %(arch)s on %(n)d GPUs, in the
+calling convention of the reference's generated packages
+(pipedream-fork/runtime/translation/models/%(arch)s/gpus=N/__init__.py): ``arch()``,
+``model(criterion)`` -> [(stage module, input names, output names), ..., (criterion, [...], ["loss"])],
+``full_model()``.  ``conf`` selects the split: "hybrid" (the partitioner's stages, replicated as in
+hybrid_conf.json) or "mp" (one stage per GPU, mp_conf.json)."""
+from ddlbench_b200.models.gnmt import GNMT
+
+ARCH = "%(arch)s"
+NUM_LAYERS = %(layers)d
+CUTS = {"hybrid": %(hybrid)r, "mp": %(mp)r}
+
+
+def arch():
+    return ARCH
+
+
+def full_model(vocab_size=32320, hidden=1024, dropout=0.2):
+    return GNMT(vocab_size, hidden, NUM_LAYERS, dropout)
+
+
+def stages(conf="mp", **kw):
+    """The ``GNMTStage`` modules (Stage0 .. StageK-1 of the reference's generated files)."""
+    cuts = CUTS[conf]
+    return full_model(**kw).split(len(cuts), cuts)
+
+
+def model(criterion, conf="mp", **kw):
+    parts = stages(conf, **kw)
+    out = [(p, list(p.input_names), list(p.output_names)) for p in parts]
+    return out + [(criterion, [parts[-1].output_names[0], "target"], ["loss"])]
+'''
+
+
+def write_stage_package(d: str, arch: str, model: GNMT, hybrid_cuts, mp_cuts) -> None:
+    """``<d>/__init__.py``: importable stage-module package next to the conf files (the reference
+    ships generated ``stageK.py`` files; here the stages are slices of one model definition, so the
+    package is a thin, parameterised constructor instead of copied layer code)."""
+    n_layers = sum(1 for name, _, _, _ in model.spec if name.startswith("enc.rnn"))
+    with open(os.path.join(d, "__init__.py"), "w") as f:
+        f.write(_PKG % {"arch": arch, "n": int(os.path.basename(d).split("=")[1]), "layers": n_layers,
+                        "hybrid": list(hybrid_cuts), "mp": list(mp_cuts)})
 
 
 def cli(argv=None) -> int:
