@@ -594,6 +594,20 @@ class AvgPool(Op):
             ctx["id"] = True
             return x
         ctx["id"] = False
+        ctx["native"] = False
+        if ops.avgpool_supported(x):
+            if self.adaptive:
+                y = ops.avgpool_fwd(x, self.out, 0, 0, 0, True)
+            elif self.k[0] == self.k[1] and self.s[0] == self.s[1] and self.p[0] == self.p[1] and not self.ceil:
+                oh = (x.shape[2] + 2 * self.p[0] - self.k[0]) // self.s[0] + 1
+                ow = (x.shape[3] + 2 * self.p[1] - self.k[1]) // self.s[1] + 1
+                y = ops.avgpool_fwd(x, (oh, ow), self.k[0], self.s[0], self.p[0], False, self.cip)
+            else:
+                y = None
+            if y is not None:
+                if training:
+                    ctx["native"], ctx["shape"] = True, tuple(x.shape)
+                return y
         if training:
             ctx["x"] = x
         if self.adaptive:
@@ -606,6 +620,13 @@ class AvgPool(Op):
             return [None]
         if ctx["id"]:
             return [dy]
+        if ctx.get("native"):
+            if self.adaptive:
+                dx = ops.avgpool_bwd(dy, ctx["shape"], 0, 0, 0, True)
+            else:
+                dx = ops.avgpool_bwd(dy, ctx["shape"], self.k[0], self.s[0], self.p[0], False, self.cip)
+            assert dx is not None
+            return [dx]
         if self.adaptive:
             return [aten._adaptive_avg_pool2d_backward(dy, ctx["x"])]
         return [aten.avg_pool2d_backward(dy, ctx["x"], self.k, self.s, self.p, self.ceil, self.cip,
@@ -656,14 +677,20 @@ class DropoutOp(Op):
         if not training or self.p == 0.0:
             ctx["mask"] = None
             return xs[0]
+        nat = ops.dropout_fwd(xs[0], self.p) if xs[0].is_cuda else None
+        if nat is not None:
+            ctx["mask"], ctx["native"] = nat[1], True
+            return nat[0]
         y, mask = aten.native_dropout(xs[0], self.p, True)
-        ctx["mask"] = mask
+        ctx["mask"], ctx["native"] = mask, False
         return y
 
     def backward(self, P, G, dys, ctx, accumulate, need):
         dy = _sum_grads(dys)
         if ctx.get("mask") is None:
             return [dy]
+        if ctx.get("native"):
+            return [ops.dropout_bwd(dy, ctx["mask"], self.p)]
         return [aten.native_dropout_backward(dy, ctx["mask"], 1.0 / (1.0 - self.p))]
 
 

@@ -88,6 +88,7 @@ class Trainer:
     # ------------------------------------------------------------------ one eager step
     def _step_eager(self, x: torch.Tensor, target: torch.Tensor, update: bool = True) -> torch.Tensor:
         ex = self.ex
+        ops.rng_tick(self.device)          # fresh dropout masks every step (also inside the graph)
         outs, ctx = ex.forward([x], training=True)
         stats, dlogits = ex.loss(outs[0], target)
         ex.backward(ctx, [dlogits])

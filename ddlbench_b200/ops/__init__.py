@@ -491,6 +491,79 @@ def maxpool_bwd(dy: torch.Tensor, idx: torch.Tensor, in_shape, k: int, s: int, p
     return dx
 
 
+
+# ------------------------------------------------------------------------------- avg pool / dropout
+def avgpool_supported(x: torch.Tensor) -> bool:
+    return _nhwc_ok(x) and x.dim() == 4
+
+
+def avgpool_fwd(x: torch.Tensor, out_hw, k: int, s: int, p: int, adaptive: bool,
+                count_include_pad: bool = True) -> Optional[torch.Tensor]:
+    """NHWC bf16 average pool (fixed window or adaptive); None if the kernel declines."""
+    n, c = x.shape[:2]
+    y = torch.empty((n, c, out_hw[0], out_hw[1]), dtype=x.dtype, device=x.device,
+                    memory_format=torch.channels_last)
+    if ext().avgpool(False, x, y, k, s, p, adaptive, count_include_pad):
+        _count()
+        return y
+    return None
+
+
+def avgpool_bwd(dy: torch.Tensor, in_shape, k: int, s: int, p: int, adaptive: bool,
+                count_include_pad: bool = True) -> Optional[torch.Tensor]:
+    dx = torch.empty(tuple(in_shape), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+    if ext().avgpool(True, dy.contiguous(memory_format=torch.channels_last), dx, k, s, p, adaptive,
+                     count_include_pad):
+        _count()
+        return dx
+    return None
+
+
+_RNG_STEP: dict = {}
+
+
+def rng_step(device) -> torch.Tensor:
+    """Device-resident step counter mixed into the dropout Philox counter (one int64 per device)."""
+    device = torch.device(device)
+    t = _RNG_STEP.get(device)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int64, device=device)
+        _RNG_STEP[device] = t
+    return t
+
+
+def rng_tick(device) -> None:
+    """Advance the step counter — once per training step, INSIDE a captured graph (a plain in-place
+    add), so every replay draws fresh dropout masks while a recomputed forward of the same step
+    (GPipe checkpointing) reproduces them."""
+    if torch.device(device).type == "cuda":
+        rng_step(device).add_(1)
+
+
+def dropout_fwd(x: torch.Tensor, p: float):
+    """-> (y, mask bits uint8[numel/8]) on the native kernel, or None when not applicable."""
+    dense = x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last))
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.numel() % 8 == 0 and dense):
+        return None
+    y = torch.empty_like(x)
+    mask = torch.empty(x.numel() // 8, dtype=torch.uint8, device=x.device)
+    # seed: torch's CUDA seed; salt: 63 fresh bits from the HOST generator (a restored RNG state —
+    # GPipe recompute — gives the same salt; every other call a different one)
+    seed = torch.cuda.initial_seed() & 0x7FFFFFFFFFFFFFFF
+    salt = int(torch.randint(0, 2 ** 62, (1,)).item())
+    ext().dropout_fwd(x, y, mask, float(p), seed, salt, rng_step(x.device))
+    _count()
+    return y, mask
+
+
+def dropout_bwd(dy: torch.Tensor, mask: torch.Tensor, p: float) -> torch.Tensor:
+    dy = dy if (dy.is_contiguous() or (dy.dim() == 4 and dy.is_contiguous(memory_format=torch.channels_last))) \
+        else dy.contiguous()
+    dx = torch.empty_like(dy)
+    ext().dropout_bwd(dy, mask, dx, 1.0 / (1.0 - p))
+    _count()
+    return dx
+
 # ------------------------------------------------------------------------------- GEMM
 def gemm_tn_supported(a: torch.Tensor, b: torch.Tensor) -> bool:
     return (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and

@@ -92,6 +92,14 @@ int ddl_set_mask(const int64_t* lengths, void* mask, int T, int B, cudaStream_t 
 int ddl_gap_fwd(const void* x, void* y, int N, int HW, int C, cudaStream_t st);
 int ddl_gap_bwd(const void* dy, void* dx, int N, int HW, int C, int sms, cudaStream_t st);
 
+// ---- elementwise.cu (average pooling, dropout)
+int ddl_avgpool(int backward, const void* in, void* out, int N, int H, int W, int C, int Ho, int Wo,
+                int k, int s, int p, int adaptive, int count_include_pad, int sms, cudaStream_t st);
+int ddl_dropout_fwd(const void* x, void* y, void* mask, int64_t n, float p, uint64_t seed, uint64_t salt,
+                    const long long* step, int sms, cudaStream_t st);
+int ddl_dropout_bwd(const void* dy, const void* mask, void* dx, int64_t n, float scale, int sms,
+                    cudaStream_t st);
+
 // ---- pool.cu
 int ddl_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, int Ho, int Wo,
                     int k, int s, int p, int sms, cudaStream_t st);

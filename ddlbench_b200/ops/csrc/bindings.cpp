@@ -552,6 +552,39 @@ bool wgrad_conv(at::Tensor dy, at::Tensor x, at::Tensor ws, at::Tensor out, bool
   check(rc, "wgrad_conv");
   return true;
 }
+
+// ---- elementwise.cu
+// in / out: [N, C, H, W] channels_last bf16 (forward: in = x, out = y; backward: in = dy, out = dx)
+bool avgpool(bool backward, at::Tensor in, at::Tensor out, int64_t k, int64_t s, int64_t p, bool adaptive,
+             bool count_include_pad) {
+  TORCH_CHECK(in.dim() == 4 && out.dim() == 4 && is_bf16(in) && is_bf16(out));
+  TORCH_CHECK(in.is_contiguous(at::MemoryFormat::ChannelsLast) && out.is_contiguous(at::MemoryFormat::ChannelsLast));
+  const at::Tensor& big = backward ? out : in;      // the un-pooled tensor
+  const at::Tensor& small = backward ? in : out;
+  c10::cuda::CUDAGuard g(in.device());
+  const int rc = ddl_avgpool(backward ? 1 : 0, in.data_ptr(), out.data_ptr(), (int)big.size(0), (int)big.size(2),
+                             (int)big.size(3), (int)big.size(1), (int)small.size(2), (int)small.size(3), (int)k,
+                             (int)s, (int)p, adaptive ? 1 : 0, count_include_pad ? 1 : 0, sm_count(), cur_stream());
+  if (rc == -1) return false;
+  check(rc, "avgpool");
+  return true;
+}
+void dropout_fwd(at::Tensor x, at::Tensor y, at::Tensor mask, double p, int64_t seed, int64_t salt,
+                 c10::optional<at::Tensor> step) {
+  TORCH_CHECK(is_bf16(x) && is_bf16(y) && mask.scalar_type() == at::kByte && x.numel() % 8 == 0);
+  TORCH_CHECK(mask.numel() * 8 >= x.numel());
+  c10::cuda::CUDAGuard g(x.device());
+  check(ddl_dropout_fwd(x.data_ptr(), y.data_ptr(), mask.data_ptr(), x.numel(), (float)p, (uint64_t)seed,
+                        (uint64_t)salt, (const long long*)optr(step), sm_count(), cur_stream()),
+        "dropout_fwd");
+}
+void dropout_bwd(at::Tensor dy, at::Tensor mask, at::Tensor dx, double scale) {
+  TORCH_CHECK(is_bf16(dy) && is_bf16(dx) && mask.scalar_type() == at::kByte && dy.numel() % 8 == 0);
+  c10::cuda::CUDAGuard g(dy.device());
+  check(ddl_dropout_bwd(dy.data_ptr(), mask.data_ptr(), dx.data_ptr(), dy.numel(), (float)scale, sm_count(),
+                        cur_stream()),
+        "dropout_bwd");
+}
 std::string gemm_info() {
   char buf[512];
   ddl_gemm_selftest_info(buf, sizeof(buf));
@@ -849,6 +882,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_bf16_nt_mn", &gemm_bf16_nt_mn);
   m.def("gemm_bf16_tn_bnfold", &gemm_bf16_tn_bnfold);
   m.def("gemm_bf16_tn_bnbwd", &gemm_bf16_tn_bnbwd);
+  m.def("avgpool", &avgpool);
+  m.def("dropout_fwd", &dropout_fwd);
+  m.def("dropout_bwd", &dropout_bwd);
   m.def("igemm_gemm", &igemm_gemm);
   m.def("igemm_conv_fprop", &igemm_conv_fprop);
   m.def("igemm_conv_dgrad", &igemm_conv_dgrad);

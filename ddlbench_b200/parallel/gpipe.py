@@ -216,6 +216,9 @@ class GPipe:
         the last partition (None elsewhere).  ``x`` is needed on the first partition's rank and
         ``target`` on the last partition's rank (reference: input -> first device, target ->
         last device, ``imagenet_gpipe.py:169-170``)."""
+        from .. import ops
+        for ex in self.execs.values():      # one tick per step: recomputed micro-batches see the same masks
+            ops.rng_tick(ex.device)
         if self.distributed:
             return self._step_distributed(x, target)
         return self._step_local(x, target)

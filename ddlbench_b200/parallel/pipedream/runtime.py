@@ -393,6 +393,9 @@ class StageRuntime:
         stages receive them.  Last stage returns stats[3] (loss, #top1, #top5)."""
         t = self.topo
         ex = self.ex
+        if self.training:
+            from ... import ops as _ops
+            _ops.rng_tick(self.device)         # dropout masks differ from minibatch to minibatch
         if t.is_first:
             xs = [ex.prepare_input(inputs)]
             target = target.to(self.device)

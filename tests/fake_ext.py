@@ -365,6 +365,40 @@ class FullFakeExt(FakeExt):
         self.calls.append("bn_bwd_fused:declined")
         return False
 
+    # bool avgpool(backward, in, out, k, s, p, adaptive, count_include_pad)
+    def avgpool(self, backward, inp, out, k, s, p, adaptive, cip):
+        self.calls.append("avgpool:%d" % int(backward))
+        a, op = _plain(inp), _plain(out)
+        assert a.dim() == 4 and op.dim() == 4 and a.dtype == BF16 and op.dtype == BF16
+        assert a.is_contiguous(memory_format=CL) and op.is_contiguous(memory_format=CL)
+        big = op if backward else a
+        small = a if backward else op
+        x = torch.zeros(big.shape, dtype=torch.float32) if backward else a.float()
+        x = x.contiguous().requires_grad_(True)
+        y = F.adaptive_avg_pool2d(x, tuple(small.shape[2:])) if adaptive else F.avg_pool2d(x, k, s, p, False, cip)
+        assert tuple(y.shape) == tuple(small.shape)
+        if backward:
+            y.backward(a.float().contiguous())
+            op.copy_(x.grad.to(BF16))
+        else:
+            op.copy_(y.detach().to(BF16))
+        return True
+
+    def dropout_fwd(self, x, y, mask, p, seed, salt, step):
+        self.calls.append("dropout_fwd")
+        xp, yp, mp = _plain(x), _plain(y), _plain(mask)
+        g = torch.Generator().manual_seed((seed ^ salt ^ int(_plain(step).item() if step is not None else 0)) & 0x7FFFFFFF)
+        keep = torch.rand(xp.numel(), generator=g) >= p
+        yp.copy_((xp.float().reshape(-1) * keep / (1 - p)).reshape(xp.shape).to(BF16))
+        bits = keep.view(-1, 8).to(torch.int32)
+        mp.view(-1)[:xp.numel() // 8].copy_((bits << torch.arange(8, dtype=torch.int32)).sum(-1).to(torch.uint8))
+
+    def dropout_bwd(self, dy, mask, dx, scale):
+        self.calls.append("dropout_bwd")
+        d, m = _plain(dy), _plain(mask).view(-1)[:_plain(dy).numel() // 8].view(-1, 1).to(torch.int32)
+        keep = ((m >> torch.arange(8, dtype=torch.int32)) & 1).view(-1).bool()
+        _plain(dx).copy_((d.float().reshape(-1) * keep * scale).reshape(d.shape).to(BF16))
+
     def bn_replicas(self):
         return R
 

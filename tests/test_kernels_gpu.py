@@ -319,3 +319,62 @@ def test_dwconv3x3(n, c, hw, stride):
     dx, dw = ops.dwconv_bwd(dy, x, w, stride, 1)
     torch.testing.assert_close(dx.float(), xr.grad, rtol=3e-2, atol=3e-2)
     torch.testing.assert_close(dw, wr.grad, rtol=2e-2, atol=2e-2 * max(1.0, wr.grad.abs().max().item()))
+
+
+@pytest.mark.parametrize("n,c,hw,k,s,p,cip", [(4, 64, 14, 3, 1, 1, True), (2, 192, 35, 3, 1, 1, False),
+                                             (3, 32, 17, 2, 2, 0, True), (2, 64, 8, 5, 3, 2, True)])
+def test_avgpool_fixed_window(n, c, hw, k, s, p, cip):
+    torch.manual_seed(0)
+    x = _nhwc(n, c, hw, hw)
+    oh = (hw + 2 * p - k) // s + 1
+    y = ops.avgpool_fwd(x, (oh, oh), k, s, p, False, cip)
+    xr = x.float().requires_grad_(True)
+    y_ref = torch.nn.functional.avg_pool2d(xr, k, s, p, False, cip)
+    torch.testing.assert_close(y.float(), y_ref.detach(), rtol=1e-2, atol=1e-2)
+    dy = torch.randn_like(y_ref).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y_ref.backward(dy.float())
+    dx = ops.avgpool_bwd(dy, x.shape, k, s, p, False, cip)
+    torch.testing.assert_close(dx.float(), xr.grad, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("n,c,hw,out", [(4, 64, 13, 6), (2, 512, 14, 7), (3, 128, 9, 1), (2, 64, 10, 4)])
+def test_avgpool_adaptive(n, c, hw, out):
+    torch.manual_seed(0)
+    x = _nhwc(n, c, hw, hw)
+    y = ops.avgpool_fwd(x, (out, out), 0, 0, 0, True)
+    xr = x.float().requires_grad_(True)
+    y_ref = torch.nn.functional.adaptive_avg_pool2d(xr, out)
+    torch.testing.assert_close(y.float(), y_ref.detach(), rtol=1e-2, atol=1e-2)
+    dy = torch.randn_like(y_ref).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y_ref.backward(dy.float())
+    dx = ops.avgpool_bwd(dy, x.shape, 0, 0, 0, True)
+    torch.testing.assert_close(dx.float(), xr.grad, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("p", [0.5, 0.1])
+def test_dropout_philox(p):
+    torch.manual_seed(0)
+    x = torch.randn(64, 4096, device=DEV).to(torch.bfloat16)
+    y, mask = ops.dropout_fwd(x, p)
+    bits = ((mask.view(-1, 1).to(torch.int32) >> torch.arange(8, device=DEV, dtype=torch.int32)) & 1).view(-1).bool()
+    keep = bits.float().mean().item()
+    assert abs(keep - (1 - p)) < 0.01, keep                     # drop rate
+    ref = torch.where(bits.view_as(x), x.float() / (1 - p), torch.zeros_like(x, dtype=torch.float32))
+    torch.testing.assert_close(y.float(), ref, rtol=1e-2, atol=1e-2)
+    dy = torch.randn_like(x)
+    dx = ops.dropout_bwd(dy, mask, p)
+    torch.testing.assert_close(dx.float(), torch.where(bits.view_as(x), dy.float() / (1 - p), torch.zeros_like(ref)),
+                               rtol=1e-2, atol=1e-2)
+    # a new step -> a different mask; same step + same host RNG state -> the same mask (recompute)
+    st = torch.get_rng_state()
+    _, m1 = ops.dropout_fwd(x, p)
+    torch.set_rng_state(st)
+    _, m2 = ops.dropout_fwd(x, p)
+    assert torch.equal(m1, m2)
+    ops.rng_tick(x.device)
+    torch.set_rng_state(st)
+    _, m3 = ops.dropout_fwd(x, p)
+    assert not torch.equal(m1, m3)
+    # neighbouring bytes are not correlated (each thread draws two Philox blocks)
+    b = mask.view(-1)[:4096].to(torch.float32)
+    assert abs(torch.corrcoef(torch.stack([b[:-1], b[1:]]))[0, 1].item()) < 0.1
