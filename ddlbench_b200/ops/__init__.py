@@ -53,6 +53,8 @@ def load_ext(build_if_missing: bool = True):
             mod = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(mod)
             assert mod.bn_replicas() == BN_REPLICAS, "BN_REPLICAS mismatch with the extension"
+            if os.environ.get("DDLB_PDL", "1") == "0":     # profiling aid: true per-kernel durations
+                mod.set_pdl(False)
             _ext = mod
         except BaseException as e:  # noqa: BLE001 - remembered and re-raised on GPU use
             _ext_err = e
@@ -765,6 +767,11 @@ def gemm_ig(a: torch.Tensor, b: torch.Tensor, b_mn: bool = False,
             relu: bool = False, bn_finalize=None) -> Optional[torch.Tensor]:
     """D[M, N] = a[M, K] @ (b[N, K]^T if not b_mn else b[K, N]) on the persistent kernel."""
     n = b.shape[1] if b_mn else b.shape[0]
+    if (GEMM_PAIR and not b_mn and col_sums is None and bn_finalize is None and
+            a.shape[0] >= GEMM_PAIR_MIN[0] and n >= GEMM_PAIR_MIN[1] and a.shape[1] >= GEMM_PAIR_MIN[2]):
+        out = gemm_pair(a, b, bias, relu)
+        if out is not None:
+            return out
     out = torch.empty((a.shape[0], n), dtype=torch.bfloat16, device=a.device)
     rc = ext().igemm_gemm(a, b, out, b_mn, col_sums, bias, relu, *_fin_args(bn_finalize), *_ig_ws(a.device))
     if rc < 0:
@@ -772,6 +779,30 @@ def gemm_ig(a: torch.Tensor, b: torch.Tensor, b_mn: bool = False,
     _count()
     if bn_finalize is not None and rc == 0:
         _finalize_after(col_sums, bn_finalize, a.shape[0], n)
+    return out
+
+
+GEMM_PAIR = os.environ.get("DDLB_GEMM_PAIR", "1") == "1"
+# (M, N, K) from which the CTA-pair kernel takes over from the single-CTA one: a 256-row tile grid
+# of at least one wave of 74 clusters and a reduction long enough to be bandwidth- rather than
+# epilogue-bound (profiles/gemm_tcgen05_vs_cublas.json)
+GEMM_PAIR_MIN = (2048, 256, 512)
+
+
+def gemm_pair(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None,
+              relu: bool = False, out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """D[M, N] = a[M, K] @ b[N, K]^T (+ bias)(ReLU) on the CTA-pair (``cta_group::2``) persistent
+    kernel (csrc/gemm2cta_tcgen05.cu); None if the shape is declined."""
+    if not (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and
+            b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1 and a.shape[1] == b.shape[1]):
+        return None
+    if a.shape[0] < 32 or b.shape[0] < 64:
+        return None
+    if out is None:
+        out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.bfloat16, device=a.device)
+    if not ext().gemm2cta(a, b, out, bias, relu):
+        return None
+    _count()
     return out
 
 

@@ -27,7 +27,8 @@ EXT_NAME = "_ddlb_ext"
 
 CUDA_SOURCES = ["sgd.cu", "xent.cu", "bn.cu", "bn_cluster.cu", "allreduce.cu", "misc.cu", "pool.cu", "gemm_tcgen05.cu", "conv_tcgen05.cu", "im2col.cu",
                 "gemm_wgrad_tcgen05.cu", "dwconv.cu",
-                "gemm_bnfold_tcgen05.cu", "gemm_bnbwd_tcgen05.cu", "igemm_tcgen05.cu", "elementwise.cu"]
+                "gemm_bnfold_tcgen05.cu", "gemm_bnbwd_tcgen05.cu", "igemm_tcgen05.cu", "elementwise.cu",
+                "gemm2cta_tcgen05.cu"]
 CPP_SOURCES = ["bindings.cpp"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

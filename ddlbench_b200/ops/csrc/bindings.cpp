@@ -465,6 +465,21 @@ int64_t igemm_gemm(at::Tensor A, at::Tensor B, at::Tensor D, bool b_mn, c10::opt
   check(rc, "igemm_gemm");
   return 0;
 }
+// D = A[M,K] B[N,K]^T (+bias)(ReLU) on the CTA-pair kernel; false: shape declined
+bool gemm2cta(at::Tensor A, at::Tensor B, at::Tensor D, c10::optional<at::Tensor> bias, bool relu) {
+  TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && D.dim() == 2 && is_bf16(A) && is_bf16(B) && is_bf16(D));
+  TORCH_CHECK(A.stride(1) == 1 && B.stride(1) == 1 && D.stride(1) == 1);
+  const int M = (int)A.size(0), K = (int)A.size(1), N = (int)B.size(0);
+  TORCH_CHECK(B.size(1) == K && D.size(0) == M && D.size(1) == N, "gemm2cta: shapes");
+  if (bias.has_value() && bias->defined()) TORCH_CHECK(is_bf16(*bias) && bias->numel() == N);
+  c10::cuda::CUDAGuard g(A.device());
+  const int rc = ddl_gemm2cta(A.data_ptr(), B.data_ptr(), D.data_ptr(), M, N, K, (int)A.stride(0),
+                              (int)B.stride(0), (int)D.stride(0), optr(bias), relu ? 1 : 0, sm_count(),
+                              cur_stream());
+  if (rc == -1) return false;
+  check(rc, "gemm2cta");
+  return true;
+}
 int64_t igemm_conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int64_t pad_h, int64_t pad_w,
                       int64_t stride, c10::optional<at::Tensor> col_sums,
                       c10::optional<at::Tensor> bias, bool relu, c10::optional<at::Tensor> ticket,
@@ -886,6 +901,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dropout_fwd", &dropout_fwd);
   m.def("dropout_bwd", &dropout_bwd);
   m.def("igemm_gemm", &igemm_gemm);
+  m.def("gemm2cta", &gemm2cta);
+  m.def("igemm_set_trace", [](c10::optional<at::Tensor> buf) {
+    if (buf.has_value() && buf->defined()) {
+      TORCH_CHECK(buf->scalar_type() == at::kLong && buf->is_cuda() && buf->is_contiguous());
+      ddl_igemm_set_trace((unsigned long long*)buf->data_ptr());
+    } else {
+      ddl_igemm_set_trace(nullptr);
+    }
+  }, "debug: per-CTA stage timestamps ([ctas][16] int64) of the following igemm launches");
   m.def("igemm_conv_fprop", &igemm_conv_fprop);
   m.def("igemm_conv_dgrad", &igemm_conv_dgrad);
   m.def("wgrad_gemm", &wgrad_gemm);

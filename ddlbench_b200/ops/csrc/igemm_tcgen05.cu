@@ -64,6 +64,14 @@ struct IgemmParams {
   const __nv_bfloat16* bias;      // [Nout] or null
   int relu;
   int kb_per_split;               // k-blocks per split-K slice (gridDim.z slices)
+  int ncls;                       // > 1: gridDim.z indexes output CLASSES (stride-2 dgrad parities),
+                                  // each with its own tap range, output extent and store map
+  struct Cls { int OW, OH, tiles_w, tiles_h, pix_tiles, tap0, ntaps, pad; } cls[4];
+  int split_l2;                   // cluster split-K flavour: 1 = exchange through L2 (global
+                                  // workspace), 0 = through distributed shared memory
+  unsigned long long* trace;      // debug: per-CTA globaltimer stamps [cta][16] (null: off)
+  int split_w;                    // > 0: CLUSTER split-K (cluster = the gridDim.z slices of a tile);
+                                  // each CTA finishes split_w = BLOCK_N / slices columns of the tile
   float* splitk_ws;               // fp32 scratch [tiles][slices][128 x BLOCK_N] (split-K only)
   unsigned int* splitk_tickets;   // one per tile, zero on entry, self-resetting
   unsigned int* ticket;           // fused BatchNorm finalize: one counter PER n-tile (null: sums only)
@@ -137,11 +145,47 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// stage stamps of one thread per CTA (tools/igemm_trace.py): 0 entry, 1 after prologue + pdl_wait,
+// 2 accumulator ready, 3 cluster barrier 1, 4 scatter done, 5 cluster barrier 2, 6 tile staged +
+// store issued, 7 statistics flushed, 8 ticket / finalize done, 9 exit
+#define IG_STAMP(k)                                                                            \
+  do {                                                                                         \
+    if (p.trace && threadIdx.x == 64)                                                          \
+      p.trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (k)] = gtimer(); \
+  } while (0)
+
+// ---- thread-block-cluster helpers (split-K through distributed shared memory)
+__device__ __forceinline__ void cluster_arrive_rel() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acq() {
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
 template <int BLOCK_N, int kStages, bool kBMn, bool kStats, bool kSmall>
 __global__ void __launch_bounds__(kThreads, (IgSmem<BLOCK_N, kStages, kStats, kSmall>::kMinCtas))
 igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_d,
+                  const __grid_constant__ CUtensorMap map_ds,   // cluster split-K: split_w-column store box
+                  const __grid_constant__ CUtensorMap map_d1,   // store maps of output classes 1..3
+                  const __grid_constant__ CUtensorMap map_d2,
+                  const __grid_constant__ CUtensorMap map_d3,
                   const __grid_constant__ IgemmParams p) {
   using L = IgSmem<BLOCK_N, kStages, kStats, kSmall>;
   constexpr uint32_t kTmemCols = kSmall ? BLOCK_N : 2 * BLOCK_N;   // one / two accumulators
@@ -162,18 +206,30 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
   // this CTA: n-tile blockIdx.x (fastest: CTAs sharing an A tile run together, L2 reuse), pixel
   // tiles [tp0, tp1), k-blocks [kb0, kb1) of every tile (split-K over blockIdx.z)
   const int tile_n = blockIdx.x;
+  // output class of this CTA (multi-class launches: gridDim.z = classes, never split-K)
+  const bool multi = !kSmall && p.ncls > 1;
+  const int cls = multi ? (int)blockIdx.z : 0;
+  const int c_OW = multi ? p.cls[cls].OW : p.OW, c_OH = multi ? p.cls[cls].OH : p.OH;
+  const int c_tiles_w = multi ? p.cls[cls].tiles_w : p.tiles_w;
+  const int c_tiles_h = multi ? p.cls[cls].tiles_h : p.tiles_h;
+  const int c_pix_tiles = multi ? p.cls[cls].pix_tiles : p.pix_tiles;
+  const int c_tap0 = multi ? p.cls[cls].tap0 : 0;
+  const int c_ntaps = multi ? p.cls[cls].ntaps : p.ntaps;
+  const CUtensorMap* md_cls = cls == 0 ? &map_d : cls == 1 ? &map_d1 : cls == 2 ? &map_d2 : &map_d3;
   const int tp0 = blockIdx.y * p.tiles_per_cta;
-  const int tp1 = min(tp0 + p.tiles_per_cta, p.pix_tiles);
-  const int total_kb = p.ntaps * p.kc_blocks;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int kb1 = min(kb0 + p.kb_per_split, total_kb);
-  const bool split = !kSmall && gridDim.z > 1;      // the one-tile variant never splits K
+  const int tp1 = min(tp0 + p.tiles_per_cta, c_pix_tiles);
+  const int total_kb = c_ntaps * p.kc_blocks;
+  const int kb0 = multi ? 0 : blockIdx.z * p.kb_per_split;
+  const int kb1 = multi ? total_kb : min(kb0 + p.kb_per_split, total_kb);
+  const bool split = !kSmall && !multi && gridDim.z > 1;      // the one-tile variant never splits K
+  const bool csplit = split && p.split_w > 0;       // slices of a tile = one thread-block cluster
 
   pdl_trigger();
+  IG_STAMP(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    tma_prefetch_desc(&map_d);
+    tma_prefetch_desc(md_cls);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -193,16 +249,17 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();      // everything above overlapped the previous grid; from here we read its output
+  IG_STAMP(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       uint32_t it = 0;
       for (int tp = tp0; tp < tp1; ++tp) {
-        const int w0 = (tp % p.tiles_w) * p.TW;
-        const int h0 = ((tp / p.tiles_w) % p.tiles_h) * p.TH;
-        const int n0 = (tp / (p.tiles_w * p.tiles_h)) * p.TN;
-        int t = kb0 / p.kc_blocks, cb = kb0 % p.kc_blocks;
+        const int w0 = (tp % c_tiles_w) * p.TW;
+        const int h0 = ((tp / c_tiles_w) % c_tiles_h) * p.TH;
+        const int n0 = (tp / (c_tiles_w * c_tiles_h)) * p.TN;
+        int t = c_tap0 + kb0 / p.kc_blocks, cb = kb0 % p.kc_blocks;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
@@ -224,6 +281,11 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
           if (++cb == p.kc_blocks) { cb = 0; ++t; }
         }
       }
+    }
+    if (csplit) {          // every thread of the cluster takes part in the cluster barriers
+      __syncwarp();
+      if (!p.split_l2) { cluster_arrive_rel(); cluster_wait_acq(); }
+      cluster_arrive_rel(); cluster_wait_acq();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -257,6 +319,11 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
         __syncwarp();
       }
     }
+    if (csplit) {
+      __syncwarp();
+      if (!p.split_l2) { cluster_arrive_rel(); cluster_wait_acq(); }
+      cluster_arrive_rel(); cluster_wait_acq();
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (128 threads)
     const int et = threadIdx.x - 64;
@@ -276,10 +343,10 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
     uint8_t* stage = smem + L::kOutOffset;
     for (int tp = tp0; tp < tp1; ++tp, ++iter) {
       const uint32_t acc = iter & 1, acc_ph = (iter >> 1) & 1;
-      const int w0 = (tp % p.tiles_w) * p.TW;
-      const int h0 = ((tp / p.tiles_w) % p.tiles_h) * p.TH;
-      const int n0 = (tp / (p.tiles_w * p.tiles_h)) * p.TN;
-      const bool valid = (w0 + lw < p.OW) && (h0 + lh < p.OH) && (n0 + ln < p.NB);
+      const int w0 = (tp % c_tiles_w) * p.TW;
+      const int h0 = ((tp / c_tiles_w) % c_tiles_h) * p.TH;
+      const int n0 = (tp / (c_tiles_w * c_tiles_h)) * p.TN;
+      const bool valid = (w0 + lw < c_OW) && (h0 + lh < c_OH) && (n0 + ln < p.NB);
       const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
       // split-K: slice z of tile t parks its partial sums in slot [t][z] of the workspace, laid
       // out [(col/4)][row][4] fp32 so that a warp's 16-byte accesses are 512 contiguous bytes.
@@ -290,6 +357,129 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
       float* wst = split ? p.splitk_ws + (size_t)(tp * gridDim.x + tile_n) * gridDim.z * slot_elems : nullptr;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
+      IG_STAMP(2);
+      if (csplit) {
+        // ---- split-K across a thread-block cluster, reduced through DISTRIBUTED SHARED MEMORY.
+        // The S slices of this tile are the S CTAs of one cluster (co-scheduled by the hardware).
+        // Each CTA owns W = BLOCK_N / S output columns: it scatters the other column slices of
+        // its partial accumulator straight into their owners' (by now idle) rings with
+        // st.shared::cluster, and after a cluster barrier adds the S-1 partials it received to
+        // its own TMEM slice and runs the epilogue for those W columns.  No global workspace, no
+        // atomics, no serial last-arriver: the reduction is spread over all S CTAs.
+        const int S = (int)gridDim.z, rank = (int)blockIdx.z, W = p.split_w;
+        float* rbuf = reinterpret_cast<float*>(smem);          // [S-1][128][W] fp32 over the ring
+        const uint32_t rbuf_u32 = smem_u32(rbuf);
+        const bool via_l2 = p.split_l2 != 0;
+        // L2 flavour: every CTA parks the column slices it does NOT own in its own 64 KB slot of
+        // the global workspace ([column quad][row][4 floats]: coalesced both ways, stays in L2),
+        // ONE cluster barrier, then each CTA pulls the S-1 partials of its slice with ld.global.cg.
+        // (Measured: remote st.shared::cluster stores run at ~12 B/clk per SM, several times
+        // slower than the same bytes through L2 — profiles/r2/igemm_trace_*.log.)
+        const size_t slot_f4 = (size_t)BLOCK_M * BLOCK_N / 4;
+        float4* ws_tile = reinterpret_cast<float4*>(p.splitk_ws) +
+                          (size_t)(tp * gridDim.x + tile_n) * S * slot_f4;
+        // (1) DSMEM flavour: all tensor cores of the cluster are done reading their rings
+        if (!via_l2) { cluster_arrive_rel(); cluster_wait_acq(); }
+        IG_STAMP(3);
+        // (2) scatter
+#pragma unroll 1
+        for (int g = 0; g < BLOCK_N / 32; ++g) {
+          const int dest = (g * 32) / W;
+          if (dest == rank) continue;
+          uint32_t r[32];
+          tmem_ld_32x32(tacc + g * 32, r);
+          // receive buffer layout [slot][column quad][row][4 floats]: a warp's 16-byte stores are
+          // 512 contiguous bytes (coalesced on the SM-to-SM network, conflict-free when read back)
+          const int slot = rank - (rank > dest ? 1 : 0);
+          const int q0 = ((g * 32) % W) / 4;
+          const uint32_t local = rbuf_u32 + (uint32_t)((((slot * (W / 4) + q0) * BLOCK_M) + row) * 16);
+          if (via_l2) {
+            float4* dst = ws_tile + (size_t)rank * slot_f4 + (size_t)(g * 8) * BLOCK_M + row;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              __stcg(dst + j * BLOCK_M, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                    __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+            continue;
+          }
+          const uint32_t remote = mapa_u32(local, (uint32_t)dest);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_cluster_f4(remote + j * (BLOCK_M * 16), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                          __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        // (3) every partial sum has landed
+        IG_STAMP(4);
+        cluster_arrive_rel(); cluster_wait_acq();
+        IG_STAMP(5);
+        // (4) own slice
+        const bool wide = W == 64;                   // 64 columns: the swizzled staging + map_d
+#pragma unroll 1
+        for (int g = 0; g < W / 32; ++g) {
+          float f[32];
+          {
+            uint32_t r[32];
+            tmem_ld_32x32(tacc + rank * W + g * 32, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+          }
+          for (int sl = 0; sl < S - 1; ++sl) {
+            const int srck = sl + (sl >= rank ? 1 : 0);        // the sl-th OTHER slice
+            const float4* src = via_l2 ? ws_tile + (size_t)srck * slot_f4 +
+                                             (size_t)((rank * W + g * 32) / 4) * BLOCK_M + row
+                                       : reinterpret_cast<const float4*>(rbuf) +
+                                             ((size_t)(sl * (W / 4) + g * 8) * BLOCK_M + row);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = via_l2 ? __ldcg(src + j * BLOCK_M) : src[j * BLOCK_M];
+              f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = f[i];
+            if (p.bias) v += bias_s[rank * W + g * 32 + i];
+            if (p.relu) v = fmaxf(v, 0.f);
+            f[i] = valid ? v : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            bf16x8 pk = pack8(f + j * 8);
+            const int chunk = g * 4 + j;             // 16-byte chunk inside the row
+            if (wide)
+              *reinterpret_cast<bf16x8*>(stage + row * 128 + ((chunk ^ (row & 7)) * 16)) = pk;
+            else   // 64-byte rows, SWIZZLE_64B: chunk ^= address bits [7:8]
+              *reinterpret_cast<bf16x8*>(stage + row * 64 + ((chunk ^ ((row >> 1) & 3)) * 16)) = pk;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int col0 = tile_n * BLOCK_N + rank * W;
+        if (et == 0 && col0 < p.Nout) {
+          tma_store_4d(wide ? &map_d : &map_ds, stage, col0, w0, h0, n0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        IG_STAMP(6);
+        ++done_tiles;
+        if (kStats && p.col_sums) {
+          const int pairs = W / 2, groups = 128 / pairs, rows_per = BLOCK_M / groups;
+          const int pair = et % pairs, grp = et / pairs;
+          const int c = pair * 2;
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+          for (int rr = 0; rr < rows_per; ++rr) {
+            const int r_ = grp * rows_per + rr;
+            const uint8_t* src = wide ? stage + r_ * 128 + (((c >> 3) ^ (r_ & 7)) * 16) + (c & 7) * 2
+                                      : stage + r_ * 64 + (((c >> 3) ^ ((r_ >> 1) & 3)) * 16) + (c & 7) * 2;
+            const float2 fv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src));
+            a0 += fv.x; a1 += fv.y;
+            b0 = fmaf(fv.x, fv.x, b0); b1 = fmaf(fv.y, fv.y, b1);
+          }
+          atomicAdd(&stat_s[rank * W + c], a0);
+          atomicAdd(&stat_s[rank * W + c + 1], a1);
+          atomicAdd(&stat_s[BLOCK_N + rank * W + c], b0);
+          atomicAdd(&stat_s[BLOCK_N + rank * W + c + 1], b1);
+        }
+        continue;
+      }
       if (split) {
         float* mine = wst + (size_t)blockIdx.z * slot_elems;
 #pragma unroll
@@ -370,9 +560,10 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
         for (int h = 0; h < BLOCK_N / 64; ++h)
           if (tile_n * BLOCK_N + h * 64 < p.Nout)
-            tma_store_4d(&map_d, stage + h * (BLOCK_M * 128), tile_n * BLOCK_N + h * 64, w0, h0, n0);
+            tma_store_4d(md_cls, stage + h * (BLOCK_M * 128), tile_n * BLOCK_N + h * 64, w0, h0, n0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+      IG_STAMP(6);
       ++done_tiles;
       if (kStats && p.col_sums) {
         // per-channel sum / sum-of-squares of the (bf16-rounded) tile: every thread owns a column
@@ -400,7 +591,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
       // combine the row groups in shared memory, flush this CTA's sums with one vector of atomics;
       // the CTA that completes the LAST pixel tile of this n-tile finalizes its BLOCK_N channels
       // (one channel per thread: every n-tile is finalized in parallel by a different CTA)
-      {
+      if (!csplit) {
         const int c = (et % (BLOCK_N / 2)) * 2;
         atomicAdd(&stat_s[c], s0);
         atomicAdd(&stat_s[c + 1], s1);
@@ -409,19 +600,24 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       float* cs = p.col_sums + (size_t)(blockIdx.y % DDL_BN_REPLICAS) * 2 * p.Nout;
-      for (int i = et; i < BLOCK_N; i += 128) {
+      // (cluster split-K: this CTA produced only its own split_w columns of the tile)
+      const int i_lo = csplit ? (int)blockIdx.z * p.split_w : 0;
+      const int i_hi = csplit ? i_lo + p.split_w : BLOCK_N;
+      for (int i = i_lo + et; i < i_hi; i += 128) {
         const int col = tile_n * BLOCK_N + i;
         if (col < p.Nout) {
           atomicAdd(&cs[col], stat_s[i]);
           atomicAdd(&cs[p.Nout + col], stat_s[BLOCK_N + i]);
         }
       }
+      IG_STAMP(7);
       if (!kSmall && p.ticket) {
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) {
           const unsigned int t = atomicAdd(&p.ticket[tile_n], (unsigned int)done_tiles);
-          flag_last = (t + (unsigned int)done_tiles == (unsigned int)p.pix_tiles);
+          flag_last = (t + (unsigned int)done_tiles ==
+                       (unsigned int)c_pix_tiles * (csplit ? gridDim.z : 1u));
           if (flag_last) p.ticket[tile_n] = 0u;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -454,7 +650,9 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
         }
       }
     }
+    IG_STAMP(8);
     if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    IG_STAMP(9);
   }
   tc_fence_before();
   __syncthreads();
@@ -469,7 +667,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
 // box {bc, bw, bh, bn} elements loaded, `step` = element stride on W and H.
 static inline int make_map_4d(CUtensorMap* map, const void* ptr, int64_t C, int64_t W, int64_t H,
                               int64_t N, int64_t sW, int64_t sH, int64_t sN, int bc, int bw, int bh,
-                              int bn, int step) {
+                              int bn, int step, int swizzle_bytes = 128) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return -2;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -480,10 +678,14 @@ static inline int make_map_4d(CUtensorMap* map, const void* ptr, int64_t C, int6
   if (box[1] > 256 || box[2] > 256 || box[3] > 256) return -1;
   if ((strides[0] % 16) || (strides[1] % 16) || (strides[2] % 16)) return -1;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -3;
 }
+
+static unsigned long long* g_ig_trace = nullptr;
 
 struct IgTensor {       // NHWC view: extents and element strides (C is contiguous)
   const void* ptr;
@@ -507,6 +709,11 @@ struct IgProblem {
   float* splitk_ws;               // zero fp32 scratch for split-K (may be null: never split)
   unsigned int* splitk_tickets;
   int splitk_tiles;               // capacity of both, in 128x128 tiles
+  // multi-class launch (stride-2 data gradient: one class per output parity): class c writes d_cls[c]
+  // from taps [cls_tap0[c], cls_tap0[c+1]); class 0's tensor is also `d`
+  int ncls;
+  IgTensor d_cls[4];
+  int cls_tap0[5];
 };
 
 template <int BLOCK_N, int kStages, bool kBMn, bool kStats, bool kSmall>
@@ -534,8 +741,31 @@ static int launch_ig(const IgProblem& q, IgemmParams& p, int sms, cudaStream_t s
   }
   p.tiles_n = (int)((q.d.C + BLOCK_N - 1) / BLOCK_N);
   p.pix_tiles = p.tiles_w * p.tiles_h * (int)((q.d.N + p.TN - 1) / p.TN);
-  const long long total = (long long)p.pix_tiles * p.tiles_n;
+  long long total = (long long)p.pix_tiles * p.tiles_n;
   const int total_kb = p.ntaps * p.kc_blocks;
+  CUtensorMap mdc[4] = {md, md, md, md};
+  int max_pix_tiles = p.pix_tiles;
+  p.ncls = (!kSmall && q.ncls > 1) ? q.ncls : 1;
+  if (p.ncls > 1) {
+    total = 0;
+    max_pix_tiles = 0;
+    for (int c = 0; c < p.ncls; ++c) {
+      const IgTensor& d = q.d_cls[c];
+      if ((rc = make_map_4d(&mdc[c], d.ptr, d.C, d.W, d.H, d.N, d.sW, d.sH, d.sN, 64, p.TW, p.TH, p.TN, 1)))
+        return rc;
+      IgemmParams::Cls& k = p.cls[c];
+      k.OW = (int)d.W; k.OH = (int)d.H;
+      k.tiles_w = (int)((d.W + p.TW - 1) / p.TW);
+      k.tiles_h = (int)((d.H + p.TH - 1) / p.TH);
+      k.pix_tiles = k.tiles_w * k.tiles_h * (int)((d.N + p.TN - 1) / p.TN);
+      k.tap0 = q.cls_tap0[c];
+      k.ntaps = q.cls_tap0[c + 1] - q.cls_tap0[c];
+      k.pad = 0;
+      total += (long long)k.pix_tiles * p.tiles_n;
+      if (k.pix_tiles > max_pix_tiles) max_pix_tiles = k.pix_tiles;
+    }
+    md = mdc[0];
+  }
   // Work decomposition.  Enough tiles: ONE wave of at most 2 CTAs per SM, every CTA a chunk of
   // consecutive pixel tiles (set-up, statistics flush and ticket are paid once per chunk).  Too
   // few tiles to fill the machine and a long reduction (the 14x14 / 7x7 layers): split-K over
@@ -543,25 +773,79 @@ static int launch_ig(const IgProblem& q, IgemmParams& p, int sms, cudaStream_t s
   int per = (int)((total + 2LL * sms - 1) / (2LL * sms));
   if (per > 16) per = 16;
   if (kSmall) per = 1;
+  // split-K flavour: default = the slices of a tile form a thread-block cluster (co-scheduled), every
+  // slice finishes its own columns and the partial sums are exchanged through L2 ("dsmem": through
+  // distributed shared memory instead); "slots" = round-2's first scheme (partial tiles
+  // parked in a global fp32 workspace, the last slice to arrive reduces) kept for A/B runs
+  static const int split_mode = [] {
+    const char* e = std::getenv("DDLB_IG_SPLIT");
+    return (e && !strcmp(e, "slots")) ? 1 : (e && !strcmp(e, "off")) ? 2 : (e && !strcmp(e, "dsmem")) ? 3 : 0;
+  }();
   int splits = 1;
-  if (!kSmall && total < sms && total_kb >= 8 && q.splitk_ws && BLOCK_N == 128) {
-    splits = (int)((3LL * sms / 2 + total - 1) / total);
-    if (splits > total_kb / 4) splits = total_kb / 4;
-    if (splits > 8) splits = 8;
-    while (splits > 1 && total * splits > q.splitk_tiles) --splits;   // slots available
-    if (splits < 1) splits = 1;
+  p.split_w = 0;
+  p.split_l2 = 0;
+  if (!kSmall && p.ncls == 1 && total < sms && total_kb >= 8 && BLOCK_N == 128 && split_mode != 2) {
+    if (split_mode == 0 || split_mode == 3) {
+      // 2 or 4 slices: enough CTAs for every SM, at most the 2-per-SM residency
+      splits = (total * 4 <= 2LL * sms && total_kb >= 16) ? 4 : 2;
+      for (; splits > 1; splits /= 2) {
+        const int kbps = (total_kb + splits - 1) / splits;
+        if ((total_kb + kbps - 1) / kbps == splits) break;          // no empty slice
+      }
+      if (splits > 1) {
+        p.split_w = BLOCK_N / splits;
+        // exchange through L2 when the workspace has a slot per (tile, slice); DDLB_IG_SPLIT=dsmem
+        // forces the distributed-shared-memory exchange
+        p.split_l2 = (split_mode == 0 && q.splitk_ws && total * splits <= q.splitk_tiles) ? 1 : 0;
+      }
+    } else if (q.splitk_ws) {
+      splits = (int)((3LL * sms / 2 + total - 1) / total);
+      if (splits > total_kb / 4) splits = total_kb / 4;
+      if (splits > 8) splits = 8;
+      while (splits > 1 && total * splits > q.splitk_tiles) --splits;   // slots available
+      if (splits < 1) splits = 1;
+    }
   }
+  p.trace = g_ig_trace;
   if (splits > 1) per = 1;
   p.kb_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;      // no empty slices
+  if (p.split_w && BLOCK_N / splits != p.split_w) return -4;      // (cannot happen: checked above)
   p.splitk_ws = q.splitk_ws;
   p.splitk_tickets = q.splitk_tickets;
   p.tiles_per_cta = per;
-  const int chunks = (p.pix_tiles + per - 1) / per;
+  const int chunks = (max_pix_tiles + per - 1) / per;
   if (chunks > 65535 || p.tiles_n > 65535) return -1;
-  cudaError_t err = launch_pdl((igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats, kSmall>),
-                               dim3(p.tiles_n, chunks, splits), dim3(kThreads), (size_t)L::kDynamic,
-                               st, ma, mb, md, p);
+  if (p.ncls > 1) splits = p.ncls;          // gridDim.z = classes (kb_per_split covers every tap)
+  CUtensorMap mds = md;
+  if (p.split_w == 32) {
+    if ((rc = make_map_4d(&mds, q.d.ptr, q.d.C, q.d.W, q.d.H, q.d.N, q.d.sW, q.d.sH, q.d.sN, 32, p.TW,
+                          p.TH, p.TN, 1, /*swizzle_bytes=*/64)))
+      return rc;
+  }
+  cudaError_t err;
+  if (p.split_w) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.tiles_n, chunks, splits);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)L::kDynamic;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)splits;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    err = cudaLaunchKernelEx(&cfg, igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats, kSmall>, ma, mb, md,
+                             mds, mdc[1], mdc[2], mdc[3], p);
+  } else {
+    err = launch_pdl((igemm_bf16_kernel<BLOCK_N, kStages, kBMn, kStats, kSmall>),
+                     dim3(p.tiles_n, chunks, splits), dim3(kThreads), (size_t)L::kDynamic, st, ma, mb,
+                     md, mds, mdc[1], mdc[2], mdc[3], p);
+  }
   if (err != cudaSuccess) return (int)err;
   err = cudaGetLastError();
   if (err != cudaSuccess) return (int)err;
@@ -760,26 +1044,57 @@ extern "C" int ddl_igemm_conv_dgrad(const void* dy, const void* w, void* dx, int
     if (e != cudaSuccess) return (int)e;
   }
   q.a = ddl::gemm::dense_nhwc(dy, NB, OH, OW, Cout);
+  // the parity classes that have taps, largest first (class 0 fixes the pixel box): ONE launch with
+  // gridDim.z = classes when there are several (DDLB_IG_S2_MULTI=0: one launch per class)
+  static const bool multi_ok = [] {
+    const char* e = std::getenv("DDLB_IG_S2_MULTI");
+    return !(e && e[0] == '0');
+  }();
+  int ncls = 0, ntaps_all = 0;
+  q.cls_tap0[0] = 0;
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       const int Ha = (H - a + 1) / 2, Wb = (W - b + 1) / 2;
       if (Ha <= 0 || Wb <= 0) continue;
-      q.ntaps = 0;
+      int n = 0;
       for (int kh = 0; kh < KH; ++kh)
         for (int kw = 0; kw < KW; ++kw) {
           const int nh = a + pad_h - kh, nw = b + pad_w - kw;
           if ((nh % 2) || (nw % 2)) continue;
-          q.tap_dh[q.ntaps] = (short)(nh / 2);
-          q.tap_dw[q.ntaps] = (short)(nw / 2);
-          q.tap_bcol[q.ntaps] = (kh * KW + kw) * Cin;
-          ++q.ntaps;
+          q.tap_dh[ntaps_all + n] = (short)(nh / 2);
+          q.tap_dw[ntaps_all + n] = (short)(nw / 2);
+          q.tap_bcol[ntaps_all + n] = (kh * KW + kw) * Cin;
+          ++n;
         }
-      if (q.ntaps == 0) continue;
+      if (n == 0) continue;
       const __nv_bfloat16* base = (const __nv_bfloat16*)dx + ((int64_t)a * W + b) * Cin;
-      q.d = IgTensor{base, Cin, Wb, Ha, NB, 2 * (int64_t)Cin, 2 * (int64_t)W * Cin,
-                     (int64_t)H * W * Cin};
-      const int rc = ddl::gemm::run_ig(q, sms, st);
-      if (rc) return rc;
+      q.d_cls[ncls] = IgTensor{base, Cin, Wb, Ha, NB, 2 * (int64_t)Cin, 2 * (int64_t)W * Cin,
+                               (int64_t)H * W * Cin};
+      ntaps_all += n;
+      q.cls_tap0[++ncls] = ntaps_all;
     }
+  if (ncls == 0) return 0;
+  if (ncls > 1 && multi_ok) {
+    q.ncls = ncls;
+    q.d = q.d_cls[0];
+    q.ntaps = q.cls_tap0[1];                   // class 0's taps (variant choice / k-loop bound of class 0)
+    return ddl::gemm::run_ig(q, sms, st);
+  }
+  IgProblem one = q;
+  one.ncls = 1;
+  for (int c = 0; c < ncls; ++c) {
+    one.d = q.d_cls[c];
+    one.ntaps = q.cls_tap0[c + 1] - q.cls_tap0[c];
+    for (int t = 0; t < one.ntaps; ++t) {
+      one.tap_dh[t] = q.tap_dh[q.cls_tap0[c] + t];
+      one.tap_dw[t] = q.tap_dw[q.cls_tap0[c] + t];
+      one.tap_bcol[t] = q.tap_bcol[q.cls_tap0[c] + t];
+    }
+    const int rc = ddl::gemm::run_ig(one, sms, st);
+    if (rc) return rc;
+  }
   return 0;
 }
+
+// debug: per-CTA stage timestamps of the next igemm launches go to `buf` ([ctas][16] uint64; null: off)
+extern "C" void ddl_igemm_set_trace(unsigned long long* buf) { ddl::gemm::g_ig_trace = buf; }

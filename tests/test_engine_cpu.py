@@ -253,20 +253,28 @@ def test_im2col_kernel_index_math_emulated(n, c, hw, k, s, p):
     kpad = (K + 7) // 8 * 8
     rowlen = (W + 2 * p) * c
     out = torch.zeros(n * OH * OW, kpad)
-    for blk in range(n * OH):
-        nn_, oh = divmod(blk, OH)
-        ih0 = oh * s - p
-        rows = torch.zeros(k * rowlen)
-        for i in range(k * rowlen):
-            kh, j = divmod(i, rowlen)
-            ih, iwc = ih0 + kh, j - p * c
-            if 0 <= ih < H and 0 <= iwc < W * c:
-                rows[i] = xh[(nn_ * H + ih) * W * c + iwc]
-        for ow in range(OW):
-            base = ow * s * c
+    G = 4                                                   # kIm2colRows: output rows per CTA
+    groups = (OH + G - 1) // G
+    koff = [(kk // R) * rowlen + (kk % R) if kk < K else -1 for kk in range(kpad)]
+    for blk in range(n * groups):
+        nn_, g = divmod(blk, groups)
+        oh0 = g * G
+        nrows = min(G, OH - oh0)
+        in_rows = (nrows - 1) * s + k
+        ih0 = oh0 * s - p
+        rows = torch.zeros(in_rows * rowlen + 1)            # + the zero slot
+        for r in range(in_rows):
+            ih = ih0 + r
+            for j in range(rowlen):
+                iwc = j - p * c
+                if 0 <= ih < H and 0 <= iwc < W * c:
+                    rows[r * rowlen + j] = xh[(nn_ * H + ih) * W * c + iwc]
+        for px in range(nrows * OW):
+            r, ow = divmod(px, OW)
+            base = r * s * rowlen + ow * s * c
             for kk in range(kpad):
-                if kk < K:
-                    out[(nn_ * OH + oh) * OW + ow, kk] = rows[(kk // R) * rowlen + base + (kk % R)]
+                src = base + koff[kk] if koff[kk] >= 0 else in_rows * rowlen
+                out[(nn_ * OH + oh0) * OW + px, kk] = rows[src]
     torch.testing.assert_close(out, ref.im2col_rows(x, k, k, s, p))
 
 

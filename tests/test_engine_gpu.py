@@ -122,20 +122,22 @@ def test_resnet50_imagenet_gradients_against_fp32():
     yb = mb(x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
     F.cross_entropy(yb.float(), t.cuda()).backward()
     tb = dict(mb.named_parameters())
-    num = num_t = den = 0.0
-    worst = (0.0, "")
+    import collections
+    acc = collections.defaultdict(lambda: [0.0, 0.0, 0.0])      # group -> [ours^2, torch^2, ref^2]
     for name in cpu.store.layout.entries:
         r = cpu.store.g_views[name]
         a = gpu.store.g_views[name].float().cpu()
         b = tb[name].grad.float().cpu()
-        e = (a - r).pow(2).sum().item()
-        num += e
-        num_t += (b - r).pow(2).sum().item()
-        den += r.pow(2).sum().item()
-        rel = (e / (r.pow(2).sum().item() + 1e-20)) ** 0.5
-        if rel > worst[0]:
-            worst = (rel, name)
-    err, err_t = (num / den) ** 0.5, (num_t / den) ** 0.5
-    print("resnet50 224x224 gradient error vs fp32: ours %.4f, torch bf16 autograd %.4f, worst layer %s %.3f"
-          % (err, err_t, worst[1], worst[0]))
-    assert err < 1.25 * err_t + 0.02, (err, err_t, worst)
+        part = name.split(".")[1] if name.count(".") >= 2 else name.split(".")[0]
+        grp = part.split("_")[0] if part.startswith("layer") else "stem/fc"
+        for key in (grp, "all"):
+            acc[key][0] += (a - r).pow(2).sum().item()
+            acc[key][1] += (b - r).pow(2).sum().item()
+            acc[key][2] += r.pow(2).sum().item()
+    report = {k: (round((v[0] / v[2]) ** 0.5, 4), round((v[1] / v[2]) ** 0.5, 4)) for k, v in sorted(acc.items())}
+    print("resnet50 224x224 gradient error vs fp32, per stage (ours, torch bf16 autograd):", report)
+    # batch 8 at random init is an ill-conditioned point (bf16 BatchNorm noise is amplified through
+    # 50 layers: stock PyTorch bf16 is itself > 100 % off in the early stages) — the claim is that
+    # the engine is no worse than stock bf16 autograd, stage by stage
+    for k, (err, err_t) in report.items():
+        assert err < 1.25 * err_t + 0.02, (k, err, err_t)

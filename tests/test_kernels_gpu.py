@@ -328,13 +328,30 @@ def test_avgpool_fixed_window(n, c, hw, k, s, p, cip):
     x = _nhwc(n, c, hw, hw)
     oh = (hw + 2 * p - k) // s + 1
     y = ops.avgpool_fwd(x, (oh, oh), k, s, p, False, cip)
-    xr = x.float().requires_grad_(True)
+    # reference on the CPU: this build's CUDA avg_pool2d backward disagrees with its own CPU result
+    # for channels_last fp32 inputs (tools/avgdbg.py: 1.47 max abs difference)
+    xr = x.float().cpu().contiguous().requires_grad_(True)
     y_ref = torch.nn.functional.avg_pool2d(xr, k, s, p, False, cip)
-    torch.testing.assert_close(y.float(), y_ref.detach(), rtol=1e-2, atol=1e-2)
-    dy = torch.randn_like(y_ref).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(y.float().cpu(), y_ref.detach(), rtol=1e-2, atol=1e-2)
+    dy = torch.randn_like(y_ref).to(torch.bfloat16)
     y_ref.backward(dy.float())
-    dx = ops.avgpool_bwd(dy, x.shape, k, s, p, False, cip)
-    torch.testing.assert_close(dx.float(), xr.grad, rtol=2e-2, atol=2e-2)
+    dx = ops.avgpool_bwd(dy.cuda().contiguous(memory_format=torch.channels_last), x.shape, k, s, p, False, cip)
+    torch.testing.assert_close(dx.float().cpu(), xr.grad, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("n,c,hw,k,s,p", [(4, 3, 224, 7, 2, 3), (2, 3, 33, 7, 2, 3), (3, 3, 32, 3, 1, 1),
+                                         (2, 1, 28, 5, 1, 2)])
+def test_im2col_rows(n, c, hw, k, s, p):
+    """Patch matrix of the first convolution (csrc/im2col.cu) against the host reference."""
+    from ddlbench_b200.ops import reference as ref
+    torch.manual_seed(0)
+    x = torch.randn(n, c, hw, hw, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    before = ops.launches
+    a = ops.im2col_rows(x, k, k, s, p)
+    assert ops.launches == before + 1
+    want = ref.im2col_rows(x.float().cpu(), k, k, s, p)
+    assert a.shape == want.shape
+    torch.testing.assert_close(a.float().cpu(), want, rtol=0, atol=0)
 
 
 @pytest.mark.parametrize("n,c,hw,out", [(4, 64, 13, 6), (2, 512, 14, 7), (3, 128, 9, 1), (2, 64, 10, 4)])
@@ -342,13 +359,13 @@ def test_avgpool_adaptive(n, c, hw, out):
     torch.manual_seed(0)
     x = _nhwc(n, c, hw, hw)
     y = ops.avgpool_fwd(x, (out, out), 0, 0, 0, True)
-    xr = x.float().requires_grad_(True)
+    xr = x.float().cpu().contiguous().requires_grad_(True)
     y_ref = torch.nn.functional.adaptive_avg_pool2d(xr, out)
-    torch.testing.assert_close(y.float(), y_ref.detach(), rtol=1e-2, atol=1e-2)
-    dy = torch.randn_like(y_ref).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(y.float().cpu(), y_ref.detach(), rtol=1e-2, atol=1e-2)
+    dy = torch.randn_like(y_ref).to(torch.bfloat16)
     y_ref.backward(dy.float())
-    dx = ops.avgpool_bwd(dy, x.shape, 0, 0, 0, True)
-    torch.testing.assert_close(dx.float(), xr.grad, rtol=2e-2, atol=2e-2)
+    dx = ops.avgpool_bwd(dy.cuda().contiguous(memory_format=torch.channels_last), x.shape, 0, 0, 0, True)
+    torch.testing.assert_close(dx.float().cpu(), xr.grad, rtol=2e-2, atol=2e-2)
 
 
 @pytest.mark.parametrize("p", [0.5, 0.1])
