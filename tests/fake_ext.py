@@ -174,6 +174,23 @@ class FakeExt:
             self._fin(cs, N, M, ticket, stat, rm, rv, eps, mom)
         return 1 if (col_sums is not None and ticket is not None and stat is not None) else 0
 
+    # bool gemm2cta(A, B, D, bias?, relu)   (CTA-pair GEMM: same contract as igemm_gemm without stats)
+    def gemm2cta(self, A, B, D, bias, relu):
+        self.calls.append("gemm2cta")
+        A, B, Dp = _plain(A), _plain(B), _plain(D)
+        assert A.dim() == 2 and B.dim() == 2 and A.dtype == BF16 and B.dtype == BF16 and Dp.dtype == BF16
+        assert A.shape[1] == B.shape[1] and tuple(Dp.shape) == (A.shape[0], B.shape[0])
+        if A.shape[1] % 8 or A.stride(0) % 8 or B.stride(0) % 8 or Dp.stride(0) % 8:
+            return False
+        d = A.float() @ B.float().t()
+        if bias is not None:
+            d = d + _plain(bias).float()
+        Dp.copy_((d.relu() if relu else d).to(BF16))
+        return True
+
+    def igemm_set_trace(self, buf):
+        self.calls.append("igemm_set_trace")
+
     # bool igemm_conv_fprop(x, w, y, pad_h, pad_w, stride, col_sums?, bias?, relu, ticket?, stat?, rm?, rv?, eps, mom)
     def igemm_conv_fprop(self, x, w, y, pad_h, pad_w, stride, col_sums, bias, relu, ticket, stat, rm, rv, eps, mom,
                          sk_ws=None, sk_tickets=None):

@@ -207,17 +207,20 @@ def check_gemm_stats(m, k, n):
 def main():
     bench = os.environ.get("BENCH", "0") == "1"
     quick = os.environ.get("QUICK", "0") == "1"
+    only = [t for t in os.environ.get("ONLY", "").split(",") if t]      # layer-name substrings
     ok, rows = True, []
     groups = [(RESNET50, False), (ODD, False), (VGG224, True)]
     for cfgs, br in groups:
         for c in (cfgs[:4] if quick else cfgs):
+            if only and not any(t in c[0] for t in only):
+                continue
             o, row = check_conv(*c, bias_relu=br, bench=bench and cfgs is RESNET50)
             ok = ok and o
             if row:
                 rows.append(row)
-    for shp in [(32, 2048, 1000), (8, 25088, 4096), (32, 4096, 1000), (5, 64, 24)]:
+    for shp in ([] if only else [(32, 2048, 1000), (8, 25088, 4096), (32, 4096, 1000), (5, 64, 24)]):
         ok = check_linear(*shp) and ok
-    for shp in [(32 * 112 * 112, 152, 64), (1000, 72, 200)]:
+    for shp in ([] if only else [(32 * 112 * 112, 152, 64), (1000, 72, 200)]):
         ok = check_gemm_stats(*shp) and ok
     if bench and rows:
         tot = {k: round(sum(r[k] for r in rows), 1) for k in rows[0] if k.endswith("_us")}

@@ -165,6 +165,26 @@ def test_igemm_linear_paths(fake_ig, monkeypatch):
     _close(G["fc.weight"], dz.t() @ xr, 3e-2)
 
 
+def test_gemm_ig_dispatches_big_problems_to_the_pair_kernel(fake_ig, monkeypatch):
+    """ops.gemm_ig: stats-free K-major GEMMs above GEMM_PAIR_MIN go to the CTA-pair kernel, everything
+    else (small, MN-major B, statistics) stays on the single-CTA kernel."""
+    fake = fake_ig
+    monkeypatch.setattr(ops, "GEMM_PAIR_MIN", (64, 32, 32))
+    a, w, b = _t(64, 32), _t(72, 32), _t(72)
+    y = ops.gemm_ig(a, w, bias=b, relu=True)
+    assert fake.calls == ["gemm2cta"]
+    _close(y, (a.as_subclass(torch.Tensor).float() @ w.as_subclass(torch.Tensor).float().t() +
+               b.as_subclass(torch.Tensor).float()).relu())
+    fake.calls.clear()
+    ops.gemm_ig(_t(64, 72), w, b_mn=True)                       # data gradient: B is MN-major
+    ops.gemm_ig(_t(16, 32), w)                                  # below the size threshold
+    assert fake.calls == ["igemm_gemm", "igemm_gemm"]
+    fake.calls.clear()
+    monkeypatch.setattr(ops, "GEMM_PAIR", False)
+    ops.gemm_ig(a, w)
+    assert fake.calls == ["igemm_gemm"]
+
+
 def test_stem_im2col_paths(fake):
     torch.manual_seed(1)
     op = _conv_op(3, 64, 7, 2, 3)

@@ -276,6 +276,29 @@ def test_igemm_family_subprocess():
     assert p.returncode == 0, "igemm family check failed"
 
 
+# The small-M / long-K layers split K across a thread-block cluster; the default exchange of the
+# partial sums goes through L2, this runs the distributed-shared-memory flavour and the round-2
+# "slots" scheme on the layers that split (and the one-launch-per-class stride-2 data gradient).
+@pytest.mark.parametrize("env", [{"DDLB_IG_SPLIT": "dsmem"}, {"DDLB_IG_SPLIT": "slots"},
+                                 {"DDLB_IG_SPLIT": "off", "DDLB_IG_S2_MULTI": "0"}])
+def test_igemm_split_variants_subprocess(env):
+    script = os.path.join(os.path.dirname(__file__), "igemm_check.py")
+    e = dict(os.environ, ONLY="l3.b1,l4.b1,l4.conv2,l3.conv2,odd.3x3.s2", **env)
+    p = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=600, env=e)
+    sys.stdout.write(p.stdout[-3000:])
+    sys.stderr.write(p.stderr[-3000:])
+    assert p.returncode == 0, "igemm split-K variant check failed"
+
+
+# CTA-pair (cta_group::2, 256-row tiles, multicast commit) GEMM against fp32, ragged shapes included.
+def test_gemm_pair_subprocess():
+    script = os.path.join(os.path.dirname(__file__), "gemm_pair_check.py")
+    p = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=600)
+    sys.stdout.write(p.stdout[-3000:])
+    sys.stderr.write(p.stderr[-3000:])
+    assert p.returncode == 0, "CTA-pair GEMM check failed"
+
+
 # Round-1 one-tile-per-CTA implicit-GEMM convolution (kept as the A/B baseline of the persistent
 # kernel; validated on hardware at the start of round 2), isolated in a child process.
 def test_tcgen05_conv3x3():
