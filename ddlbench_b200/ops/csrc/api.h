@@ -154,6 +154,7 @@ int ddl_igemm_conv_dgrad(const void* dy, const void* w, void* dx, int NB, int H,
                          float* splitk_ws, unsigned int* splitk_tickets, int splitk_tiles, int sms,
                          cudaStream_t st);
 void ddl_igemm_set_trace(unsigned long long* buf);
+void ddl_wgrad_set_trace(unsigned long long* buf);
 // ---- gemm2cta_tcgen05.cu  (CTA-pair `cta_group::2` persistent GEMM, 256 x 256 tiles; -1: declined)
 int ddl_gemm2cta(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb,
                  int ldd, const void* bias, int relu, int sms, cudaStream_t st);

@@ -902,6 +902,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dropout_bwd", &dropout_bwd);
   m.def("igemm_gemm", &igemm_gemm);
   m.def("gemm2cta", &gemm2cta);
+  m.def("wgrad_set_trace", [](c10::optional<at::Tensor> buf) {
+    if (buf.has_value() && buf->defined()) {
+      TORCH_CHECK(buf->scalar_type() == at::kLong && buf->is_cuda() && buf->is_contiguous());
+      ddl_wgrad_set_trace((unsigned long long*)buf->data_ptr());
+    } else {
+      ddl_wgrad_set_trace(nullptr);
+    }
+  }, "debug: per-CTA stage timestamps ([ctas][16] int64) of the following weight-gradient launches");
   m.def("igemm_set_trace", [](c10::optional<at::Tensor> buf) {
     if (buf.has_value() && buf->defined()) {
       TORCH_CHECK(buf->scalar_type() == at::kLong && buf->is_cuda() && buf->is_contiguous());

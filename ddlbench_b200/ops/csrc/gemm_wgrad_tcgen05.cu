@@ -57,6 +57,20 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
 //                            wgrad_reduce_kernel then sums the planes into `out`.  No atomics: fp32
 //                            vector atomics at this volume cost several times the GEMM itself
 //                            (profiles/r2/conv_vs_cudnn_v3_atomics_splitk.json).
+__device__ unsigned long long* g_wgrad_trace_dev = nullptr;
+__device__ __forceinline__ unsigned long long wg_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// debug stamps (tools/wgrad_trace.py): [cta][16]: 0 entry, 1 prologue done, 2 accumulator ready,
+// 3 epilogue done, 4.. : producer issued k-block 0, 4, 8, 12, ...
+#define WG_STAMP(k)                                                                             \
+  do {                                                                                          \
+    if (g_wgrad_trace_dev)                                                                      \
+      g_wgrad_trace_dev[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (k)] = wg_timer(); \
+  } while (0)
+
 struct WgradOut {
   void* out;
   int out_bf16;
@@ -94,61 +108,169 @@ __device__ __forceinline__ void wgrad_store32(const WgradOut& o, size_t idx, con
   }
 }
 
-// Epilogue of both weight-gradient kernels (128 threads, thread = one row of the 128 x BLOCK_N
-// tile).  `row` / `col0`: global coordinates of the tile inside D; `ncols`: valid columns from col0.
+// Staged tile (shared memory, row stride BLOCK_N + 4 floats) -> row-major global memory, whole rows
+// per warp.  MODE 0: bf16 store, 1: bf16 accumulate, 2: fp32 store, 3: fp32 accumulate, 4: fp32
+// plane (st.global.cg).  `dst` indexed in elements of its type; `base` = element offset of the tile.
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+template <int BLOCK_N, int MODE>
+__device__ __forceinline__ void wgrad_copy_rows(uint32_t st_u32, int wq, int lane, void* dst, size_t base,
+                                                int ldd) {
+  constexpr int LDS = BLOCK_N + 4;
+  constexpr int LPR = BLOCK_N / 4;            // lanes per row (16-byte pieces)
+  constexpr int RPI = 32 / LPR;               // rows per warp instruction
+  constexpr int ITERS = 32 / RPI;             // this warp's rows: wq + 4 * k
+  const int sub = lane / LPR, c = (lane % LPR) * 4;
+#pragma unroll
+  for (int i0 = 0; i0 < ITERS; i0 += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = wq + 4 * ((i0 + u) * RPI + sub);
+      v[u] = lds_f4(st_u32 + (uint32_t)((r * LDS + c) * 4));
+    }
+    if (MODE == 1 || MODE == 3) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = wq + 4 * ((i0 + u) * RPI + sub);
+        const size_t idx = base + (size_t)r * ldd + c;
+        if (MODE == 1) {
+          const uint2 g = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dst) + idx);
+          const float2 g0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g.x));
+          const float2 g1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g.y));
+          v[u].x += g0.x; v[u].y += g0.y; v[u].z += g1.x; v[u].w += g1.y;
+        } else {
+          const float4 g = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dst) + idx);
+          v[u].x += g.x; v[u].y += g.y; v[u].z += g.z; v[u].w += g.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = wq + 4 * ((i0 + u) * RPI + sub);
+      const size_t idx = base + (size_t)r * ldd + c;
+      if (MODE == 0 || MODE == 1) {
+        uint2 pk;
+        *reinterpret_cast<__nv_bfloat162*>(&pk.x) = __floats2bfloat162_rn(v[u].x, v[u].y);
+        *reinterpret_cast<__nv_bfloat162*>(&pk.y) = __floats2bfloat162_rn(v[u].z, v[u].w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst) + idx) = pk;
+      } else if (MODE == 4) {
+        __stcg(reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + idx), v[u]);
+      } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + idx) = v[u];
+      }
+    }
+  }
+}
+
+// Epilogue of both weight-gradient kernels (128 threads).  `row0` / `col0`: global coordinates of the
+// tile inside D; `ncols`: valid columns from col0; `stage`: the (idle by now) operand ring.
+//
+// TMEM hands every thread one ROW of the tile, but D is row-major: written straight from the
+// registers each warp store would touch 32 different rows (16 bytes each) — measured 8-11 us per
+// CTA of partial-sector traffic, more than the whole main loop of the 14x14 / 7x7 layers
+// (profiles/r2/traces/wgrad_trace_v1.log).  So the tile is transposed through shared memory
+// (row stride BLOCK_N + 4 floats: conflict-free 16-byte accesses both ways) and every warp then
+// writes whole 512-byte rows.
 template <int BLOCK_N>
-__device__ __forceinline__ void wgrad_epilogue(uint32_t tmem_base, int warp, int lane, float* D,
-                                               int ldd, int row, int nrows, int col0, int ncols,
-                                               const WgradOut& o, int split, int splits) {
-  const int quad = warp & 3;
-  const bool vec_ok = (ldd & 7) == 0 && (col0 & 7) == 0;
+__device__ __forceinline__ void wgrad_epilogue(uint32_t tmem_base, int warp, int lane, float* stage,
+                                               float* D, int ldd, int row0, int nrows, int col0,
+                                               int ncols, const WgradOut& o, int split, int splits) {
+  constexpr int LDS = BLOCK_N + 4;
+  const int wq = warp & 3;                       // TMEM lane quadrant == this warp's index here
+  {
+    const uint32_t mine = smem_u32(stage) + (uint32_t)((wq * 32 + lane) * LDS * 4);
+#pragma unroll
+    for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(cb * 32), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mine + (cb * 32 + 4 * j) * 4),
+                     "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                     : "memory");
+    }
+  }
+  if (threadIdx.x == 64) WG_STAMP(13);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (threadIdx.x == 64) WG_STAMP(14);
+  const bool vec_ok = (ldd & 3) == 0 && (col0 & 3) == 0;
   const bool direct = o.out != nullptr && splits == 1;
   float* plane = (o.out != nullptr) ? D + (size_t)split * o.plane_stride : D;
+  // full tiles (every real layer): branch-free, 8-deep unrolled copy loops — one warp per SM
+  // sub-partition here, so the shared-memory loads of 8 rows are issued before the first store
+  // (the generic loop below is a serial ld -> st chain: 4.3 us per tile, traces/wgrad_trace_v3.log)
+  if (o.out != nullptr && vec_ok && ncols >= BLOCK_N && row0 + BLOCK_M <= nrows) {
+    const int mode = !direct ? 4 : (o.out_bf16 ? (o.accumulate ? 1 : 0) : (o.accumulate ? 3 : 2));
+    const uint32_t st_u32 = smem_u32(stage);
+    const size_t base = (size_t)row0 * ldd + col0;
+    switch (mode) {
+      case 0: wgrad_copy_rows<BLOCK_N, 0>(st_u32, wq, lane, o.out, base, ldd); break;
+      case 1: wgrad_copy_rows<BLOCK_N, 1>(st_u32, wq, lane, o.out, base, ldd); break;
+      case 2: wgrad_copy_rows<BLOCK_N, 2>(st_u32, wq, lane, o.out, base, ldd); break;
+      case 3: wgrad_copy_rows<BLOCK_N, 3>(st_u32, wq, lane, o.out, base, ldd); break;
+      default: wgrad_copy_rows<BLOCK_N, 4>(st_u32, wq, lane, plane, base, ldd); break;
+    }
+    return;
+  }
+  for (int r = wq; r < BLOCK_M; r += 4) {
+    const int grow = row0 + r;
+    if (grow >= nrows) break;
 #pragma unroll
-  for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
-    uint32_t r[32];
-    tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * 32), r);
-    const int c0 = cb * 32;
-    if (row < nrows && c0 < ncols) {
-      const size_t idx = (size_t)row * ldd + col0 + c0;
-      if (direct && vec_ok && c0 + 32 <= ncols) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        wgrad_store32(o, idx, v);
-      } else if (direct) {
-        for (int j = 0; j < 32 && c0 + j < ncols; ++j) {
-          float v = __uint_as_float(r[j]);
-          if (o.out_bf16) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(o.out) + idx + j;
-            if (o.accumulate) v += __bfloat162float(*dst);
-            *dst = __float2bfloat16_rn(v);
+    for (int c = lane * 4; c < BLOCK_N; c += 128) {
+      if (c >= ncols) continue;
+      const float4 v4 = *reinterpret_cast<const float4*>(stage + (size_t)r * LDS + c);
+      float v[4] = {v4.x, v4.y, v4.z, v4.w};
+      const size_t idx = (size_t)grow * ldd + col0 + c;
+      const bool full = vec_ok && c + 4 <= ncols;
+      const int cnt = min(4, ncols - c);
+      if (direct) {
+        if (o.out_bf16) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(o.out) + idx;
+          if (full) {
+            if (o.accumulate) {
+              const uint2 g = *reinterpret_cast<const uint2*>(dst);
+              const float2 g0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g.x));
+              const float2 g1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g.y));
+              v[0] += g0.x; v[1] += g0.y; v[2] += g1.x; v[3] += g1.y;
+            }
+            uint2 pk;
+            *reinterpret_cast<__nv_bfloat162*>(&pk.x) = __floats2bfloat162_rn(v[0], v[1]);
+            *reinterpret_cast<__nv_bfloat162*>(&pk.y) = __floats2bfloat162_rn(v[2], v[3]);
+            *reinterpret_cast<uint2*>(dst) = pk;
           } else {
-            float* dst = reinterpret_cast<float*>(o.out) + idx + j;
-            *dst = o.accumulate ? *dst + v : v;
+            for (int j = 0; j < cnt; ++j) {
+              float f = v[j];
+              if (o.accumulate) f += __bfloat162float(dst[j]);
+              dst[j] = __float2bfloat16_rn(f);
+            }
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(o.out) + idx;
+          if (full) {
+            float4 t = make_float4(v[0], v[1], v[2], v[3]);
+            if (o.accumulate) {
+              const float4 g = *reinterpret_cast<const float4*>(dst);
+              t.x += g.x; t.y += g.y; t.z += g.z; t.w += g.w;
+            }
+            *reinterpret_cast<float4*>(dst) = t;
+          } else {
+            for (int j = 0; j < cnt; ++j) dst[j] = o.accumulate ? dst[j] + v[j] : v[j];
           }
         }
       } else if (o.out != nullptr) {
-        // partial tile -> this split's plane: 128 contiguous bytes per thread
+        // partial tile -> this split's plane
         float* dst = plane + idx;
-        if (vec_ok && c0 + 32 <= ncols) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            __stcg(reinterpret_cast<float4*>(dst + 4 * j),
-                   make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
-        } else {
-          for (int j = 0; j < 32 && c0 + j < ncols; ++j) dst[j] = __uint_as_float(r[j]);
-        }
-      } else if (vec_ok && c0 + 32 <= ncols) {
-        float* dst = D + idx;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          atomicAdd(reinterpret_cast<float4*>(dst + 4 * j),
-                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+        if (full) __stcg(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+        else
+          for (int j = 0; j < cnt; ++j) dst[j] = v[j];
+      } else if (full) {
+        atomicAdd(reinterpret_cast<float4*>(D + idx), make_float4(v[0], v[1], v[2], v[3]));
       } else {
-        for (int j = 0; j < 32 && c0 + j < ncols; ++j) atomicAdd(D + idx + j, __uint_as_float(r[j]));
+        for (int j = 0; j < cnt; ++j) atomicAdd(D + idx + j, v[j]);
       }
     }
   }
@@ -241,6 +363,7 @@ struct WgradSmem {
   static constexpr int kTmemPtrOffset = kBarOffset + (2 * kStages + 1) * 8;
   static constexpr int kTotal = kTmemPtrOffset + 16;
   static constexpr int kDynamic = kTotal + 1024;
+  static_assert(kRingBytes >= BLOCK_M * (BLOCK_N + 4) * 4, "the epilogue stages the fp32 tile in the ring");
 };
 
 template <int BLOCK_N, int kStages>
@@ -249,8 +372,9 @@ gemm_bf16_mn_kernel(const __grid_constant__ CUtensorMap map_a,
                     const __grid_constant__ CUtensorMap map_b, WgradParams wp) {
   using L = WgradSmem<BLOCK_N, kStages>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
+  // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the
+  // shared address space and emits LDS / STS instead of generic LD / ST for the staging accesses)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
@@ -268,6 +392,7 @@ gemm_bf16_mn_kernel(const __grid_constant__ CUtensorMap map_a,
   const int num_k_blocks = kb1 - kb0;            // >= 1 by construction of the grid
 
   pdl_trigger();
+  if (threadIdx.x == 64) WG_STAMP(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -284,6 +409,7 @@ gemm_bf16_mn_kernel(const __grid_constant__ CUtensorMap map_a,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();
+  if (threadIdx.x == 64) WG_STAMP(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -293,6 +419,7 @@ gemm_bf16_mn_kernel(const __grid_constant__ CUtensorMap map_a,
         const uint32_t ph = (i / kStages) & 1;
         const int krow = (kb0 + i) * kMnBox;
         mbar_wait(&empty_bar[s], ph ^ 1);
+        if ((i & 3) == 0 && i < 36) WG_STAMP(4 + (i >> 2));
         uint8_t* a_dst = smem + s * L::kStageBytes;
         uint8_t* b_dst = a_dst + L::kABytes;
         mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
@@ -334,12 +461,14 @@ gemm_bf16_mn_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else {
     // ------------------------------------------------------------------ epilogue (128 thr)
-    const int row = tile_m * BLOCK_M + (warp & 3) * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait(tmem_full_bar, 0);       // every MMA has completed: the ring is idle and becomes the staging tile
     tc_fence_after();
+    if (threadIdx.x == 64) WG_STAMP(2);
     const int col0 = tile_n * BLOCK_N;
-    wgrad_epilogue<BLOCK_N>(tmem_base, warp, lane, wp.D, wp.ldd, row, wp.M, col0, wp.N - col0, wp.o,
-                            (int)blockIdx.y, (int)gridDim.y);
+    wgrad_epilogue<BLOCK_N>(tmem_base, warp, lane, reinterpret_cast<float*>(smem), wp.D, wp.ldd,
+                            tile_m * BLOCK_M, wp.M, col0, wp.N - col0, wp.o, (int)blockIdx.y,
+                            (int)gridDim.y);
+    if (threadIdx.x == 64) WG_STAMP(3);
   }
   tc_fence_before();
   __syncthreads();
@@ -435,8 +564,9 @@ conv_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy,
                        const __grid_constant__ CUtensorMap map_x, ConvWgradParams wp) {
   using L = WgradSmem<BLOCK_N, kStages>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
+  // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the
+  // shared address space and emits LDS / STS instead of generic LD / ST for the staging accesses)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
@@ -454,6 +584,7 @@ conv_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy,
   const int num_k_blocks = t1 - t0;
 
   pdl_trigger();
+  if (threadIdx.x == 64) WG_STAMP(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_dy);
     tma_prefetch_desc(&map_x);
@@ -470,6 +601,7 @@ conv_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();
+  if (threadIdx.x == 64) WG_STAMP(1);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -481,6 +613,7 @@ conv_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy,
         const int h0 = ((pt / wp.tiles_w) % wp.tiles_h) * wp.TH;
         const int n0 = (pt / (wp.tiles_w * wp.tiles_h)) * wp.TN;
         mbar_wait(&empty_bar[s], ph ^ 1);
+        if ((i & 3) == 0 && i < 36) WG_STAMP(4 + (i >> 2));
         uint8_t* a_dst = smem + s * L::kStageBytes;
         uint8_t* b_dst = a_dst + L::kABytes;
         mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
@@ -517,12 +650,15 @@ conv_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy,
       __syncwarp();
     }
   } else {
-    const int row = tile_m * BLOCK_M + (warp & 3) * 32 + lane;    // output channel
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) WG_STAMP(2);
+    if (threadIdx.x == 96) WG_STAMP(15);
     const int ci0 = tile_n * BLOCK_N;
-    wgrad_epilogue<BLOCK_N>(tmem_base, warp, lane, wp.D, wp.ldd, row, wp.Cout, tap * wp.Cin + ci0,
-                            wp.Cin - ci0, wp.o, (int)blockIdx.y, (int)gridDim.y);
+    wgrad_epilogue<BLOCK_N>(tmem_base, warp, lane, reinterpret_cast<float*>(smem), wp.D, wp.ldd,
+                            tile_m * BLOCK_M, wp.Cout, tap * wp.Cin + ci0, wp.Cin - ci0, wp.o,
+                            (int)blockIdx.y, (int)gridDim.y);
+    if (threadIdx.x == 64) WG_STAMP(3);
   }
   tc_fence_before();
   __syncthreads();
@@ -650,4 +786,9 @@ extern "C" int ddl_wgrad_conv(const void* dy, const void* x, float* ws, long lon
       : launch_conv_wgrad<128, 3>(dy, x, ws, NB, H, W, OH, OW, Cin, Cout, KH, KW, pad_h, pad_w, stride, sms, st, o, mp, &used);
   if (rc || used == 1) return rc;
   return launch_wgrad_reduce(ws, used, plane, plane, out, out_bf16, accumulate, st);
+}
+
+// debug: per-CTA stage timestamps of the following weight-gradient launches ([ctas][16] uint64; null: off)
+extern "C" void ddl_wgrad_set_trace(unsigned long long* buf) {
+  cudaMemcpyToSymbol(ddl::gemm::g_wgrad_trace_dev, &buf, sizeof(buf));
 }

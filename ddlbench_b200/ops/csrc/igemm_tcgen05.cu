@@ -191,8 +191,9 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
   constexpr uint32_t kTmemCols = kSmall ? BLOCK_N : 2 * BLOCK_N;   // one / two accumulators
   constexpr int kStep = kSmall ? 32 : 64;              // columns drained per epilogue step
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
+  // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the
+  // shared address space and emits LDS / STS instead of generic LD / ST for the staging accesses)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;           // [2]
