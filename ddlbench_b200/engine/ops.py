@@ -357,7 +357,10 @@ class ConvBnAct(Op, _ConvMixin):
             (ig or self._is_gemm(x) or self._is_stem_gemm(x) or self._is_conv_tc(x, P[self.k_w]))
         mom = self.momentum * BN_MOMENTUM_SCALE[0]
         stat_ready = None
-        if fuse_stats and (FUSE_BN_FINALIZE or ig) and not getattr(self, "defer_apply", False):
+        if fuse_stats and ig and ops.BN_APPLY_FINALIZE and not getattr(self, "defer_apply", False):
+            # sums only: the BatchNorm apply kernel finalizes them (ops.bn_forward, stats_ready)
+            c, fused = self._conv_fwd(x, P[self.k_w], col_sums=self.ws.sums, ctx=ctx)
+        elif fuse_stats and (FUSE_BN_FINALIZE or ig) and not getattr(self, "defer_apply", False):
             # statistics AND their finalize ride in the GEMM epilogue (last CTA).  Measured
             # slower than a separate 4 us finalize launch (the last CTA gathers R*2*N values
             # with 128 threads and every CTA pays a fence + ticket), so this is off by default.

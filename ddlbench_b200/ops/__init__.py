@@ -153,6 +153,11 @@ BNFOLD_KERNEL = os.environ.get("DDLB_BN_FOLD_KERNEL", "1") == "1"
 BN_REPLICAS = 8  # must match DDL_BN_REPLICAS (csrc/common.cuh); checked at first use
 
 
+# BatchNorm after a convolution whose epilogue accumulated the statistics: 1 = the apply kernel turns
+# the sums into (mean, invstd) itself (no finalize in the convolution's tail, no finalize launch)
+BN_APPLY_FINALIZE = os.environ.get("DDLB_BN_APPLY_FIN", "1") == "1"
+
+
 class BnWorkspace:
     """Per-layer fp32 scratch: R replicated partial-sum buffers (self-zeroing), the
     last-CTA ticket counters, and the backward coefficients."""
@@ -196,6 +201,14 @@ def bn_forward(x, res, gamma, beta, running_mean, running_var, eps: float, momen
                 return y, stat.view(2, C)
         if stat_ready is not None:
             _count(-1)      # (mean, invstd) were finalized inside the producing GEMM
+        elif stats_ready and BN_APPLY_FINALIZE:
+            # the apply kernel finalizes the statistics itself from the producer's sums
+            y = torch.empty_like(x)
+            if e.bn_apply_sums(x, res, y, ws.sums, ws.counter, stat, running_mean, running_var, gamma,
+                               beta, mask_out, M, C, eps, momentum, act):
+                _count()
+                return y, stat.view(2, C)
+            e.bn_finalize(ws.sums, stat, running_mean, running_var, M, C, eps, momentum)
         elif stats_ready:
             e.bn_finalize(ws.sums, stat, running_mean, running_var, M, C, eps, momentum)
         else:

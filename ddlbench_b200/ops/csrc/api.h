@@ -30,6 +30,10 @@ int ddl_bn_finalize(float* sums, float* stat, float* running_mean, float* runnin
 int ddl_bn_apply(const void* x, const void* res, void* y, const float* stat, const void* gamma,
                  const void* beta, int param_is_bf16, void* mask_out, int64_t M, int C, int act,
                  int sms, cudaStream_t st);
+int ddl_bn_apply_sums(const void* x, const void* res, void* y, float* sums, float* stat_out,
+                      float* running_mean, float* running_var, unsigned int* ticket,
+                      const void* gamma, const void* beta, int param_is_bf16, void* mask_out,
+                      int64_t M, int C, float eps, float momentum, int act, int sms, cudaStream_t st);
 int ddl_bn_bwd_reduce(const void* dy, const void* dy2, const void* y, const void* x, void* dz_out,
                       const float* stat, float* sums, unsigned int* counter, const void* gamma,
                       int param_is_bf16, float* coef, void* dgamma, void* dbeta, int grad_is_bf16,

@@ -108,6 +108,26 @@ void bn_apply(at::Tensor x, c10::optional<at::Tensor> res, at::Tensor y, at::Ten
                      (int)act, sm_count(), cur_stream()),
         "bn_apply");
 }
+// BatchNorm apply that finalizes the statistics itself from the producer's replicated sums; false:
+// shape declined (finalize separately and call bn_apply)
+bool bn_apply_sums(at::Tensor x, c10::optional<at::Tensor> res, at::Tensor y, at::Tensor sums,
+                   at::Tensor counter, at::Tensor stat_out, c10::optional<at::Tensor> rmean,
+                   c10::optional<at::Tensor> rvar, at::Tensor gamma, at::Tensor beta,
+                   c10::optional<at::Tensor> mask_out, int64_t M, int64_t C, double eps, double mom,
+                   int64_t act) {
+  c10::cuda::CUDAGuard g(x.device());
+  TORCH_CHECK(!mask_out.has_value() || mask_out->numel() * 8 >= M * C, "activation mask too small");
+  TORCH_CHECK(sums.numel() >= 2 * ddl_bn_replicas() * C && stat_out.numel() >= 2 * C && counter.numel() >= 64);
+  // tickets: counter[48:64)
+  const int rc = ddl_bn_apply_sums(x.data_ptr(), optr(res), y.data_ptr(), sums.data_ptr<float>(),
+                                   stat_out.data_ptr<float>(), (float*)optr(rmean), (float*)optr(rvar),
+                                   (unsigned int*)counter.data_ptr<int>() + 48, gamma.data_ptr(),
+                                   beta.data_ptr(), is_bf16(gamma), optr(mask_out), M, (int)C, (float)eps,
+                                   (float)mom, (int)act, sm_count(), cur_stream());
+  if (rc == -1) return false;
+  check(rc, "bn_apply_sums");
+  return true;
+}
 void bn_bwd_reduce(at::Tensor dy, c10::optional<at::Tensor> dy2, c10::optional<at::Tensor> y,
                    at::Tensor x, c10::optional<at::Tensor> dz_out, at::Tensor stat,
                    at::Tensor sums, at::Tensor counter, at::Tensor gamma, at::Tensor coef,
@@ -877,6 +897,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_stats", &bn_stats);
   m.def("bn_finalize", &bn_finalize);
   m.def("bn_apply", &bn_apply);
+  m.def("bn_apply_sums", &bn_apply_sums);
   m.def("bn_bwd_reduce", &bn_bwd_reduce);
   m.def("bn_bwd_apply", &bn_bwd_apply);
   m.def("bn_bwd_fused", &bn_bwd_fused);

@@ -259,23 +259,79 @@ __global__ void bn_finalize_kernel(float* __restrict__ sums, float* __restrict__
 }
 
 // y = act((x - mean) * invstd * gamma + beta [+ res])
+//
+// `sums` != null ("apply-side finalize"): (mean, invstd) are not read from `stat` but computed here
+// from the R replicated per-channel sum / sum-of-squares buffers the producing convolution's
+// epilogue accumulated (sums[r][0][c], sums[r][1][c]) — every CTA needs 16 L2 loads per channel it
+// owns.  The convolution then ends with fire-and-forget reductions (no fence, no ticket, no
+// last-CTA finalize tail on the critical path, no finalize launch).  The row-block-0 CTAs write
+// (mean, invstd) to `stat_out` for the backward pass and update the running statistics; the LAST
+// CTA of a channel block to have read the sums (ticket taken right after its loads, checked after
+// its row loop: the atomic's round trip hides behind the streaming work) re-zeroes them.
 template <typename PT>
 __global__ void __launch_bounds__(kBnThreads, 4)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                 __nv_bfloat16* __restrict__ y, const float* __restrict__ stat,
                 const PT* __restrict__ gamma, const PT* __restrict__ beta,
-                uint8_t* __restrict__ mask_out, int64_t M, int C, int rows_per_block, int act) {
+                uint8_t* __restrict__ mask_out, int64_t M, int C, int rows_per_block, int act,
+                float* __restrict__ sums, float* __restrict__ stat_out,
+                float* __restrict__ running_mean, float* __restrict__ running_var,
+                unsigned int* __restrict__ ticket, float eps, float momentum) {
   pdl_enter();
   const int cv_total = C >> 3;
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
-  if (cv >= cv_total) return;
+  if (cv >= cv_total) return;        // (never taken in sums mode: the host requires full blocks)
   float sc[8], sh[8];
+  unsigned int arrived = 0;
+  if (sums) {
+    // one pass over the CTA's channels (blockDim.x * 8 of them): 16 L2 loads per channel per CTA,
+    // coefficients parked in shared memory for the row lanes
+    __shared__ float s_sc[kBnThreads * 8], s_sh[kBnThreads * 8];
+    const float inv_m = 1.f / (float)M;
+    const int nch = blockDim.x * 8, ch0 = blockIdx.y * nch;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    for (int i = tid; i < nch; i += nthr) {
+      const int c = ch0 + i;
+      float s_ = 0.f, q_ = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = cv * 8 + k;
-    const float g = to_f(gamma[c]), b = to_f(beta[c]);
-    sc[k] = g * stat[C + c];
-    sh[k] = fmaf(-stat[c], sc[k], b);
+      for (int r = 0; r < DDL_BN_REPLICAS; ++r) {
+        s_ += __ldcg(sums + (size_t)(2 * r) * C + c);
+        q_ += __ldcg(sums + (size_t)(2 * r + 1) * C + c);
+      }
+      const float mean = s_ * inv_m;
+      const float var = fmaxf(fmaf(-mean, mean, q_ * inv_m), 0.f);
+      const float istd = rsqrtf(var + eps);
+      if (blockIdx.x == 0) {
+        stat_out[c] = mean;
+        stat_out[C + c] = istd;
+        if (running_mean) {
+          const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+          running_mean[c] = fmaf(momentum, mean - running_mean[c], running_mean[c]);
+          running_var[c] = fmaf(momentum, unbiased - running_var[c], running_var[c]);
+        }
+      }
+      const float g = to_f(gamma[c]), b = to_f(beta[c]);
+      s_sc[i] = g * istd;
+      s_sh[i] = fmaf(-mean, g * istd, b);
+    }
+    __syncthreads();                 // the CTA has read its sums
+    if (tid == 0) {
+      __threadfence();
+      arrived = atomicAdd(ticket + blockIdx.y, 1u);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = s_sc[threadIdx.x * 8 + k];
+      sh[k] = s_sh[threadIdx.x * 8 + k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cv * 8 + k;
+      const float g = to_f(gamma[c]), b = to_f(beta[c]);
+      sc[k] = g * stat[C + c];
+      sh[k] = fmaf(-stat[c], sc[k], b);
+    }
   }
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
@@ -327,6 +383,19 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
     const bf16x8 p = pack8(f);
     *reinterpret_cast<bf16x8*>(y + off) = p;
     if (mask_out) mask_out[r * cv_total + cv] = act_bits(p, act);
+  }
+  if (sums) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0 && threadIdx.y == 0) s_last = (arrived == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+      // every CTA of this channel block has read the sums: leave them zero for the next forward
+      const int ch0 = blockIdx.y * blockDim.x * 8, nch = blockDim.x * 8;
+      const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+      for (int i = tid; i < 2 * DDL_BN_REPLICAS * nch; i += nthr)
+        sums[(size_t)(i / nch) * C + ch0 + (i % nch)] = 0.f;
+      if (tid == 0) ticket[blockIdx.y] = 0u;
+    }
   }
 }
 
@@ -618,11 +687,36 @@ extern "C" int ddl_bn_apply(const void* x, const void* res, void* y, const float
   if (param_is_bf16)
     launch_pdl(bn_apply_kernel<bf16>, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st, 
         (const bf16*)x, (const bf16*)res, (bf16*)y, stat, (const bf16*)gamma, (const bf16*)beta,
-        (uint8_t*)mask_out, M, C, d.rows_per_block, act);
+        (uint8_t*)mask_out, M, C, d.rows_per_block, act, (float*)nullptr, (float*)nullptr,
+        (float*)nullptr, (float*)nullptr, (unsigned int*)nullptr, 0.f, 0.f);
   else
     launch_pdl(bn_apply_kernel<float>, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st, 
         (const bf16*)x, (const bf16*)res, (bf16*)y, stat, (const float*)gamma, (const float*)beta,
-        (uint8_t*)mask_out, M, C, d.rows_per_block, act);
+        (uint8_t*)mask_out, M, C, d.rows_per_block, act, (float*)nullptr, (float*)nullptr,
+        (float*)nullptr, (float*)nullptr, (unsigned int*)nullptr, 0.f, 0.f);
+  return (int)cudaGetLastError();
+}
+
+// Apply-side finalize: statistics from the replicated sums (see bn_apply_kernel).  `ticket`: >= 16
+// zero counters (self-resetting).  Returns -1 when the shape does not fit (caller finalizes separately).
+extern "C" int ddl_bn_apply_sums(const void* x, const void* res, void* y, float* sums, float* stat_out,
+                                 float* running_mean, float* running_var, unsigned int* ticket,
+                                 const void* gamma, const void* beta, int param_is_bf16,
+                                 void* mask_out, int64_t M, int C, float eps, float momentum, int act,
+                                 int sms, cudaStream_t st) {
+  if (C % 8) return -1;
+  BnDims d = bn_dims(M, C, sms, 8, 2);
+  if ((C / 8) % d.cvb || d.gy > 16) return -1;       // full channel blocks only
+  if (param_is_bf16)
+    launch_pdl(bn_apply_kernel<bf16>, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st,
+        (const bf16*)x, (const bf16*)res, (bf16*)y, (const float*)nullptr, (const bf16*)gamma,
+        (const bf16*)beta, (uint8_t*)mask_out, M, C, d.rows_per_block, act, sums, stat_out,
+        running_mean, running_var, ticket, eps, momentum);
+  else
+    launch_pdl(bn_apply_kernel<float>, dim3(dim3(d.gx, d.gy)), dim3(dim3(d.cvb, d.rl)), 0, st,
+        (const bf16*)x, (const bf16*)res, (bf16*)y, (const float*)nullptr, (const float*)gamma,
+        (const float*)beta, (uint8_t*)mask_out, M, C, d.rows_per_block, act, sums, stat_out,
+        running_mean, running_var, ticket, eps, momentum);
   return (int)cudaGetLastError();
 }
 

@@ -474,6 +474,20 @@ class FullFakeExt(FakeExt):
         self._finalize(v[0], v[1], stat, rmean, rvar, M, C, eps, mom)
         sp.zero_()                                     # the kernel leaves its workspace zeroed
 
+    def bn_apply_sums(self, x, res, y, sums, counter, stat, rmean, rvar, gamma, beta, mask_out, M, C, eps, mom, act):
+        """Apply-side finalize: statistics from the producer's replicated sums, which are left zeroed."""
+        self.calls.append("bn_apply_sums")
+        if (C // 8) % min(C // 8, 256):
+            return False
+        assert _plain(counter).numel() >= 64 and int(_plain(counter)[48:64].abs().sum()) == 0
+        sp = _plain(sums)
+        v = sp[:R * 2 * C].view(R, 2, C).sum(0)
+        self._finalize(v[0], v[1], stat, rmean, rvar, M, C, eps, mom)
+        sp.zero_()
+        self.bn_apply(x, res, y, stat, gamma, beta, mask_out, M, C, act)
+        self.calls.pop()
+        return True
+
     def bn_apply(self, x, res, y, stat, gamma, beta, mask_out, M, C, act):
         self.calls.append("bn_apply")
         st = _plain(stat).view(-1)

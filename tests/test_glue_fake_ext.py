@@ -381,18 +381,19 @@ def test_resnet50_through_device_branches_with_every_optin_switch(monkeypatch):
             results[label] = run(True, 2 if label in ("all", "igemm") else 1) + (set(fe.calls),)
     (l_d, w_d, used_d), (l_f, w_f, used_f), (l_a, w_a, used_a) = (results[k] for k in ("default", "fold+wgrad1x1", "all"))
     # the shipped configuration: every convolution / FC layer on the persistent implicit-GEMM family,
-    # statistics + finalize fused, no library convolution anywhere in the step
+    # statistics in the convolution epilogue, finalized by the BatchNorm apply kernel itself, no
+    # library convolution anywhere in the step
     l_i, w_i, used_i = results["igemm"]
     assert {"igemm_conv_fprop", "igemm_conv_dgrad", "wgrad_conv", "wgrad_gemm", "igemm_gemm", "im2col_rows",
-            "bn_apply", "bn_bwd_reduce", "bn_bwd_apply", "xent", "sgd_flat"} <= used_i, used_i
-    assert not ({"bn_stats", "bn_finalize", "gemm_bf16_tn", "conv_bf16_nhwc"} & used_i), used_i
+            "bn_apply_sums", "bn_bwd_reduce", "bn_bwd_apply", "xent", "sgd_flat"} <= used_i, used_i
+    assert not ({"bn_stats", "bn_finalize", "bn_apply", "gemm_bf16_tn", "conv_bf16_nhwc"} & used_i), used_i
     assert lib_convs == [], lib_convs
     assert l_i == pytest.approx(ref_losses, rel=3e-2) and torch.isfinite(w_i).all()
     assert "gemm_bf16_tn_bnfold" not in used_d and {"gemm_bf16_tn_bnfold", "gemm_bf16_nt_mn",
                                                     "gemm_bf16_tn_bnbwd"} <= used_f
     assert l_f == pytest.approx(l_d, rel=5e-3) and ((w_f - w_d).norm() / w_d.norm()).item() < 1e-3
     for k in ("im2col_rows", "conv_bf16_nhwc", "conv_wgrad_bf16_nhwc", "gemm_bf16_tn_bnfold", "gemm_bf16_nt_mn",
-              "gemm_bf16_tn", "bn_finalize", "bn_apply", "bn_bwd_reduce", "bn_bwd_apply",
+              "gemm_bf16_tn", "bn_finalize", "bn_apply_sums", "bn_bwd_reduce", "bn_bwd_apply",
               "maxpool_fwd", "maxpool_bwd", "gap_fwd", "gap_bwd", "xent", "sgd_flat"):
         assert k in used_a, k
     assert "bn_stats" not in used_a            # every convolution delivered its statistics fused

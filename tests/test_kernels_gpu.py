@@ -377,6 +377,42 @@ def test_im2col_rows(n, c, hw, k, s, p):
     torch.testing.assert_close(a.float().cpu(), want, rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("n,c,hw,has_res", [(8, 64, 14, False), (4, 256, 7, True), (2, 2048, 7, True), (32, 128, 28, False)])
+def test_bn_apply_finalizes_from_replicated_sums(n, c, hw, has_res):
+    """Apply-side finalize (csrc/bn.cu, bn_apply_kernel with `sums`): statistics from the replicated
+    sum / sum-of-squares buffers, y = relu(bn(x) + res), stat_out, running statistics, and the
+    workspace / ticket left zeroed for the next forward."""
+    torch.manual_seed(0)
+    x = _nhwc(n, c, hw, hw)
+    res = _nhwc(n, c, hw, hw) if has_res else None
+    M = n * hw * hw
+    xf = x.permute(0, 2, 3, 1).reshape(M, c).float()
+    ws = ops.BnWorkspace(c, "cuda")
+    sv = ws.sums.view(ops.BN_REPLICAS, 2, c)
+    half = M // 3
+    sv[0, 0], sv[0, 1] = xf[:half].sum(0), (xf[:half] ** 2).sum(0)          # spread over two replicas
+    sv[5, 0], sv[5, 1] = xf[half:].sum(0), (xf[half:] ** 2).sum(0)
+    gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    mask = torch.empty(x.numel() // 8, dtype=torch.uint8, device="cuda")
+    y, stat = ops.bn_forward(x, res, gamma, beta, rm, rv, 1e-5, 0.1, ops.ACT_RELU, ws, stats_ready=True,
+                             mask_out=mask)
+    mean, var = xf.mean(0), xf.var(0, unbiased=False)
+    want = (xf - mean) * torch.rsqrt(var + 1e-5) * gamma + beta
+    if has_res:
+        want = want + res.permute(0, 2, 3, 1).reshape(M, c).float()
+    want = want.relu()
+    got = y.permute(0, 2, 3, 1).reshape(M, c).float()
+    torch.testing.assert_close(got, want, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(stat[0], mean, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(stat[1], torch.rsqrt(var + 1e-5), rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(rm, 0.1 * mean, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(rv, 0.9 + 0.1 * var * M / (M - 1), rtol=1e-3, atol=1e-4)
+    assert float(ws.sums.abs().sum()) == 0.0 and int(ws.counter.abs().sum()) == 0
+    bits = ((got > 0).view(M, c // 8, 8).to(torch.int32) << torch.arange(8, device="cuda", dtype=torch.int32)).sum(-1)
+    assert torch.equal(mask.view(M, c // 8).to(torch.int32), bits)
+
+
 @pytest.mark.parametrize("n,c,hw,out", [(4, 64, 13, 6), (2, 512, 14, 7), (3, 128, 9, 1), (2, 64, 10, 4)])
 def test_avgpool_adaptive(n, c, hw, out):
     torch.manual_seed(0)
