@@ -75,8 +75,17 @@ def prepare_data(a, rank: int = 0):
     corpus (there is no network here).  A directory with other content is never written to."""
     d = a.data_dir or os.path.join(os.environ.get("TMPDIR", "/tmp"), "ddlb_gnmt_data")
     names = WMT16 if os.path.exists(os.path.join(d, WMT16["vocab"])) else PLAIN
-    if not os.path.exists(os.path.join(d, names["train"][0])):
-        if os.path.isdir(d) and os.listdir(d) and not os.path.exists(os.path.join(d, PLAIN["vocab"])):
+    need = not os.path.exists(os.path.join(d, names["train"][0]))
+    if dist.is_initialized():
+        # rank 0 decides for everybody: another rank may look at the directory while rank 0 is
+        # already writing the corpus and would otherwise skip the barrier below
+        flag = [need]
+        dist.broadcast_object_list(flag, src=0)
+        need = flag[0]
+    if need:
+        # (only rank 0 inspects the directory: the others may see it half written)
+        if rank == 0 and os.path.isdir(d) and os.listdir(d) and \
+                not os.path.exists(os.path.join(d, PLAIN["vocab"])):
             raise FileNotFoundError("%s has neither the WMT16 files (%s, %s, ...) nor train.src/train.tgt/vocab.txt"
                                     % (d, WMT16["vocab"], WMT16["train"][0]))
         if rank == 0:
