@@ -45,8 +45,9 @@ STEM_IM2COL = _os.environ.get("DDLB_STEM_IM2COL", "0") == "1"
 # ops.gemm_tn_bnfold); pending (not yet written) outputs are tracked by object identity
 BN_FOLD = _os.environ.get("DDLB_BN_FOLD", "0") == "1"
 PENDING_FOLD: Dict[int, "ops.BnFold"] = {}
-# hand-written depthwise 3x3 convolution (csrc/dwconv.cu): opt-in until validated
-DWCONV = _os.environ.get("DDLB_DWCONV", "0") == "1"
+# hand-written depthwise 3x3 convolution (csrc/dwconv.cu; numerics validated on hardware:
+# tests/test_kernels_gpu.py::test_dwconv3x3): default on, DDLB_DWCONV=0 falls back to cuDNN's grouped conv
+DWCONV = _os.environ.get("DDLB_DWCONV", "1") == "1"
 # weight gradient of 1x1 convolutions / linear layers on tcgen05 (csrc/gemm_wgrad_tcgen05.cu): opt-in
 WGRAD_TCGEN05 = _os.environ.get("DDLB_WGRAD_TCGEN05", "0") == "1"
 # data gradient of those 3x3 convolutions through the same kernel (flipped, transposed filter)
