@@ -9,12 +9,17 @@ reference's ``['host:gpu', ...]`` list: its length is the number of workers.
 Differences by design: when every entry of ``machines`` names the same host (the normal case:
 all GPUs of an NVSwitch box) the workers are local processes started through
 ``torch.distributed.run``; with several hosts one ``ddlbench_b200.launch`` per host is started
-over ``ssh -n`` (the reference's fan-out, ``driver.py:313-356``, minus docker), all pointing at
-the first host as rendezvous.  ``module`` (``models.<arch>.gpus=<N>``) selects the architecture —
+over ``ssh -n`` (the reference's fan-out, ``driver.py:313-356``), all pointing at the first host as
+rendezvous.  ``--docker`` runs every node's launcher inside the configuration's ``container``
+(one container per node, ``docker run --gpus all --net=host --ipc=host --shm-size 16g`` with the
+repository, the data directory, the log directory and ``--mount_directories`` mounted — the
+reference's ``--launch_single_container`` mode, ``driver.py:276-318``, with ``nvidia-docker``
+replaced by ``--gpus all``).  ``module`` (``models.<arch>.gpus=<N>``) selects the architecture —
 stage modules are sliced from the layer graph instead of being imported; ``model_type:
 translation`` starts the GNMT harness.
-The launcher writes ``<log_directory>/<timestamp>/{config.yml, machinefile, output.log}`` and
-records the git commit like the reference (``driver.py:73-100``).
+The launcher writes ``<log_directory>/<timestamp>/{config.yml, machinefile, output.log,
+command_history.txt, git_info.log}`` (commit + working-tree diff) like the reference
+(``driver.py:170-200``).
 """
 from __future__ import annotations
 
@@ -111,12 +116,31 @@ def worker_args(conf: Dict, resume: str = "", dataset: str = "imagenet") -> List
     return build_command(conf, resume, dataset)[build_command(conf, resume, dataset).index("ddlbench_b200.cli"):]
 
 
+def docker_prefix(conf: Dict, repo: str, mounts=()) -> List[str]:
+    """``docker run`` argv (up to and including ``/bin/bash -c``) for one node's container."""
+    dirs = [repo]
+    for d in [conf.get("data_dir"), conf.get("log_directory")] + list(mounts or ()):
+        if d and d != "synthetic" and os.path.isabs(str(d)) and str(d) not in dirs:
+            dirs.append(str(d))
+    cmd = ["docker", "run", "--rm", "--gpus", "all", "--net=host", "--ipc=host", "--shm-size", "16g"]
+    for d in dirs:
+        cmd += ["-v", "%s:%s" % (d, d)]
+    return cmd + ["-w", repo, str(conf["container"]), "/bin/bash", "-c"]
+
+
 def build_node_commands(conf: Dict, resume: str = "", dataset: str = "imagenet",
-                        port: int = 29450, repo: str = "") -> "List[tuple]":
-    """[(host, argv)] — one entry for a single-host run, one ``ssh`` command per host otherwise."""
+                        port: int = 29450, repo: str = "", docker: bool = False,
+                        mounts=()) -> "List[tuple]":
+    """[(host, argv)] — one entry for a single-host run, one ``ssh`` command per host otherwise;
+    ``docker``: each node's launcher runs inside ``conf['container']``."""
     hosts = hosts_of(conf)
     wargs = worker_args(conf, resume, dataset)
     names = list(hosts)
+    repo = repo or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if docker and len(names) == 1:
+        inner = ("python -m torch.distributed.run --nnodes=1 --nproc-per-node=%d --master-addr 127.0.0.1 "
+                 "--master-port %d -m %s" % (hosts[names[0]], port, " ".join(wargs)))
+        return [(names[0], docker_prefix(conf, repo, mounts) + [inner])]
     if len(names) == 1:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                "--nproc-per-node=%d" % hosts[names[0]], "--master-addr", "127.0.0.1",
@@ -125,7 +149,6 @@ def build_node_commands(conf: Dict, resume: str = "", dataset: str = "imagenet",
     per = set(hosts.values())
     if len(per) != 1:
         raise ValueError("every host must run the same number of workers, got %s" % hosts)
-    repo = repo or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     if "-g" in wargs:                       # cli workers: GPUs per node + number of nodes
         wargs[wargs.index("-g") + 1] = str(hosts[names[0]])
         wargs += ["-n", str(len(names))]
@@ -135,6 +158,9 @@ def build_node_commands(conf: Dict, resume: str = "", dataset: str = "imagenet",
                  "--nproc_per_node %d --master_addr %s --master_port %d --no-rank-args "
                  "--pid-file driver_node%d.pids -m %s" % (
                      repo, len(names), i, hosts[h], names[0], port, i, " ".join(wargs)))
+        if docker:
+            import shlex
+            inner = " ".join(shlex.quote(c) for c in docker_prefix(conf, repo, mounts) + [inner])
         out.append((h, ["ssh", "-n", h, "-o", "StrictHostKeyChecking=no", inner]))
     return out
 
@@ -146,11 +172,14 @@ def main(argv=None) -> int:
     ap.add_argument("--dataset", default="imagenet")
     ap.add_argument("--dry_run", action="store_true", help="print the command, do not launch")
     ap.add_argument("--quiet", action="store_true")
+    ap.add_argument("--docker", "--launch_single_container", action="store_true", dest="docker",
+                    help="run each node's launcher inside the configuration's container")
+    ap.add_argument("--mount_directories", nargs="*", default=[], help="extra directories to mount (docker)")
     a = ap.parse_args(argv)
     conf = load(a.config_file)
     out_dir = os.path.join(conf["log_directory"],
                            datetime.datetime.now().isoformat().split(".")[0].replace(":", "-"))
-    nodes = build_node_commands(conf, a.resume, a.dataset)
+    nodes = build_node_commands(conf, a.resume, a.dataset, docker=a.docker, mounts=a.mount_directories)
     cmd = nodes[0][1]
     if a.dry_run:
         for _, c in nodes:
@@ -161,10 +190,16 @@ def main(argv=None) -> int:
         yaml.safe_dump(conf, f)
     with open(os.path.join(out_dir, "machinefile"), "w") as f:
         f.write("\n".join(str(m) for m in conf["machines"]) + "\n")
+    with open(os.path.join(out_dir, "command_history.txt"), "w") as f:
+        for _, c in nodes:
+            f.write(" ".join(c) + "\n")
     try:
         commit = subprocess.run(["git", "rev-parse", "HEAD"], capture_output=True, text=True).stdout.strip()
+        diff = subprocess.run(["git", "diff"], capture_output=True, text=True).stdout
     except Exception:  # noqa: BLE001
-        commit = "unknown"
+        commit, diff = "unknown", ""
+    with open(os.path.join(out_dir, "git_info.log"), "w") as f:
+        f.write(commit + "\n" + diff)
     env = dict(os.environ)
     for k, name in (("learning_rate", "DDLB_LR"), ("weight_decay", "DDLB_WD")):
         if conf.get(k) is not None:

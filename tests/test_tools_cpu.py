@@ -280,6 +280,26 @@ def test_driver_multi_host_and_translation_commands():
     assert "ddlbench_b200.harness.translation" in cmd and cmd[cmd.index("--stages") + 1] == "4"
 
 
+def test_driver_docker_mode_wraps_each_node_in_the_configured_container(tmp_path, capsys):
+    """``--docker`` / ``--launch_single_container``: one container per node (the reference's
+    ``driver.py:276-318``), repository + data + log directories mounted."""
+    conf = driver.load("configs/driver/resnet50_16hybrid_2nodes.yml")
+    two = driver.build_node_commands(conf, docker=True, mounts=["/scratch"])
+    for i, (host, cmd) in enumerate(two):
+        assert cmd[0] == "ssh" and host == "node%d" % i
+        inner = cmd[-1]
+        assert inner.startswith("docker run") and "--gpus all" in inner and "--net=host" in inner
+        assert str(conf["container"]) in inner and "-v /scratch:/scratch" in inner
+        assert "ddlbench_b200.launch" in inner and "--node_rank %d" % i in inner
+    one_conf = driver.load("configs/driver/vgg16_4pipedream.yml")
+    (host, cmd), = driver.build_node_commands(one_conf, docker=True)
+    assert cmd[:2] == ["docker", "run"] and cmd[-2] == "-c" and "torch.distributed.run" in cmd[-1]
+    assert cmd[cmd.index("/bin/bash") - 1] == str(one_conf["container"])
+    # the CLI prints the same thing with --dry_run
+    assert driver.main(["--config_file", "configs/driver/vgg16_4pipedream.yml", "--dry_run", "--docker"]) == 0
+    assert capsys.readouterr().out.startswith("docker run")
+
+
 def test_launcher_terminate_stops_exactly_the_recorded_pids(tmp_path):
     """``launch.py --terminate <pidfile>`` signals the recorded children only (the reference's
     ``terminate_runtime.py`` runs ``pkill -f`` on every machine)."""
