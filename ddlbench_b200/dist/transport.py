@@ -20,7 +20,7 @@ tokens.
 path: ``p2p_put`` stores the tensor straight into the consumer's symmetric-memory ring slot over
 NVLink and raises a sequence flag, ``p2p_wait`` makes the consumer's stream spin on it
 (``ops/csrc/allreduce.cu``), credits flow back the same way.  Protocol-tested off-line
-(``tests/test_symm_p2p_cpu.py``); not yet run on hardware — ``bench/p2p_bandwidth.py`` measures the
+(``tests/test_symm_p2p_cpu.py``); HUNG in the 4-GPU hardware run of round 2 (not validated, keep DDLB_P2P=nccl) — ``bench/p2p_bandwidth.py`` measures the
 two kernels, ``tools/validate_pipe_graphs.sh`` A/Bs the pipeline with it.
 """
 from __future__ import annotations

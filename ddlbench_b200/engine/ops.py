@@ -37,9 +37,10 @@ WGRAD_OVERLAP = {"stream": None, "keep": []}
 FUSE_BN_FINALIZE = _os.environ.get("DDLB_FUSE_FINALIZE", "0") == "1"
 # BN backward reads the 1-bit activation mask written by the forward instead of y
 ACT_BITMASK_ON = _os.environ.get("DDLB_ACT_BITMASK", "1") == "1"
-# tcgen05 implicit-GEMM for the 3x3 convolutions (csrc/conv_tcgen05.cu): opt-in until validated
+# round-1 one-tile implicit GEMM for the 3x3 convolutions (csrc/conv_tcgen05.cu): validated, A/B baseline
+# of the persistent family (only consulted with DDLB_IGEMM=0)
 CONV3X3_TCGEN05 = _os.environ.get("DDLB_CONV3X3_TCGEN05", "0") == "1"
-# first convolution (3 input channels) as im2col + tcgen05 GEMM (csrc/im2col.cu): opt-in until validated
+# first convolution as im2col + round-1 GEMM with DDLB_IGEMM=0 (the default path always uses im2col + igemm)
 STEM_IM2COL = _os.environ.get("DDLB_STEM_IM2COL", "0") == "1"
 # BatchNorm application deferred into the consuming 1x1-convolution GEMM (opt-in, see
 # ops.gemm_tn_bnfold); pending (not yet written) outputs are tracked by object identity
@@ -53,10 +54,10 @@ WGRAD_TCGEN05 = _os.environ.get("DDLB_WGRAD_TCGEN05", "0") == "1"
 # data gradient of those 3x3 convolutions through the same kernel (flipped, transposed filter)
 CONV3X3_DGRAD = CONV3X3_TCGEN05 and _os.environ.get("DDLB_CONV3X3_DGRAD", "0") == "1"
 # element-wise half of the BatchNorm backward folded into the 1x1 data-gradient GEMM's operand
-# load (csrc/gemm_bnbwd_tcgen05.cu, ops.bn_backward_dgrad_fold): opt-in until validated
+# load (csrc/gemm_bnbwd_tcgen05.cu, ops.bn_backward_dgrad_fold): validated, round-1 family only
 BN_BWD_FOLD = _os.environ.get("DDLB_BN_BWD_FOLD", "0") == "1"
 # data gradient of the 1x1 convolutions on the (validated) tcgen05 TN GEMM: dx = dy @ W needs W^T
-# as the K-major B operand, i.e. one small transpose per layer and step; opt-in until measured
+# as the K-major B operand, i.e. one small transpose per layer and step; round-1 family only (the default dgrad reads the filter MN-major)
 # against the library's dgrad
 DGRAD1X1_TCGEN05 = _os.environ.get("DDLB_DGRAD1X1_TCGEN05", "0") == "1"
 # weight-gradient kernels on a side stream during backward

@@ -23,8 +23,10 @@
 // fused BatchNorm sum / sum-of-squares (rows of pixels outside the image are zeroed) -> 4-D TMA
 // store, which clips the out-of-image part of the box.
 //
-// STATUS: compiled for sm_100a and wired behind DDLB_CONV3X3_TCGEN05=1 (default off); numerics
-// test in tests/test_kernels_gpu.py::test_tcgen05_conv3x3 (opt-in) — not yet run on hardware.
+// STATUS: validated on hardware at the start of round 2 (tests/conv_check.py, 14 shapes incl.
+// stride 2, statistics, bias + ReLU); superseded on the default path by the persistent family in
+// igemm_tcgen05.cu (two CTAs per SM, double-buffered TMEM, dgrad without weight transposes) and
+// kept behind DDLB_IGEMM=0 + DDLB_CONV3X3_TCGEN05=1 as the one-tile-per-CTA A/B baseline.
 #include <cuda.h>
 #include <cstdio>
 

@@ -14,8 +14,8 @@
 // one vector atomic per 4 channels.
 // (reference: cuDNN grouped-convolution kernels chosen by PyTorch.)
 //
-// STATUS: opt-in (DDLB_DWCONV=1); written after round 1's GPU minutes were spent, numerics test
-// opt-in — not yet run on hardware.
+// STATUS: default path for depthwise 3x3 layers (DDLB_DWCONV=0: cuDNN grouped convolution); numerics
+// validated on hardware (tests/test_kernels_gpu.py::test_dwconv3x3), speed not yet compared to cuDNN.
 #include "api.h"
 #include "common.cuh"
 

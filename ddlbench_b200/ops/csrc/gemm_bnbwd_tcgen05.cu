@@ -18,9 +18,9 @@
 // (c0 = gamma*invstd, c1 = mean(dz), c2 = mean(dz*xhat)):
 //     A = c0,  Bx = -c0*invstd*c2,  K = c0*(mean*invstd*c2 - c1)          (as bn_bwd_apply_kernel)
 //
-// STATUS: opt-in (DDLB_BN_BWD_FOLD=1).  Written after round 1's GPU minutes were spent: compiles
-// for sm_100a; the engine side is tested off-line against autograd with a stand-in for this
-// kernel (tests/test_glue_fake_ext.py); the kernel itself has not run yet.
+// STATUS: validated on hardware at the start of round 2 (profiles/r2/optin_validation_first_run.log:
+// dx / dc / dz / dgamma / dbeta against the unfused path on four shapes); round-1 family
+// (DDLB_IGEMM=0 + DDLB_BN_BWD_FOLD=1), kept as an A/B baseline.
 #include <cuda.h>
 #include <cstdio>
 

@@ -16,9 +16,10 @@
 // scale = gamma * invstd, shift = beta - mean * scale are derived per CTA from the finalized
 // statistics, so no extra launch prepares them.
 //
-// STATUS: opt-in (DDLB_BN_FOLD=1).  Written after round 1's GPU minutes were spent: compiles for
-// sm_100a, the engine side (plan marking, deferred values, backward) is CPU-tested against
-// autograd with the reference implementation of this op; the kernel itself has not run yet.
+// STATUS: validated on hardware at the start of round 2 (profiles/r2/optin_validation_first_run.log:
+// y / mask / GEMM output against the unfused path on four shapes); belongs to the round-1 one-tile
+// GEMM family (DDLB_IGEMM=0 + DDLB_BN_FOLD=1) and is kept as an A/B baseline — the persistent
+// implicit-GEMM family that is the default today has no operand-transform stage.
 #include <cuda.h>
 #include <cstdio>
 

@@ -15,12 +15,16 @@
 // (tiles_m * tiles_n) x splits and every CTA adds its fp32 partial tile into D with 16-byte
 // vector atomics straight from the TMEM read-out (no shared-memory staging, no second pass).
 //
-// STATUS: opt-in (DDLB_WGRAD_TCGEN05=1).  Written after round 1's GPU minutes were spent: it
-// compiles for sm_100a but has not run on hardware.  LBO = stride between 64-element MN atoms,
+// STATUS: the default weight-gradient path (ops.conv_wgrad_into / ops.wgrad_gemm_into); validated on
+// hardware (tests/igemm_check.py, every ResNet-50 / VGG shape against fp32 autograd).  Split-K
+// partial tiles are written with plain stores into fp32 planes and summed by wgrad_reduce_kernel;
+// the vector-atomic mode described above is the legacy entry point (ddl_gemm_bf16_nt_mn).  The
+// hardware confirmed descriptor variant 0: LBO = stride between 64-element MN atoms,
 // SBO = stride between 8-row K groups follows the canonical Major-MN SWIZZLE_128B layout
 // ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units documented in CUTLASS
 // (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>); `desc_variant`
-// (env DDLB_WGRAD_DESC_VARIANT=1) swaps the two for bring-up should the hardware disagree.
+// (env DDLB_WGRAD_DESC_VARIANT=1) swaps the two — it fails on hardware (max error 21 on the first
+// shape, profiles/r2/optin_validation_first_run.log), kept only as the record of that bring-up.
 #include <cuda.h>
 #include <cstdio>
 

@@ -21,13 +21,13 @@ reference's single-process layout, or a single device for tests).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
 from ..dist.transport import DistP2P, PairGroups
-from ..engine import FwdContext, StageExecutor
+from ..engine import StageExecutor
 from ..engine import ops as E
 from ..models.graph import LayerGraphModel
 from .pipedream.runtime import infer_boundary_specs
