@@ -238,6 +238,140 @@ def test_conv_tcgen05_tiling_logic_emulated(nb, ci, co, hw, k, stride):
     torch.testing.assert_close(y, ref, rtol=1e-10, atol=1e-10)
 
 
+@pytest.mark.parametrize("nb,ci,co,hw,k,stride,pad", [(2, 16, 24, 9, 3, 2, 1), (2, 8, 16, 8, 3, 2, 1), (3, 8, 8, 7, 1, 2, 0),
+                                                      (2, 8, 16, 10, 5, 2, 2), (2, 16, 8, 6, 3, 1, 1)])
+def test_igemm_dgrad_parity_classes_emulated(nb, ci, co, hw, k, stride, pad):
+    """Host emulation of ``ddl_igemm_conv_dgrad`` (csrc/igemm_tcgen05.cu): a stride-2 data gradient is
+    one stride-1 problem per output parity class (a, b) over the taps with (a + pad - kh) and
+    (b + pad - kw) even, reading dY at the class pixel + tap offset (nh/2, nw/2) (zero outside:
+    the TMA fill), multiplying by the KRSC filter block of the tap read MN-major (W[:, tap, :] as
+    [Cout][Cin], no transpose), and storing through the strided view dX[:, a::2, b::2, :].  Classes
+    without taps stay zero (the memset).  Must equal autograd's input gradient."""
+    import torch.nn.functional as Fn
+    torch.manual_seed(0)
+    oh = (hw + 2 * pad - k) // stride + 1
+    x = torch.randn(nb, ci, hw, hw, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(co, ci, k, k, dtype=torch.float64)
+    y = Fn.conv2d(x, w, stride=stride, padding=pad)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    dyh = dy.permute(0, 2, 3, 1)                                   # NHWC [nb, oh, oh, co]
+    wk = w.permute(0, 2, 3, 1).reshape(co, k * k * ci)             # KRSC filter matrix
+    dx = torch.zeros(nb, hw, hw, ci, dtype=torch.float64)
+    classes = [(0, 0)] if stride == 1 else [(a, b) for a in range(2) for b in range(2)]
+    launched = 0
+    for a, b in classes:
+        Ha, Wb = (hw - a + stride - 1) // stride, (hw - b + stride - 1) // stride
+        taps = []
+        for kh in range(k):
+            for kw in range(k):
+                nh, nw = a + pad - kh, b + pad - kw
+                if stride == 1:
+                    taps.append((pad - kh, pad - kw, (kh * k + kw) * ci))
+                elif nh % 2 == 0 and nw % 2 == 0:
+                    taps.append((nh // 2, nw // 2, (kh * k + kw) * ci))
+        if not taps or Ha <= 0 or Wb <= 0:
+            continue
+        launched += 1
+        out = torch.zeros(nb, Ha, Wb, ci, dtype=torch.float64)
+        for dh, dw, bcol in taps:
+            shifted = torch.zeros(nb, Ha, Wb, co, dtype=torch.float64)     # dY box at the tap offset
+            for i in range(Ha):
+                for j in range(Wb):
+                    p_, q_ = i + dh, j + dw
+                    if 0 <= p_ < oh and 0 <= q_ < oh:
+                        shifted[:, i, j] = dyh[:, p_, q_]
+            out += shifted @ wk[:, bcol:bcol + ci]                         # B MN-major: [K = Cout][N = Cin]
+        dx[:, a::stride, b::stride] = out
+    assert launched >= 1
+    torch.testing.assert_close(dx.permute(0, 3, 1, 2), x.grad, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("S,total_kb", [(2, 9), (4, 16), (4, 10), (2, 72)])
+def test_igemm_cluster_splitk_exchange_emulated(S, total_kb):
+    """Host emulation of the cluster split-K epilogue (csrc/igemm_tcgen05.cu, ``csplit``): slice z
+    accumulates k-blocks [z*kbps, (z+1)*kbps), owns W = 128 / S output columns, parks the 32-column
+    groups it does NOT own in its slot of the workspace laid out [column quad][row][4] (L2
+    flavour) or in the owner's receive buffer [slot][column quad][row][4] with slot = source index
+    among the other slices (DSMEM flavour); every owner then adds the S - 1 partials of its columns
+    to its own.  Both flavours must reproduce the full reduction, and the host's slice count must
+    leave no slice empty."""
+    torch.manual_seed(0)
+    BM, BN = 128, 128
+    W = BN // S
+    kbps = -(-total_kb // S)
+    assert -(-total_kb // kbps) == S, "launch_ig would have fallen back to fewer slices"
+    partial_kb = torch.randn(total_kb, BM, BN, dtype=torch.float64)
+    acc = [partial_kb[z * kbps:min((z + 1) * kbps, total_kb)].sum(0) for z in range(S)]
+    # L2 flavour: ws[src][quad][row][4]
+    ws = torch.zeros(S, BN // 4, BM, 4, dtype=torch.float64)
+    # DSMEM flavour: rbuf[owner][slot][quad in slice][row][4]
+    rbuf = torch.zeros(S, S - 1, W // 4, BM, 4, dtype=torch.float64)
+    for rank in range(S):
+        for g in range(BN // 32):
+            dest = (g * 32) // W
+            if dest == rank:
+                continue
+            for j in range(8):
+                quad = acc[rank][:, g * 32 + 4 * j: g * 32 + 4 * j + 4]          # [row][4]
+                ws[rank, g * 8 + j] = quad
+                slot = rank - (1 if rank > dest else 0)
+                rbuf[dest, slot, ((g * 32) % W) // 4 + j] = quad
+    for via_l2 in (True, False):
+        out = torch.zeros(BM, BN, dtype=torch.float64)
+        for rank in range(S):
+            for g in range(W // 32):
+                f = acc[rank][:, rank * W + g * 32: rank * W + g * 32 + 32].clone()
+                for sl in range(S - 1):
+                    srck = sl + (1 if sl >= rank else 0)
+                    for j in range(8):
+                        q = ws[srck, (rank * W + g * 32) // 4 + j] if via_l2 else rbuf[rank, sl, g * 8 + j]
+                        f[:, 4 * j:4 * j + 4] += q
+                out[:, rank * W + g * 32: rank * W + g * 32 + 32] = f
+        torch.testing.assert_close(out, partial_kb.sum(0), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("tiles_m,tiles_n,group_m,clusters", [(32, 32, 8, 74), (7, 2, 8, 14), (25, 1, 8, 25), (3, 17, 8, 51),
+                                                             (9, 5, 4, 74)])
+def test_gemm_pair_tile_walk_and_operand_split_emulated(tiles_m, tiles_n, group_m, clusters):
+    """Host emulation of csrc/gemm2cta_tcgen05.cu: (1) ``tile_coords`` — the persistent walk of cluster c
+    over tiles c, c + clusters, ... with m-tiles grouped for L2 reuse visits every (m, n) tile exactly
+    once; (2) the CTA-pair operand split — CTA r stages rows [256 tm + 128 r, +128) of A and rows
+    [BN tn + BN/2 r, +BN/2) of B, the pair's MMA is A_pair (256 x K) times B_pair^T (K x BN), CTA r's
+    TMEM holds output rows 128 r .. 128 r + 127: reassembling the tiles must give A B^T."""
+    def tile_coords(t):
+        per_group = group_m * tiles_n
+        g = t // per_group
+        first = g * group_m
+        gsz = min(group_m, tiles_m - first)
+        r = t - g * per_group
+        return first + r % gsz, r // gsz
+    seen = set()
+    for c in range(min(clusters, tiles_m * tiles_n)):
+        for t in range(c, tiles_m * tiles_n, clusters):
+            tm, tn = tile_coords(t)
+            assert 0 <= tm < tiles_m and 0 <= tn < tiles_n and (tm, tn) not in seen
+            seen.add((tm, tn))
+    assert len(seen) == tiles_m * tiles_n
+    if tiles_m * tiles_n > 40:
+        return
+    torch.manual_seed(0)
+    BN, K = 64, 24
+    M, N = tiles_m * 256 - 100, tiles_n * BN - 8                           # ragged edges: TMA zero fill / clipped store
+    A = torch.randn(M, K, dtype=torch.float64)
+    B = torch.randn(N, K, dtype=torch.float64)
+    Ap = torch.zeros(tiles_m * 256, K, dtype=torch.float64); Ap[:M] = A
+    Bp = torch.zeros(tiles_n * BN, K, dtype=torch.float64); Bp[:N] = B
+    D = torch.zeros(tiles_m * 256, tiles_n * BN, dtype=torch.float64)
+    for tm, tn in seen:
+        a_cta = [Ap[tm * 256 + 128 * r: tm * 256 + 128 * (r + 1)] for r in range(2)]
+        b_cta = [Bp[tn * BN + (BN // 2) * r: tn * BN + (BN // 2) * (r + 1)] for r in range(2)]
+        b_pair = torch.cat(b_cta)                                            # both halves feed both tensor cores
+        for r in range(2):                                                   # CTA r's accumulator = its 128 rows
+            D[tm * 256 + 128 * r: tm * 256 + 128 * (r + 1), tn * BN:(tn + 1) * BN] = a_cta[r] @ b_pair.t()
+    torch.testing.assert_close(D[:M, :N], A @ B.t(), rtol=1e-12, atol=1e-12)
+
+
 @pytest.mark.parametrize("n,c,hw,k,s,p", [(2, 3, 20, 7, 2, 3), (1, 3, 9, 3, 1, 1), (2, 1, 12, 3, 1, 1)])
 def test_im2col_kernel_index_math_emulated(n, c, hw, k, s, p):
     """The staging / gather arithmetic of csrc/im2col.cu (rows[] fill, k -> (kh, rem), base offset)
