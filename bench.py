@@ -373,11 +373,22 @@ def _e2e_jpeg(args, trainer, dev, rank, n, dist, timed_loop, max_over_ranks, Dev
         while not os.path.exists(ready):
             time.sleep(0.1)
     gen_s = time.time() - t0
-    workers = max(2, min(int(os.environ.get("BENCH_DECODE_THREADS", "32")), (os.cpu_count() or 8) // n))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 8
+    workers = max(2, min(int(os.environ.get("BENCH_DECODE_THREADS", "32")), cores // n))
+    # decode in worker PROCESSES (data/decode_worker.py): the thread pool is GIL-bound near 900-2000
+    # images/s whatever the core count; BENCH_DECODE_PROCS=0 keeps the threads.  The reference arm gets
+    # up to 24 DataLoader worker processes per GPU (baseline/run_reference.py::_cores); we take the
+    # cores that are there, minus two for the training loop and the copy thread
+    procs = int(os.environ.get("BENCH_DECODE_PROCS", str(max(0, min(64, cores // n - 2)))))
+    if gpu_decode or procs < 6:            # a handful of processes is no better than the thread pool
+        procs = 0
     try:
         src = JpegFolder(tmp, DATASET, PER_GPU_BATCH, split="train", shuffle=True, seed=3, rank=rank,
-                         world=n, workers=workers, pinned=True, prefetch=6, gpu_decode=gpu_decode,
-                         device=dev)
+                         world=n, workers=workers, pinned=True, prefetch=8 if procs else 6,
+                         gpu_decode=gpu_decode, device=dev, decode_procs=procs)
         pre = DevicePrefetcher(src, dev)
         ms, losses = timed_loop(trainer, pre, steps, warm, read_loss=True)
         ms = max_over_ranks(ms, dev)
@@ -387,9 +398,13 @@ def _e2e_jpeg(args, trainer, dev, rank, n, dist, timed_loop, max_over_ranks, Dev
                "h2d_bytes_per_step": pre.h2d_bytes, "d2h_bytes_per_step": 12,
                "last_loss": (losses[-1] if losses else None),
                "input": "synthetic JPEG tree (baseline/jpeg_tree.py, the one the reference arm reads), "
-                        "decoded + RandomResizedCrop/flip by data.JpegFolder on %d host threads inside "
-                        "the timed loop; uint8 batch H2D from pinned memory every step; loss read back" % workers,
-               "decode_threads": workers, "datagen_seconds": round(gen_s, 1),
+                        "decoded + RandomResizedCrop/flip by data.JpegFolder on %s inside "
+                        "the timed loop; uint8 batch H2D from pinned memory every step; loss read back" % (
+                            ("%d worker processes" % procs) if (procs and src._procs_error is None)
+                            else ("%d host threads" % workers)),
+               "decode_threads": workers, "decode_procs": (procs if src._procs_error is None else 0),
+               "decode_procs_error": src._procs_error, "host_cores": cores,
+               "datagen_seconds": round(gen_s, 1),
                "decode": "nvJPEG on the device (torchvision.io.decode_jpeg)" if gpu_decode else "host (PIL/libjpeg)"}
     except Exception as e:  # noqa: BLE001
         out = {"value": None, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}

@@ -7,8 +7,11 @@ tensors (``benchmark/imagenet/imagenet_pytorch.py:68-110``, ``cifar10_pytorch.py
 same thing the synthetic source yields — a PINNED uint8 [B, H, W, C] batch + int64 labels — so
 everything downstream (double-buffered H2D copy stream, fused u8->bf16 normalise kernel,
 captured step) is shared.  Decode runs in a thread pool (PIL releases the GIL inside libjpeg)
-with ``prefetch`` batches in flight; ``gpu_decode=True`` ships the compressed bytes instead and
-decodes with nvJPEG on the device (``torchvision.io.decode_jpeg(device=cuda)``).
+with ``prefetch`` batches in flight, or — ``decode_procs=N`` / ``DDLB_DECODE_PROCS=N`` — in N worker
+PROCESSES that write into a shared ring of batch slots (``decode_worker.py``: the thread pool is
+bound by the GIL at ~900 images/s, processes scale with the cores; any failure of the process pool
+falls back to the threads); ``gpu_decode=True`` ships the compressed bytes instead and decodes with
+nvJPEG on the device (``torchvision.io.decode_jpeg(device=cuda)``).
 
 Sharding for data parallelism follows ``DistributedSampler(num_replicas, rank)`` semantics
 (``imagenet_horovod.py:113-123``): a per-epoch seeded permutation, padded to a multiple of the
@@ -17,6 +20,9 @@ world size, strided by rank.
 from __future__ import annotations
 
 import os
+import queue
+import sys
+import tempfile
 import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, List, Optional, Tuple
@@ -25,6 +31,7 @@ import numpy as np
 import torch
 
 from ..models import DATASETS
+from . import decode_worker
 from .synthetic import MEAN_STD
 
 _EXT = (".jpeg", ".jpg", ".png", ".ppm", ".bmp")
@@ -50,7 +57,8 @@ class JpegFolder:
     def __init__(self, datadir: str, dataset: str, batch_size: int, split: str = "train",
                  shuffle: bool = True, seed: int = 1, rank: int = 0, world: int = 1,
                  workers: Optional[int] = None, pinned: bool = False, augment: Optional[bool] = None,
-                 prefetch: int = 3, gpu_decode: bool = False, device="cpu"):
+                 prefetch: int = 3, gpu_decode: bool = False, device="cpu",
+                 decode_procs: Optional[int] = None):
         c, hw, ncls, _ = DATASETS[dataset]
         name = {"highres": "HIGHRES", "imagenet": "IMAGENET", "cifar10": "CIFAR10",
                 "mnist": "MNIST"}[dataset]
@@ -77,6 +85,18 @@ class JpegFolder:
         self.epoch = 0
         self._lock = threading.Lock()
         self._pending: Dict[int, object] = {}
+        # optional process pool for the decode (started lazily on the first batch)
+        if decode_procs is None:
+            decode_procs = int(os.environ.get("DDLB_DECODE_PROCS", "0") or 0)
+        self.decode_procs = 0 if (self.gpu_decode or getattr(self, "_scan_override", None) is not None) \
+            else max(0, int(decode_procs))
+        self._ppool: Optional[decode_worker.DecodePool] = None
+        self._ring = None
+        self._ring_path = ""
+        self._free_slots: "queue.Queue[int]" = queue.Queue()
+        self._procs_error: Optional[str] = None
+        self._procs_lock = threading.Lock()
+        self._closed = False
         self._order = self._make_order()
         self.length = len(self._order) // batch_size           # drop_last
         if self.length == 0:
@@ -106,46 +126,94 @@ class JpegFolder:
 
     # ---------------------------------------------------------------- decode
     def _load_one(self, path: str, rng: np.random.RandomState) -> np.ndarray:
-        from PIL import Image
-        with Image.open(path) as im:
-            im = im.convert("L" if self.channels == 1 else "RGB")
-            s = self.size
-            if self.dataset in ("imagenet", "highres"):
-                if self.augment and self.dataset == "imagenet":
-                    # RandomResizedCrop(224) + horizontal flip
-                    w, h = im.size
-                    area = w * h * rng.uniform(0.08, 1.0)
-                    ar = np.exp(rng.uniform(np.log(3 / 4), np.log(4 / 3)))
-                    cw = int(min(w, max(1, round(np.sqrt(area * ar)))))
-                    ch = int(min(h, max(1, round(np.sqrt(area / ar)))))
-                    x0, y0 = rng.randint(0, w - cw + 1), rng.randint(0, h - ch + 1)
-                    im = im.resize((s, s), Image.BILINEAR, box=(x0, y0, x0 + cw, y0 + ch))
-                elif im.size != (s, s):
-                    # Resize(256/224*s) + CenterCrop(s)
-                    w, h = im.size
-                    r = (s * 256 // 224) / min(w, h)
-                    im = im.resize((max(s, round(w * r)), max(s, round(h * r))), Image.BILINEAR)
-                    w, h = im.size
-                    im = im.crop(((w - s) // 2, (h - s) // 2, (w - s) // 2 + s, (h - s) // 2 + s))
-            elif im.size != (s, s):
-                im = im.resize((s, s), Image.BILINEAR)
-            a = np.asarray(im, dtype=np.uint8)
-        return self._augment(a, rng)
+        return decode_worker.load_image(path, self.dataset, self.size, self.channels, self.augment, rng)
 
     def _augment(self, a: np.ndarray, rng: np.random.RandomState) -> np.ndarray:
-        """[H, W(, C)] uint8 of the training size -> augmented [s, s, C] (CIFAR pad-crop, flip)."""
-        s = self.size
-        if a.ndim == 2:
-            a = a[:, :, None]
-        if self.augment:
-            if self.dataset == "cifar10":                      # RandomCrop(32, padding=4)
-                p = np.zeros((s + 8, s + 8, a.shape[2]), np.uint8)
-                p[4:4 + s, 4:4 + s] = a
-                y0, x0 = rng.randint(0, 9), rng.randint(0, 9)
-                a = p[y0:y0 + s, x0:x0 + s]
-            if self.dataset != "mnist" and rng.rand() < 0.5:
-                a = a[:, ::-1]
-        return np.ascontiguousarray(a)
+        return decode_worker.augment_array(a, self.dataset, self.size, self.augment, rng)
+
+    # ---------------------------------------------------------------- process pool
+    def _start_procs(self) -> bool:
+        """Ring file + worker processes.  False (and the thread pool stays in charge) on any failure."""
+        with self._procs_lock:             # several batch threads arrive here at once
+            return self._start_procs_locked()
+
+    def _start_procs_locked(self) -> bool:
+        if self._ppool is not None:
+            return True
+        if self._procs_error is not None or self.decode_procs <= 0:
+            return False
+        try:
+            slots = self.prefetch + 2
+            shape = (slots,) + tuple(self.shape)
+            need = int(np.prod(shape))
+            base = tempfile.gettempdir()
+            try:        # tmpfs when it has room (a full tmpfs would SIGBUS the writers), else a disk-backed map
+                if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK):
+                    st = os.statvfs("/dev/shm")
+                    if st.f_bavail * st.f_frsize > 4 * need + (64 << 20):
+                        base = "/dev/shm"
+            except OSError:
+                pass
+            fd, path = tempfile.mkstemp(prefix="ddlb_ring_%d_" % os.getpid(), dir=base)
+            try:
+                os.ftruncate(fd, need)
+            finally:
+                os.close(fd)
+            self._ring_path, self._ring_shape = path, shape
+            self._ring = np.memmap(path, dtype=np.uint8, mode="r+", shape=shape)
+            # plain `python decode_worker.py` children (no CUDA context, no inherited threads, no
+            # re-import of the parent's __main__): see decode_worker.DecodePool
+            pool = decode_worker.DecodePool(self.decode_procs)
+            for k in range(slots):
+                self._free_slots.put(k)
+            self._ppool = pool
+            return True
+        except Exception as e:  # noqa: BLE001 - the loader must keep working on threads
+            self._fail_procs("start: %s: %s" % (type(e).__name__, e))
+            return False
+
+    def _fail_procs(self, why: str) -> None:
+        if self._closed:                   # batches still in flight while the loader shuts down
+            return
+        if self._procs_error is None:
+            self._procs_error = why[:300]
+            print("JpegFolder: decode processes disabled (%s); using the thread pool" % self._procs_error,
+                  file=sys.stderr, flush=True)
+        pool, self._ppool = self._ppool, None
+        if pool is not None:
+            try:
+                pool.close()
+            except Exception:  # noqa: BLE001
+                pass
+
+    def _decode_batch_procs(self, sel, epoch: int, out: np.ndarray) -> bool:
+        """Decode the batch ``sel`` into ``out`` with the worker processes; False -> caller falls back."""
+        pool = self._ppool
+        if pool is None or self._closed:
+            return False
+        try:
+            slot = self._free_slots.get(timeout=60)
+        except queue.Empty:
+            self._fail_procs("no free ring slot for 60 s")
+            return False
+        try:
+            items = [(k, int(j), self.samples[j][0]) for k, j in enumerate(sel)]
+            chunk = max(1, min(4, len(items) // max(self.decode_procs, 1) or 1))
+            futs = [pool.submit(dict(ring_path=self._ring_path, ring_shape=self._ring_shape, slot=slot,
+                                     items=items[c:c + chunk], dataset=self.dataset, size=self.size,
+                                     channels=self.channels, augment=self.augment, seed=self.seed,
+                                     epoch=epoch)) for c in range(0, len(items), chunk)]
+            import time
+            deadline = time.time() + 60.0                       # one budget for the whole batch
+            for f in futs:
+                f.result(timeout=max(0.1, deadline - time.time()))
+            np.copyto(out, self._ring[slot])
+            return True
+        except Exception as e:  # noqa: BLE001 - broken pool, worker crash, timeout
+            self._fail_procs("%s: %s" % (type(e).__name__, e))
+            return False
+        finally:
+            self._free_slots.put(slot)
 
     def _transform_decoded(self, d: torch.Tensor, rng: np.random.RandomState) -> torch.Tensor:
         """The transforms of ``_load_one`` on an already decoded [C, H, W] uint8 tensor (device
@@ -193,7 +261,7 @@ class JpegFolder:
             from torchvision.io import ImageReadMode, decode_jpeg, read_file
             raw = [read_file(self.samples[j][0]) for j in sel]
             mode = ImageReadMode.GRAY if self.channels == 1 else ImageReadMode.RGB
-            rngs = [np.random.RandomState((self.seed * 1000003 + epoch * 7919 + int(j)) & 0x7FFFFFFF) for j in sel]
+            rngs = [decode_worker.sample_rng(self.seed, epoch, j) for j in sel]
             try:
                 dec = decode_jpeg(raw, device=self.device, mode=mode)
                 img = torch.stack([self._transform_decoded(d, r) for d, r in zip(dec, rngs)]).contiguous()
@@ -208,10 +276,12 @@ class JpegFolder:
             img, labels = img.pin_memory(), labels.pin_memory()
         out = img.numpy()
 
+        if self.decode_procs > 0 and self._start_procs() and self._decode_batch_procs(sel, epoch, out):
+            return img, labels
+
         def one(kj):
             k, j = kj
-            rng = np.random.RandomState((self.seed * 1000003 + epoch * 7919 + int(j)) & 0x7FFFFFFF)
-            out[k] = self._load_one(self.samples[j][0], rng)
+            out[k] = self._load_one(self.samples[j][0], decode_worker.sample_rng(self.seed, epoch, j))
 
         list(self.img_pool.map(one, enumerate(sel)))
         return img, labels
@@ -237,8 +307,25 @@ class JpegFolder:
         return int(np.prod(self.shape)) + self.batch_size * 8
 
     def close(self) -> None:
+        self._closed = True
         self.pool.shutdown(wait=False, cancel_futures=True)
         self.img_pool.shutdown(wait=False, cancel_futures=True)
+        pool, self._ppool = self._ppool, None
+        if pool is not None:
+            pool.close()
+        self._ring = None
+        if self._ring_path:
+            try:
+                os.unlink(self._ring_path)
+            except OSError:
+                pass
+            self._ring_path = ""
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 # ------------------------------------------------------------------------------------------

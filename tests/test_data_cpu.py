@@ -114,3 +114,82 @@ def test_native_mnist_and_cifar_files(tmp_path):
     cfg = RunConfig.from_env(benchmark="cifar10", framework="pytorch", arch="resnet18", synthetic=False,
                              datadir=str(tmp_path), batch_size=10, device="cpu")
     assert isinstance(make_source(cfg, 10, "cpu"), ArrayFolder)
+
+
+def test_decode_worker_processes_match_the_thread_pool_bit_for_bit(tmp_path):
+    """``decode_procs=N``: plain ``python decode_worker.py`` children write into the shared ring; the
+    batches must be IDENTICAL to the thread pool's (same per-sample generator, same transforms), for
+    the augmented training split, the validation split, across epochs and for non-square inputs."""
+    from PIL import Image
+    generate_jpeg_tree(str(tmp_path), "imagenet", train=48, val=16, workers=1, verbose=False)
+    rng = np.random.RandomState(0)                    # a few files that are NOT of the training size
+    d = os.path.join(tmp_path, "IMAGENET", "train", "class_0")
+    for k, (w, h) in enumerate(((300, 260), (500, 375), (231, 480))):
+        Image.fromarray(rng.randint(0, 256, (h, w, 3), dtype=np.uint8), "RGB").save(os.path.join(d, "odd_%d.JPEG" % k))
+    for split in ("train", "val"):
+        thr = JpegFolder(str(tmp_path), "imagenet", 8, split=split, seed=5, workers=2)
+        prc = JpegFolder(str(tmp_path), "imagenet", 8, split=split, seed=5, workers=2, decode_procs=3)
+        try:
+            for epoch in range(2):
+                thr.set_epoch(epoch)
+                prc.set_epoch(epoch)
+                for i in range(len(thr)):
+                    (xa, ta), (xb, tb) = thr.batch(i), prc.batch(i)
+                    assert torch.equal(ta, tb) and torch.equal(xa, xb), (split, epoch, i)
+            assert prc._procs_error is None and prc._ppool is not None and prc._ppool.n == 3
+            ring = prc._ring_path
+            assert os.path.exists(ring)
+        finally:
+            thr.close()
+            prc.close()
+        assert not os.path.exists(ring)                # the ring file is removed with the loader
+
+
+def test_decode_worker_pool_failure_falls_back_to_threads(tmp_path, capfd):
+    """Workers that die (or never start) must not take the loader down: the remaining batches come
+    from the thread pool, and the reason is kept for the bench line (``decode_procs_error``)."""
+    generate_jpeg_tree(str(tmp_path), "cifar10", train=64, val=8, workers=1, verbose=False)
+    ref = JpegFolder(str(tmp_path), "cifar10", 8, seed=2, workers=2)
+    src = JpegFolder(str(tmp_path), "cifar10", 8, seed=2, workers=2, decode_procs=2)
+    try:
+        x0, _ = src.batch(0)
+        assert src._procs_error is None and torch.equal(x0, ref.batch(0)[0])
+        with src._lock:                               # drop prefetched work, then kill the workers
+            for f in src._pending.values():
+                f.cancel()
+            src._pending.clear()
+        for p in src._ppool._procs:
+            p.kill()
+        for i in range(1, len(src)):
+            assert torch.equal(src.batch(i)[0], ref.batch(i)[0])
+        assert src._procs_error is not None and src._ppool is None
+        assert "decode processes disabled" in capfd.readouterr().err
+    finally:
+        src.close()
+        ref.close()
+    # a pool that cannot start: same fallback
+    import ddlbench_b200.data.decode_worker as dw
+    real = dw.DecodePool
+
+    class Boom:
+        def __init__(self, n):
+            raise OSError("no processes today")
+    dw.DecodePool = Boom
+    try:
+        bad = JpegFolder(str(tmp_path), "cifar10", 8, seed=2, workers=2, decode_procs=4)
+        assert torch.equal(bad.batch(0)[0], ref.batch(0)[0] if False else JpegFolder(str(tmp_path), "cifar10", 8, seed=2, workers=2).batch(0)[0])
+        assert "no processes today" in bad._procs_error
+        bad.close()
+    finally:
+        dw.DecodePool = real
+
+
+def test_decode_worker_module_is_importable_without_torch():
+    import subprocess
+    import sys
+    code = ("import sys, importlib.util; spec = importlib.util.spec_from_file_location('dw', sys.argv[1]); "
+            "m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m); "
+            "assert 'torch' not in sys.modules; print('ok')")
+    import ddlbench_b200.data.decode_worker as dw
+    r = subprocess.run([sys.executable, "-c", code, dw.__file__], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
