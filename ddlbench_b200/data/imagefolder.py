@@ -51,6 +51,26 @@ def scan_tree(root: str) -> Tuple[List[Tuple[str, int]], List[str]]:
     return samples, classes
 
 
+def _remove_stale_rings(base: str) -> None:
+    """Ring files of loaders whose process died without ``close()`` (name = ddlb_ring_<pid>_*)."""
+    try:
+        for name in os.listdir(base):
+            if not name.startswith("ddlb_ring_"):
+                continue
+            try:
+                pid = int(name.split("_")[2])
+                os.kill(pid, 0)                       # raises if the owner is gone
+            except (ValueError, IndexError, PermissionError):
+                continue
+            except ProcessLookupError:
+                try:
+                    os.unlink(os.path.join(base, name))
+                except OSError:
+                    pass
+    except OSError:
+        pass
+
+
 class JpegFolder:
     """Drop-in for ``SyntheticImages`` backed by an image tree."""
 
@@ -154,6 +174,7 @@ class JpegFolder:
                         base = "/dev/shm"
             except OSError:
                 pass
+            _remove_stale_rings(base)
             fd, path = tempfile.mkstemp(prefix="ddlb_ring_%d_" % os.getpid(), dir=base)
             try:
                 os.ftruncate(fd, need)
@@ -198,7 +219,9 @@ class JpegFolder:
             return False
         try:
             items = [(k, int(j), self.samples[j][0]) for k, j in enumerate(sel)]
-            chunk = max(1, min(4, len(items) // max(self.decode_procs, 1) or 1))
+            # 2-4 images per request: `prefetch` batches are in flight, so even 16 requests per batch
+            # keep 64 workers busy, and the parent's per-request cost (pickle + pipe + future) halves
+            chunk = max(2 if len(items) >= 16 else 1, min(4, len(items) // max(self.decode_procs, 1)))
             futs = [pool.submit(dict(ring_path=self._ring_path, ring_shape=self._ring_shape, slot=slot,
                                      items=items[c:c + chunk], dataset=self.dataset, size=self.size,
                                      channels=self.channels, augment=self.augment, seed=self.seed,
