@@ -206,9 +206,11 @@ def main(argv: Optional[List[str]] = None) -> Dict[str, float]:
         if os.path.isfile(a.resume):
             say("=> loading checkpoint '{}'".format(a.resume))
             ck = torch.load(a.resume, map_location="cpu")
-            trainer.ex.load_state_dict(ck["state_dict"])
-            if "optimizer" in ck and not trainer.ex.store.shard_optimizer:
-                trainer.ex.store.mom.copy_(ck["optimizer"]["momentum"].to(trainer.ex.store.mom.device))
+            trainer.ex.load_state_dict(ck["state_dict"])              # weights + BatchNorm buffers
+            opt = ck.get("optimizer", {})
+            if "master" in opt and "momentum" in opt:
+                # full fp32 master + momentum (every rank re-slices its own shard when sharded)
+                trainer.ex.store.load_full_state(opt["master"], opt["momentum"])
             start_epoch, best_prec1 = ck["epoch"], ck.get("best_prec1", 0.0)
             say("=> loaded checkpoint '{}' (epoch {})".format(a.resume, ck["epoch"]))
         else:
@@ -230,7 +232,8 @@ def main(argv: Optional[List[str]] = None) -> Dict[str, float]:
         master, mom = trainer.ex.store.gather_full_state(trainer.group)      # collective when sharded
         if rank == 0:
             save_checkpoint({"epoch": epoch + 1, "arch": arch, "state_dict": trainer.ex.state_dict(),
-                             "best_prec1": best_prec1, "optimizer": {"momentum": mom.detach().cpu()}},
+                             "best_prec1": best_prec1,
+                             "optimizer": {"master": master.detach().cpu(), "momentum": mom.detach().cpu()}},
                             is_best, a.checkpoint_dir)
     out["best_prec1"] = best_prec1
     trainer.check()
