@@ -19,14 +19,17 @@ weights, random-init weights.
   region is ~0.1 s; box-to-box noise is a few %).
 * ``e2e`` — the same metric end to end through the public API, LIKE FOR LIKE with the reference
   arm: the SAME synthetic JPEG tree (``baseline/jpeg_tree.py``) is read from disk, decoded and
-  augmented inside the timed loop (``data.JpegFolder``, thread pool), every step's uint8 batch is
-  copied from pinned host memory (copy stream) and the loss is read back to the host.
+  augmented inside the timed loop (``data.JpegFolder``; decode worker processes, BENCH_DECODE_PROCS=0
+  for the thread pool), every step's uint8 batch is copied from pinned host memory (copy stream) and
+  the loss is read back to the host.
   ``e2e_pinned_u8`` is the same loop fed from pre-decoded pinned batches (input pipeline excluded).
 * ``extra.torch_bf16_graph`` — stock PyTorch (cuDNN/cuBLAS, torch.optim.SGD) bf16 channels-last
   under a whole-step CUDA graph, measured in the same process: the iso-precision comparator.
 * ``checks`` (N>1) — the fused all-reduce kernel (peer loads/stores and NVLS multimem) against
   ``dist.all_reduce`` on a seeded buffer before timing, and the spread of the weights across ranks
   after timing; a failure makes the run exit non-zero.
+* ``exposed_comm`` (N>1, opt-in BENCH_EXPOSED_COMM=1, not yet run on hardware) — the step without the
+  gradient all-reduce (independent replicas) and the difference to the distributed step.
 
 Pipeline configs (BASELINE.json configs 3-5), same JSON schema:
   ``gpipe_vgg16_c10_4``  VGG-16 / CIFAR-10 shape, GPipe 4 stages, micro-batch 64 x 32 chunks
@@ -205,6 +208,47 @@ def _allreduce_checks(trainer, dev, dist, world, rank):
     return out
 
 
+def _exposed_comm(args, dev, n, src_dev, ms_step, lr, wd, max_over_ranks):
+    """Opt-in (BENCH_EXPOSED_COMM=1): the same step WITHOUT the gradient all-reduce — an independent,
+    non-distributed replica of the trainer on every rank (its own separate SGD launch included) —
+    timed concurrently on all ranks; ``exposed_comm_ms`` = distributed step - this one.  No collective
+    is issued inside the measured part and every rank always reaches the final reduction, so a
+    failure on one rank cannot strand the others."""
+    import torch
+    from ddlbench_b200.harness import Trainer
+    ms_local, err = float("nan"), None
+    local = None
+    try:
+        local = Trainer(ARCH, DATASET, PER_GPU_BATCH, device=str(dev), dtype=torch.bfloat16, lr=lr,
+                        momentum=0.9, weight_decay=wd, cuda_graph=not args.no_graph, distributed=False,
+                        tcgen05=not args.no_tcgen05)
+        mean, std = src_dev.mean, src_dev.std
+        for i in range(max(args.warmup, 3)):
+            local.step_u8(*src_dev.batch(i), mean, std)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for i in range(args.steps):
+            local.step_u8(*src_dev.batch(i), mean, std)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms_local = e0.elapsed_time(e1) / args.steps
+    except Exception as e:  # noqa: BLE001
+        err = "%s: %s" % (type(e).__name__, str(e)[:200])
+    finally:
+        del local
+        torch.cuda.empty_cache()
+    failed = max_over_ranks(0.0 if err is None else 1.0, dev)            # every rank gets here
+    ms_max = max_over_ranks(ms_local if err is None else -1.0, dev)
+    if failed > 0:
+        return {"error": err or "failed on another rank"}
+    return {"ms_per_step_without_allreduce": round(ms_max, 4),
+            "exposed_comm_ms": round(ms_step - ms_max, 4),
+            "note": "independent non-distributed replicas (separate SGD launch) timed concurrently on all "
+                    "ranks, max over ranks; negative = the fused all-reduce + SGD step is shorter than a "
+                    "local step with its own optimizer launch"}
+
+
 def _weight_spread(trainer, dev, dist):
     import torch
     w = trainer.ex.store.w_flat[trainer.ex.store.latest].float()
@@ -285,6 +329,10 @@ def run_ours(args) -> dict:
         checks["weight_spread"] = _weight_spread(trainer, dev, dist)
         checks["weights_ok"] = checks["weight_spread"] == 0.0
 
+    exposed = None
+    if n > 1 and os.environ.get("BENCH_EXPOSED_COMM", "0") == "1":
+        exposed = _exposed_comm(args, dev, n, src_dev, ms_step, lr, wd, max_over_ranks)
+
     extra = {}
     if rank == 0 and not args.no_torch_baseline:
         try:
@@ -331,6 +379,8 @@ def run_ours(args) -> dict:
     }
     if checks:
         out["checks"] = checks
+    if exposed is not None:
+        out["exposed_comm"] = exposed
     if e2e_nvjpeg is not None:
         out["e2e_nvjpeg"] = e2e_nvjpeg
     if rank == 0:
